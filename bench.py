@@ -1,0 +1,323 @@
+#!/usr/bin/env python
+"""bench.py -- CDPR instance-steps/s of the batched hot path on N B200s (weak scaling), one JSON line.
+
+  python bench.py --gpus N --steps K --warmup W            own arm (CUDA path through the C ABI)
+  python bench.py --impl reference --gpus N --steps K ...  reference arm: the reference's own force-law
+                                                           code (oracle/_ref) in the reduced model on the host cores
+
+A bench "step" is one pass of the hot path over one batch: `instances` independent robots per GPU, each
+advanced `sim_steps` physics steps by ONE persistent kernel launch (BASELINE.json configs[2]: 2^20 instances x
+1000 steps under per-instance sine velocity commands, fp64; NC = 8 is the north_star's synthetic 8-cable
+extension of the 4-cable reference robot).  For N > 1 every rank owns its own 2^20 instances (configs[3]) and the
+decimated trajectory (a snapshot every 100 steps) is all-gathered over NCCL on a side stream inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "CDPR instance-steps/sec"
+UNIT = "instance-steps/s"
+# Algorithmic FP64 work per instance-step (FMA = 2 flop, sqrt = div = 1):
+#   platform part 196 (diagonal body inertia, as in sdf/cube.sdf:331-338) + per cable 52 (kinematics) + 32 (force
+#   law, FIR form of the D-term) + 14 (damping + wrench)
+def flops_per_instance_step(nc: int) -> int:
+    return 196 + nc * (52 + 32 + 14)
+
+
+def state_bytes_per_instance(nc: int) -> int:
+    # what the persistent kernel reads + writes per instance and launch: platform 13, per cable i_err, target,
+    # window 11, ctl (4 B) in; platform 13, per cable i_err, last_time, window 11, ctl, 6 telemetry columns out
+    return 8 * (13 + nc * 13 + 3) + 4 * nc + 8 * (13 + nc * 19) + 4 * nc
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index: int):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def make_oracle_config(nc: int):
+    from oracle import binding as ob
+    return ob.default_config(nc)
+
+
+def cpu_arm(kind: str, nc: int, sim_steps: int, target_seconds: float, passes: int, cores: int):
+    """Times the CPU oracle (kind 'port') or the reference's own force law inside the reduced model (kind
+    'reference') on a bounded sample of the same workload.  Returns (instance-steps/s, sample description)."""
+    from oracle import binding as ob
+    from cdpr_simulation_b200 import workloads as wl
+    cfg = make_oracle_config(nc)
+
+    def run(n):
+        amp, freq, phase, pose7, twist6 = wl.c3_instances(n, seed=1)
+        b = ob.Batch(cfg, n, pose7, twist6, amp, freq, phase)
+        t0 = time.perf_counter()
+        if kind == "reference":
+            b.step_reference_forcelaw(sim_steps, cores)
+        else:
+            b.step(sim_steps, cores)
+        return time.perf_counter() - t0
+
+    n0 = 8 * cores
+    t = run(n0)
+    rate = n0 * sim_steps / t
+    n = int(max(cores, min(1 << 20, rate * target_seconds / sim_steps)))
+    n = (n + cores - 1) // cores * cores
+    times = [run(n) for _ in range(max(1, passes))]
+    best = n * sim_steps / float(np.mean(times))
+    return best, f"{n} instances x {sim_steps} steps (same generator and seed as the GPU batch, first {n} instances), " \
+                 f"{len(times)} pass(es), {cores} OpenMP threads", float(np.mean(times)) * 1e3
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import binding as ob
+    ob.build()
+    kind = "reference" if ob.ref_available() else "port"
+    cores = host_cores()
+    value, sample, ms = cpu_arm(kind, args.nc, args.sim_steps, args.ref_seconds, args.steps, cores)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"C3 sample: sine velocity commands, NC={args.nc}, {args.sim_steps} physics steps per pass, "
+                               "reduced model with the reference's Pid.cpp/JointForceCalculator.cpp as the force law, host cores only"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def own_arm(args):
+    import torch
+    import torch.distributed as dist
+    import cdpr_simulation_b200 as cb
+    from cdpr_simulation_b200 import workloads as wl
+    from cdpr_simulation_b200.distributed import TrajectoryGather
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    nc, n, k_sim = args.nc, args.instances, args.sim_steps
+    cfg = cb.default_config(nc)
+    # rank-specific slice of the C3/C4 generator (global instance id = rank * n + local id)
+    amp, freq, phase, pose7, twist6 = wl.c3_instances(n, seed=1 + 1000 * rank)
+
+    def pinned(a):
+        t = torch.empty(a.shape, dtype=torch.from_numpy(a).dtype, pin_memory=True)
+        t.numpy()[...] = a
+        return t
+    pin_in = [pinned(a) for a in (amp, freq, phase, pose7, twist6)]
+    pin_out = [torch.empty(s, dtype=torch.float64, pin_memory=True) for s in ((n, 7), (n, 6), (n, nc), (n, nc), (n, nc))]
+
+    stream = torch.cuda.Stream()
+    batch = cb.CdprBatch(cfg, n, device=local_rank)
+    batch.set_stream(stream.cuda_stream)
+    assert batch.kernel_variant == "fast"
+    gather = TrajectoryGather(batch, every=args.snapshot_every, steps_per_pass=k_sim, stream=stream) if world > 1 else None
+
+    def load_inputs():
+        batch.set_platform_state(pin_in[3].numpy(), pin_in[4].numpy())
+        batch.set_sine_cmd(pin_in[0].numpy(), pin_in[1].numpy(), pin_in[2].numpy())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    fp64_peak = cb.measure_fp64_tflops(local_rank, 8192)
+
+    # ---------------- value: inputs resident in HBM, device-timed ----------------
+    with torch.cuda.stream(stream):
+        load_inputs()
+        for _ in range(args.warmup):
+            if gather: gather.before_pass()
+            batch.step(k_sim)
+            if gather: gather.after_pass()
+        barrier()
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        launches0 = batch.launch_count
+        kernel_ms = []
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        for _ in range(args.steps):
+            if gather: gather.before_pass()
+            batch.step(k_sim)
+            if gather: gather.after_pass()
+            kernel_ms.append(batch.last_kernel_ms)   # CUDA events recorded by the library around its launch
+        if gather: gather.finish()
+        ev1.record(stream)
+        barrier()
+        clocks = sampler.stop() if rank == 0 else None
+        ms_total = ev0.elapsed_time(ev1)
+        launches = batch.launch_count - launches0
+
+        # ---------------- e2e: host buffers in, host buffers out, through the public API ----------------
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            batch.reset()
+            load_inputs()                                   # H2D from pinned memory
+            if gather: gather.before_pass()
+            batch.step(k_sim)
+            if gather: gather.after_pass()
+            batch.platform_state((pin_out[0].numpy(), pin_out[1].numpy()))   # D2H
+            batch.joint_states(tuple(t.numpy() for t in pin_out[2:]))
+        if gather: gather.finish()
+        barrier()
+        e2e_s = time.perf_counter() - t0
+
+    t = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, e2e_ms = float(t[0]), float(t[1])
+    total_units = float(world) * n * k_sim * args.steps
+    value = total_units / (ms_total * 1e-3)
+    e2e_value = total_units / (e2e_ms * 1e-3)
+    h2d = sum(x.numel() * x.element_size() for x in pin_in)
+    d2h = sum(x.numel() * x.element_size() for x in pin_out)
+
+    if rank == 0:
+        kms = float(np.mean(kernel_ms))
+        flops = flops_per_instance_step(nc) * float(n) * k_sim
+        achieved = flops / (kms * 1e-3) / 1e12
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        hbm_bytes = state_bytes_per_instance(nc) * float(n)
+        roofline = {
+            "bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak if fp64_peak > 0 else None,
+            "traffic": None,
+            "kernel": f"k_step_fast<{nc},11>", "kernel_ms": kms,
+            "flops_per_instance_step": flops_per_instance_step(nc),
+            "peak_source": "DFMA issue rate measured in this run by cdpr_measure_fp64_tflops (MEASURED_PEAKS.json has no FP64 entry; "
+                           "nominal B200 FP64 is 37 TFLOP/s)",
+            "hbm": {"achieved": hbm_bytes / (kms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": hbm_bytes / (kms * 1e-3) / 1e9 / hbm_peak,
+                    "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
+                    "note": "state is read and written once per launch of 1000 steps: the kernel is FP64-issue bound, not HBM bound"},
+        }
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            v, sample, _ = cpu_arm("port", nc, k_sim, args.cpu_seconds, 1, host_cores())
+            cpu = {"value": v, "unit": UNIT, "cores": host_cores(), "kind": "port", "sample": sample}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"C3: {n} instances/GPU x {k_sim} physics steps per pass, per-instance sine velocity commands, "
+                                   f"NC={nc} ({'synthetic 8-cable extension' if nc == 8 else 'reference 4-cable robot'})",
+                       "instances_per_gpu": n, "sim_steps_per_pass": k_sim, "n_cables": nc,
+                       "l2": "resident state per GPU (%.1f GB) is larger than L2; no flush needed" % (batch_state_gb(batch)),
+                       "multi_gpu": None if world == 1 else f"snapshot every {args.snapshot_every} steps all-gathered over NCCL on a side stream"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms / args.steps,
+                    "what": "reset + H2D(pose, twist, sine params) + step + D2H(platform pose/twist, joint states), pinned host buffers"},
+            "gpu_launches": int(launches),
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    batch.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def batch_state_gb(batch) -> float:
+    import ctypes
+    return batch._L.cdpr_state_bytes(batch._h) / 1e9
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="own", choices=["own", "reference"])
+    ap.add_argument("--nc", type=int, default=8, choices=[4, 8])
+    ap.add_argument("--instances", type=int, default=1 << 20, help="instances per GPU")
+    ap.add_argument("--sim-steps", type=int, default=1000, help="physics steps per pass (one kernel launch)")
+    ap.add_argument("--snapshot-every", type=int, default=100)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--ref-seconds", type=float, default=6.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "own":
+        args.warmup = 3
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        own_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,809 @@
+// api.cu -- host side of libcdpr_b200.so: the C ABI of include/cdpr_b200.h over the sm_100a kernels.
+// No CPU fallback anywhere: without a CUDA device every entry point fails.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/cdpr_b200.h"
+#include "common.cuh"
+#include "misc_kernels.cuh"
+#include "step_fast.cuh"
+#include "step_general.cuh"
+
+using namespace cdpr;
+
+static thread_local std::string g_create_error;
+
+struct cdpr_batch {
+  cdpr_config cfg;
+  int device = 0;
+  long long n = 0, np = 0;
+  bool general = false;
+  DevLayout L{};
+  RobotConsts rc{};
+  PidConsts pc[2]{};
+  double fir[2][kMaxDbuf]{};
+  int mode = MODE_POSITION;
+  bool vel_pending = false, pos_pending = false;
+  int sec = 0, nsec = 0, dt_ns = 0;
+  long long step_count = 0;
+  bool sine_on = false;
+  int sine_period = 10;
+  double sine_time = 0.0, sine_pub_dt = 0.01;
+  double *snap = nullptr;
+  long long snap_every = 0, snap_written = 0, snap_capacity = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool timed = false;
+  long long launches = 0;
+  void *stage = nullptr;
+  size_t stage_bytes = 0;
+  double *cost_dev = nullptr;
+  float *cmd_dev = nullptr;
+  size_t cmd_dev_bytes = 0;
+  std::vector<void *> allocs;
+  std::string err;
+};
+
+#define CK(h, call)                                                                         \
+  do {                                                                                      \
+    cudaError_t e_ = (call);                                                                \
+    if (e_ != cudaSuccess) {                                                                \
+      (h)->err = std::string(#call) + ": " + cudaGetErrorString(e_);                        \
+      return CDPR_ERR_CUDA;                                                                 \
+    }                                                                                       \
+  } while (0)
+
+static int fail(cdpr_handle h, int code, const std::string &msg) {
+  if (h) h->err = msg; else g_create_error = msg;
+  return code;
+}
+
+// ---------------------------------------------------------------------------------------------
+// constants
+// ---------------------------------------------------------------------------------------------
+extern "C" int cdpr_config_default(cdpr_config *cfg, int n_cables) {
+  if (!cfg || n_cables < 1 || n_cables > CDPR_MAX_CABLES) return CDPR_ERR_BAD_ARG;
+  std::memset(cfg, 0, sizeof(*cfg));
+  cfg->n_cables = n_cables;
+  // sdf/cube.sdf: frame anchors :383,559,735,911; platform anchors :458,634,810,986 relative to :310.
+  // Cables 4..7 (synthetic 8-cable extension): same corners on the lower frame face z = 0.
+  const double sx[4] = {-1, -1, 1, 1}, sy[4] = {-1, 1, 1, -1};
+  for (int c = 0; c < n_cables; ++c) {
+    cfg->frame_anchor[c][0] = 0.3 * sx[c & 3];
+    cfg->frame_anchor[c][1] = 0.3 * sy[c & 3];
+    cfg->frame_anchor[c][2] = c < 4 ? 0.6 : 0.0;
+    cfg->platform_anchor[c][0] = 0.03 * sx[c & 3];
+    cfg->platform_anchor[c][1] = 0.03 * sy[c & 3];
+    cfg->platform_anchor[c][2] = 0.0;
+  }
+  cfg->home_pos[2] = 0.3;
+  cfg->home_quat[0] = 1.0;
+  cfg->mass = 1.0;
+  cfg->inertia[0] = cfg->inertia[1] = cfg->inertia[2] = 1.0;
+  cfg->gravity[2] = -9.8;
+  cfg->cable_damping = 1.0;
+  cfg->effort_limit = 100.0;
+  cfg->dt = 0.001;
+  cdpr_pid_params &v = cfg->vel_pid, &p = cfg->pos_pid;  // launch/cdpr_gazebo.launch:19-39
+  v.forward_gain = 0.0; v.p_gain = 200.0; v.i_gain = 20.0; v.d_gain = 1.0;
+  v.d_degree = 2; v.d_buffer_length = 11; v.i_limit = 100.0; v.cmd_limit = 100.0;
+  v.p_cutoff = 0.1; v.p_quality = 0.707; v.p_cascade = 0;
+  v.d_cutoff = 0.1; v.d_quality = 0.707; v.d_cascade = 0;
+  p = v;
+  p.forward_gain = 0.0; p.p_gain = 200.0; p.i_gain = 70.0; p.d_gain = 80.0;
+  p.p_cascade = p.d_cascade = 0;
+  cfg->velocity_epsilon = -0.001;
+  cfg->sine_publish_hz = 100.0;
+  return CDPR_OK;
+}
+
+static void biquad_coeffs(double fc, double q, double out[5]) {  // Filter.h:130-140 with fs = 1 (Pid.cpp:34)
+  const double k = std::tan(M_PI * fc / 1.0);
+  const double den = k * k + k / q + 1.0;
+  out[0] = k * k / den;
+  out[1] = 2 * out[0];
+  out[2] = out[0];
+  out[3] = 2 * (k * k - 1.0) / den;
+  out[4] = (k * k - k / q + 1.0) / den;
+}
+
+static void make_pid_consts(const cdpr_pid_params &p, PidConsts &o) {  // Pid.cpp:63-77
+  std::memset(&o, 0, sizeof(o));
+  o.kf = p.forward_gain; o.kp = p.p_gain; o.ki = p.i_gain; o.kd = p.d_gain;
+  o.i_max = std::fabs(p.i_limit); o.i_min = -std::fabs(p.i_limit);
+  o.i_max_over_ki = o.i_max / p.i_gain; o.i_min_over_ki = o.i_min / p.i_gain;
+  o.cmd_max = std::fabs(p.cmd_limit); o.cmd_min = -std::fabs(p.cmd_limit);
+  o.degree = p.d_degree; o.len = p.d_buffer_length; o.p_casc = p.p_cascade; o.d_casc = p.d_cascade;
+  if (p.p_cascade > 0) biquad_coeffs(p.p_cutoff, p.p_quality, o.pf);
+  if (p.d_cascade > 0) biquad_coeffs(p.d_cutoff, p.d_quality, o.df);
+}
+
+// FIR form of Pid::derive for uniformly spaced samples: weights w_j with
+//   d/dt p(now) = sum_j w_j * y_j,   p = least-squares polynomial of `degree` through the window.
+// Row 1 of (V^T V)^-1 V^T on the abscissae x_j = (j - (len-1)) / (len-1), divided by the span.
+static void fir_weights(int degree, int len, double dt, double *w) {
+  for (int j = 0; j < kMaxDbuf; ++j) w[j] = 0.0;
+  if (degree < 1 || len < 2) return;
+  const int m = degree + 1;
+  long double G[kMaxDegree + 1][kMaxDegree + 2];
+  std::vector<long double> x(len);
+  for (int j = 0; j < len; ++j) x[j] = (long double)(j - (len - 1)) / (long double)(len - 1);
+  for (int r = 0; r < m; ++r) {
+    for (int q = 0; q < m; ++q) {
+      long double s = 0;
+      for (int j = 0; j < len; ++j) s += powl(x[j], r + q);
+      G[r][q] = s;
+    }
+    G[r][m] = (r == 1) ? 1.0L : 0.0L;
+  }
+  for (int col = 0; col < m; ++col) {
+    int piv = col;
+    for (int r = col + 1; r < m; ++r) if (fabsl(G[r][col]) > fabsl(G[piv][col])) piv = r;
+    for (int q = 0; q <= m; ++q) std::swap(G[col][q], G[piv][q]);
+    for (int r = 0; r < m; ++r) {
+      if (r == col) continue;
+      const long double f = G[r][col] / G[col][col];
+      for (int q = col; q <= m; ++q) G[r][q] -= f * G[col][q];
+    }
+  }
+  const long double span = (long double)(len - 1) * (long double)dt;
+  for (int j = 0; j < len; ++j) {
+    long double s = 0;
+    for (int k = 0; k < m; ++k) s += (G[k][m] / G[k][k]) * powl(x[j], k);
+    w[j] = (double)(s / span);
+  }
+}
+
+static void quat_rot_host(const double q[4], double R[3][3]) {
+  const double w = q[0], x = q[1], y = q[2], z = q[3];
+  R[0][0] = 1 - 2 * (y * y + z * z); R[0][1] = 2 * (x * y - w * z); R[0][2] = 2 * (x * z + w * y);
+  R[1][0] = 2 * (x * y + w * z); R[1][1] = 1 - 2 * (x * x + z * z); R[1][2] = 2 * (y * z - w * x);
+  R[2][0] = 2 * (x * z - w * y); R[2][1] = 2 * (y * z + w * x); R[2][2] = 1 - 2 * (x * x + y * y);
+}
+
+static int make_robot_consts(const cdpr_config &c, RobotConsts &o, std::string &err) {
+  std::memset(&o, 0, sizeof(o));
+  double R[3][3];
+  quat_rot_host(c.home_quat, R);
+  for (int i = 0; i < c.n_cables; ++i) {
+    double d[3];
+    for (int k = 0; k < 3; ++k) {
+      o.a[i][k] = c.frame_anchor[i][k];
+      o.b[i][k] = c.platform_anchor[i][k];
+    }
+    for (int k = 0; k < 3; ++k) {
+      const double r = R[k][0] * o.b[i][0] + R[k][1] * o.b[i][1] + R[k][2] * o.b[i][2];
+      d[k] = o.a[i][k] - c.home_pos[k] - r;
+    }
+    o.home_len[i] = std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+  }
+  for (int k = 0; k < 3; ++k) o.mg[k] = c.mass * c.gravity[k];
+  o.h = c.dt; o.h_over_m = c.dt / c.mass; o.half_h = 0.5 * c.dt;
+  const double *I = c.inertia;
+  const double a = I[0], b = I[1], cc = I[2], d = I[3], e = I[4], f = I[5];  // [a d e; d b f; e f c]
+  const double det = a * (b * cc - f * f) - d * (d * cc - f * e) + e * (d * f - b * e);
+  if (!(det != 0.0) || !(c.mass > 0.0)) { err = "singular inertia or non-positive mass"; return CDPR_ERR_BAD_ARG; }
+  for (int k = 0; k < 6; ++k) o.ib[k] = I[k];
+  o.ib_inv[0] = (b * cc - f * f) / det; o.ib_inv[1] = (a * cc - e * e) / det; o.ib_inv[2] = (a * b - d * d) / det;
+  o.ib_inv[3] = (e * f - d * cc) / det; o.ib_inv[4] = (d * f - e * b) / det; o.ib_inv[5] = (d * e - a * f) / det;
+  o.diag_inertia = (d == 0.0 && e == 0.0 && f == 0.0) ? 1 : 0;
+  o.cdamp = c.cable_damping; o.effort_limit = c.effort_limit; o.vel_eps = c.velocity_epsilon;
+  o.effort_limit_abs = c.effort_limit >= 0.0 ? c.effort_limit : INFINITY;
+  return CDPR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// lifecycle
+// ---------------------------------------------------------------------------------------------
+static int dev_alloc(cdpr_handle h, void **p, size_t bytes) {
+  cudaError_t e = cudaMalloc(p, bytes);
+  if (e != cudaSuccess) { h->err = std::string("cudaMalloc: ") + cudaGetErrorString(e); return CDPR_ERR_NOMEM; }
+  h->allocs.push_back(*p);
+  return CDPR_OK;
+}
+
+static int ensure_stage(cdpr_handle h, size_t bytes) {
+  if (bytes <= h->stage_bytes) return CDPR_OK;
+  if (h->stage) cudaFree(h->stage);
+  h->stage = nullptr; h->stage_bytes = 0;
+  cudaError_t e = cudaMalloc(&h->stage, bytes);
+  if (e != cudaSuccess) { h->err = std::string("cudaMalloc(stage): ") + cudaGetErrorString(e); return CDPR_ERR_NOMEM; }
+  h->stage_bytes = bytes;
+  return CDPR_OK;
+}
+
+static inline unsigned grid_for(long long n, int tpb) { return (unsigned)((n + tpb - 1) / tpb); }
+
+static int reset_to_load_state(cdpr_handle h) {
+  const DevLayout &L = h->L;
+  CK(h, cudaMemsetAsync(L.cab, 0, sizeof(double) * L.nc * CAB_F * L.np, h->stream));
+  CK(h, cudaMemsetAsync(L.pid, 0, sizeof(double) * L.nc * 2 * PID_F * L.np, h->stream));
+  CK(h, cudaMemsetAsync(L.win_y, 0, sizeof(double) * L.nc * 2 * L.len * L.np, h->stream));
+  if (L.win_x) CK(h, cudaMemsetAsync(L.win_x, 0, sizeof(double) * L.nc * 2 * L.len * L.np, h->stream));
+  if (L.filt) CK(h, cudaMemsetAsync(L.filt, 0, sizeof(double) * L.nc * 2 * 2 * L.casc * 4 * L.np, h->stream));
+  const cdpr_config &c = h->cfg;
+  k_init_state<<<grid_for(L.np, 256), 256, 0, h->stream>>>(L, h->rc, c.home_pos[0], c.home_pos[1], c.home_pos[2], c.home_quat[0],
+                                                           c.home_quat[1], c.home_quat[2], c.home_quat[3],
+                                                           (unsigned)c.vel_pid.d_buffer_length, (unsigned)c.pos_pid.d_buffer_length);
+  CK(h, cudaGetLastError());
+  h->mode = MODE_POSITION;  // CdprGazeboPlugin.cpp:154
+  h->vel_pending = h->pos_pending = false;
+  h->sec = h->nsec = 0;
+  h->step_count = 0;
+  h->sine_time = 0.0;
+  return CDPR_OK;
+}
+
+extern "C" int cdpr_create(const cdpr_config *cfg, int64_t n_instances, int device, cdpr_handle *out) {
+  if (!cfg || !out) return fail(nullptr, CDPR_ERR_BAD_ARG, "null argument");
+  *out = nullptr;
+  if (cfg->n_cables < 1 || cfg->n_cables > CDPR_MAX_CABLES)
+    return fail(nullptr, CDPR_ERR_BAD_CABLE_COUNT, "invalid joint count");  // CdprGazeboPlugin.cpp:167-169
+  if (n_instances < 1 || n_instances > (1LL << 31) - 256) return fail(nullptr, CDPR_ERR_BAD_ARG, "n_instances out of range");
+  const cdpr_pid_params *pp[2] = {&cfg->vel_pid, &cfg->pos_pid};
+  for (int k = 0; k < 2; ++k) {
+    if (pp[k]->d_buffer_length < 2 || pp[k]->d_buffer_length > CDPR_MAX_DBUF || pp[k]->d_degree < 0 ||
+        pp[k]->d_degree > CDPR_MAX_DEGREE || pp[k]->d_degree + 1 > pp[k]->d_buffer_length || pp[k]->p_cascade < 0 ||
+        pp[k]->p_cascade > CDPR_MAX_CASCADE || pp[k]->d_cascade < 0 || pp[k]->d_cascade > CDPR_MAX_CASCADE)
+      return fail(nullptr, CDPR_ERR_BAD_ARG, "pid parameters out of range");
+  }
+  const double ns = cfg->dt * 1e9;
+  if (!(cfg->dt > 0.0) || std::fabs(ns - std::round(ns)) > 1e-6 || ns > 1e9)
+    return fail(nullptr, CDPR_ERR_BAD_ARG, "dt must be a whole number of nanoseconds in (0, 1 s]");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device < 0 || device >= ndev)
+    return fail(nullptr, CDPR_ERR_NO_DEVICE, "no CUDA device (this library has no CPU fallback)");
+  cdpr_handle h = new (std::nothrow) cdpr_batch();
+  if (!h) return fail(nullptr, CDPR_ERR_NOMEM, "out of host memory");
+  h->cfg = *cfg;
+  h->device = device;
+  int rc = make_robot_consts(*cfg, h->rc, h->err);
+  if (rc != CDPR_OK) { g_create_error = h->err; delete h; return rc; }
+  make_pid_consts(cfg->vel_pid, h->pc[PID_VEL]);
+  make_pid_consts(cfg->pos_pid, h->pc[PID_POS]);
+  fir_weights(cfg->vel_pid.d_degree, cfg->vel_pid.d_buffer_length, cfg->dt, h->fir[PID_VEL]);
+  fir_weights(cfg->pos_pid.d_degree, cfg->pos_pid.d_buffer_length, cfg->dt, h->fir[PID_POS]);
+  h->dt_ns = (int)std::llround(ns);
+  h->sine_pub_dt = 1.0 / cfg->sine_publish_hz;  // sinevelocitytest.cpp:48
+  h->sine_period = (int)std::llround(h->sine_pub_dt / cfg->dt);
+  if (h->sine_period < 1) h->sine_period = 1;
+  // Which kernel variant? The fast one needs: hold impossible, no filters, cmdLimit != 0, window 11 for both Pids.
+  const bool fast_ok = cfg->velocity_epsilon < 0.0 && cfg->vel_pid.p_cascade == 0 && cfg->vel_pid.d_cascade == 0 &&
+                       cfg->pos_pid.p_cascade == 0 && cfg->pos_pid.d_cascade == 0 && cfg->vel_pid.cmd_limit != 0.0 &&
+                       cfg->pos_pid.cmd_limit != 0.0 && cfg->vel_pid.d_buffer_length == 11 && cfg->pos_pid.d_buffer_length == 11 &&
+                       (cfg->n_cables == 4 || cfg->n_cables == 8);
+  h->general = !fast_ok;
+
+  auto bail = [&](int code) { g_create_error = h->err; cdpr_destroy(h); return code; };
+  if (cudaSetDevice(device) != cudaSuccess) { h->err = "cudaSetDevice failed"; return bail(CDPR_ERR_CUDA); }
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { h->err = "stream create failed"; return bail(CDPR_ERR_CUDA); }
+  h->own_stream = true;
+  cudaEventCreate(&h->ev0);
+  cudaEventCreate(&h->ev1);
+  h->n = n_instances;
+  h->np = (n_instances + kTpb - 1) / kTpb * kTpb;
+  DevLayout &L = h->L;
+  L.n = (int)h->n; L.np = h->np; L.nc = cfg->n_cables;
+  L.len = std::max(cfg->vel_pid.d_buffer_length, cfg->pos_pid.d_buffer_length);
+  L.casc = std::max(std::max(cfg->vel_pid.p_cascade, cfg->vel_pid.d_cascade), std::max(cfg->pos_pid.p_cascade, cfg->pos_pid.d_cascade));
+  const size_t col = sizeof(double) * (size_t)L.np;
+  if ((rc = dev_alloc(h, (void **)&L.plat, col * 13))) return bail(rc);
+  if ((rc = dev_alloc(h, (void **)&L.cab, col * L.nc * CAB_F))) return bail(rc);
+  if ((rc = dev_alloc(h, (void **)&L.pid, col * L.nc * 2 * PID_F))) return bail(rc);
+  if ((rc = dev_alloc(h, (void **)&L.win_y, col * L.nc * 2 * L.len))) return bail(rc);
+  if (h->general) {
+    if ((rc = dev_alloc(h, (void **)&L.win_x, col * L.nc * 2 * L.len))) return bail(rc);
+    if (L.casc > 0 && (rc = dev_alloc(h, (void **)&L.filt, col * L.nc * 2 * 2 * L.casc * 4))) return bail(rc);
+  }
+  if ((rc = dev_alloc(h, (void **)&L.ctl, sizeof(uint32_t) * (size_t)L.np * L.nc))) return bail(rc);
+  if ((rc = dev_alloc(h, (void **)&L.sine, col * 3))) return bail(rc);
+  if (cudaMemsetAsync(L.sine, 0, col * 3, h->stream) != cudaSuccess) { h->err = "memset failed"; return bail(CDPR_ERR_CUDA); }
+  if ((rc = reset_to_load_state(h))) return bail(rc);
+  if (!h->general) {
+    const int smem4 = 11 * 4 * kTpb * 8, smem8 = 11 * 8 * kTpb * 8;
+    cudaFuncSetAttribute(k_step_fast<4, 11>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem4);
+    cudaFuncSetAttribute(k_step_fast<8, 11>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem8);
+    cudaFuncSetAttribute(k_step_fast<4, 11>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(k_step_fast<8, 11>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  }
+  if (cudaStreamSynchronize(h->stream) != cudaSuccess) { h->err = "initialisation kernels failed"; return bail(CDPR_ERR_CUDA); }
+  *out = h;
+  return CDPR_OK;
+}
+
+extern "C" int cdpr_destroy(cdpr_handle h) {
+  if (!h) return CDPR_ERR_BAD_ARG;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  for (void *p : h->allocs) cudaFree(p);
+  if (h->stage) cudaFree(h->stage);
+  if (h->cost_dev) cudaFree(h->cost_dev);
+  if (h->cmd_dev) cudaFree(h->cmd_dev);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return CDPR_OK;
+}
+
+extern "C" int cdpr_reset(cdpr_handle h) {
+  if (!h) return CDPR_ERR_BAD_ARG;
+  cudaSetDevice(h->device);
+  int rc = reset_to_load_state(h);
+  if (rc) return rc;
+  h->snap_written = 0;
+  h->launches += 1;
+  return CDPR_OK;
+}
+
+extern "C" const char *cdpr_last_error(cdpr_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int cdpr_set_stream(cdpr_handle h, void *cuda_stream) {
+  if (!h) return CDPR_ERR_BAD_ARG;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+  h->stream = (cudaStream_t)cuda_stream;
+  h->own_stream = false;
+  return CDPR_OK;
+}
+
+extern "C" int cdpr_synchronize(cdpr_handle h) {
+  if (!h) return CDPR_ERR_BAD_ARG;
+  cudaSetDevice(h->device);
+  CK(h, cudaStreamSynchronize(h->stream));
+  return CDPR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// commands
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+static int scatter_cmd(cdpr_handle h, const T *host, int64_t n_instances, int n_axes, int field) {
+  if (!h || !host) return CDPR_ERR_BAD_ARG;
+  // the plugin drops a Joy message whose axes.size() != cWireCount (CdprGazeboPlugin.cpp:68,77)
+  if (n_axes != h->L.nc) return fail(h, CDPR_ERR_BAD_LENGTH, "command length != cable count: dropped");
+  if (n_instances != h->n) return fail(h, CDPR_ERR_BAD_ARG, "n_instances does not match the handle");
+  cudaSetDevice(h->device);
+  const size_t bytes = sizeof(T) * (size_t)h->n * h->L.nc;
+  int rc = ensure_stage(h, bytes);
+  if (rc) return rc;
+  CK(h, cudaMemcpyAsync(h->stage, host, bytes, cudaMemcpyHostToDevice, h->stream));
+  k_scatter_cab<T><<<grid_for(h->n, 256), 256, 0, h->stream>>>(h->L, field, (const T *)h->stage);
+  CK(h, cudaGetLastError());
+  CK(h, cudaStreamSynchronize(h->stream));  // the caller may reuse its buffer
+  return CDPR_OK;
+}
+
+extern "C" int cdpr_set_velocity_cmd(cdpr_handle h, const float *axes, int64_t n_instances, int n_axes) {
+  int rc = scatter_cmd<float>(h, axes, n_instances, n_axes, CAB_VEL_TARGET);
+  if (rc == CDPR_OK) h->vel_pending = true;
+  return rc;
+}
+extern "C" int cdpr_set_position_cmd(cdpr_handle h, const float *axes, int64_t n_instances, int n_axes) {
+  int rc = scatter_cmd<float>(h, axes, n_instances, n_axes, CAB_POS_TARGET);
+  if (rc == CDPR_OK) h->pos_pending = true;
+  return rc;
+}
+extern "C" int cdpr_set_effort_cmd(cdpr_handle h, const double *force, int64_t n_instances, int n_axes) {
+  int rc = scatter_cmd<double>(h, force, n_instances, n_axes, CAB_FORCE_CMD);
+  if (rc == CDPR_OK) h->mode = MODE_FORCE;  // JointForceCalculator.h:92-95: immediate
+  return rc;
+}
+
+extern "C" int cdpr_set_sine_cmd(cdpr_handle h, const double *amp, const double *freq, const double *phase, int64_t n_instances) {
+  if (!h) return CDPR_ERR_BAD_ARG;
+  if (!amp) { h->sine_on = false; return CDPR_OK; }
+  if (n_instances != h->n) return fail(h, CDPR_ERR_BAD_ARG, "n_instances does not match the handle");
+  cudaSetDevice(h->device);
+  const size_t bytes = sizeof(double) * (size_t)h->n;
+  std::vector<double> def;
+  const double *src[3] = {amp, freq, phase};
+  const double defaults[3] = {0.05, 0.1, 0.0};  // sinevelocitytest.cpp:8-9
+  for (int k = 0; k < 3; ++k) {
+    if (!src[k]) { def.assign((size_t)h->n, defaults[k]); src[k] = def.data(); }
+    CK(h, cudaMemcpyAsync(h->L.sine + (size_t)k * h->L.np, src[k], bytes, cudaMemcpyHostToDevice, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+  }
+  h->sine_on = true;
+  h->sine_time = 0.0;
+  return CDPR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// stepping
+// ---------------------------------------------------------------------------------------------
+static int reset_pid(cdpr_handle h, int k) {
+  const unsigned len = (unsigned)(k == PID_VEL ? h->cfg.vel_pid.d_buffer_length : h->cfg.pos_pid.d_buffer_length);
+  k_reset_pid<<<grid_for(h->L.np, 256), 256, 0, h->stream>>>(h->L, k, len);
+  CK(h, cudaGetLastError());
+  ++h->launches;
+  return CDPR_OK;
+}
+
+static void fill_args(cdpr_handle h, StepArgs &A, int k_steps, bool sine) {
+  std::memset(&A, 0, sizeof(A));
+  A.L = h->L; A.rc = h->rc; A.pc[0] = h->pc[0]; A.pc[1] = h->pc[1];
+  A.live_idx = (h->mode == MODE_POSITION) ? PID_POS : PID_VEL;
+  A.live = h->pc[A.live_idx];
+  std::memcpy(A.fir, h->fir[A.live_idx], sizeof(A.fir));
+  A.mode = h->mode; A.k_steps = k_steps; A.n0 = h->step_count;
+  A.sec0 = h->sec; A.nsec0 = h->nsec; A.dt_ns = h->dt_ns; A.t0 = time_double(h->sec, h->nsec);
+  A.sine_on = sine ? 1 : 0; A.sine_period = h->sine_period; A.sine_time0 = h->sine_time; A.sine_pub_dt = h->sine_pub_dt;
+  A.snap = h->snap; A.snap_every = h->snap ? h->snap_every : 0; A.snap_written0 = h->snap_written; A.snap_capacity = h->snap_capacity;
+}
+
+static int launch_step(cdpr_handle h, const StepArgs &A) {
+  const unsigned grid = (unsigned)(h->np / kTpb);
+  if (h->general) {
+    k_step_general<<<grid, kTpb, 0, h->stream>>>(A);
+  } else if (h->L.nc == 4) {
+    k_step_fast<4, 11><<<grid, kTpb, 11 * 4 * kTpb * sizeof(double), h->stream>>>(A);
+  } else {
+    k_step_fast<8, 11><<<grid, kTpb, 11 * 8 * kTpb * sizeof(double), h->stream>>>(A);
+  }
+  CK(h, cudaGetLastError());
+  ++h->launches;
+  return CDPR_OK;
+}
+
+static void advance_host_clock(cdpr_handle h, long long k, bool sine) {
+  if (sine) {  // one publish at every step n with (n - 1) % period == 0
+    for (long long n = h->step_count + 1; n <= h->step_count + k; ++n)
+      if ((n - 1) % h->sine_period == 0) h->sine_time = h->sine_time + h->sine_pub_dt;
+  }
+  if (h->snap && h->snap_every > 0) h->snap_written += (h->step_count + k) / h->snap_every - h->step_count / h->snap_every;
+  long long ns = (long long)h->nsec + (long long)h->dt_ns * k;
+  h->sec += (int)(ns / 1000000000LL);
+  h->nsec = (int)(ns % 1000000000LL);
+  h->step_count += k;
+}
+
+extern "C" int cdpr_step(cdpr_handle h, int64_t k_steps) {
+  if (!h || k_steps < 0) return CDPR_ERR_BAD_ARG;
+  if (k_steps == 0) return CDPR_OK;
+  cudaSetDevice(h->device);
+  CK(h, cudaEventRecord(h->ev0, h->stream));
+  long long remaining = k_steps;
+  while (remaining > 0) {
+    // CdprGazeboPlugin::update, .cpp:206-221: a pending velocity command is fanned out first, then a
+    // pending position command; each setter resets its Pid when the mode changes (JointForceCalculator.cpp:99-119)
+    if (h->vel_pending) {
+      if (h->mode != MODE_VELOCITY) { int rc = reset_pid(h, PID_VEL); if (rc) return rc; }
+      h->mode = MODE_VELOCITY; h->vel_pending = false;
+    }
+    if (h->pos_pending) {
+      if (h->mode != MODE_POSITION) { int rc = reset_pid(h, PID_POS); if (rc) return rc; }
+      h->mode = MODE_POSITION; h->pos_pending = false;
+    }
+    long long seg = std::min<long long>(remaining, 1 << 30);
+    bool sine = false;
+    if (h->sine_on) {
+      if (h->mode == MODE_VELOCITY) sine = true;
+      else {
+        const long long r = h->step_count % h->sine_period;
+        if (r == 0) {  // the next step publishes: setVelocityTarget switches the mode and resets the Pid
+          int rc = reset_pid(h, PID_VEL); if (rc) return rc;
+          h->mode = MODE_VELOCITY; sine = true;
+        } else seg = std::min<long long>(seg, h->sine_period - r);
+      }
+    }
+    StepArgs A;
+    fill_args(h, A, (int)seg, sine);
+    int rc = launch_step(h, A);
+    if (rc) return rc;
+    advance_host_clock(h, seg, sine);
+    remaining -= seg;
+  }
+  CK(h, cudaEventRecord(h->ev1, h->stream));
+  h->timed = true;
+  return CDPR_OK;
+}
+
+extern "C" int64_t cdpr_step_count(cdpr_handle h) { return h ? h->step_count : -1; }
+extern "C" double cdpr_sim_time(cdpr_handle h) { return h ? time_double(h->sec, h->nsec) : -1.0; }
+
+// ---------------------------------------------------------------------------------------------
+// outputs
+// ---------------------------------------------------------------------------------------------
+extern "C" int cdpr_get_platform_state(cdpr_handle h, double *pose7, double *twist6) {
+  if (!h) return CDPR_ERR_BAD_ARG;
+  cudaSetDevice(h->device);
+  const size_t nb = sizeof(double) * (size_t)h->n;
+  int rc = ensure_stage(h, nb * 13);
+  if (rc) return rc;
+  double *dp = (double *)h->stage, *dt = dp + 7 * h->n;
+  k_pack_platform<<<grid_for(h->n, 256), 256, 0, h->stream>>>(h->L, pose7 ? dp : nullptr, twist6 ? dt : nullptr);
+  CK(h, cudaGetLastError());
+  if (pose7) CK(h, cudaMemcpyAsync(pose7, dp, nb * 7, cudaMemcpyDeviceToHost, h->stream));
+  if (twist6) CK(h, cudaMemcpyAsync(twist6, dt, nb * 6, cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaStreamSynchronize(h->stream));
+  return CDPR_OK;
+}
+
+extern "C" int cdpr_set_platform_state(cdpr_handle h, const double *pose7, const double *twist6) {
+  if (!h) return CDPR_ERR_BAD_ARG;
+  cudaSetDevice(h->device);
+  const size_t nb = sizeof(double) * (size_t)h->n;
+  int rc = ensure_stage(h, nb * 13);
+  if (rc) return rc;
+  double *dp = (double *)h->stage, *dt = dp + 7 * h->n;
+  if (pose7) CK(h, cudaMemcpyAsync(dp, pose7, nb * 7, cudaMemcpyHostToDevice, h->stream));
+  if (twist6) CK(h, cudaMemcpyAsync(dt, twist6, nb * 6, cudaMemcpyHostToDevice, h->stream));
+  k_unpack_platform<<<grid_for(h->n, 256), 256, 0, h->stream>>>(h->L, pose7 ? dp : nullptr, twist6 ? dt : nullptr, 1);
+  CK(h, cudaGetLastError());
+  CK(h, cudaStreamSynchronize(h->stream));
+  return CDPR_OK;
+}
+
+extern "C" int cdpr_get_joint_states(cdpr_handle h, double *position, double *velocity, double *effort) {
+  if (!h) return CDPR_ERR_BAD_ARG;
+  cudaSetDevice(h->device);
+  const size_t nb = sizeof(double) * (size_t)h->n * h->L.nc;
+  int rc = ensure_stage(h, nb * 3);
+  if (rc) return rc;
+  double *d0 = (double *)h->stage, *d1 = d0 + h->n * h->L.nc, *d2 = d1 + h->n * h->L.nc;
+  k_joint_states<<<grid_for(h->n, 256), 256, 0, h->stream>>>(h->L, h->rc, position ? d0 : nullptr, velocity ? d1 : nullptr,
+                                                             effort ? d2 : nullptr);
+  CK(h, cudaGetLastError());
+  if (position) CK(h, cudaMemcpyAsync(position, d0, nb, cudaMemcpyDeviceToHost, h->stream));
+  if (velocity) CK(h, cudaMemcpyAsync(velocity, d1, nb, cudaMemcpyDeviceToHost, h->stream));
+  if (effort) CK(h, cudaMemcpyAsync(effort, d2, nb, cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaStreamSynchronize(h->stream));
+  return CDPR_OK;
+}
+
+extern "C" int cdpr_get_pid_state(cdpr_handle h, double *out) {
+  if (!h || !out) return CDPR_ERR_BAD_ARG;
+  cudaSetDevice(h->device);
+  const size_t nb = sizeof(double) * (size_t)h->n * h->L.nc * 6;
+  int rc = ensure_stage(h, nb);
+  if (rc) return rc;
+  k_pid_state<<<grid_for(h->n, 256), 256, 0, h->stream>>>(h->L, h->mode, (double *)h->stage);
+  CK(h, cudaGetLastError());
+  CK(h, cudaMemcpyAsync(out, h->stage, nb, cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaStreamSynchronize(h->stream));
+  return CDPR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// checkpoint / resume: header + the raw device arrays in the order of common.cuh
+// ---------------------------------------------------------------------------------------------
+struct BlobHeader {
+  uint64_t magic;
+  int64_t n, np;
+  int32_t nc, len, casc, general, mode, vel_pending, pos_pending, sec, nsec, sine_on;
+  int64_t step_count;
+  double sine_time;
+  uint8_t pad[160];
+};
+static const uint64_t kMagic = 0x3030324252504443ULL;  // "CDPRB200"
+
+struct Section { void *ptr; size_t bytes; };
+static std::vector<Section> sections(cdpr_handle h) {
+  const DevLayout &L = h->L;
+  const size_t col = sizeof(double) * (size_t)L.np;
+  std::vector<Section> s = {{L.plat, col * 13}, {L.cab, col * L.nc * CAB_F}, {L.pid, col * L.nc * 2 * PID_F}, {L.win_y, col * L.nc * 2 * L.len}};
+  if (L.win_x) s.push_back({L.win_x, col * L.nc * 2 * L.len});
+  if (L.filt) s.push_back({L.filt, col * L.nc * 2 * 2 * L.casc * 4});
+  s.push_back({L.ctl, sizeof(uint32_t) * (size_t)L.np * L.nc});
+  s.push_back({L.sine, col * 3});
+  return s;
+}
+
+extern "C" size_t cdpr_state_bytes(cdpr_handle h) {
+  if (!h) return 0;
+  size_t b = sizeof(BlobHeader);
+  for (auto &s : sections(h)) b += s.bytes;
+  return b;
+}
+
+extern "C" int cdpr_get_state(cdpr_handle h, void *blob, size_t bytes) {
+  if (!h || !blob || bytes < cdpr_state_bytes(h)) return CDPR_ERR_BAD_ARG;
+  cudaSetDevice(h->device);
+  BlobHeader hd;
+  std::memset(&hd, 0, sizeof(hd));
+  hd.magic = kMagic; hd.n = h->n; hd.np = h->np; hd.nc = h->L.nc; hd.len = h->L.len; hd.casc = h->L.casc; hd.general = h->general;
+  hd.mode = h->mode; hd.vel_pending = h->vel_pending; hd.pos_pending = h->pos_pending; hd.sec = h->sec; hd.nsec = h->nsec;
+  hd.sine_on = h->sine_on; hd.step_count = h->step_count; hd.sine_time = h->sine_time;
+  std::memcpy(blob, &hd, sizeof(hd));
+  uint8_t *o = (uint8_t *)blob + sizeof(hd);
+  for (auto &s : sections(h)) {
+    CK(h, cudaMemcpyAsync(o, s.ptr, s.bytes, cudaMemcpyDeviceToHost, h->stream));
+    o += s.bytes;
+  }
+  CK(h, cudaStreamSynchronize(h->stream));
+  return CDPR_OK;
+}
+
+extern "C" int cdpr_set_state(cdpr_handle h, const void *blob, size_t bytes) {
+  if (!h || !blob || bytes < cdpr_state_bytes(h)) return CDPR_ERR_BAD_ARG;
+  BlobHeader hd;
+  std::memcpy(&hd, blob, sizeof(hd));
+  if (hd.magic != kMagic || hd.n != h->n || hd.np != h->np || hd.nc != h->L.nc || hd.len != h->L.len || hd.casc != h->L.casc ||
+      hd.general != (int)h->general)
+    return fail(h, CDPR_ERR_BAD_ARG, "checkpoint does not match this handle's shape");
+  cudaSetDevice(h->device);
+  const uint8_t *o = (const uint8_t *)blob + sizeof(hd);
+  for (auto &s : sections(h)) {
+    CK(h, cudaMemcpyAsync(s.ptr, o, s.bytes, cudaMemcpyHostToDevice, h->stream));
+    o += s.bytes;
+  }
+  CK(h, cudaStreamSynchronize(h->stream));
+  h->mode = hd.mode; h->vel_pending = hd.vel_pending; h->pos_pending = hd.pos_pending; h->sec = hd.sec; h->nsec = hd.nsec;
+  h->sine_on = hd.sine_on; h->step_count = hd.step_count; h->sine_time = hd.sine_time;
+  return CDPR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// snapshots
+// ---------------------------------------------------------------------------------------------
+extern "C" int cdpr_set_snapshots(cdpr_handle h, int64_t every, void *dev_buf, int64_t capacity) {
+  if (!h || every < 0 || capacity < 0) return CDPR_ERR_BAD_ARG;
+  if (every == 0 || !dev_buf) { h->snap = nullptr; h->snap_every = 0; h->snap_written = 0; h->snap_capacity = 0; return CDPR_OK; }
+  h->snap = (double *)dev_buf; h->snap_every = every; h->snap_capacity = capacity; h->snap_written = 0;
+  return CDPR_OK;
+}
+extern "C" int64_t cdpr_snapshot_count(cdpr_handle h) { return h ? std::min(h->snap_written, h->snap_capacity) : -1; }
+
+// ---------------------------------------------------------------------------------------------
+// kinematics only
+// ---------------------------------------------------------------------------------------------
+static int launch_ik(cdpr_handle h, const IkArgs &A, bool aos) {
+  const unsigned grid = grid_for(A.n, 256);
+  if (h->L.nc == 4) { if (aos) k_ik<4, true><<<grid, 256, 0, h->stream>>>(A); else k_ik<4, false><<<grid, 256, 0, h->stream>>>(A); }
+  else if (h->L.nc == 8) { if (aos) k_ik<8, true><<<grid, 256, 0, h->stream>>>(A); else k_ik<8, false><<<grid, 256, 0, h->stream>>>(A); }
+  else return fail(h, CDPR_ERR_UNSUPPORTED, "cdpr_ik supports 4 or 8 cables");
+  CK(h, cudaGetLastError());
+  ++h->launches;
+  return CDPR_OK;
+}
+
+extern "C" int cdpr_ik_device(cdpr_handle h, int64_t n, const void *dev_state13, void *dev_out) {
+  if (!h || n < 1 || !dev_state13 || !dev_out) return CDPR_ERR_BAD_ARG;
+  cudaSetDevice(h->device);
+  IkArgs A;
+  std::memset(&A, 0, sizeof(A));
+  A.rc = h->rc; A.nc = h->L.nc; A.n = n; A.state13 = (const double *)dev_state13; A.out = (double *)dev_out;
+  CK(h, cudaEventRecord(h->ev0, h->stream));
+  int rc = launch_ik(h, A, false);
+  if (rc) return rc;
+  CK(h, cudaEventRecord(h->ev1, h->stream));
+  h->timed = true;
+  return CDPR_OK;
+}
+
+extern "C" int cdpr_ik(cdpr_handle h, int64_t n, const double *pose7, const double *twist6, double *length, double *length_rate, double *wmat) {
+  if (!h || n < 1 || !pose7 || !twist6 || !length || !length_rate || !wmat) return CDPR_ERR_BAD_ARG;
+  cudaSetDevice(h->device);
+  const int nc = h->L.nc;
+  const size_t in_b = sizeof(double) * (size_t)n * 13, out_b = sizeof(double) * (size_t)n * nc * 8;
+  int rc = ensure_stage(h, in_b + out_b);
+  if (rc) return rc;
+  double *dp = (double *)h->stage, *dt = dp + 7 * n, *dl = dt + 6 * n, *dr = dl + n * nc, *dw = dr + n * nc;
+  CK(h, cudaMemcpyAsync(dp, pose7, sizeof(double) * n * 7, cudaMemcpyHostToDevice, h->stream));
+  CK(h, cudaMemcpyAsync(dt, twist6, sizeof(double) * n * 6, cudaMemcpyHostToDevice, h->stream));
+  IkArgs A;
+  std::memset(&A, 0, sizeof(A));
+  A.rc = h->rc; A.nc = nc; A.n = n; A.pose7 = dp; A.twist6 = dt; A.length = dl; A.length_rate = dr; A.wmat = dw;
+  CK(h, cudaEventRecord(h->ev0, h->stream));
+  rc = launch_ik(h, A, true);
+  if (rc) return rc;
+  CK(h, cudaEventRecord(h->ev1, h->stream));
+  h->timed = true;
+  CK(h, cudaMemcpyAsync(length, dl, sizeof(double) * n * nc, cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaMemcpyAsync(length_rate, dr, sizeof(double) * n * nc, cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaMemcpyAsync(wmat, dw, sizeof(double) * n * nc * 6, cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaStreamSynchronize(h->stream));
+  return CDPR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// sampled rollouts
+// ---------------------------------------------------------------------------------------------
+extern "C" int cdpr_rollout(cdpr_handle h, int64_t n_robots, int64_t n_seq, const double *pose7, const double *twist6, const float *cmds,
+                            int64_t n_cmd, int64_t steps_per_cmd, const double target_pos[3], double lambda, void *dev_cost_seq,
+                            double *host_cost) {
+  if (!h || !cmds || !target_pos || n_robots < 1 || n_seq < 1 || n_cmd < 1 || steps_per_cmd < 1) return CDPR_ERR_BAD_ARG;
+  if (n_robots * n_seq != h->n) return fail(h, CDPR_ERR_BAD_ARG, "n_robots * n_seq must equal the handle's instance count");
+  if (n_cmd * steps_per_cmd > (1 << 30)) return fail(h, CDPR_ERR_BAD_ARG, "rollout too long");
+  cudaSetDevice(h->device);
+  int rc = reset_to_load_state(h);
+  if (rc) return rc;
+  if (pose7 || twist6) {
+    const size_t nb = sizeof(double) * (size_t)n_robots;
+    if ((rc = ensure_stage(h, nb * 13))) return rc;
+    double *dp = (double *)h->stage, *dt = dp + 7 * n_robots;
+    if (pose7) CK(h, cudaMemcpyAsync(dp, pose7, nb * 7, cudaMemcpyHostToDevice, h->stream));
+    if (twist6) CK(h, cudaMemcpyAsync(dt, twist6, nb * 6, cudaMemcpyHostToDevice, h->stream));
+    k_unpack_platform<<<grid_for(h->n, 256), 256, 0, h->stream>>>(h->L, pose7 ? dp : nullptr, twist6 ? dt : nullptr, n_seq);
+    CK(h, cudaGetLastError());
+  }
+  const size_t cmd_bytes = sizeof(float) * (size_t)n_seq * n_cmd * h->L.nc;
+  if (cmd_bytes > h->cmd_dev_bytes) {
+    if (h->cmd_dev) cudaFree(h->cmd_dev);
+    h->cmd_dev = nullptr; h->cmd_dev_bytes = 0;
+    if (cudaMalloc((void **)&h->cmd_dev, cmd_bytes) != cudaSuccess) return fail(h, CDPR_ERR_NOMEM, "cudaMalloc(cmds) failed");
+    h->cmd_dev_bytes = cmd_bytes;
+  }
+  if (!h->cost_dev && cudaMalloc((void **)&h->cost_dev, sizeof(double) * (size_t)h->np) != cudaSuccess)
+    return fail(h, CDPR_ERR_NOMEM, "cudaMalloc(cost) failed");
+  CK(h, cudaMemcpyAsync(h->cmd_dev, cmds, cmd_bytes, cudaMemcpyHostToDevice, h->stream));
+  // the first command arrives with step 1: setVelocityTarget from Position mode resets the velocity Pid
+  // (already in its reset state) and switches the mode (JointForceCalculator.cpp:111-119)
+  h->mode = MODE_VELOCITY;
+  StepArgs A;
+  fill_args(h, A, (int)(n_cmd * steps_per_cmd), false);
+  A.snap = nullptr; A.snap_every = 0;
+  A.cmd_table = h->cmd_dev; A.n_seq = (int)n_seq; A.n_cmd = (int)n_cmd; A.steps_per_cmd = (int)steps_per_cmd;
+  A.cost = h->cost_dev; A.target[0] = target_pos[0]; A.target[1] = target_pos[1]; A.target[2] = target_pos[2]; A.lambda = lambda;
+  CK(h, cudaEventRecord(h->ev0, h->stream));
+  if ((rc = launch_step(h, A))) return rc;
+  if (dev_cost_seq) {
+    k_reduce_cost_seq<<<grid_for(n_seq, 128), 128, 0, h->stream>>>(h->cost_dev, n_robots, n_seq, (double *)dev_cost_seq);
+    CK(h, cudaGetLastError());
+    ++h->launches;
+  }
+  CK(h, cudaEventRecord(h->ev1, h->stream));
+  h->timed = true;
+  const bool snap_keep = h->snap != nullptr;
+  double *snap_saved = h->snap; h->snap = nullptr;
+  advance_host_clock(h, n_cmd * steps_per_cmd, false);
+  if (snap_keep) h->snap = snap_saved;
+  if (host_cost) {
+    CK(h, cudaMemcpyAsync(host_cost, h->cost_dev, sizeof(double) * (size_t)h->n, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+  }
+  return CDPR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// raw device access, measurement helpers
+// ---------------------------------------------------------------------------------------------
+extern "C" int64_t cdpr_padded_instances(cdpr_handle h) { return h ? h->np : -1; }
+extern "C" void *cdpr_device_platform_state(cdpr_handle h) { return h ? h->L.plat : nullptr; }
+extern "C" int64_t cdpr_launch_count(cdpr_handle h) { return h ? h->launches : -1; }
+extern "C" const char *cdpr_kernel_variant(cdpr_handle h) { return !h ? "" : (h->general ? "general" : "fast"); }
+
+extern "C" float cdpr_last_kernel_ms(cdpr_handle h) {
+  if (!h || !h->timed) return -1.0f;
+  cudaSetDevice(h->device);
+  if (cudaEventSynchronize(h->ev1) != cudaSuccess) return -1.0f;
+  float ms = -1.0f;
+  if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) != cudaSuccess) return -1.0f;
+  return ms;
+}
+
+extern "C" double cdpr_measure_fp64_tflops(int device, int iters) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return -1.0;
+  cudaSetDevice(device);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return -1.0;
+  if (iters < 1) iters = 4096;
+  const int blocks = prop.multiProcessorCount * 8, tpb = 256;
+  double *out = nullptr;
+  if (cudaMalloc((void **)&out, sizeof(double) * blocks * tpb) != cudaSuccess) return -1.0;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  k_dfma_peak<<<blocks, tpb>>>(out, iters / 8 + 1, 1.0);  // warm-up
+  double best = -1.0;
+  for (int rep = 0; rep < 3; ++rep) {
+    cudaEventRecord(e0);
+    k_dfma_peak<<<blocks, tpb>>>(out, iters, 1.0 + rep);
+    cudaEventRecord(e1);
+    if (cudaEventSynchronize(e1) != cudaSuccess) { best = -1.0; break; }
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double flops = 2.0 * 64.0 * (double)iters * (double)blocks * tpb;
+    best = std::max(best, flops / (ms * 1e-3) / 1e12);
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(out);
+  return best;
+}

@@ -1,0 +1,104 @@
+// common.cuh -- device-side data layout and constant blocks of the batched CDPR step.
+//
+// HBM layout (struct-of-arrays; instance index i is the fastest-varying one; Np = N padded to a
+// multiple of 128 so every column starts 1 KB aligned):
+//   plat  [13][Np]                px py pz | qw qx qy qz | vx vy vz | wx wy wz
+//   cab   [NC][CAB_F][Np]         last_pos, force_cmd, pos_target, vel_target, effort, pid_force
+//   pid   [NC][2][PID_F][Np]      last_time, p_err, i_err, d_err, cmd      (pid 0 = velocity, 1 = position)
+//   win_y [NC][2][LEN][Np]        D-term error window, logical order (oldest first) = Pid::mDbufferY
+//   win_x [NC][2][LEN][Np]        D-term time stamps = Pid::mDbufferX      (general variant only)
+//   filt  [NC][2][2][CASC][4][Np] biquad x1 x2 y1 y2 (P filter, D filter)  (general variant only)
+//   ctl   [NC][Np] uint32         bit0 vel.wasLast, bit1 pos.wasLast, bits8-15 vel.missing, 16-23 pos.missing
+//   sine  [3][Np]                 amp, freq, phase of the in-kernel sinevelocitytest generator
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace cdpr {
+
+constexpr int kMaxCables = 8;
+constexpr int kMaxDbuf = 32;
+constexpr int kMaxDegree = 4;
+constexpr int kMaxCascade = 4;
+constexpr int kTpb = 128;  // threads per block of the step kernels = instances per block
+
+enum CabField { CAB_LAST_POS = 0, CAB_FORCE_CMD, CAB_POS_TARGET, CAB_VEL_TARGET, CAB_EFFORT, CAB_PID_FORCE, CAB_F };
+enum PidField { PID_LAST_TIME = 0, PID_P_ERR, PID_I_ERR, PID_D_ERR, PID_CMD, PID_F };
+enum { PID_VEL = 0, PID_POS = 1 };
+enum { MODE_FORCE = 0, MODE_POSITION = 1, MODE_VELOCITY = 2 };
+
+struct DevLayout {
+  double *plat, *cab, *pid, *win_y, *win_x, *filt, *sine;
+  uint32_t *ctl;
+  long long np;  // padded instance count (column stride)
+  int n;         // live instances
+  int nc, len, casc;
+};
+
+__host__ __device__ inline long long cab_off(const DevLayout &L, int c, int f) { return ((long long)c * CAB_F + f) * L.np; }
+__host__ __device__ inline long long pid_off(const DevLayout &L, int c, int k, int f) { return (((long long)c * 2 + k) * PID_F + f) * L.np; }
+__host__ __device__ inline long long win_off(const DevLayout &L, int c, int k, int j) { return (((long long)c * 2 + k) * L.len + j) * L.np; }
+__host__ __device__ inline long long filt_off(const DevLayout &L, int c, int k, int pd, int s, int f) {
+  return (((((long long)c * 2 + k) * 2 + pd) * L.casc + s) * 4 + f) * L.np;
+}
+
+// gains of one gazebo::common::Pid, pre-digested on the host (Pid.cpp:63-77)
+struct PidConsts {
+  double kf, kp, ki, kd;
+  double i_max, i_min, i_max_over_ki, i_min_over_ki;  // iTerm / mIgain of Pid.cpp:145,149
+  double cmd_max, cmd_min;
+  int degree, len, p_casc, d_casc;
+  double pf[5], df[5];  // biquad a0 a1 a2 b1 b2 (Filter.h:130-140), identical for every stage
+};
+
+// robot constants (sdf/cube.sdf) in the form the kernels consume; passed as a __grid_constant__
+// kernel parameter so compile-time-indexed reads become constant-bank operands of DFMA.
+struct RobotConsts {
+  double a[kMaxCables][3];  // frame anchors
+  double b[kMaxCables][3];  // platform anchors (body frame)
+  double home_len[kMaxCables];
+  double mg[3];             // mass * gravity
+  double h, h_over_m, half_h;
+  double ib[6], ib_inv[6];  // xx yy zz xy xz yz
+  int diag_inertia;
+  double cdamp, effort_limit;  // effort_limit < 0: no truncation
+  double effort_limit_abs;     // effort_limit, or +inf when truncation is off
+  double vel_eps;
+};
+
+struct StepArgs {
+  DevLayout L;
+  RobotConsts rc;
+  PidConsts pc[2];     // [PID_VEL], [PID_POS]
+  PidConsts live;      // copy of pc[live_idx]: the Pid the fast kernel runs
+  int live_idx;
+  double fir[kMaxDbuf];  // D-term FIR weights of the LIVE pid, logical order, already divided by the window span
+  int mode;            // batch-uniform JointForceCalculator::UpdateMode
+  int k_steps;
+  long long n0;        // physics steps done before this launch
+  int sec0, nsec0, dt_ns;
+  double t0;           // time_double(sec0, nsec0)
+  // sine generator (sinevelocitytest.cpp)
+  int sine_on, sine_period;
+  double sine_time0, sine_pub_dt;
+  // snapshots
+  double *snap;
+  long long snap_every, snap_written0, snap_capacity;
+  // rollout mode (cdpr_rollout)
+  const float *cmd_table;  // [n_seq][n_cmd][NC]
+  int n_seq, n_cmd, steps_per_cmd;
+  double *cost;            // [N] or nullptr
+  double target[3], lambda;
+};
+
+// gazebo::common::Time::Double(): two roundings, never contracted
+__host__ __device__ inline double time_double(int sec, int nsec) {
+#ifdef __CUDA_ARCH__
+  return __dadd_rn((double)sec, __dmul_rn((double)nsec, 1e-9));
+#else
+  volatile double frac = (double)nsec * 1e-9;
+  return (double)sec + frac;
+#endif
+}
+
+}  // namespace cdpr

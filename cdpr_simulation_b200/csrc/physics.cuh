@@ -1,0 +1,104 @@
+// physics.cuh -- device functions shared by the step kernels: rotation matrix and the rigid-body
+// update of the reduced model (stands in for Gazebo/ODE's world step).
+#pragma once
+#include "common.cuh"
+
+namespace cdpr {
+
+struct FastState {
+  double px, py, pz, qw, qx, qy, qz, vx, vy, vz, wx, wy, wz;
+};
+struct Rot {
+  double r00, r01, r02, r10, r11, r12, r20, r21, r22;
+};
+
+__device__ __forceinline__ double clampd(double v, double lo, double hi) { return fmin(fmax(v, lo), hi); }
+
+// 1/sqrt(x) for normal, positive x without the special-case branch of CUDA's rsqrt(): MUFU.RSQ64H
+// seed (rel. error < 2^-22) and one third-order Newton step y += y*e*(1/2 + 3/8 e), e = 1 - x*y*y,
+// which leaves ~2^-66 of method error, i.e. the result is within ~1 ulp.
+__device__ __forceinline__ double rsqrt_nr(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double e = fma(-(x * y), y, 1.0);
+  return fma(y * e, fma(0.375, e, 0.5), y);
+}
+
+// rotation matrix of the platform (unit quaternion w x y z)
+__device__ __forceinline__ Rot make_rot(const FastState &S) {
+  const double xx = S.qx * S.qx, yy = S.qy * S.qy, zz = S.qz * S.qz;
+  const double xy = S.qx * S.qy, xz = S.qx * S.qz, yz = S.qy * S.qz;
+  const double wx_ = S.qw * S.qx, wy_ = S.qw * S.qy, wz_ = S.qw * S.qz;
+  Rot R;
+  R.r00 = 1.0 - 2.0 * (yy + zz); R.r01 = 2.0 * (xy - wz_); R.r02 = 2.0 * (xz + wy_);
+  R.r10 = 2.0 * (xy + wz_); R.r11 = 1.0 - 2.0 * (xx + zz); R.r12 = 2.0 * (yz - wx_);
+  R.r20 = 2.0 * (xz - wy_); R.r21 = 2.0 * (yz + wx_); R.r22 = 1.0 - 2.0 * (xx + yy);
+  return R;
+}
+
+__device__ __forceinline__ void load_plat(const DevLayout &L, long long i, FastState &S) {
+  const double *p = L.plat + i;
+  const long long np = L.np;
+  S.px = p[0]; S.py = p[np]; S.pz = p[2 * np];
+  S.qw = p[3 * np]; S.qx = p[4 * np]; S.qy = p[5 * np]; S.qz = p[6 * np];
+  S.vx = p[7 * np]; S.vy = p[8 * np]; S.vz = p[9 * np];
+  S.wx = p[10 * np]; S.wy = p[11 * np]; S.wz = p[12 * np];
+}
+__device__ __forceinline__ void store_plat(double *p, long long stride, const FastState &S) {
+  p[0] = S.px; p[stride] = S.py; p[2 * stride] = S.pz;
+  p[3 * stride] = S.qw; p[4 * stride] = S.qx; p[5 * stride] = S.qy; p[6 * stride] = S.qz;
+  p[7 * stride] = S.vx; p[8 * stride] = S.vy; p[9 * stride] = S.vz;
+  p[10 * stride] = S.wx; p[11 * stride] = S.wy; p[12 * stride] = S.wz;
+}
+
+// (fx..fz, mx..mz) = net force / torque about the COM in frame axes, gravity included
+__device__ __forceinline__ void rigid_body_step(const RobotConsts &rc, FastState &S, const Rot &R, double fx, double fy, double fz,
+                                                double mx, double my, double mz) {
+  const double r00 = R.r00, r01 = R.r01, r02 = R.r02, r10 = R.r10, r11 = R.r11, r12 = R.r12, r20 = R.r20, r21 = R.r21, r22 = R.r22;
+  // ---- rigid-body step, ODE order (a9): I_w = R I_b R^T, explicit gyroscopic torque
+  const double wbx = fma(r00, S.wx, fma(r10, S.wy, r20 * S.wz));
+  const double wby = fma(r01, S.wx, fma(r11, S.wy, r21 * S.wz));
+  const double wbz = fma(r02, S.wx, fma(r12, S.wy, r22 * S.wz));
+  double lbx, lby, lbz;
+  if (rc.diag_inertia) {
+    lbx = rc.ib[0] * wbx; lby = rc.ib[1] * wby; lbz = rc.ib[2] * wbz;
+  } else {
+    lbx = fma(rc.ib[0], wbx, fma(rc.ib[3], wby, rc.ib[4] * wbz));
+    lby = fma(rc.ib[3], wbx, fma(rc.ib[1], wby, rc.ib[5] * wbz));
+    lbz = fma(rc.ib[4], wbx, fma(rc.ib[5], wby, rc.ib[2] * wbz));
+  }
+  const double lwx = fma(r00, lbx, fma(r01, lby, r02 * lbz));
+  const double lwy = fma(r10, lbx, fma(r11, lby, r12 * lbz));
+  const double lwz = fma(r20, lbx, fma(r21, lby, r22 * lbz));
+  mx -= fma(S.wy, lwz, -(S.wz * lwy));
+  my -= fma(S.wz, lwx, -(S.wx * lwz));
+  mz -= fma(S.wx, lwy, -(S.wy * lwx));
+  const double mbx = fma(r00, mx, fma(r10, my, r20 * mz));
+  const double mby = fma(r01, mx, fma(r11, my, r21 * mz));
+  const double mbz = fma(r02, mx, fma(r12, my, r22 * mz));
+  double abx, aby, abz;
+  if (rc.diag_inertia) {
+    abx = rc.ib_inv[0] * mbx; aby = rc.ib_inv[1] * mby; abz = rc.ib_inv[2] * mbz;
+  } else {
+    abx = fma(rc.ib_inv[0], mbx, fma(rc.ib_inv[3], mby, rc.ib_inv[4] * mbz));
+    aby = fma(rc.ib_inv[3], mbx, fma(rc.ib_inv[1], mby, rc.ib_inv[5] * mbz));
+    abz = fma(rc.ib_inv[4], mbx, fma(rc.ib_inv[5], mby, rc.ib_inv[2] * mbz));
+  }
+  const double alx = fma(r00, abx, fma(r01, aby, r02 * abz));
+  const double aly = fma(r10, abx, fma(r11, aby, r12 * abz));
+  const double alz = fma(r20, abx, fma(r21, aby, r22 * abz));
+
+  S.vx = fma(rc.h_over_m, fx, S.vx); S.vy = fma(rc.h_over_m, fy, S.vy); S.vz = fma(rc.h_over_m, fz, S.vz);
+  S.wx = fma(rc.h, alx, S.wx); S.wy = fma(rc.h, aly, S.wy); S.wz = fma(rc.h, alz, S.wz);
+  S.px = fma(rc.h, S.vx, S.px); S.py = fma(rc.h, S.vy, S.py); S.pz = fma(rc.h, S.vz, S.pz);
+  // q += h * 1/2 (0, w) (x) q, then renormalise
+  const double hx = rc.half_h * S.wx, hy = rc.half_h * S.wy, hz = rc.half_h * S.wz;
+  const double nw = fma(-hx, S.qx, fma(-hy, S.qy, fma(-hz, S.qz, S.qw)));
+  const double nx = fma(hx, S.qw, fma(hy, S.qz, fma(-hz, S.qy, S.qx)));
+  const double ny = fma(-hx, S.qz, fma(hy, S.qw, fma(hz, S.qx, S.qy)));
+  const double nz = fma(hx, S.qy, fma(-hy, S.qx, fma(hz, S.qw, S.qz)));
+  const double inv = rsqrt_nr(fma(nw, nw, fma(nx, nx, fma(ny, ny, nz * nz))));
+  S.qw = nw * inv; S.qx = nx * inv; S.qy = ny * inv; S.qz = nz * inv;
+}
+
+}  // namespace cdpr

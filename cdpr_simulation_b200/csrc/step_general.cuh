@@ -1,0 +1,233 @@
+// step_general.cuh -- the catch-all variant of the K-step kernel: full semantics of
+// JointForceCalculator (three modes, velocity hold through the position Pid on
+// |target| <= velocityEpsilon, JointForceCalculator.cpp:59-96) and gazebo::common::Pid
+// (biquad cascades on the P input and D output, Pid.cpp:27-44,133,157; cmdLimit == 0 quirk,
+// Pid.cpp:175-184; non-uniform time stamps in the D window, Pid.cpp:193-247).
+//
+// One thread per instance; the platform state lives in registers for the K steps, the per-cable
+// controller state is read-modify-written in HBM/L2 every step (coalesced: consecutive threads,
+// consecutive addresses).  This variant is HBM/L2-bound, not FP64-bound; the reference's launch
+// configuration never needs it (see step_fast.cuh).
+#pragma once
+#include "common.cuh"
+#include "physics.cuh"
+
+namespace cdpr {
+
+// Pid::CascadeFilter::update (Pid.cpp:38-44) over BiQuad::process (Filter.h:152-165)
+__device__ inline double cascade_update(const DevLayout &L, int c, int k, int pd, int stages, const double *co, double x, long long i) {
+  double out = x;
+  for (int s = 0; s < stages; ++s) {
+    double *x1 = L.filt + filt_off(L, c, k, pd, s, 0) + i, *x2 = L.filt + filt_off(L, c, k, pd, s, 1) + i;
+    double *y1 = L.filt + filt_off(L, c, k, pd, s, 2) + i, *y2 = L.filt + filt_off(L, c, k, pd, s, 3) + i;
+    const double y0 = co[0] * out + co[1] * *x1 + co[2] * *x2 - co[3] * *y1 - co[4] * *y2;
+    *x2 = *x1; *x1 = out; *y2 = *y1; *y1 = y0;
+    out = y0;
+  }
+  return out;
+}
+
+// Pid::derive (Pid.cpp:193-217): shift the window, append, and once full return the derivative at
+// `now` of the least-squares polynomial through it.  The fit runs in window-relative, span-scaled
+// time (same polynomial as the reference's absolute-time fit, but well conditioned).
+__device__ inline double derive_general(const DevLayout &L, const PidConsts &pc, int c, int k, unsigned &missing, double value,
+                                        double now, long long i) {
+  const int len = pc.len;
+  double xs[kMaxDbuf], ys[kMaxDbuf];
+  for (int j = 1; j < len; ++j) {
+    xs[j - 1] = L.win_x[win_off(L, c, k, j) + i];
+    ys[j - 1] = L.win_y[win_off(L, c, k, j) + i];
+  }
+  xs[len - 1] = now;
+  ys[len - 1] = value;
+  for (int j = 0; j < len; ++j) {
+    L.win_x[win_off(L, c, k, j) + i] = xs[j];
+    L.win_y[win_off(L, c, k, j) + i] = ys[j];
+  }
+  missing -= (missing > 0u) ? 1u : 0u;
+  if (missing != 0u || pc.degree < 1) return 0.0;
+  const int m = pc.degree + 1;
+  const double span = now - xs[0];
+  double sx[2 * kMaxDegree + 1], M[kMaxDegree + 1][kMaxDegree + 2];
+  for (int p = 0; p <= 2 * pc.degree; ++p) sx[p] = 0.0;
+  for (int r = 0; r < m; ++r) M[r][m] = 0.0;
+  for (int j = 0; j < len; ++j) {
+    const double x = (xs[j] - now) / span;
+    double pw = 1.0;
+    for (int p = 0; p <= 2 * pc.degree; ++p) {
+      sx[p] += pw;
+      if (p < m) M[p][m] += pw * ys[j];
+      pw *= x;
+    }
+  }
+  for (int r = 0; r < m; ++r)
+    for (int q = 0; q < m; ++q) M[r][q] = sx[r + q];
+  // Gaussian elimination with partial pivoting on the (degree+1)^2 normal equations
+  for (int col = 0; col < m; ++col) {
+    int piv = col;
+    for (int r = col + 1; r < m; ++r)
+      if (fabs(M[r][col]) > fabs(M[piv][col])) piv = r;
+    if (M[piv][col] == 0.0) return 0.0;
+    if (piv != col)
+      for (int q = col; q <= m; ++q) { const double t = M[col][q]; M[col][q] = M[piv][q]; M[piv][q] = t; }
+    for (int r = col + 1; r < m; ++r) {
+      const double f = M[r][col] / M[col][col];
+      for (int q = col; q <= m; ++q) M[r][q] -= f * M[col][q];
+    }
+  }
+  double coef[kMaxDegree + 1];
+  for (int r = m - 1; r >= 0; --r) {
+    double s = M[r][m];
+    for (int q = r + 1; q < m; ++q) s -= M[r][q] * coef[q];
+    coef[r] = s / M[r][r];
+  }
+  return coef[1] / span;
+}
+
+// Pid::update (Pid.cpp:122-191) on the state columns of (cable c, pid k)
+__device__ inline double pid_update_general(const DevLayout &L, const PidConsts &pc, int c, int k, unsigned &ctl, double desired,
+                                            double actual, double now, long long i) {
+  double *last_time = L.pid + pid_off(L, c, k, PID_LAST_TIME) + i;
+  double *cmdp = L.pid + pid_off(L, c, k, PID_CMD) + i;
+  double cmd_out;
+  if (!((ctl >> k) & 1u)) {
+    ctl |= 1u << k;
+    cmd_out = 0.0;
+  } else {
+    double *p_err = L.pid + pid_off(L, c, k, PID_P_ERR) + i;
+    double *i_err = L.pid + pid_off(L, c, k, PID_I_ERR) + i;
+    double *d_err = L.pid + pid_off(L, c, k, PID_D_ERR) + i;
+    const double f_term = pc.kf * desired;
+    const double error = desired - actual;
+    const double dt = now - *last_time;
+    const double pe = cascade_update(L, c, k, 0, pc.p_casc, pc.pf, error, i);
+    *p_err = pe;
+    const double p_term = pc.kp * pe;
+    const double prev_ierr = *i_err;
+    double ie = prev_ierr + dt * error;
+    double i_term = pc.ki * ie;
+    if (i_term > pc.i_max) { i_term = pc.i_max; ie = pc.i_max_over_ki; }
+    else if (i_term < pc.i_min) { i_term = pc.i_min; ie = pc.i_min_over_ki; }
+    double de = *d_err;
+    if (dt > 0.0) {
+      unsigned missing = (ctl >> (8 + 8 * k)) & 0xffu;
+      const double derived = derive_general(L, pc, c, k, missing, error, now, i);
+      ctl = (ctl & ~(0xffu << (8 + 8 * k))) | (missing << (8 + 8 * k));
+      de = cascade_update(L, c, k, 1, pc.d_casc, pc.df, derived, i);
+      *d_err = de;
+    }
+    const double d_term = pc.kd * de;
+    const double cmd_raw = f_term + p_term + i_term + d_term;
+    double cmd = *cmdp;
+    if (pc.cmd_max > pc.cmd_min) cmd = clampd(cmd_raw, pc.cmd_min, pc.cmd_max);
+    if (cmd != cmd_raw) {
+      ie = prev_ierr;
+      cmd += dt * error * pc.ki;
+    }
+    *i_err = ie;
+    cmd_out = cmd;
+  }
+  *cmdp = cmd_out;
+  *last_time = now;
+  return cmd_out;
+}
+
+__global__ void __launch_bounds__(kTpb) k_step_general(const __grid_constant__ StepArgs A) {
+  const long long i = (long long)blockIdx.x * kTpb + threadIdx.x;
+  if (i >= A.L.n) return;
+  const DevLayout &L = A.L;
+  const RobotConsts &rc = A.rc;
+  const long long np = L.np;
+  const int nc = L.nc;
+  FastState S;
+  load_plat(L, i, S);
+  double amp = 0.0, freq = 0.0, phase = 0.0;
+  if (A.sine_on) { amp = L.sine[i]; freq = L.sine[np + i]; phase = L.sine[2 * np + i]; }
+  const float *cmd_row = nullptr;
+  if (A.cmd_table) cmd_row = A.cmd_table + (size_t)(i % A.n_seq) * A.n_cmd * nc;
+  double cost = 0.0;
+  int sec = A.sec0, nsec = A.nsec0;
+  double sine_time = A.sine_time0;
+  int sine_ctr = (int)(A.n0 % (A.sine_period > 0 ? A.sine_period : 1));
+  int cmd_ctr = 0, cmd_idx = 0;
+  long long snap_idx = A.snap_written0;
+  long long snap_ctr = A.snap_every > 0 ? (A.n0 % A.snap_every) : 0;
+
+  for (int s = 0; s < A.k_steps; ++s) {
+    nsec += A.dt_ns;
+    if (nsec >= 1000000000) { nsec -= 1000000000; ++sec; }
+    const double now = time_double(sec, nsec);
+    if (A.sine_on) {
+      if (sine_ctr == 0) {
+        const double arg = __dadd_rn(__dmul_rn(__dmul_rn(__dmul_rn(sine_time, freq), 2.0), 3.14159265358979323846), phase);
+        const double vel = (double)(float)__dmul_rn(amp, sin(arg));
+        for (int c = 0; c < nc; ++c) L.cab[cab_off(L, c, CAB_VEL_TARGET) + i] = vel;
+        sine_time = __dadd_rn(sine_time, A.sine_pub_dt);
+      }
+      sine_ctr = (sine_ctr + 1 == A.sine_period) ? 0 : sine_ctr + 1;
+    }
+    if (cmd_row) {
+      if (cmd_ctr == 0 && cmd_idx < A.n_cmd) {
+        for (int c = 0; c < nc; ++c) L.cab[cab_off(L, c, CAB_VEL_TARGET) + i] = (double)cmd_row[cmd_idx * nc + c];
+        ++cmd_idx;
+      }
+      cmd_ctr = (cmd_ctr + 1 == A.steps_per_cmd) ? 0 : cmd_ctr + 1;
+    }
+    const Rot R = make_rot(S);
+    double fx = rc.mg[0], fy = rc.mg[1], fz = rc.mg[2], mx = 0.0, my = 0.0, mz = 0.0;
+    for (int c = 0; c < nc; ++c) {
+      const double bx = rc.b[c][0], by = rc.b[c][1], bz = rc.b[c][2];
+      const double rx = R.r00 * bx + R.r01 * by + R.r02 * bz;
+      const double ry = R.r10 * bx + R.r11 * by + R.r12 * bz;
+      const double rz = R.r20 * bx + R.r21 * by + R.r22 * bz;
+      const double dx = (rc.a[c][0] - S.px) - rx, dy = (rc.a[c][1] - S.py) - ry, dz = (rc.a[c][2] - S.pz) - rz;
+      const double len = sqrt(dx * dx + dy * dy + dz * dz);
+      const double ux = dx / len, uy = dy / len, uz = dz / len;
+      const double cx = ry * uz - rz * uy, cy = rz * ux - rx * uz, cz = rx * uy - ry * ux;
+      const double qd = ux * S.vx + uy * S.vy + uz * S.vz + cx * S.wx + cy * S.wy + cz * S.wz;
+      const double qp = rc.home_len[c] - len;
+
+      unsigned ctl = L.ctl[(long long)c * np + i];
+      double *last_pos = L.cab + cab_off(L, c, CAB_LAST_POS) + i;
+      double force;
+      if (A.mode == MODE_FORCE) {
+        *last_pos = qp;
+        force = L.cab[cab_off(L, c, CAB_FORCE_CMD) + i];
+      } else if (A.mode == MODE_VELOCITY) {
+        const double vt = L.cab[cab_off(L, c, CAB_VEL_TARGET) + i];
+        if (fabs(vt) > rc.vel_eps) {
+          *last_pos = qp;
+          force = pid_update_general(L, A.pc[PID_VEL], c, PID_VEL, ctl, vt, qd, now, i);
+        } else {  // hold the last position with the position Pid
+          force = pid_update_general(L, A.pc[PID_POS], c, PID_POS, ctl, *last_pos, qp, now, i);
+        }
+      } else {
+        *last_pos = qp;
+        force = pid_update_general(L, A.pc[PID_POS], c, PID_POS, ctl, L.cab[cab_off(L, c, CAB_POS_TARGET) + i], qp, now, i);
+      }
+      L.ctl[(long long)c * np + i] = ctl;
+      const double eff = (rc.effort_limit >= 0.0) ? clampd(force, -rc.effort_limit, rc.effort_limit) : force;
+      L.cab[cab_off(L, c, CAB_EFFORT) + i] = eff;
+      L.cab[cab_off(L, c, CAB_PID_FORCE) + i] = force;
+      const double tau = eff - rc.cdamp * qd;
+      fx += tau * ux; fy += tau * uy; fz += tau * uz;
+      mx += tau * cx; my += tau * cy; mz += tau * cz;
+    }
+    rigid_body_step(rc, S, R, fx, fy, fz, mx, my, mz);
+    if (A.cost) {
+      const double ex = S.px - A.target[0], ey = S.py - A.target[1], ez = S.pz - A.target[2];
+      cost += fma(ex, ex, fma(ey, ey, ez * ez)) + A.lambda * fma(S.wx, S.wx, fma(S.wy, S.wy, S.wz * S.wz));
+    }
+    if (A.snap_every > 0) {
+      if (++snap_ctr == A.snap_every) {
+        snap_ctr = 0;
+        if (snap_idx < A.snap_capacity) store_plat(A.snap + snap_idx * 13 * (long long)L.n + i, L.n, S);
+        ++snap_idx;
+      }
+    }
+  }
+  store_plat(L.plat + i, np, S);
+  if (A.cost) A.cost[i] = cost;
+}
+
+}  // namespace cdpr

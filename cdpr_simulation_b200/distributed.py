@@ -1,0 +1,87 @@
+"""Multi-GPU plumbing: one process per GPU, instances sharded by contiguous range, no collective inside a step.
+
+NCCL (torch.distributed) is used only where the path has a real exchange:
+  * the decimated trajectory gather (snapshots written by the step kernel straight into the send buffer,
+    all-gathered on a side stream while the next pass runs), and
+  * the all-reduce of the per-sequence rollout cost vector.
+Everything here also runs on CPU tensors with the gloo backend (tests/test_distributed_gloo.py)."""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from .workloads import shard_range
+
+
+def world():
+    return (dist.get_rank(), dist.get_world_size()) if dist.is_available() and dist.is_initialized() else (0, 1)
+
+
+def gather_trajectory(local: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """local: [n_snap, 13, n_local] of this rank; returns [world, n_snap, 13, n_local] ordered by rank, i.e. by
+    global instance id when every rank owns the same number of instances."""
+    rank, ws = world()
+    if out is None:
+        out = torch.empty((ws,) + tuple(local.shape), dtype=local.dtype, device=local.device)
+    if ws == 1:
+        out[0].copy_(local)
+        return out
+    dist.all_gather_into_tensor(out.view(-1), local.contiguous().view(-1))
+    return out
+
+
+def allreduce_cost(cost_seq: torch.Tensor) -> torch.Tensor:
+    """Sum over ranks of the per-sequence rollout cost (each rank holds the sum over ITS robots)."""
+    _, ws = world()
+    if ws > 1:
+        dist.all_reduce(cost_seq, op=dist.ReduceOp.SUM)
+    return cost_seq
+
+
+def global_trajectory_to_instance_major(gathered: torch.Tensor) -> torch.Tensor:
+    """[world, n_snap, 13, n_local] -> [n_snap, 13, world * n_local] (global instance id fastest)."""
+    ws, n_snap, f, n_local = gathered.shape
+    return gathered.permute(1, 2, 0, 3).reshape(n_snap, f, ws * n_local)
+
+
+class TrajectoryGather:
+    """Double-buffered snapshot send buffers + an all-gather per pass on a side stream.
+
+    before_pass(): point the step kernel at the send buffer of this pass (after the gather that last read it).
+    after_pass():  enqueue the all-gather of that buffer behind the step kernel, on the communication stream.
+    finish():      make the compute stream wait for every outstanding gather."""
+
+    def __init__(self, batch, every: int, steps_per_pass: int, stream: torch.cuda.Stream):
+        self.batch, self.every, self.stream = batch, int(every), stream
+        self.n_snap = steps_per_pass // self.every
+        _, ws = world()
+        dev = torch.device("cuda", batch.device)
+        self.send = [torch.empty((self.n_snap, 13, batch.n), dtype=torch.float64, device=dev) for _ in range(2)]
+        self.recv = torch.empty((ws, self.n_snap, 13, batch.n), dtype=torch.float64, device=dev)
+        self.comm = torch.cuda.Stream(device=dev)
+        self.free = [None, None]
+        self.i = 0
+
+    def before_pass(self):
+        slot = self.i % 2
+        if self.free[slot] is not None:
+            self.stream.wait_event(self.free[slot])
+        self.batch.set_snapshots(self.every, self.send[slot].data_ptr(), self.n_snap)
+
+    def after_pass(self):
+        slot = self.i % 2
+        done = torch.cuda.Event()
+        done.record(self.stream)
+        with torch.cuda.stream(self.comm):
+            self.comm.wait_event(done)
+            gather_trajectory(self.send[slot], self.recv)
+            ev = torch.cuda.Event()
+            ev.record(self.comm)
+            self.free[slot] = ev
+        self.i += 1
+
+    def finish(self):
+        self.stream.wait_stream(self.comm)
+
+
+__all__ = ["shard_range", "gather_trajectory", "allreduce_cost", "global_trajectory_to_instance_major", "TrajectoryGather", "world"]

@@ -1,0 +1,172 @@
+/*
+ * cdpr_b200.h -- C ABI of the B200-native batched CDPR step (libcdpr_b200.so).
+ *
+ * One handle = N independent robots ("instances") resident on one B200.  The entry points
+ * are what a binding of the reference plugin's hot path would call; each cites the
+ * reference interface it replaces (paths relative to /root/reference/src/cdpr_gazebo/).
+ * Plain pointers and sizes only; no C++ or torch types cross this boundary.
+ *
+ * Layout conventions
+ *   host buffers ("reference layout", array-of-structs, instance-major):
+ *     axes      float32 [N][NC]        like sensor_msgs/Joy.axes (CdprGazeboPlugin.cpp:67-83)
+ *     pose7     float64 [N][7]         x y z qx qy qz qw        (CdprGazeboPlugin.cpp:262-269)
+ *     twist6    float64 [N][6]         lin xyz, ang xyz         (CdprGazeboPlugin.cpp:270-277)
+ *     joint     float64 [N][NC]        position / velocity / effort (CdprGazeboPlugin.cpp:248-256)
+ *   device buffers (struct-of-arrays, instance index fastest): documented per call.
+ *   Cable index c is the numeric suffix of the reference joint name "cable<c>"
+ *   (CdprGazeboPlugin.cpp:150-157); instance index i is the caller's, never permuted.
+ *
+ * Every function returns CDPR_OK (0) or a negative error code and never throws.
+ * A handle is not thread-safe; distinct handles are independent (no globals).
+ * There is NO CPU fallback: cdpr_create fails with CDPR_ERR_NO_DEVICE without a CUDA device.
+ */
+#ifndef CDPR_B200_H
+#define CDPR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CDPR_MAX_CABLES 8
+#define CDPR_MAX_DBUF 32
+#define CDPR_MAX_DEGREE 4
+#define CDPR_MAX_CASCADE 4
+
+enum {
+  CDPR_OK = 0,
+  CDPR_ERR_BAD_ARG = -1,
+  CDPR_ERR_BAD_CABLE_COUNT = -2, /* gazebo::common::Exception("invalid joint count"), CdprGazeboPlugin.cpp:167-169 */
+  CDPR_ERR_BAD_LENGTH = -3,      /* command with axes.size() != NC: dropped, state untouched (CdprGazeboPlugin.cpp:68,77) */
+  CDPR_ERR_NO_DEVICE = -4,
+  CDPR_ERR_CUDA = -5,
+  CDPR_ERR_UNSUPPORTED = -6,
+  CDPR_ERR_NOMEM = -7
+};
+
+/* JointForceCalculator::UpdateMode, include/cdpr_gazebo/JointForceCalculator.h:33-35 */
+enum { CDPR_MODE_FORCE = 0, CDPR_MODE_POSITION = 1, CDPR_MODE_VELOCITY = 2 };
+
+/* gazebo::common::Pid::PidParameters, include/cdpr_gazebo/Pid.h:70-81; the ROS parameters of
+ * CdprGazeboPlugin.h:34-54 map 1:1 onto these fields. */
+typedef struct cdpr_pid_params {
+  double forward_gain, p_gain, i_gain, d_gain;
+  int32_t d_degree, d_buffer_length;
+  double i_limit, cmd_limit;
+  double p_cutoff, p_quality;
+  int32_t p_cascade;
+  double d_cutoff, d_quality;
+  int32_t d_cascade;
+} cdpr_pid_params;
+
+/* Everything the plugin reads at Load() (ROS parameters, CdprGazeboPlugin.cpp:98-139) plus the
+ * robot constants it gets implicitly from sdf/cube.sdf through Gazebo. All fields explicit. */
+typedef struct cdpr_config {
+  int32_t n_cables;                            /* cWireCount, CdprGazeboPlugin.h:20 (4); 8 = synthetic extension */
+  double frame_anchor[CDPR_MAX_CABLES][3];     /* a_i, frame coordinates (cube.sdf:383,559,735,911) */
+  double platform_anchor[CDPR_MAX_CABLES][3];  /* b_i, platform body coordinates (cube.sdf:458,634,810,986) */
+  double home_pos[3];                          /* pose where every joint coordinate is 0 (cube.sdf:310) */
+  double home_quat[4];                         /* w x y z */
+  double mass;                                 /* cube.sdf:340 */
+  double inertia[6];                           /* ixx iyy izz ixy ixz iyz, body frame (cube.sdf:331-338) */
+  double gravity[3];                           /* Gazebo world default (0,0,-9.8) */
+  double cable_damping;                        /* cube.sdf:442 */
+  double effort_limit;                         /* cube.sdf:438; <0 disables truncation */
+  double dt;                                   /* physics step, s; must be a whole number of ns */
+  cdpr_pid_params vel_pid, pos_pid;            /* launch/cdpr_gazebo.launch:19-39 */
+  double velocity_epsilon;                     /* launch/cdpr_gazebo.launch:18 */
+  double sine_publish_hz;                      /* sinevelocitytest.cpp:7 (100 Hz) */
+} cdpr_config;
+
+typedef struct cdpr_batch *cdpr_handle;
+
+/* ---- lifecycle (CdprGazeboPlugin::Load, .cpp:49-65; destructor .h:88-90) ----------------- */
+/* Reference constants. n_cables 4 = the reference robot; 8 = synthetic. */
+int cdpr_config_default(cdpr_config *cfg, int n_cables);
+/* State after Load(): platform at home, every cable in Position mode with target 0, both PIDs
+ * un-primed (CdprGazeboPlugin.cpp:153-157), sim time 0. device = CUDA ordinal. */
+int cdpr_create(const cdpr_config *cfg, int64_t n_instances, int device, cdpr_handle *out);
+int cdpr_destroy(cdpr_handle h);
+/* back to the post-Load state (Gazebo world reset + JointForceCalculator::reset, JointForceCalculator.h:69-73);
+ * keeps the sine generator parameters and the snapshot buffer, restarts both at 0. */
+int cdpr_reset(cdpr_handle h);
+/* Last error text of this handle (h may be NULL: text of the last failed cdpr_create). */
+const char *cdpr_last_error(cdpr_handle h);
+/* Kernels run on this cudaStream_t (default: a stream owned by the handle). */
+int cdpr_set_stream(cdpr_handle h, void *cuda_stream);
+int cdpr_synchronize(cdpr_handle h);
+
+/* ---- commands (topics jointVelocities / jointPositions, CdprGazeboPlugin.cpp:67-83,206-219;
+ *      JointForceCalculator::setForce, JointForceCalculator.h:92-95) ------------------------
+ * n_axes != NC  =>  CDPR_ERR_BAD_LENGTH and nothing changes (the plugin drops the message).
+ * A command becomes visible to the NEXT step; velocity is applied before position. */
+int cdpr_set_velocity_cmd(cdpr_handle h, const float *axes, int64_t n_instances, int n_axes);
+int cdpr_set_position_cmd(cdpr_handle h, const float *axes, int64_t n_instances, int n_axes);
+int cdpr_set_effort_cmd(cdpr_handle h, const double *force, int64_t n_instances, int n_axes);
+/* sinevelocitytest.cpp:33-49 run inside the step kernel, per instance: every
+ * (1/sine_publish_hz)/dt steps a new command (float)(amp*sin(time*freq*2*M_PI + phase)) goes to
+ * all cables; `time` accumulates in double from 0. amp == NULL disables the generator. */
+int cdpr_set_sine_cmd(cdpr_handle h, const double *amp, const double *freq, const double *phase, int64_t n_instances);
+
+/* ---- stepping (CdprGazeboPlugin::update .cpp:202-246 followed by the physics step) ------- */
+int cdpr_step(cdpr_handle h, int64_t k_steps);
+int64_t cdpr_step_count(cdpr_handle h);
+double cdpr_sim_time(cdpr_handle h);
+
+/* ---- outputs (publishJointStates .cpp:248-256, publishPlatformState .cpp:258-280) -------- */
+/* position/velocity follow from the CURRENT platform state; effort = force applied in the last step. */
+int cdpr_get_joint_states(cdpr_handle h, double *position, double *velocity, double *effort);
+int cdpr_get_platform_state(cdpr_handle h, double *pose7, double *twist6);
+/* overwrite platform pose/twist (Gazebo's SetWorldPose/SetWorldTwist equivalent); either may be NULL */
+int cdpr_set_platform_state(cdpr_handle h, const double *pose7, const double *twist6);
+/* telemetry of topic "pid" (Pid.cpp:140-167), all cables: [N][NC][6] = pid_force, p_err, i_err, d_err, cmd, mode */
+int cdpr_get_pid_state(cdpr_handle h, double *out);
+
+/* ---- checkpoint / resume ---------------------------------------------------------------- */
+size_t cdpr_state_bytes(cdpr_handle h);
+int cdpr_get_state(cdpr_handle h, void *blob, size_t bytes);
+int cdpr_set_state(cdpr_handle h, const void *blob, size_t bytes);
+
+/* ---- decimated trajectory snapshots (the publishPeriod gate, .cpp:236-242) --------------- */
+/* every `every` steps the step kernel writes the platform state into dev_buf, a device buffer
+ * laid out [capacity][13][n_instances] = px py pz qw qx qy qz vx vy vz wx wy wz; the write index
+ * restarts at 0 on every call of this function. every == 0 disables. */
+int cdpr_set_snapshots(cdpr_handle h, int64_t every, void *dev_buf, int64_t capacity);
+int64_t cdpr_snapshot_count(cdpr_handle h);
+
+/* ---- kinematics only (Joint::Position/GetVelocity read-backs + the wrench Jacobian) ------- */
+/* host, reference layout: length/length_rate [N][NC], wmat [N][NC][6] = (u, r x u) per cable */
+int cdpr_ik(cdpr_handle h, int64_t n, const double *pose7, const double *twist6, double *length, double *length_rate, double *wmat);
+/* device, SoA: state13 [13][n] (order as snapshots); out [NC][8][n] = L, dL/dt, u xyz, (r x u) xyz */
+int cdpr_ik_device(cdpr_handle h, int64_t n, const void *dev_state13, void *dev_out);
+
+/* ---- sampled rollouts (north_star config 5) ---------------------------------------------- */
+/* Instances are (robot r, sequence s), i = r*n_seq + s, N = n_robots*n_seq. All sequences of a
+ * robot start from that robot's entry in pose7/twist6 ([n_robots][..]; NULL = home, at rest),
+ * the controller in its post-Load state. cmds float32 [n_seq][n_cmd][NC] are velocity commands,
+ * one per `steps_per_cmd` steps. cost[i] = sum over steps of |p - target|^2 + lambda*|w|^2.
+ * dev_cost_seq (device, float64 [n_seq]) receives sum over this handle's robots of cost, in
+ * robot order (deterministic) -- the vector the caller all-reduces across GPUs. */
+int cdpr_rollout(cdpr_handle h, int64_t n_robots, int64_t n_seq, const double *pose7, const double *twist6,
+                 const float *cmds, int64_t n_cmd, int64_t steps_per_cmd, const double target_pos[3], double lambda,
+                 void *dev_cost_seq, double *host_cost /* [N] or NULL */);
+
+/* ---- raw device access for zero-copy callers (torch.distributed gathers) ----------------- */
+int64_t cdpr_padded_instances(cdpr_handle h);
+void *cdpr_device_platform_state(cdpr_handle h); /* [13][padded] float64, same order as snapshots */
+
+/* ---- measurement helpers ----------------------------------------------------------------- */
+/* sustained DFMA rate of this GPU (FP64 roofline denominator); returns TFLOP/s, <0 on error */
+double cdpr_measure_fp64_tflops(int device, int iters);
+/* elapsed ms of the kernels launched by the last cdpr_step / cdpr_ik_device / cdpr_rollout,
+ * from CUDA events recorded on the handle's stream around the launch */
+float cdpr_last_kernel_ms(cdpr_handle h);
+int64_t cdpr_launch_count(cdpr_handle h);
+const char *cdpr_kernel_variant(cdpr_handle h); /* "fast" or "general" */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

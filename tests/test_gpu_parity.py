@@ -1,0 +1,286 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star): fp64 per-step state <= 1e-9 relative; bounded divergence over
+1000 steps; bit-exact instance indexing and cable ordering."""
+import numpy as np
+import pytest
+
+import cdpr_simulation_b200 as cb
+from cdpr_simulation_b200 import workloads as wl
+from oracle import binding as ob
+from helpers import to_oracle_config, state_rel_err
+
+pytestmark = pytest.mark.gpu
+
+PER_STEP_TOL = 1e-9
+DIVERGENCE_TOL_1000 = 1e-7
+
+
+def make_pair(nc, n, seed=1, cfg_edit=None, sine=True):
+    cfg = cb.default_config(nc)
+    if cfg_edit:
+        cfg_edit(cfg)
+    amp, freq, phase, pose7, twist6 = wl.c3_instances(n, seed)
+    gpu = cb.CdprBatch(cfg, n)
+    gpu.set_platform_state(pose7, twist6)
+    if sine:
+        gpu.set_sine_cmd(amp, freq, phase)
+        orc = ob.Batch(to_oracle_config(cfg), n, pose7, twist6, amp, freq, phase)
+    else:
+        orc = ob.Batch(to_oracle_config(cfg), n, pose7, twist6)
+    return cfg, gpu, orc
+
+
+@pytest.mark.parametrize("nc", [4, 8])
+def test_ik_matches_oracle(built_lib, nc):
+    cfg = cb.default_config(nc)
+    pose7, twist6 = wl.c2_poses(4099, seed=0)  # ragged: not a multiple of the block size
+    with cb.CdprBatch(cfg, 1) as gpu:
+        ln, lr, w = gpu.ik(pose7, twist6)
+    oln, olr, ow = ob.ik(to_oracle_config(cfg), pose7, twist6)
+    assert np.max(np.abs(ln - oln) / oln) < 1e-14
+    assert np.max(np.abs(lr - olr)) < 1e-14
+    assert np.max(np.abs(w - ow)) < 1e-14
+
+
+@pytest.mark.parametrize("nc", [4, 8])
+def test_per_step_state_parity_sine(built_lib, nc):
+    """Every one of the first 40 steps (priming, window fill, first D-term samples), one step per launch."""
+    cfg, gpu, orc = make_pair(nc, 257)
+    assert gpu.kernel_variant == "fast"
+    worst = 0.0
+    for step in range(1, 41):
+        gpu.step(1); orc.step(1)
+        pg, tg = gpu.platform_state(); po, to = orc.platform_state()
+        worst = max(worst, state_rel_err(pg, tg, po, to))
+        jg = gpu.joint_states(); jo = orc.joint_states()
+        for a, b in zip(jg, jo):
+            assert np.max(np.abs(a - b)) < 1e-9 * max(1.0, np.max(np.abs(b))), f"joint states differ at step {step}"
+    assert worst < PER_STEP_TOL, worst
+    gpu.close()
+
+
+@pytest.mark.parametrize("nc,k", [(4, 1000), (8, 1000)])
+def test_1000_step_divergence_bounded(built_lib, nc, k):
+    """One persistent launch of 1000 steps against 1000 oracle steps."""
+    cfg, gpu, orc = make_pair(nc, 300)
+    gpu.step(k); orc.step(k)
+    pg, tg = gpu.platform_state(); po, to = orc.platform_state()
+    err = state_rel_err(pg, tg, po, to)
+    assert err < DIVERGENCE_TOL_1000, err
+    assert gpu.step_count == k and abs(gpu.sim_time - k * cfg.dt) < 1e-12
+    gpu.close()
+
+
+def test_launch_split_invariance(built_lib):
+    """K steps in one launch == the same K steps in uneven launches, bitwise (state round-trips through HBM)."""
+    _, a, _ = make_pair(4, 200)
+    _, b, _ = make_pair(4, 200)
+    a.step(137)
+    for k in (1, 2, 10, 11, 13, 100):
+        b.step(k)
+    pa, ta = a.platform_state(); pb, tb = b.platform_state()
+    assert np.array_equal(pa, pb) and np.array_equal(ta, tb)
+    for x, y in zip(a.joint_states(), b.joint_states()):
+        assert np.array_equal(x, y)
+    assert np.array_equal(a.pid_state(), b.pid_state())
+    a.close(); b.close()
+
+
+def test_instance_indexing_and_cable_order_bit_exact(built_lib):
+    """Permuting the instances permutes the outputs bit-for-bit; a cable's column only depends on its own index."""
+    n, nc = 333, 4
+    cfg = cb.default_config(nc)
+    amp, freq, phase, pose7, twist6 = wl.c3_instances(n, 3)
+    perm = np.random.default_rng(0).permutation(n)
+    outs = []
+    for order in (np.arange(n), perm):
+        with cb.CdprBatch(cfg, n) as g:
+            g.set_platform_state(pose7[order], twist6[order])
+            g.set_sine_cmd(amp[order], freq[order], phase[order])
+            g.step(64)
+            outs.append((g.platform_state(), g.joint_states()))
+    (p0, t0), j0 = outs[0]
+    (p1, t1), j1 = outs[1]
+    assert np.array_equal(p0[perm], p1) and np.array_equal(t0[perm], t1)
+    for a, b in zip(j0, j1):
+        assert np.array_equal(a[perm], b)
+    # cable order: per-cable velocity commands, oracle agrees column by column
+    axes = np.tile(np.array([0.01, -0.02, 0.03, -0.04], dtype=np.float32), (n, 1))
+    with cb.CdprBatch(cfg, n) as g:
+        g.set_platform_state(pose7, twist6)
+        g.set_velocity_cmd(axes)
+        g.step(50)
+        jg = g.joint_states()
+    o = ob.Batch(to_oracle_config(cfg), n, pose7, twist6)
+    o.velocity_cmd(axes); o.step(50)
+    jo = o.joint_states()
+    for a, b in zip(jg, jo):
+        assert np.max(np.abs(a - b)) < 1e-9
+
+
+def test_position_force_modes_and_switches(built_lib):
+    """Position hold after Load, then velocity, then position again, then a raw effort command."""
+    n, nc = 130, 4
+    cfg, gpu, orc = make_pair(nc, n, sine=False)
+    rng = np.random.default_rng(5)
+    def check(tag):
+        pg, tg = gpu.platform_state(); po, to = orc.platform_state()
+        e = state_rel_err(pg, tg, po, to)
+        assert e < 1e-8, (tag, e)
+        for a, b in zip(gpu.joint_states(), orc.joint_states()):
+            assert np.max(np.abs(a - b)) < 1e-8, tag
+    gpu.step(25); orc.step(25); check("position hold after Load")
+    v = rng.uniform(-0.05, 0.05, (n, nc)).astype(np.float32)
+    gpu.set_velocity_cmd(v); orc.velocity_cmd(v)
+    gpu.step(40); orc.step(40); check("velocity")
+    p = rng.uniform(-0.02, 0.02, (n, nc)).astype(np.float32)
+    gpu.set_position_cmd(p); orc.position_cmd(p)
+    gpu.step(40); orc.step(40); check("position")
+    # both pending in the same step: velocity is applied first, position wins (CdprGazeboPlugin.cpp:206-219)
+    gpu.set_velocity_cmd(v); gpu.set_position_cmd(p); orc.velocity_cmd(v); orc.position_cmd(p)
+    gpu.step(15); orc.step(15); check("velocity+position")
+    f = rng.uniform(2.0, 6.0, (n, nc))
+    gpu.set_effort_cmd(f); orc.effort_cmd(f)
+    gpu.step(30); orc.step(30); check("force")
+    gpu.set_velocity_cmd(v); orc.velocity_cmd(v)
+    gpu.step(30); orc.step(30); check("force->velocity")
+    gpu.close()
+
+
+def test_malformed_command_is_dropped(built_lib):
+    n = 64
+    cfg, gpu, orc = make_pair(4, n, sine=False)
+    gpu.step(5)
+    before = gpu.get_state()
+    with pytest.raises(cb.CdprError) as ei:
+        gpu.set_velocity_cmd(np.zeros((n, 3), dtype=np.float32))
+    assert ei.value.code == cb.api.ERR_BAD_LENGTH
+    with pytest.raises(cb.CdprError):
+        gpu.set_position_cmd(np.zeros((n, 5), dtype=np.float32))
+    assert np.array_equal(before, gpu.get_state())
+    gpu.close()
+
+
+def general_cfg(cfg):
+    cfg.velocity_epsilon = 0.02       # hold below 2 cm/s: both Pids live, non-uniform D windows
+    cfg.vel_pid.p_cascade = 1         # biquad on the P input
+    cfg.vel_pid.d_cascade = 2         # two biquads on the D output
+
+
+@pytest.mark.parametrize("nc", [4, 8])
+def test_general_variant_hold_and_filters(built_lib, nc):
+    cfg, gpu, orc = make_pair(nc, 150, cfg_edit=general_cfg)
+    assert gpu.kernel_variant == "general"
+    worst = 0.0
+    for k in (1, 1, 1, 7, 20, 70, 400, 1500):   # sine commands cross the epsilon band several times
+        gpu.step(k); orc.step(k)
+        pg, tg = gpu.platform_state(); po, to = orc.platform_state()
+        worst = max(worst, state_rel_err(pg, tg, po, to))
+    assert worst < 1e-7, worst
+    gpu.close()
+
+
+def test_general_variant_cmd_limit_zero_and_short_window(built_lib):
+    def edit(cfg):
+        cfg.vel_pid.cmd_limit = 0.0       # Pid.cpp:175-184: mCmd frozen, anti-windup accumulates
+        cfg.vel_pid.d_buffer_length = 5
+        cfg.vel_pid.d_degree = 1
+    cfg, gpu, orc = make_pair(4, 100, cfg_edit=edit)
+    assert gpu.kernel_variant == "general"
+    gpu.step(300); orc.step(300)
+    pg, tg = gpu.platform_state(); po, to = orc.platform_state()
+    assert state_rel_err(pg, tg, po, to) < 1e-7
+    gpu.close()
+
+
+def test_checkpoint_resume_bitwise(built_lib):
+    _, a, _ = make_pair(8, 140)
+    a.step(77)
+    blob = a.get_state()
+    a.step(200)
+    ref = a.platform_state()
+    _, b, _ = make_pair(8, 140)
+    b.set_state(blob)
+    assert b.step_count == 77
+    b.step(200)
+    out = b.platform_state()
+    assert np.array_equal(ref[0], out[0]) and np.array_equal(ref[1], out[1])
+    a.close(); b.close()
+
+
+def test_snapshots_match_stepwise_states(built_lib):
+    import torch
+    n, every, k = 190, 25, 200
+    _, a, _ = make_pair(4, n)
+    buf = torch.zeros((k // every, 13, n), dtype=torch.float64, device="cuda")
+    a.set_snapshots(every, buf.data_ptr(), buf.shape[0])
+    a.step(k)
+    a.synchronize()
+    assert a.snapshot_count == k // every
+    snaps = buf.cpu().numpy()
+    _, b, _ = make_pair(4, n)
+    for s in range(k // every):
+        b.step(every)
+        pose, twist = b.platform_state()
+        assert np.array_equal(snaps[s, 0:3].T, pose[:, 0:3])
+        assert np.array_equal(snaps[s, 3].T, pose[:, 6]) and np.array_equal(snaps[s, 4:7].T, pose[:, 3:6])
+        assert np.array_equal(snaps[s, 7:13].T, twist)
+    a.close(); b.close()
+
+
+def test_shard_equivalence_bitwise(built_lib):
+    """1 handle over all instances == concatenation of 3 contiguous shards."""
+    n, nc = 1000, 8
+    cfg = cb.default_config(nc)
+    amp, freq, phase, pose7, twist6 = wl.c3_instances(n, 7)
+    def run(lo, hi):
+        with cb.CdprBatch(cfg, hi - lo) as g:
+            g.set_platform_state(pose7[lo:hi], twist6[lo:hi]); g.set_sine_cmd(amp[lo:hi], freq[lo:hi], phase[lo:hi])
+            g.step(120)
+            return g.platform_state()
+    full = run(0, n)
+    parts = [run(*wl.shard_range(n, r, 3)) for r in range(3)]
+    assert np.array_equal(full[0], np.concatenate([p[0] for p in parts]))
+    assert np.array_equal(full[1], np.concatenate([p[1] for p in parts]))
+
+
+def test_rollout_costs_match_oracle(built_lib):
+    import torch
+    nc, n_robots, n_seq, n_cmd, spc = 4, 3, 40, 6, 10
+    cfg = cb.default_config(nc)
+    cmds = wl.c5_rollouts(n_seq, n_cmd, nc)
+    _, _, _, pose7, twist6 = wl.c3_instances(n_robots, 11)
+    target, lam = np.array([0.0, 0.0, 0.31]), 0.1
+    with cb.CdprBatch(cfg, n_robots * n_seq) as g:
+        dev = torch.zeros(n_seq, dtype=torch.float64, device="cuda")
+        cost = g.rollout(n_robots, n_seq, cmds, spc, target, lam, pose7, twist6, dev_cost_seq=dev.data_ptr())
+        g.synchronize()
+        cost_seq = dev.cpu().numpy()
+    ocost = np.zeros(n_robots * n_seq)
+    o = ob.Batch(to_oracle_config(cfg), n_robots * n_seq, np.repeat(pose7, n_seq, axis=0), np.repeat(twist6, n_seq, axis=0))
+    for c in range(n_cmd):
+        o.velocity_cmd(np.tile(cmds[:, c, :], (n_robots, 1)))
+        for _ in range(spc):
+            o.step(1)
+            pose, twist = o.platform_state()
+            ocost += np.sum((pose[:, :3] - target) ** 2, axis=1) + lam * np.sum(twist[:, 3:] ** 2, axis=1)
+    assert np.max(np.abs(cost - ocost) / ocost) < 1e-9
+    assert np.max(np.abs(cost_seq - ocost.reshape(n_robots, n_seq).sum(axis=0)) / cost_seq) < 1e-9
+
+
+def test_full_size_properties(built_lib):
+    """At a size the oracle cannot follow: unit quaternions, finite state, platform stays inside the frame,
+    static-equilibrium tension near m g / (4 * 0.617802) for slow commands."""
+    n = 1 << 16
+    cfg = cb.default_config(4)
+    amp, freq, phase, pose7, twist6 = wl.c3_instances(n, 1)
+    with cb.CdprBatch(cfg, n) as g:
+        g.set_platform_state(pose7, twist6); g.set_sine_cmd(amp, freq, phase)
+        g.step(1000)
+        pose, twist = g.platform_state()
+        _, _, eff = g.joint_states()
+    assert np.all(np.isfinite(pose)) and np.all(np.isfinite(twist))
+    assert np.max(np.abs(np.linalg.norm(pose[:, 3:], axis=1) - 1.0)) < 1e-14
+    assert np.all(np.abs(pose[:, :2]) < 0.3) and np.all((pose[:, 2] > 0.0) & (pose[:, 2] < 0.6))
+    assert abs(np.median(eff.sum(axis=1)) - 4 * 3.9657) < 1.5
