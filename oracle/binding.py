@@ -87,6 +87,21 @@ def lib():
         L.orc_time_double.restype = C.c_double
         L.orc_batch_last_outputs.argtypes = [C.c_void_p, C.c_int64, _dp, _dp, _dp, _dp]
         L.orc_batch_pid_terms.argtypes = [C.c_void_p, C.c_int64, _dp]
+        L.orc_pid_new.argtypes = [C.POINTER(PidParams), C.c_int]; L.orc_pid_new.restype = C.c_void_p
+        L.orc_pid_free.argtypes = [C.c_void_p]
+        L.orc_pid_reset.argtypes = [C.c_void_p]
+        L.orc_pid_update.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double]; L.orc_pid_update.restype = C.c_double
+        L.orc_pid_derive.argtypes = [C.c_void_p, C.c_double, C.c_double]; L.orc_pid_derive.restype = C.c_double
+        L.orc_pid_derive_abs.argtypes = [C.c_void_p, C.c_double, C.c_double]; L.orc_pid_derive_abs.restype = C.c_double
+        L.orc_pid_get.argtypes = [C.c_void_p, _dp]
+        L.orc_cable_new.argtypes = [C.POINTER(Config)]; L.orc_cable_new.restype = C.c_void_p
+        L.orc_cable_free.argtypes = [C.c_void_p]
+        L.orc_cable_mode.argtypes = [C.c_void_p]; L.orc_cable_mode.restype = C.c_int
+        L.orc_cable_last_position.argtypes = [C.c_void_p]; L.orc_cable_last_position.restype = C.c_double
+        L.orc_cable_set_position_target.argtypes = [C.c_void_p, C.c_double]
+        L.orc_cable_set_velocity_target.argtypes = [C.c_void_p, C.c_double]
+        L.orc_cable_set_force.argtypes = [C.c_void_p, C.c_double]
+        L.orc_cable_update.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_double, C.c_double]; L.orc_cable_update.restype = C.c_double
         _lib = L
     return _lib
 

@@ -636,3 +636,25 @@ void orc_batch_pid_terms(const orc_robot *robots, int64_t n, double *out) {
       }
   }
 }
+
+/* ---- opaque single-object helpers for the ctypes tests --------------------------------------- */
+orc_pid *orc_pid_new(const orc_pid_params *prm, int derive_absolute_time) {
+  orc_pid *p = (orc_pid *)malloc(sizeof(orc_pid));
+  orc_pid_init(p, prm);
+  p->derive_absolute_time = derive_absolute_time;
+  return p;
+}
+void orc_pid_free(orc_pid *p) { free(p); }
+/* out[8]: dbg_p, dbg_i, dbg_d, p_err, i_err, d_err, cmd, last_time */
+void orc_pid_get(const orc_pid *p, double *out) {
+  out[0] = p->dbg_p; out[1] = p->dbg_i; out[2] = p->dbg_d; out[3] = p->p_err; out[4] = p->i_err; out[5] = p->d_err;
+  out[6] = p->cmd; out[7] = p->last_time;
+}
+orc_cable *orc_cable_new(const orc_config *cfg) {
+  orc_cable *c = (orc_cable *)malloc(sizeof(orc_cable));
+  orc_cable_init(c, cfg, 0, 0);
+  return c;
+}
+void orc_cable_free(orc_cable *c) { free(c); }
+int orc_cable_mode(const orc_cable *c) { return c->mode; }
+double orc_cable_last_position(const orc_cable *c) { return c->last_position; }

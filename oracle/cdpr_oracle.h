@@ -183,6 +183,14 @@ void orc_batch_joint_states(const orc_robot *robots, int64_t n, double *pos, dou
 void orc_batch_last_outputs(const orc_robot *robots, int64_t n, double *jpos, double *jvel, double *pid_force, double *effort);
 void orc_batch_pid_terms(const orc_robot *robots, int64_t n, double *out);
 
+orc_pid *orc_pid_new(const orc_pid_params *prm, int derive_absolute_time);
+void orc_pid_free(orc_pid *p);
+void orc_pid_get(const orc_pid *p, double *out);
+orc_cable *orc_cable_new(const orc_config *cfg);
+void orc_cable_free(orc_cable *c);
+int orc_cable_mode(const orc_cable *c);
+double orc_cable_last_position(const orc_cable *c);
+
 #ifdef __cplusplus
 }
 #endif

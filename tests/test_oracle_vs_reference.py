@@ -1,0 +1,197 @@
+"""Pins the CPU oracle (L1, oracle/cdpr_oracle.c) to the REFERENCE's own force-law code (L0): src/Pid.cpp and
+src/JointForceCalculator.cpp compiled unmodified from /root/reference against oracle/ref_shim (oracle/_ref/).
+
+P / I / clamp / anti-windup / filters / mode machine: bit-exact.  D-term: the reference's absolute-time normal
+equations are ill-conditioned by construction, so L1 (window-relative fit) is pinned to L0 within
+the reference's own conditioning noise, and both are compared with the analytic derivative."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import binding as ob
+
+pytestmark = pytest.mark.skipif(not ob.ref_available(), reason="oracle/_ref not built (reference sources absent)")
+
+
+def pid_params(cfg_pid, **kw):
+    p = ob.PidParams()
+    C.memmove(C.byref(p), C.byref(cfg_pid), C.sizeof(p))
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+def run_pid_pair(prm, desired, actual, times):
+    L, R = ob.lib(), ob.ref()
+    o = L.orc_pid_new(C.byref(prm), 0)
+    r = R.ref_pid_create(C.byref(prm))
+    out_o, out_r = [], []
+    terms = np.zeros(3); got = np.zeros(8)
+    for d, a, t in zip(desired, actual, times):
+        co = L.orc_pid_update(o, d, a, t)
+        cr = R.ref_pid_update_terms(r, d, a, t, terms)
+        L.orc_pid_get(o, got)
+        out_o.append((co, got[0], got[1], got[2]))
+        out_r.append((cr, terms[0], terms[1], terms[2]))
+    L.orc_pid_free(o); R.ref_pid_destroy(r)
+    return np.array(out_o), np.array(out_r)
+
+
+def gazebo_times(n, dt_ns=1_000_000):
+    return np.array([ob.lib().orc_time_double((k * dt_ns) // 10**9, (k * dt_ns) % 10**9) for k in range(1, n + 1)])
+
+
+@pytest.mark.parametrize("which", ["vel", "pos"])
+def test_pid_p_i_clamp_antiwindup_bit_exact(which):
+    """D gain 0 isolates everything except the derivative: commands and P/I terms must be identical bits,
+    including the integral clamp with back-calculation and the command clamp + anti-windup quirk (Pid.cpp:143-184)."""
+    cfg = ob.default_config(4)
+    base = cfg.vel_pid if which == "vel" else cfg.pos_pid
+    rng = np.random.default_rng(0)
+    for i_limit, cmd_limit, scale in [(100.0, 100.0, 0.05), (0.5, 100.0, 0.2), (100.0, 3.0, 0.2), (0.3, 1.5, 0.5), (2.5, 0.0, 0.1)]:
+        prm = pid_params(base, d_gain=0.0, i_limit=i_limit, cmd_limit=cmd_limit, forward_gain=0.3)
+        n = 600
+        t = gazebo_times(n)
+        desired = scale * np.sin(2 * np.pi * 0.7 * t) + 0.1 * scale
+        actual = desired - scale * rng.normal(size=n)
+        o, r = run_pid_pair(prm, desired, actual, t)
+        assert np.array_equal(o[:, 0], r[:, 0]), (i_limit, cmd_limit)
+        assert np.array_equal(o[1:, 1], r[1:, 1]) and np.array_equal(o[1:, 2], r[1:, 2])
+        if cmd_limit not in (0.0,):
+            assert np.max(np.abs(o[:, 0])) <= cmd_limit + 1.0   # anti-windup may exceed the clamp slightly (H6)
+
+
+def test_pid_biquad_cascades_bit_exact():
+    cfg = ob.default_config(4)
+    prm = pid_params(cfg.vel_pid, d_gain=0.0, p_cascade=3, p_cutoff=0.1, p_quality=0.707)
+    t = gazebo_times(400)
+    rng = np.random.default_rng(1)
+    desired = 0.05 * np.sin(2 * np.pi * 2.0 * t)
+    actual = desired + 0.01 * rng.normal(size=t.size)
+    o, r = run_pid_pair(prm, desired, actual, t)
+    assert np.array_equal(o[:, 0], r[:, 0]) and np.array_equal(o[1:, 1], r[1:, 1])
+
+
+def test_pid_first_update_and_nonpositive_dt():
+    """First update after a reset returns 0 and records nothing; dt <= 0 keeps the previous D error (Pid.cpp:123-126,154)."""
+    cfg = ob.default_config(4)
+    prm = pid_params(cfg.pos_pid, d_gain=0.0)
+    t = np.array([0.001, 0.002, 0.002, 0.003, 0.0025, 0.004])
+    desired = np.full(t.size, 0.01); actual = np.linspace(0.0, 0.004, t.size)
+    o, r = run_pid_pair(prm, desired, actual, t)
+    assert o[0, 0] == 0.0 and r[0, 0] == 0.0
+    assert np.array_equal(o[:, 0], r[:, 0])
+
+
+def test_dterm_within_reference_conditioning_noise():
+    """derive(): L1 (window-relative) vs L0 (reference, absolute time) vs the analytic derivative of a 0.1 Hz sine.
+    Measured here: the reference's own relative error is ~4e-6 for t <= 1 s and grows with t."""
+    L, R = ob.lib(), ob.ref()
+    cfg = ob.default_config(4)
+    prm = pid_params(cfg.vel_pid)
+    n = 1000
+    t = gazebo_times(n)
+    y = np.sin(2 * np.pi * 0.1 * t)
+    dy = 2 * np.pi * 0.1 * np.cos(2 * np.pi * 0.1 * t)
+    o = L.orc_pid_new(C.byref(prm), 0); r = R.ref_pid_create(C.byref(prm))
+    d1 = np.array([L.orc_pid_derive(o, yy, tt) for yy, tt in zip(y, t)])
+    d0 = np.array([R.ref_pid_derive(r, yy, tt) for yy, tt in zip(y, t)])
+    L.orc_pid_free(o); R.ref_pid_destroy(r)
+    assert np.all(d1[:10] == 0.0) and np.all(d0[:10] == 0.0)        # 0 until 11 samples were seen (Pid.cpp:203)
+    e1 = np.abs(d1[10:] - dy[10:]) / np.abs(dy[10:])
+    e0 = np.abs(d0[10:] - dy[10:]) / np.abs(dy[10:])
+    gap = np.abs(d1[10:] - d0[10:]) / np.abs(dy[10:])
+    assert e1.max() < 2e-5            # truncation error of a quadratic through 10 ms of a 0.1 Hz sine
+    assert e0.max() < 1e-3            # reference: truncation + round-off amplified by cond(V^T V)
+    assert gap.max() < 1e-3 and np.median(gap) < 1e-4
+    # the oracle is never farther from the truth than the reference is (up to its own truncation error)
+    assert e1.max() <= e0.max() + 2e-5
+
+
+def test_dterm_fir_equivalence_any_degree():
+    """With uniform steps the fit is a fixed FIR: L1 on a polynomial of the fit's degree returns its exact derivative."""
+    L = ob.lib()
+    cfg = ob.default_config(4)
+    for deg, ln in [(1, 2), (1, 5), (2, 11), (3, 9), (2, 20)]:
+        prm = pid_params(cfg.vel_pid, d_degree=deg, d_buffer_length=ln)
+        o = L.orc_pid_new(C.byref(prm), 0)
+        t = gazebo_times(60)
+        coef = np.arange(1, deg + 2, dtype=float)            # 1 + 2 t + 3 t^2 ...
+        y = sum(c * t ** k for k, c in enumerate(coef))
+        dy = sum(k * c * t ** (k - 1) for k, c in enumerate(coef) if k > 0)
+        d = np.array([L.orc_pid_derive(o, yy, tt) for yy, tt in zip(y, t)])
+        L.orc_pid_free(o)
+        assert np.all(d[: ln - 1] == 0.0)
+        assert np.max(np.abs(d[ln - 1:] - dy[ln - 1:])) < 1e-9
+
+
+def drive_plugins(eps, script, nc=4, d_gain=None, n_steps=400, seed=0):
+    """Same command script and joint read-backs into the oracle cables and the reference plugin."""
+    L, R = ob.lib(), ob.ref()
+    cfg = ob.default_config(nc)
+    cfg.velocity_epsilon = eps
+    if d_gain is not None:
+        cfg.vel_pid.d_gain = d_gain; cfg.pos_pid.d_gain = d_gain
+    ref = R.ref_plugin_create(nc, C.byref(cfg.vel_pid), C.byref(cfg.pos_pid), eps)
+    cables = [L.orc_cable_new(C.byref(cfg)) for _ in range(nc)]
+    rng = np.random.default_rng(seed)
+    q = np.zeros(nc); out = []
+    for step in range(1, n_steps + 1):
+        ns = step * 1_000_000
+        sec, nsec = ns // 10**9, ns % 10**9
+        R.ref_plugin_set_time(ref, sec, nsec)
+        for kind, at, val in script:
+            if at == step:
+                axes = np.asarray(val, dtype=np.float32)
+                if kind == "vel":
+                    R.ref_plugin_velocity_cmd(ref, axes); [L.orc_cable_set_velocity_target(c, float(a)) for c, a in zip(cables, axes)]
+                elif kind == "pos":
+                    R.ref_plugin_position_cmd(ref, axes); [L.orc_cable_set_position_target(c, float(a)) for c, a in zip(cables, axes)]
+                else:
+                    f = np.asarray(val, dtype=np.float64)
+                    R.ref_plugin_effort_cmd(ref, f); [L.orc_cable_set_force(c, float(a)) for c, a in zip(cables, f)]
+        qd = 0.05 * rng.normal(size=nc)
+        q = q + 1e-3 * qd
+        row = []
+        for c in range(nc):
+            R.ref_plugin_set_joint(ref, c, q[c], qd[c])
+            fr = R.ref_plugin_update_cable(ref, c, None)
+            fo = L.orc_cable_update(cables[c], sec, nsec, q[c], qd[c])
+            row.append((fr, fo))
+        out.append(row)
+    R.ref_plugin_destroy(ref)
+    [L.orc_cable_free(c) for c in cables]
+    return np.array(out)  # [step][cable][ref, oracle]
+
+
+SCRIPT = [("vel", 5, [0.03, -0.03, 0.0005, 0.0]), ("vel", 90, [0.0, 0.0, 0.04, -0.04]), ("pos", 150, [0.01, -0.01, 0.0, 0.02]),
+          ("vel", 200, [0.05, 0.05, 0.05, 0.05]), ("eff", 260, [4.0, 4.1, 4.2, 4.3]), ("pos", 300, [0.0, 0.0, 0.0, 0.0]),
+          ("vel", 330, [0.0005, 0.0, -0.0005, 0.03])]
+
+
+@pytest.mark.parametrize("eps", [-0.001, 0.001, 0.035])
+def test_force_calculator_mode_machine_bit_exact_without_d(eps):
+    """Force / Position / Velocity modes, Pid resets on mode change, hold through the position Pid when
+    |target| <= epsilon (JointForceCalculator.cpp:59-119) -- identical forces, bit for bit, with the D gain at 0."""
+    out = drive_plugins(eps, SCRIPT, d_gain=0.0)
+    assert np.array_equal(out[..., 0], out[..., 1])
+    assert np.any(out[..., 0] != 0.0)
+
+
+@pytest.mark.parametrize("eps", [-0.001, 0.035])
+def test_force_calculator_with_d_within_noise(eps):
+    out = drive_plugins(eps, SCRIPT)
+    ref, orc = out[..., 0], out[..., 1]
+    # the D-term differentiates white noise here (worst case for conditioning); forces are O(10) N
+    assert np.max(np.abs(ref - orc)) < 1e-3 * max(1.0, np.max(np.abs(ref)))
+
+
+def test_reduced_model_trajectory_l1_vs_l0_force_law():
+    """Whole step: oracle kinematics/integration with (a) the oracle force law, (b) the reference's compiled force law."""
+    cfg = ob.default_config(4)
+    a = ob.Batch(cfg, 4, amp=[0.05, 0.03, 0.06, 0.01], freq=[0.1, 0.2, 0.05, 0.15], phase=[0, 1, 2, 3])
+    b = ob.Batch(cfg, 4, amp=[0.05, 0.03, 0.06, 0.01], freq=[0.1, 0.2, 0.05, 0.15], phase=[0, 1, 2, 3])
+    a.step(1500); b.step_reference_forcelaw(1500)
+    pa, ta = a.platform_state(); pb, tb = b.platform_state()
+    assert np.max(np.abs(pa - pb)) < 1e-7 and np.max(np.abs(ta - tb)) < 1e-5
