@@ -87,6 +87,7 @@ def lib():
         L.orc_time_double.restype = C.c_double
         L.orc_batch_last_outputs.argtypes = [C.c_void_p, C.c_int64, _dp, _dp, _dp, _dp]
         L.orc_batch_pid_terms.argtypes = [C.c_void_p, C.c_int64, _dp]
+        L.orc_batch_targets.argtypes = [C.c_void_p, C.c_int64, _dp, _dp, _dp]
         L.orc_pid_new.argtypes = [C.POINTER(PidParams), C.c_int]; L.orc_pid_new.restype = C.c_void_p
         L.orc_pid_free.argtypes = [C.c_void_p]
         L.orc_pid_reset.argtypes = [C.c_void_p]
@@ -194,6 +195,12 @@ class Batch:
         """(joint_pos, joint_vel, pid_force, effort) as seen by the plugin in the LAST update() call."""
         out = [np.empty((self.n, self.nc)) for _ in range(4)]
         lib().orc_batch_last_outputs(self.ptr, self.n, *out)
+        return out
+
+    def targets(self):
+        """(velocity_target, position_target, mode) per cable, as latched in the force calculators."""
+        out = [np.empty((self.n, self.nc)) for _ in range(3)]
+        lib().orc_batch_targets(self.ptr, self.n, *out)
         return out
 
     def pid_terms(self):

@@ -658,3 +658,14 @@ orc_cable *orc_cable_new(const orc_config *cfg) {
 void orc_cable_free(orc_cable *c) { free(c); }
 int orc_cable_mode(const orc_cable *c) { return c->mode; }
 double orc_cable_last_position(const orc_cable *c) { return c->last_position; }
+
+/* latched targets and mode per cable: vel_target[n][nc], pos_target[n][nc], mode[n][nc] (as double) */
+void orc_batch_targets(const orc_robot *robots, int64_t n, double *vel_target, double *pos_target, double *mode) {
+  for (int64_t i = 0; i < n; ++i) {
+    const orc_robot *r = &robots[i];
+    for (int c = 0; c < r->cfg.n_cables; ++c) {
+      int64_t o = i * r->cfg.n_cables + c;
+      vel_target[o] = r->cable[c].velocity_target; pos_target[o] = r->cable[c].position_target; mode[o] = r->cable[c].mode;
+    }
+  }
+}

@@ -183,6 +183,7 @@ void orc_batch_joint_states(const orc_robot *robots, int64_t n, double *pos, dou
 void orc_batch_last_outputs(const orc_robot *robots, int64_t n, double *jpos, double *jvel, double *pid_force, double *effort);
 void orc_batch_pid_terms(const orc_robot *robots, int64_t n, double *out);
 
+void orc_batch_targets(const orc_robot *robots, int64_t n, double *vel_target, double *pos_target, double *mode);
 orc_pid *orc_pid_new(const orc_pid_params *prm, int derive_absolute_time);
 void orc_pid_free(orc_pid *p);
 void orc_pid_get(const orc_pid *p, double *out);

@@ -57,7 +57,8 @@ def test_pid_p_i_clamp_antiwindup_bit_exact(which):
         actual = desired - scale * rng.normal(size=n)
         o, r = run_pid_pair(prm, desired, actual, t)
         assert np.array_equal(o[:, 0], r[:, 0]), (i_limit, cmd_limit)
-        assert np.array_equal(o[1:, 1], r[1:, 1]) and np.array_equal(o[1:, 2], r[1:, 2])
+        # the reference publishes its terms through float32 Joy.axes (Pid.cpp:140-141)
+        assert np.array_equal(o[1:, 1:3].astype(np.float32), r[1:, 1:3].astype(np.float32))
         if cmd_limit not in (0.0,):
             assert np.max(np.abs(o[:, 0])) <= cmd_limit + 1.0   # anti-windup may exceed the clamp slightly (H6)
 
@@ -70,7 +71,7 @@ def test_pid_biquad_cascades_bit_exact():
     desired = 0.05 * np.sin(2 * np.pi * 2.0 * t)
     actual = desired + 0.01 * rng.normal(size=t.size)
     o, r = run_pid_pair(prm, desired, actual, t)
-    assert np.array_equal(o[:, 0], r[:, 0]) and np.array_equal(o[1:, 1], r[1:, 1])
+    assert np.array_equal(o[:, 0], r[:, 0]) and np.array_equal(o[1:, 1].astype(np.float32), r[1:, 1].astype(np.float32))
 
 
 def test_pid_first_update_and_nonpositive_dt():
