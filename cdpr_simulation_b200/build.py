@@ -6,7 +6,8 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libcdpr_b200.so")
+# CDPR_B200_LIB selects another build of the same library (kernel tuning experiments only)
+LIB = os.environ.get("CDPR_B200_LIB") or os.path.join(HERE, "libcdpr_b200.so")
 SOURCES = ["api.cu"]
 HEADERS = ["common.cuh", "physics.cuh", "step_fast.cuh", "step_general.cuh", "misc_kernels.cuh", "../../include/cdpr_b200.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-shared"]
@@ -22,7 +23,8 @@ def stale() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if force or stale():
         nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+        extra = os.environ.get("CDPR_NVCC_EXTRA", "").split()
+        cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)

@@ -26,6 +26,8 @@ struct cdpr_batch {
   RobotConsts rc{};
   PidConsts pc[2]{};
   double fir[2][kMaxDbuf]{};
+  double dmom[2][3]{};
+  bool dmom_ok[2]{};
   int mode = MODE_POSITION;
   bool vel_pending = false, pos_pending = false;
   int sec = 0, nsec = 0, dt_ns = 0;
@@ -159,6 +161,40 @@ static void fir_weights(int degree, int len, double dt, double *w) {
   }
 }
 
+// The FIR weights of a degree <= 2 fit are a quadratic in the centred sample position k = j - (len-1)/2.
+// Returns false when they are not (degree > 2): the kernel then keeps the plain FIR.
+static bool fir_as_quadratic(const double *w, int len, double *abc) {
+  const long double K = 0.5L * (len - 1);
+  // least-squares quadratic through (k_j, w_j) via normal equations in long double, then check the residual
+  long double s[5] = {0, 0, 0, 0, 0}, t[3] = {0, 0, 0};
+  for (int j = 0; j < len; ++j) {
+    const long double k = j - K;
+    long double p = 1;
+    for (int q = 0; q < 5; ++q) { s[q] += p; if (q < 3) t[q] += p * w[j]; p *= k; }
+  }
+  long double M[3][4] = {{s[0], s[1], s[2], t[0]}, {s[1], s[2], s[3], t[1]}, {s[2], s[3], s[4], t[2]}};
+  for (int col = 0; col < 3; ++col) {
+    int piv = col;
+    for (int r = col + 1; r < 3; ++r) if (fabsl(M[r][col]) > fabsl(M[piv][col])) piv = r;
+    if (M[piv][col] == 0) return false;
+    for (int q = 0; q < 4; ++q) std::swap(M[col][q], M[piv][q]);
+    for (int r = 0; r < 3; ++r) {
+      if (r == col) continue;
+      const long double f = M[r][col] / M[col][col];
+      for (int q = col; q < 4; ++q) M[r][q] -= f * M[col][q];
+    }
+  }
+  long double c[3] = {M[0][3] / M[0][0], M[1][3] / M[1][1], M[2][3] / M[2][2]};
+  long double worst = 0, scale = 0;
+  for (int j = 0; j < len; ++j) {
+    const long double k = j - K;
+    worst = std::max(worst, fabsl(c[0] + c[1] * k + c[2] * k * k - w[j]));
+    scale = std::max(scale, fabsl((long double)w[j]));
+  }
+  for (int q = 0; q < 3; ++q) abc[q] = (double)c[q];
+  return worst <= 1e-13L * std::max(scale, (long double)1e-300);
+}
+
 static void quat_rot_host(const double q[4], double R[3][3]) {
   const double w = q[0], x = q[1], y = q[2], z = q[3];
   R[0][0] = 1 - 2 * (y * y + z * z); R[0][1] = 2 * (x * y - w * z); R[0][2] = 2 * (x * z + w * y);
@@ -224,6 +260,7 @@ static int reset_to_load_state(cdpr_handle h) {
   CK(h, cudaMemsetAsync(L.cab, 0, sizeof(double) * L.nc * CAB_F * L.np, h->stream));
   CK(h, cudaMemsetAsync(L.pid, 0, sizeof(double) * L.nc * 2 * PID_F * L.np, h->stream));
   CK(h, cudaMemsetAsync(L.win_y, 0, sizeof(double) * L.nc * 2 * L.len * L.np, h->stream));
+  if (L.mom) CK(h, cudaMemsetAsync(L.mom, 0, sizeof(double) * L.nc * 2 * 3 * L.np, h->stream));
   if (L.win_x) CK(h, cudaMemsetAsync(L.win_x, 0, sizeof(double) * L.nc * 2 * L.len * L.np, h->stream));
   if (L.filt) CK(h, cudaMemsetAsync(L.filt, 0, sizeof(double) * L.nc * 2 * 2 * L.casc * 4 * L.np, h->stream));
   const cdpr_config &c = h->cfg;
@@ -268,6 +305,8 @@ extern "C" int cdpr_create(const cdpr_config *cfg, int64_t n_instances, int devi
   make_pid_consts(cfg->pos_pid, h->pc[PID_POS]);
   fir_weights(cfg->vel_pid.d_degree, cfg->vel_pid.d_buffer_length, cfg->dt, h->fir[PID_VEL]);
   fir_weights(cfg->pos_pid.d_degree, cfg->pos_pid.d_buffer_length, cfg->dt, h->fir[PID_POS]);
+  h->dmom_ok[PID_VEL] = fir_as_quadratic(h->fir[PID_VEL], cfg->vel_pid.d_buffer_length, h->dmom[PID_VEL]);
+  h->dmom_ok[PID_POS] = fir_as_quadratic(h->fir[PID_POS], cfg->pos_pid.d_buffer_length, h->dmom[PID_POS]);
   h->dt_ns = (int)std::llround(ns);
   h->sine_pub_dt = 1.0 / cfg->sine_publish_hz;  // sinevelocitytest.cpp:48
   h->sine_period = (int)std::llround(h->sine_pub_dt / cfg->dt);
@@ -275,7 +314,7 @@ extern "C" int cdpr_create(const cdpr_config *cfg, int64_t n_instances, int devi
   // Which kernel variant? The fast one needs: hold impossible, no filters, cmdLimit != 0, window 11 for both Pids.
   const bool fast_ok = cfg->velocity_epsilon < 0.0 && cfg->vel_pid.p_cascade == 0 && cfg->vel_pid.d_cascade == 0 &&
                        cfg->pos_pid.p_cascade == 0 && cfg->pos_pid.d_cascade == 0 && cfg->vel_pid.cmd_limit != 0.0 &&
-                       cfg->pos_pid.cmd_limit != 0.0 && cfg->vel_pid.d_buffer_length == 11 && cfg->pos_pid.d_buffer_length == 11 &&
+                       cfg->pos_pid.cmd_limit != 0.0 && cfg->vel_pid.i_gain >= 0.0 && cfg->pos_pid.i_gain >= 0.0 && cfg->vel_pid.d_buffer_length == 11 && cfg->pos_pid.d_buffer_length == 11 &&
                        (cfg->n_cables == 4 || cfg->n_cables == 8);
   h->general = !fast_ok;
 
@@ -296,6 +335,7 @@ extern "C" int cdpr_create(const cdpr_config *cfg, int64_t n_instances, int devi
   if ((rc = dev_alloc(h, (void **)&L.cab, col * L.nc * CAB_F))) return bail(rc);
   if ((rc = dev_alloc(h, (void **)&L.pid, col * L.nc * 2 * PID_F))) return bail(rc);
   if ((rc = dev_alloc(h, (void **)&L.win_y, col * L.nc * 2 * L.len))) return bail(rc);
+  if (!h->general && (rc = dev_alloc(h, (void **)&L.mom, col * L.nc * 2 * 3))) return bail(rc);
   if (h->general) {
     if ((rc = dev_alloc(h, (void **)&L.win_x, col * L.nc * 2 * L.len))) return bail(rc);
     if (L.casc > 0 && (rc = dev_alloc(h, (void **)&L.filt, col * L.nc * 2 * 2 * L.casc * 4))) return bail(rc);
@@ -306,10 +346,17 @@ extern "C" int cdpr_create(const cdpr_config *cfg, int64_t n_instances, int devi
   if ((rc = reset_to_load_state(h))) return bail(rc);
   if (!h->general) {
     const int smem4 = 11 * 4 * kTpb * 8, smem8 = 11 * 8 * kTpb * 8;
-    cudaFuncSetAttribute(k_step_fast<4, 11>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem4);
-    cudaFuncSetAttribute(k_step_fast<8, 11>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem8);
-    cudaFuncSetAttribute(k_step_fast<4, 11>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(k_step_fast<8, 11>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    auto prep = [](const void *f, int smem) {
+      cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    };
+#define CDPR_PREP(NC_, SM_)                                                                                              \
+    prep((const void *)k_step_fast<NC_, 11, MODE_FORCE, false>, SM_); prep((const void *)k_step_fast<NC_, 11, MODE_POSITION, false>, SM_); \
+    prep((const void *)k_step_fast<NC_, 11, MODE_POSITION, true>, SM_); prep((const void *)k_step_fast<NC_, 11, MODE_VELOCITY, false>, SM_); \
+    prep((const void *)k_step_fast<NC_, 11, MODE_VELOCITY, true>, SM_)
+    CDPR_PREP(4, smem4);
+    CDPR_PREP(8, smem8);
+#undef CDPR_PREP
   }
   if (cudaStreamSynchronize(h->stream) != cudaSuccess) { h->err = "initialisation kernels failed"; return bail(CDPR_ERR_CUDA); }
   *out = h;
@@ -432,6 +479,8 @@ static void fill_args(cdpr_handle h, StepArgs &A, int k_steps, bool sine) {
   A.live_idx = (h->mode == MODE_POSITION) ? PID_POS : PID_VEL;
   A.live = h->pc[A.live_idx];
   std::memcpy(A.fir, h->fir[A.live_idx], sizeof(A.fir));
+  std::memcpy(A.dmom, h->dmom[A.live_idx], sizeof(A.dmom));
+  A.effort_ge_cmd = h->rc.effort_limit_abs >= A.live.cmd_max ? 1 : 0;
   A.mode = h->mode; A.k_steps = k_steps; A.n0 = h->step_count;
   A.sec0 = h->sec; A.nsec0 = h->nsec; A.dt_ns = h->dt_ns; A.t0 = time_double(h->sec, h->nsec);
   A.sine_on = sine ? 1 : 0; A.sine_period = h->sine_period; A.sine_time0 = h->sine_time; A.sine_pub_dt = h->sine_pub_dt;
@@ -442,10 +491,20 @@ static int launch_step(cdpr_handle h, const StepArgs &A) {
   const unsigned grid = (unsigned)(h->np / kTpb);
   if (h->general) {
     k_step_general<<<grid, kTpb, 0, h->stream>>>(A);
-  } else if (h->L.nc == 4) {
-    k_step_fast<4, 11><<<grid, kTpb, 11 * 4 * kTpb * sizeof(double), h->stream>>>(A);
   } else {
-    k_step_fast<8, 11><<<grid, kTpb, 11 * 8 * kTpb * sizeof(double), h->stream>>>(A);
+    const bool dm = h->dmom_ok[A.live_idx];
+    const size_t smem = (size_t)11 * h->L.nc * kTpb * sizeof(double);
+#define CDPR_LAUNCH(NC_, MODE_, DM_) k_step_fast<NC_, 11, MODE_, DM_><<<grid, kTpb, smem, h->stream>>>(A)
+    if (h->L.nc == 4) {
+      if (A.mode == MODE_FORCE) CDPR_LAUNCH(4, MODE_FORCE, false);
+      else if (A.mode == MODE_POSITION) { if (dm) CDPR_LAUNCH(4, MODE_POSITION, true); else CDPR_LAUNCH(4, MODE_POSITION, false); }
+      else { if (dm) CDPR_LAUNCH(4, MODE_VELOCITY, true); else CDPR_LAUNCH(4, MODE_VELOCITY, false); }
+    } else {
+      if (A.mode == MODE_FORCE) CDPR_LAUNCH(8, MODE_FORCE, false);
+      else if (A.mode == MODE_POSITION) { if (dm) CDPR_LAUNCH(8, MODE_POSITION, true); else CDPR_LAUNCH(8, MODE_POSITION, false); }
+      else { if (dm) CDPR_LAUNCH(8, MODE_VELOCITY, true); else CDPR_LAUNCH(8, MODE_VELOCITY, false); }
+    }
+#undef CDPR_LAUNCH
   }
   CK(h, cudaGetLastError());
   ++h->launches;
@@ -589,6 +648,7 @@ static std::vector<Section> sections(cdpr_handle h) {
   const DevLayout &L = h->L;
   const size_t col = sizeof(double) * (size_t)L.np;
   std::vector<Section> s = {{L.plat, col * 13}, {L.cab, col * L.nc * CAB_F}, {L.pid, col * L.nc * 2 * PID_F}, {L.win_y, col * L.nc * 2 * L.len}};
+  if (L.mom) s.push_back({L.mom, col * L.nc * 2 * 3});
   if (L.win_x) s.push_back({L.win_x, col * L.nc * 2 * L.len});
   if (L.filt) s.push_back({L.filt, col * L.nc * 2 * 2 * L.casc * 4});
   s.push_back({L.ctl, sizeof(uint32_t) * (size_t)L.np * L.nc});

@@ -6,6 +6,7 @@
 //   cab   [NC][CAB_F][Np]         last_pos, force_cmd, pos_target, vel_target, effort, pid_force
 //   pid   [NC][2][PID_F][Np]      last_time, p_err, i_err, d_err, cmd      (pid 0 = velocity, 1 = position)
 //   win_y [NC][2][LEN][Np]        D-term error window, logical order (oldest first) = Pid::mDbufferY
+//   mom   [NC][2][3][Np]          window moments S0 S1 S2 of the fast variant's D-term (see step_fast.cuh)
 //   win_x [NC][2][LEN][Np]        D-term time stamps = Pid::mDbufferX      (general variant only)
 //   filt  [NC][2][2][CASC][4][Np] biquad x1 x2 y1 y2 (P filter, D filter)  (general variant only)
 //   ctl   [NC][Np] uint32         bit0 vel.wasLast, bit1 pos.wasLast, bits8-15 vel.missing, 16-23 pos.missing
@@ -28,7 +29,7 @@ enum { PID_VEL = 0, PID_POS = 1 };
 enum { MODE_FORCE = 0, MODE_POSITION = 1, MODE_VELOCITY = 2 };
 
 struct DevLayout {
-  double *plat, *cab, *pid, *win_y, *win_x, *filt, *sine;
+  double *plat, *cab, *pid, *win_y, *win_x, *filt, *sine, *mom;
   uint32_t *ctl;
   long long np;  // padded instance count (column stride)
   int n;         // live instances
@@ -38,6 +39,7 @@ struct DevLayout {
 __host__ __device__ inline long long cab_off(const DevLayout &L, int c, int f) { return ((long long)c * CAB_F + f) * L.np; }
 __host__ __device__ inline long long pid_off(const DevLayout &L, int c, int k, int f) { return (((long long)c * 2 + k) * PID_F + f) * L.np; }
 __host__ __device__ inline long long win_off(const DevLayout &L, int c, int k, int j) { return (((long long)c * 2 + k) * L.len + j) * L.np; }
+__host__ __device__ inline long long mom_off(const DevLayout &L, int c, int k, int m) { return (((long long)c * 2 + k) * 3 + m) * L.np; }
 __host__ __device__ inline long long filt_off(const DevLayout &L, int c, int k, int pd, int s, int f) {
   return (((((long long)c * 2 + k) * 2 + pd) * L.casc + s) * 4 + f) * L.np;
 }
@@ -73,6 +75,8 @@ struct StepArgs {
   PidConsts live;      // copy of pc[live_idx]: the Pid the fast kernel runs
   int live_idx;
   double fir[kMaxDbuf];  // D-term FIR weights of the LIVE pid, logical order, already divided by the window span
+  double dmom[3];        // the same weights as a quadratic in the centred sample position: w_j = dmom[0] + dmom[1] k + dmom[2] k^2
+  int effort_ge_cmd;     // effort limit >= cmdMax of the live pid: truncation can only bite on a saturated command
   int mode;            // batch-uniform JointForceCalculator::UpdateMode
   int k_steps;
   long long n0;        // physics steps done before this launch

@@ -88,6 +88,8 @@ __global__ void k_reset_pid(DevLayout L, int k, unsigned len_k) {
     L.pid[pid_off(L, c, k, PID_I_ERR) + i] = 0.0;
     L.pid[pid_off(L, c, k, PID_D_ERR) + i] = 0.0;
     L.pid[pid_off(L, c, k, PID_CMD) + i] = 0.0;
+    if (L.mom)
+      for (int mm = 0; mm < 3; ++mm) L.mom[mom_off(L, c, k, mm) + i] = 0.0;
     for (int j = 0; j < L.len; ++j) {
       L.win_y[win_off(L, c, k, j) + i] = 0.0;
       if (L.win_x) L.win_x[win_off(L, c, k, j) + i] = 0.0;

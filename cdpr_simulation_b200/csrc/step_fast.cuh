@@ -5,43 +5,61 @@
 //   - velocity hold cannot trigger (velocityEpsilon < 0, launch/cdpr_gazebo.launch:18), so exactly one
 //     Pid per cable is live (JointForceCalculator.cpp:71-89),
 //   - no biquad stage is configured (cascade = 0, launch:29,32; CdprGazeboPlugin.cpp:133),
-//   - cmdLimit != 0,
+//   - cmdLimit != 0, iGain >= 0, window length 11,
 // which is the reference's launch configuration.  Everything else runs in step_general.cuh.
 //
-// On-chip residency:  platform state, integral errors, targets, flags    -> registers
-//                     D-term error windows (Pid::mDbufferY, LEN per cable) -> shared memory,
-//                     circular, [slot][cable][thread] so a warp reads 256 contiguous bytes
-// The D-term is the reference's least-squares polynomial derivative (Pid.cpp:193-247) written as
-// the equivalent fixed FIR over the window (uniform time stamps; weights from the host, fir[]).
+// On-chip residency:  platform state, integral errors, targets, window moments, flags -> registers
+//                     D-term error windows (Pid::mDbufferY, LEN per cable)            -> shared memory,
+//                     a ring [slot][cable][thread]: a warp touches 256 contiguous bytes per access
+//
+// D-term.  The reference fits a degree-d polynomial through the last LEN (time, error) samples and
+// evaluates its derivative at `now` (Pid.cpp:193-247).  With uniform time stamps that is a fixed FIR
+// sum_j w_j y_j whose weights are a degree-d polynomial in the sample position.  Two forms:
+//   DMOM = false  plain FIR: LEN-1 shared-memory reads + LEN DFMA per cable and step (any degree);
+//   DMOM = true   (degree <= 2) sliding moments S_m = sum_j k_j^m y_j, m = 0,1,2, k_j = j - (LEN-1)/2:
+//                 the slide needs only the sample that leaves the window, so 1 read + 1 write per cable
+//                 and step; D = a*S0 + b*S1 + c*S2.  Every kResync steps (global step index, so results
+//                 do not depend on how steps are split into launches) the moments are re-summed from
+//                 the ring, which bounds the rounding drift of the recursion.
 #pragma once
 #include "common.cuh"
 #include "physics.cuh"
 
 namespace cdpr {
 
-// One physics step for one instance.  STEADY: every live Pid is primed and its window is full
-// (Pid::mWasLastTime && mDbufferMissing == 0), so no flag logic is needed.
-template <int NC, int LEN, bool STEADY, bool LAST>
+constexpr int kResync = 64;
+#ifndef CDPR_NC4_BLOCKS
+#define CDPR_NC4_BLOCKS 4
+#endif
+#ifndef CDPR_NC8_BLOCKS
+#define CDPR_NC8_BLOCKS 2
+#endif
+
+// One physics step for one instance.
+//   STEADY: every live Pid is primed and its window is full (mWasLastTime && mDbufferMissing == 0)
+//   LAST:   last step of the launch: also writes the telemetry columns
+//   MODE:   batch-uniform JointForceCalculator::UpdateMode
+template <int NC, int LEN, bool STEADY, bool LAST, int MODE, bool DMOM>
 __device__ __forceinline__ void fast_step(const StepArgs &A, FastState &S, double (&ierr)[NC], const double (&tgt)[NC],
-                                          unsigned &primed, unsigned (&missing)[NC], double *__restrict__ win, int head,
-                                          double dt, long long i) {
+                                          double (&mom)[NC][3], unsigned &primed, unsigned (&missing)[NC],
+                                          double *__restrict__ win, int head, double dt, long long i) {
   const RobotConsts &rc = A.rc;
   const PidConsts &pc = A.live;
-  const int mode = A.mode;
   const Rot R = make_rot(S);
   const double r00 = R.r00, r01 = R.r01, r02 = R.r02, r10 = R.r10, r11 = R.r11, r12 = R.r12, r20 = R.r20, r21 = R.r21, r22 = R.r22;
 
   double fx = rc.mg[0], fy = rc.mg[1], fz = rc.mg[2];
   double mx = 0.0, my = 0.0, mz = 0.0;
 
-  // slot offsets of the samples by age (1 = previous step ... LEN-1 = oldest); warp-uniform
-  int slot[LEN];
+  // ring offsets by sample age (0 = this step's slot, which still holds the sample leaving the window)
+  int slot[DMOM ? 1 : LEN];
 #pragma unroll
-  for (int a = 0; a < LEN; ++a) {
+  for (int a = 0; a < (DMOM ? 1 : LEN); ++a) {
     int s = head - a;
     s += (s < 0) ? LEN : 0;
     slot[a] = s * (NC * kTpb);
   }
+  constexpr double K = 0.5 * (LEN - 1);
 
 #pragma unroll
   for (int c = 0; c < NC; ++c) {
@@ -53,19 +71,19 @@ __device__ __forceinline__ void fast_step(const StepArgs &A, FastState &S, doubl
     const double dx = (rc.a[c][0] - S.px) - rx, dy = (rc.a[c][1] - S.py) - ry, dz = (rc.a[c][2] - S.pz) - rz;
     const double l2 = fma(dx, dx, fma(dy, dy, dz * dz));
     const double il = rsqrt_nr(l2);
-    const double len = l2 * il;
     const double ux = dx * il, uy = dy * il, uz = dz * il;
     const double cx = fma(ry, uz, -(rz * uy)), cy = fma(rz, ux, -(rx * uz)), cz = fma(rx, uy, -(ry * ux));
-    const double qd = fma(ux, S.vx, fma(uy, S.vy, fma(uz, S.vz, fma(cx, S.wx, fma(cy, S.wy, cz * S.wz)))));
-    const double qp = rc.home_len[c] - len;
+    const double qd = fma(ux, S.vx, fma(uy, S.vy, uz * S.vz)) + fma(cx, S.wx, fma(cy, S.wy, cz * S.wz));
+    double qp = 0.0;
+    if (MODE == MODE_POSITION || LAST) qp = rc.home_len[c] - l2 * il;
 
     // ---- force law (a3, a4, a5)
-    double force;
-    if (mode == MODE_FORCE) {
+    double force, eff;
+    if (MODE == MODE_FORCE) {
       force = tgt[c];  // JointForceCalculator.cpp:67-70
-      if (LAST) A.L.cab[cab_off(A.L, c, CAB_LAST_POS) + i] = qp;
+      eff = (fabs(force) > rc.effort_limit_abs) ? copysign(rc.effort_limit_abs, force) : force;
     } else {
-      const double e = tgt[c] - ((mode == MODE_VELOCITY) ? qd : qp);
+      const double e = tgt[c] - ((MODE == MODE_VELOCITY) ? qd : qp);
       double *w = win + c * kTpb;
       if (STEADY || ((primed >> c) & 1u)) {  // Pid.cpp:127-187
         const double prev_ierr = ierr[c];
@@ -74,16 +92,28 @@ __device__ __forceinline__ void fast_step(const StepArgs &A, FastState &S, doubl
         // i_min = -i_max, cmd_min = -cmd_max by construction (Pid.cpp:70-73): one compare per clamp
         const bool isat = fabs(iterm) > pc.i_max;
         iterm = isat ? copysign(pc.i_max, iterm) : iterm;
-        ie = isat ? ((__double2hiint(iterm) < 0) ? pc.i_min_over_ki : pc.i_max_over_ki) : ie;
-        // derive(): push, then LS derivative at `now` = FIR over the window (Pid.cpp:193-217)
-        w[slot[0]] = e;
-        double d0 = A.fir[LEN - 1] * e, d1 = 0.0;
+        ie = isat ? copysign(pc.i_max_over_ki, iterm) : ie;  // i_gain >= 0 in this variant
+        // derive(): push the sample, least-squares derivative at `now` (Pid.cpp:193-217)
+        double derr;
+        if (DMOM) {
+          const double y_old = w[slot[0]];
+          w[slot[0]] = e;
+          const double s0 = mom[c][0], s1 = mom[c][1], s2 = mom[c][2];
+          const double n0 = (s0 - y_old) + e;
+          const double n1 = fma(K, e, fma(K + 1.0, y_old, s1 - s0));
+          const double n2 = fma(K * K, e, fma(-(K + 1.0) * (K + 1.0), y_old, fma(-2.0, s1, s2) + s0));
+          mom[c][0] = n0; mom[c][1] = n1; mom[c][2] = n2;
+          derr = fma(A.dmom[2], n2, fma(A.dmom[1], n1, A.dmom[0] * n0));
+        } else {
+          w[slot[0]] = e;
+          double d0 = A.fir[LEN - 1] * e, d1 = 0.0;
 #pragma unroll
-        for (int a = 1; a < LEN; ++a) {
-          if (a & 1) d1 = fma(A.fir[LEN - 1 - a], w[slot[a]], d1);
-          else d0 = fma(A.fir[LEN - 1 - a], w[slot[a]], d0);
+          for (int a = 1; a < LEN; ++a) {
+            if (a & 1) d1 = fma(A.fir[LEN - 1 - a], w[slot[a]], d1);
+            else d0 = fma(A.fir[LEN - 1 - a], w[slot[a]], d0);
+          }
+          derr = d0 + d1;
         }
-        double derr = d0 + d1;
         if (!STEADY) {
           missing[c] -= (missing[c] > 0u) ? 1u : 0u;
           if (missing[c] != 0u) derr = 0.0;
@@ -91,10 +121,15 @@ __device__ __forceinline__ void fast_step(const StepArgs &A, FastState &S, doubl
         const double cmd_raw = fma(pc.kd, derr, fma(pc.kp, e, pc.kf * tgt[c]) + iterm);
         // clamp + anti-windup (Pid.cpp:175-184): mCmd != cmd  <=>  |cmd| > cmdMax
         const bool csat = fabs(cmd_raw) > pc.cmd_max;
-        const double cmd = csat ? fma(dt * e, pc.ki, copysign(pc.cmd_max, cmd_raw)) : cmd_raw;
-        ie = csat ? prev_ierr : ie;
+        force = cmd_raw;
+        if (csat) {  // rare: saturated command
+          force = fma(dt * e, pc.ki, copysign(pc.cmd_max, cmd_raw));
+          ie = prev_ierr;
+        }
+        // Joint::SetForce truncation can only bite on a saturated command when effortLimit >= cmdMax
+        eff = force;
+        if (csat || !A.effort_ge_cmd) eff = (fabs(force) > rc.effort_limit_abs) ? copysign(rc.effort_limit_abs, force) : force;
         ierr[c] = ie;
-        force = cmd;
         if (LAST) {
           A.L.pid[pid_off(A.L, c, A.live_idx, PID_P_ERR) + i] = e;
           A.L.pid[pid_off(A.L, c, A.live_idx, PID_D_ERR) + i] = derr;
@@ -102,18 +137,16 @@ __device__ __forceinline__ void fast_step(const StepArgs &A, FastState &S, doubl
       } else {  // first update after a reset: Pid.cpp:123-126
         primed |= 1u << c;
         force = 0.0;
+        eff = 0.0;
       }
-      if (LAST) {
-        A.L.pid[pid_off(A.L, c, A.live_idx, PID_CMD) + i] = force;
-        A.L.cab[cab_off(A.L, c, CAB_LAST_POS) + i] = qp;
-      }
+      if (LAST) A.L.pid[pid_off(A.L, c, A.live_idx, PID_CMD) + i] = force;
     }
-    // ---- Joint::SetForce truncation, explicit joint damping, wrench (a8)
-    const double eff = (fabs(force) > rc.effort_limit_abs) ? copysign(rc.effort_limit_abs, force) : force;
     if (LAST) {
+      A.L.cab[cab_off(A.L, c, CAB_LAST_POS) + i] = qp;
       A.L.cab[cab_off(A.L, c, CAB_EFFORT) + i] = eff;
       A.L.cab[cab_off(A.L, c, CAB_PID_FORCE) + i] = force;
     }
+    // ---- explicit joint damping, wrench (a8)
     const double tau = fma(-rc.cdamp, qd, eff);
     fx = fma(tau, ux, fx); fy = fma(tau, uy, fy); fz = fma(tau, uz, fz);
     mx = fma(tau, cx, mx); my = fma(tau, cy, my); mz = fma(tau, cz, mz);
@@ -122,9 +155,31 @@ __device__ __forceinline__ void fast_step(const StepArgs &A, FastState &S, doubl
   rigid_body_step(rc, S, R, fx, fy, fz, mx, my, mz);
 }
 
+// exact re-summation of the window moments from the ring (newest sample in slot `head`)
 template <int NC, int LEN>
-__global__ void __launch_bounds__(kTpb, (NC <= 4) ? 4 : 2) k_step_fast(const __grid_constant__ StepArgs A) {
+__device__ __forceinline__ void resync_moments(double (&mom)[NC][3], const double *__restrict__ win, int head) {
+  constexpr double K = 0.5 * (LEN - 1);
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+#pragma unroll
+    for (int j = 0; j < LEN; ++j) {  // logical position j: oldest first
+      int sl = head + 1 + j;
+      sl -= (sl >= LEN) ? LEN : 0;
+      const double y = win[(sl * NC + c) * kTpb];
+      const double k = (double)j - K;
+      s0 += y;
+      s1 = fma(k, y, s1);
+      s2 = fma(k * k, y, s2);
+    }
+    mom[c][0] = s0; mom[c][1] = s1; mom[c][2] = s2;
+  }
+}
+
+template <int NC, int LEN, int MODE, bool DMOM>
+__global__ void __launch_bounds__(kTpb, (NC <= 4) ? CDPR_NC4_BLOCKS : CDPR_NC8_BLOCKS) k_step_fast(const __grid_constant__ StepArgs A) {
   extern __shared__ double win[];  // [LEN][NC][kTpb]
+  constexpr bool PIDMODE = (MODE != MODE_FORCE);
   const int tid = threadIdx.x;
   const long long gi = (long long)blockIdx.x * kTpb + tid;
   const bool valid = gi < A.L.n;
@@ -135,9 +190,11 @@ __global__ void __launch_bounds__(kTpb, (NC <= 4) ? 4 : 2) k_step_fast(const __g
 
   FastState S;
   load_plat(A.L, i, S);
-  double ierr[NC], tgt[NC];
+  double ierr[NC], tgt[NC], mom[NC][3];
   unsigned primed = 0, missing[NC];
-  const int tgt_field = (A.mode == MODE_FORCE) ? CAB_FORCE_CMD : (A.mode == MODE_POSITION) ? CAB_POS_TARGET : CAB_VEL_TARGET;
+  constexpr int tgt_field = (MODE == MODE_FORCE) ? CAB_FORCE_CMD : (MODE == MODE_POSITION) ? CAB_POS_TARGET : CAB_VEL_TARGET;
+  // the ring slot of a sample is (its step index) mod LEN, so the layout does not depend on launch boundaries
+  const int head0 = (int)(A.n0 % LEN);  // slot of the newest sample already in the window
   bool steady = true;
 #pragma unroll
   for (int c = 0; c < NC; ++c) {
@@ -148,8 +205,19 @@ __global__ void __launch_bounds__(kTpb, (NC <= 4) ? 4 : 2) k_step_fast(const __g
     missing[c] = (ctl >> (8 + 8 * live)) & 0xffu;
     steady = steady && ((ctl >> live) & 1u) && missing[c] == 0u;
 #pragma unroll
-    for (int j = 0; j < LEN; ++j)  // logical j -> slot j; newest (j = LEN-1) sits at head = LEN-1
-      mywin[(j * NC + c) * kTpb] = A.L.win_y[win_off(A.L, c, live, j) + i];
+    for (int m = 0; m < 3; ++m) mom[c][m] = 0.0;
+    if (PIDMODE) {
+#pragma unroll
+      for (int j = 0; j < LEN; ++j) {  // logical j (oldest first) -> slot (head0 + 1 + j) mod LEN
+        int sl = head0 + 1 + j;
+        sl -= (sl >= LEN) ? LEN : 0;
+        mywin[(sl * NC + c) * kTpb] = A.L.win_y[win_off(A.L, c, live, j) + i];
+      }
+      if (DMOM) {
+#pragma unroll
+        for (int m = 0; m < 3; ++m) mom[c][m] = A.L.mom[mom_off(A.L, c, live, m) + i];
+      }
+    }
   }
   double amp = 0.0, freq = 0.0, phase = 0.0;
   if (A.sine_on) { amp = A.L.sine[i]; freq = A.L.sine[np + i]; phase = A.L.sine[2 * np + i]; }
@@ -157,18 +225,17 @@ __global__ void __launch_bounds__(kTpb, (NC <= 4) ? 4 : 2) k_step_fast(const __g
   if (A.cmd_table) cmd_row = A.cmd_table + (size_t)(i % A.n_seq) * A.n_cmd * NC;
   double cost = 0.0;
 
-  bool warp_steady = __all_sync(0xffffffffu, steady || A.mode == MODE_FORCE);
-  int sec = A.sec0, nsec = A.nsec0, head = LEN - 1;
+  bool warp_steady = __all_sync(0xffffffffu, steady || !PIDMODE);
+  int sec = A.sec0, nsec = A.nsec0, head = head0;
   double tprev = A.t0, sine_time = A.sine_time0;
   int sine_ctr = (int)(A.n0 % (A.sine_period > 0 ? A.sine_period : 1));
   int cmd_ctr = 0, cmd_idx = 0;
-  long long n = A.n0;
+  int resync_ctr = (int)(A.n0 % kResync);
   long long snap_idx = A.snap_written0;
   long long snap_ctr = A.snap_every > 0 ? (A.n0 % A.snap_every) : 0;
 
   for (int s = 0; s < A.k_steps; ++s) {
     // World::Step: simTime += dt, then the plugin callback
-    ++n;
     nsec += A.dt_ns;
     if (nsec >= 1000000000) { nsec -= 1000000000; ++sec; }
     const double t = time_double(sec, nsec);
@@ -194,20 +261,23 @@ __global__ void __launch_bounds__(kTpb, (NC <= 4) ? 4 : 2) k_step_fast(const __g
     }
     head = (head + 1 == LEN) ? 0 : head + 1;
     if (s + 1 < A.k_steps) {
-      if (warp_steady) {
-        fast_step<NC, LEN, true, false>(A, S, ierr, tgt, primed, missing, mywin, head, dt, i);
-      } else {
-        fast_step<NC, LEN, false, false>(A, S, ierr, tgt, primed, missing, mywin, head, dt, i);
-      }
+      if (warp_steady) fast_step<NC, LEN, true, false, MODE, DMOM>(A, S, ierr, tgt, mom, primed, missing, mywin, head, dt, i);
+      else fast_step<NC, LEN, false, false, MODE, DMOM>(A, S, ierr, tgt, mom, primed, missing, mywin, head, dt, i);
     } else if (valid) {  // the last step also publishes effort / Pid telemetry columns
-      if (warp_steady) fast_step<NC, LEN, true, true>(A, S, ierr, tgt, primed, missing, mywin, head, dt, i);
-      else fast_step<NC, LEN, false, true>(A, S, ierr, tgt, primed, missing, mywin, head, dt, i);
+      if (warp_steady) fast_step<NC, LEN, true, true, MODE, DMOM>(A, S, ierr, tgt, mom, primed, missing, mywin, head, dt, i);
+      else fast_step<NC, LEN, false, true, MODE, DMOM>(A, S, ierr, tgt, mom, primed, missing, mywin, head, dt, i);
     }
     if (!warp_steady) {
       bool st = true;
 #pragma unroll
       for (int c = 0; c < NC; ++c) st = st && ((primed >> c) & 1u) && missing[c] == 0u;
       warp_steady = __all_sync(0xffffffffu, st);
+    }
+    if (DMOM && PIDMODE) {
+      if (++resync_ctr == kResync) {
+        resync_ctr = 0;
+        resync_moments<NC, LEN>(mom, mywin, head);
+      }
     }
     if (A.cost) {
       const double ex = S.px - A.target[0], ey = S.py - A.target[1], ez = S.pz - A.target[2];
@@ -216,9 +286,7 @@ __global__ void __launch_bounds__(kTpb, (NC <= 4) ? 4 : 2) k_step_fast(const __g
     if (A.snap_every > 0) {
       if (++snap_ctr == A.snap_every) {
         snap_ctr = 0;
-        if (valid && snap_idx < A.snap_capacity) {
-          store_plat(A.snap + snap_idx * 13 * (long long)A.L.n + i, A.L.n, S);
-        }
+        if (valid && snap_idx < A.snap_capacity) store_plat(A.snap + snap_idx * 13 * (long long)A.L.n + i, A.L.n, S);
         ++snap_idx;
       }
     }
@@ -227,8 +295,7 @@ __global__ void __launch_bounds__(kTpb, (NC <= 4) ? 4 : 2) k_step_fast(const __g
   if (!valid) return;
   store_plat(A.L.plat + i, np, S);
   if (A.cost) A.cost[i] = cost;
-  if (A.mode == MODE_FORCE) return;  // Force mode touches no Pid state
-  // after the loop the newest sample sits in slot `head`; logical j lives in slot (head + 1 + j) % LEN
+  if (!PIDMODE) return;  // Force mode touches no Pid state
 #pragma unroll
   for (int c = 0; c < NC; ++c) {
     A.L.pid[pid_off(A.L, c, live, PID_I_ERR) + i] = ierr[c];
@@ -242,6 +309,10 @@ __global__ void __launch_bounds__(kTpb, (NC <= 4) ? 4 : 2) k_step_fast(const __g
       int sl = head + 1 + j;
       sl -= (sl >= LEN) ? LEN : 0;
       A.L.win_y[win_off(A.L, c, live, j) + i] = mywin[(sl * NC + c) * kTpb];
+    }
+    if (DMOM) {
+#pragma unroll
+      for (int m = 0; m < 3; ++m) A.L.mom[mom_off(A.L, c, live, m) + i] = mom[c][m];
     }
   }
 }

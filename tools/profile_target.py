@@ -1,0 +1,33 @@
+#!/usr/bin/env python
+"""Minimal launcher for ncu: a few launches of the step kernel (or the IK kernel) on resident state.
+usage: python tools/profile_target.py [--nc 8] [--instances 1048576] [--sim-steps 1000] [--launches 3] [--ik]"""
+import argparse, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import cdpr_simulation_b200 as cb
+from cdpr_simulation_b200 import workloads as wl
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--nc", type=int, default=8)
+ap.add_argument("--instances", type=int, default=1 << 20)
+ap.add_argument("--sim-steps", type=int, default=1000)
+ap.add_argument("--launches", type=int, default=3)
+ap.add_argument("--ik", action="store_true")
+a = ap.parse_args()
+cfg = cb.default_config(a.nc)
+if a.ik:
+    import torch
+    pose7, twist6 = wl.c2_poses(a.instances, 0)
+    st = np.concatenate([pose7[:, :3], pose7[:, 6:7], pose7[:, 3:6], twist6], axis=1).T.copy()
+    d_in = torch.from_numpy(st).cuda(); d_out = torch.empty((a.nc, 8, a.instances), dtype=torch.float64, device="cuda")
+    with cb.CdprBatch(cfg, 1) as g:
+        for _ in range(a.launches):
+            g.ik_device(a.instances, d_in.data_ptr(), d_out.data_ptr()); g.synchronize()
+            print("ik ms", g.last_kernel_ms)
+else:
+    amp, freq, phase, pose7, twist6 = wl.c3_instances(a.instances, 1)
+    with cb.CdprBatch(cfg, a.instances) as g:
+        g.set_platform_state(pose7, twist6); g.set_sine_cmd(amp, freq, phase)
+        for _ in range(a.launches):
+            g.step(a.sim_steps); g.synchronize()
+            print("step ms", g.last_kernel_ms, "rate", a.instances * a.sim_steps / g.last_kernel_ms * 1e3)
