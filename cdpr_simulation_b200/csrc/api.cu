@@ -345,7 +345,7 @@ extern "C" int cdpr_create(const cdpr_config *cfg, int64_t n_instances, int devi
   if (cudaMemsetAsync(L.sine, 0, col * 3, h->stream) != cudaSuccess) { h->err = "memset failed"; return bail(CDPR_ERR_CUDA); }
   if ((rc = reset_to_load_state(h))) return bail(rc);
   if (!h->general) {
-    const int smem4 = 11 * 4 * kTpb * 8, smem8 = 11 * 8 * kTpb * 8;
+    const int smem4 = (int)fast_smem_bytes<4, 11>(), smem8 = (int)fast_smem_bytes<8, 11>();
     auto prep = [](const void *f, int smem) {
       cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
       cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -493,8 +493,9 @@ static int launch_step(cdpr_handle h, const StepArgs &A) {
     k_step_general<<<grid, kTpb, 0, h->stream>>>(A);
   } else {
     const bool dm = h->dmom_ok[A.live_idx];
-    const size_t smem = (size_t)11 * h->L.nc * kTpb * sizeof(double);
-#define CDPR_LAUNCH(NC_, MODE_, DM_) k_step_fast<NC_, 11, MODE_, DM_><<<grid, kTpb, smem, h->stream>>>(A)
+#define CDPR_LAUNCH(NC_, MODE_, DM_)                                                                   \
+  k_step_fast<NC_, 11, MODE_, DM_><<<(unsigned)(h->np / FastCfg<NC_>::tpb), FastCfg<NC_>::tpb,        \
+                                     fast_smem_bytes<NC_, 11>(), h->stream>>>(A)
     if (h->L.nc == 4) {
       if (A.mode == MODE_FORCE) CDPR_LAUNCH(4, MODE_FORCE, false);
       else if (A.mode == MODE_POSITION) { if (dm) CDPR_LAUNCH(4, MODE_POSITION, true); else CDPR_LAUNCH(4, MODE_POSITION, false); }

@@ -29,18 +29,25 @@ namespace cdpr {
 
 constexpr int kResync = 64;
 #ifndef CDPR_NC4_BLOCKS
-#define CDPR_NC4_BLOCKS 4
+#define CDPR_NC4_BLOCKS 2
 #endif
 #ifndef CDPR_NC8_BLOCKS
 #define CDPR_NC8_BLOCKS 2
 #endif
+#ifndef CDPR_NC4_TPB
+#define CDPR_NC4_TPB 128
+#endif
+#ifndef CDPR_NC8_TPB
+#define CDPR_NC8_TPB 128
+#endif
+template <int NC> struct FastCfg { static constexpr int tpb = (NC <= 4) ? CDPR_NC4_TPB : CDPR_NC8_TPB; static constexpr int blocks = (NC <= 4) ? CDPR_NC4_BLOCKS : CDPR_NC8_BLOCKS; };
 
 // One physics step for one instance.
 //   STEADY: every live Pid is primed and its window is full (mWasLastTime && mDbufferMissing == 0)
 //   LAST:   last step of the launch: also writes the telemetry columns
 //   MODE:   batch-uniform JointForceCalculator::UpdateMode
 template <int NC, int LEN, bool STEADY, bool LAST, int MODE, bool DMOM>
-__device__ __forceinline__ void fast_step(const StepArgs &A, FastState &S, double (&ierr)[NC], const double (&tgt)[NC],
+__device__ __forceinline__ void fast_step(const StepArgs &A, FastState &S, double (&ierr)[NC], const double *__restrict__ tgts,
                                           double (&mom)[NC][3], unsigned &primed, unsigned (&missing)[NC],
                                           double *__restrict__ win, int head, double dt, long long i) {
   const RobotConsts &rc = A.rc;
@@ -57,7 +64,7 @@ __device__ __forceinline__ void fast_step(const StepArgs &A, FastState &S, doubl
   for (int a = 0; a < (DMOM ? 1 : LEN); ++a) {
     int s = head - a;
     s += (s < 0) ? LEN : 0;
-    slot[a] = s * (NC * kTpb);
+    slot[a] = s * (NC * FastCfg<NC>::tpb);
   }
   constexpr double K = 0.5 * (LEN - 1);
 
@@ -80,11 +87,12 @@ __device__ __forceinline__ void fast_step(const StepArgs &A, FastState &S, doubl
     // ---- force law (a3, a4, a5)
     double force, eff;
     if (MODE == MODE_FORCE) {
-      force = tgt[c];  // JointForceCalculator.cpp:67-70
+      force = tgts[c * FastCfg<NC>::tpb];  // JointForceCalculator.cpp:67-70
       eff = (fabs(force) > rc.effort_limit_abs) ? copysign(rc.effort_limit_abs, force) : force;
     } else {
-      const double e = tgt[c] - ((MODE == MODE_VELOCITY) ? qd : qp);
-      double *w = win + c * kTpb;
+      const double tg = tgts[c * FastCfg<NC>::tpb];
+      const double e = tg - ((MODE == MODE_VELOCITY) ? qd : qp);
+      double *w = win + c * FastCfg<NC>::tpb;
       if (STEADY || ((primed >> c) & 1u)) {  // Pid.cpp:127-187
         const double prev_ierr = ierr[c];
         double ie = fma(dt, e, prev_ierr);
@@ -118,7 +126,7 @@ __device__ __forceinline__ void fast_step(const StepArgs &A, FastState &S, doubl
           missing[c] -= (missing[c] > 0u) ? 1u : 0u;
           if (missing[c] != 0u) derr = 0.0;
         }
-        const double cmd_raw = fma(pc.kd, derr, fma(pc.kp, e, pc.kf * tgt[c]) + iterm);
+        const double cmd_raw = fma(pc.kd, derr, fma(pc.kp, e, pc.kf * tg) + iterm);
         // clamp + anti-windup (Pid.cpp:175-184): mCmd != cmd  <=>  |cmd| > cmdMax
         const bool csat = fabs(cmd_raw) > pc.cmd_max;
         force = cmd_raw;
@@ -166,7 +174,7 @@ __device__ __forceinline__ void resync_moments(double (&mom)[NC][3], const doubl
     for (int j = 0; j < LEN; ++j) {  // logical position j: oldest first
       int sl = head + 1 + j;
       sl -= (sl >= LEN) ? LEN : 0;
-      const double y = win[(sl * NC + c) * kTpb];
+      const double y = win[(sl * NC + c) * FastCfg<NC>::tpb];
       const double k = (double)j - K;
       s0 += y;
       s1 = fma(k, y, s1);
@@ -176,21 +184,28 @@ __device__ __forceinline__ void resync_moments(double (&mom)[NC][3], const doubl
   }
 }
 
+// shared memory per block: ring [LEN][NC][tpb], targets [NC][tpb], sine parameters [3][tpb] (doubles)
+template <int NC, int LEN>
+constexpr size_t fast_smem_bytes() { return sizeof(double) * (size_t)FastCfg<NC>::tpb * (LEN * NC + NC + 3); }
+
 template <int NC, int LEN, int MODE, bool DMOM>
-__global__ void __launch_bounds__(kTpb, (NC <= 4) ? CDPR_NC4_BLOCKS : CDPR_NC8_BLOCKS) k_step_fast(const __grid_constant__ StepArgs A) {
-  extern __shared__ double win[];  // [LEN][NC][kTpb]
+__global__ void __launch_bounds__(FastCfg<NC>::tpb, FastCfg<NC>::blocks) k_step_fast(const __grid_constant__ StepArgs A) {
+  extern __shared__ double smem[];
+  constexpr int kTpbL = FastCfg<NC>::tpb;
   constexpr bool PIDMODE = (MODE != MODE_FORCE);
   const int tid = threadIdx.x;
-  const long long gi = (long long)blockIdx.x * kTpb + tid;
+  const long long gi = (long long)blockIdx.x * kTpbL + tid;
   const bool valid = gi < A.L.n;
   const long long i = valid ? gi : (long long)A.L.n - 1;  // tail threads shadow the last instance, never store
   const long long np = A.L.np;
   const int live = A.live_idx;
-  double *mywin = win + tid;
+  double *mywin = smem + tid;                          // [LEN][NC][tpb]
+  double *mytgt = smem + LEN * NC * kTpbL + tid;       // [NC][tpb]
+  double *mysine = mytgt + NC * kTpbL;                 // [3][tpb]: amp, freq, phase
 
   FastState S;
   load_plat(A.L, i, S);
-  double ierr[NC], tgt[NC], mom[NC][3];
+  double ierr[NC], mom[NC][3];
   unsigned primed = 0, missing[NC];
   constexpr int tgt_field = (MODE == MODE_FORCE) ? CAB_FORCE_CMD : (MODE == MODE_POSITION) ? CAB_POS_TARGET : CAB_VEL_TARGET;
   // the ring slot of a sample is (its step index) mod LEN, so the layout does not depend on launch boundaries
@@ -199,7 +214,7 @@ __global__ void __launch_bounds__(kTpb, (NC <= 4) ? CDPR_NC4_BLOCKS : CDPR_NC8_B
 #pragma unroll
   for (int c = 0; c < NC; ++c) {
     ierr[c] = A.L.pid[pid_off(A.L, c, live, PID_I_ERR) + i];
-    tgt[c] = A.L.cab[cab_off(A.L, c, tgt_field) + i];
+    mytgt[c * kTpbL] = A.L.cab[cab_off(A.L, c, tgt_field) + i];
     const unsigned ctl = A.L.ctl[(long long)c * np + i];
     primed |= ((ctl >> live) & 1u) << c;
     missing[c] = (ctl >> (8 + 8 * live)) & 0xffu;
@@ -211,7 +226,7 @@ __global__ void __launch_bounds__(kTpb, (NC <= 4) ? CDPR_NC4_BLOCKS : CDPR_NC8_B
       for (int j = 0; j < LEN; ++j) {  // logical j (oldest first) -> slot (head0 + 1 + j) mod LEN
         int sl = head0 + 1 + j;
         sl -= (sl >= LEN) ? LEN : 0;
-        mywin[(sl * NC + c) * kTpb] = A.L.win_y[win_off(A.L, c, live, j) + i];
+        mywin[(sl * NC + c) * kTpbL] = A.L.win_y[win_off(A.L, c, live, j) + i];
       }
       if (DMOM) {
 #pragma unroll
@@ -219,8 +234,10 @@ __global__ void __launch_bounds__(kTpb, (NC <= 4) ? CDPR_NC4_BLOCKS : CDPR_NC8_B
       }
     }
   }
-  double amp = 0.0, freq = 0.0, phase = 0.0;
-  if (A.sine_on) { amp = A.L.sine[i]; freq = A.L.sine[np + i]; phase = A.L.sine[2 * np + i]; }
+  if (A.sine_on) {
+#pragma unroll
+    for (int m = 0; m < 3; ++m) mysine[m * kTpbL] = A.L.sine[m * np + i];
+  }
   const float *cmd_row = nullptr;
   if (A.cmd_table) cmd_row = A.cmd_table + (size_t)(i % A.n_seq) * A.n_cmd * NC;
   double cost = 0.0;
@@ -233,20 +250,23 @@ __global__ void __launch_bounds__(kTpb, (NC <= 4) ? CDPR_NC4_BLOCKS : CDPR_NC8_B
   int resync_ctr = (int)(A.n0 % kResync);
   long long snap_idx = A.snap_written0;
   long long snap_ctr = A.snap_every > 0 ? (A.n0 % A.snap_every) : 0;
+  int s = 0;
 
-  for (int s = 0; s < A.k_steps; ++s) {
+  // everything of a step except the force law / physics: clock, command sources
+  auto pre_step = [&](double &dt) {
     // World::Step: simTime += dt, then the plugin callback
     nsec += A.dt_ns;
     if (nsec >= 1000000000) { nsec -= 1000000000; ++sec; }
     const double t = time_double(sec, nsec);
-    const double dt = __dsub_rn(t, tprev);
+    dt = __dsub_rn(t, tprev);
     tprev = t;
     if (A.sine_on) {  // sinevelocitytest.cpp:35-38,48: float32 axes, accumulated publisher time
       if (sine_ctr == 0) {
+        const double amp = mysine[0], freq = mysine[kTpbL], phase = mysine[2 * kTpbL];
         const double arg = __dadd_rn(__dmul_rn(__dmul_rn(__dmul_rn(sine_time, freq), 2.0), 3.14159265358979323846), phase);
         const double vel = (double)(float)__dmul_rn(amp, sin(arg));
 #pragma unroll
-        for (int c = 0; c < NC; ++c) tgt[c] = vel;
+        for (int c = 0; c < NC; ++c) mytgt[c * kTpbL] = vel;
         sine_time = __dadd_rn(sine_time, A.sine_pub_dt);
       }
       sine_ctr = (sine_ctr + 1 == A.sine_period) ? 0 : sine_ctr + 1;
@@ -254,25 +274,14 @@ __global__ void __launch_bounds__(kTpb, (NC <= 4) ? CDPR_NC4_BLOCKS : CDPR_NC8_B
     if (cmd_row) {
       if (cmd_ctr == 0 && cmd_idx < A.n_cmd) {
 #pragma unroll
-        for (int c = 0; c < NC; ++c) tgt[c] = (double)cmd_row[cmd_idx * NC + c];
+        for (int c = 0; c < NC; ++c) mytgt[c * kTpbL] = (double)cmd_row[cmd_idx * NC + c];
         ++cmd_idx;
       }
       cmd_ctr = (cmd_ctr + 1 == A.steps_per_cmd) ? 0 : cmd_ctr + 1;
     }
     head = (head + 1 == LEN) ? 0 : head + 1;
-    if (s + 1 < A.k_steps) {
-      if (warp_steady) fast_step<NC, LEN, true, false, MODE, DMOM>(A, S, ierr, tgt, mom, primed, missing, mywin, head, dt, i);
-      else fast_step<NC, LEN, false, false, MODE, DMOM>(A, S, ierr, tgt, mom, primed, missing, mywin, head, dt, i);
-    } else if (valid) {  // the last step also publishes effort / Pid telemetry columns
-      if (warp_steady) fast_step<NC, LEN, true, true, MODE, DMOM>(A, S, ierr, tgt, mom, primed, missing, mywin, head, dt, i);
-      else fast_step<NC, LEN, false, true, MODE, DMOM>(A, S, ierr, tgt, mom, primed, missing, mywin, head, dt, i);
-    }
-    if (!warp_steady) {
-      bool st = true;
-#pragma unroll
-      for (int c = 0; c < NC; ++c) st = st && ((primed >> c) & 1u) && missing[c] == 0u;
-      warp_steady = __all_sync(0xffffffffu, st);
-    }
+  };
+  auto post_step = [&]() {
     if (DMOM && PIDMODE) {
       if (++resync_ctr == kResync) {
         resync_ctr = 0;
@@ -290,6 +299,42 @@ __global__ void __launch_bounds__(kTpb, (NC <= 4) ? CDPR_NC4_BLOCKS : CDPR_NC8_B
         ++snap_idx;
       }
     }
+  };
+
+  // phase 1 (at most LEN + 1 steps after a Pid reset): some live Pid of the warp is un-primed or its window is not full
+  for (; s + 1 < A.k_steps && !warp_steady; ++s) {
+    double dt;
+    pre_step(dt);
+    fast_step<NC, LEN, false, false, MODE, DMOM>(A, S, ierr, mytgt, mom, primed, missing, mywin, head, dt, i);
+    bool st = true;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) st = st && ((primed >> c) & 1u) && missing[c] == 0u;
+    warp_steady = __all_sync(0xffffffffu, st);
+    post_step();
+  }
+  if (warp_steady && PIDMODE) {  // the flags are constants from here on: keep them out of the hot loop's registers
+    primed = (1u << NC) - 1u;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) missing[c] = 0u;
+  }
+  // phase 2: the hot loop
+  if (warp_steady) {
+    for (; s + 1 < A.k_steps; ++s) {
+      double dt;
+      pre_step(dt);
+      fast_step<NC, LEN, true, false, MODE, DMOM>(A, S, ierr, mytgt, mom, primed, missing, mywin, head, dt, i);
+      post_step();
+    }
+  }
+  // last step of the launch: also publishes the effort / Pid telemetry columns
+  if (s < A.k_steps) {
+    double dt;
+    pre_step(dt);
+    if (valid) {
+      if (warp_steady) fast_step<NC, LEN, true, true, MODE, DMOM>(A, S, ierr, mytgt, mom, primed, missing, mywin, head, dt, i);
+      else fast_step<NC, LEN, false, true, MODE, DMOM>(A, S, ierr, mytgt, mom, primed, missing, mywin, head, dt, i);
+    }
+    post_step();
   }
 
   if (!valid) return;
@@ -300,7 +345,7 @@ __global__ void __launch_bounds__(kTpb, (NC <= 4) ? CDPR_NC4_BLOCKS : CDPR_NC8_B
   for (int c = 0; c < NC; ++c) {
     A.L.pid[pid_off(A.L, c, live, PID_I_ERR) + i] = ierr[c];
     A.L.pid[pid_off(A.L, c, live, PID_LAST_TIME) + i] = tprev;
-    if (A.sine_on || A.cmd_table) A.L.cab[cab_off(A.L, c, CAB_VEL_TARGET) + i] = tgt[c];
+    if (A.sine_on || A.cmd_table) A.L.cab[cab_off(A.L, c, CAB_VEL_TARGET) + i] = mytgt[c * kTpbL];
     unsigned ctl = A.L.ctl[(long long)c * np + i];
     ctl &= ~((1u << live) | (0xffu << (8 + 8 * live)));
     ctl |= (((primed >> c) & 1u) << live) | (missing[c] << (8 + 8 * live));
@@ -308,7 +353,7 @@ __global__ void __launch_bounds__(kTpb, (NC <= 4) ? CDPR_NC4_BLOCKS : CDPR_NC8_B
     for (int j = 0; j < LEN; ++j) {
       int sl = head + 1 + j;
       sl -= (sl >= LEN) ? LEN : 0;
-      A.L.win_y[win_off(A.L, c, live, j) + i] = mywin[(sl * NC + c) * kTpb];
+      A.L.win_y[win_off(A.L, c, live, j) + i] = mywin[(sl * NC + c) * kTpbL];
     }
     if (DMOM) {
 #pragma unroll
