@@ -26,13 +26,14 @@ __device__ __forceinline__ double rsqrt_nr(double x) {
 
 // rotation matrix of the platform (unit quaternion w x y z)
 __device__ __forceinline__ Rot make_rot(const FastState &S) {
-  const double xx = S.qx * S.qx, yy = S.qy * S.qy, zz = S.qz * S.qz;
-  const double xy = S.qx * S.qy, xz = S.qx * S.qz, yz = S.qy * S.qz;
-  const double wx_ = S.qw * S.qx, wy_ = S.qw * S.qy, wz_ = S.qw * S.qz;
+  // 17 FP64 instructions: doubled components, then one FMA per off-diagonal entry
+  const double x2 = S.qx + S.qx, y2 = S.qy + S.qy, z2 = S.qz + S.qz;
+  const double wx2 = S.qw * x2, wy2 = S.qw * y2, wz2 = S.qw * z2;
+  const double ax = fma(-x2, S.qx, 1.0), ay = fma(-y2, S.qy, 1.0);
   Rot R;
-  R.r00 = 1.0 - 2.0 * (yy + zz); R.r01 = 2.0 * (xy - wz_); R.r02 = 2.0 * (xz + wy_);
-  R.r10 = 2.0 * (xy + wz_); R.r11 = 1.0 - 2.0 * (xx + zz); R.r12 = 2.0 * (yz - wx_);
-  R.r20 = 2.0 * (xz - wy_); R.r21 = 2.0 * (yz + wx_); R.r22 = 1.0 - 2.0 * (xx + yy);
+  R.r00 = fma(-z2, S.qz, ay); R.r01 = fma(x2, S.qy, -wz2); R.r02 = fma(x2, S.qz, wy2);
+  R.r10 = fma(x2, S.qy, wz2); R.r11 = fma(-z2, S.qz, ax); R.r12 = fma(y2, S.qz, -wx2);
+  R.r20 = fma(x2, S.qz, -wy2); R.r21 = fma(y2, S.qz, wx2); R.r22 = fma(-y2, S.qy, ax);
   return R;
 }
 
@@ -56,6 +57,8 @@ __device__ __forceinline__ void rigid_body_step(const RobotConsts &rc, FastState
                                                 double mx, double my, double mz) {
   const double r00 = R.r00, r01 = R.r01, r02 = R.r02, r10 = R.r10, r11 = R.r11, r12 = R.r12, r20 = R.r20, r21 = R.r21, r22 = R.r22;
   // ---- rigid-body step, ODE order (a9): I_w = R I_b R^T, explicit gyroscopic torque
+  // angular part in the body frame: alpha = R I_b^-1 (R^T M - w_b x (I_b w_b)); identical to ODE's world-frame
+  // form M - w x (R I_b R^T w) because rotations preserve cross products
   const double wbx = fma(r00, S.wx, fma(r10, S.wy, r20 * S.wz));
   const double wby = fma(r01, S.wx, fma(r11, S.wy, r21 * S.wz));
   const double wbz = fma(r02, S.wx, fma(r12, S.wy, r22 * S.wz));
@@ -67,15 +70,9 @@ __device__ __forceinline__ void rigid_body_step(const RobotConsts &rc, FastState
     lby = fma(rc.ib[3], wbx, fma(rc.ib[1], wby, rc.ib[5] * wbz));
     lbz = fma(rc.ib[4], wbx, fma(rc.ib[5], wby, rc.ib[2] * wbz));
   }
-  const double lwx = fma(r00, lbx, fma(r01, lby, r02 * lbz));
-  const double lwy = fma(r10, lbx, fma(r11, lby, r12 * lbz));
-  const double lwz = fma(r20, lbx, fma(r21, lby, r22 * lbz));
-  mx -= fma(S.wy, lwz, -(S.wz * lwy));
-  my -= fma(S.wz, lwx, -(S.wx * lwz));
-  mz -= fma(S.wx, lwy, -(S.wy * lwx));
-  const double mbx = fma(r00, mx, fma(r10, my, r20 * mz));
-  const double mby = fma(r01, mx, fma(r11, my, r21 * mz));
-  const double mbz = fma(r02, mx, fma(r12, my, r22 * mz));
+  const double mbx = fma(r00, mx, fma(r10, my, r20 * mz)) - fma(wby, lbz, -(wbz * lby));
+  const double mby = fma(r01, mx, fma(r11, my, r21 * mz)) - fma(wbz, lbx, -(wbx * lbz));
+  const double mbz = fma(r02, mx, fma(r12, my, r22 * mz)) - fma(wbx, lby, -(wby * lbx));
   double abx, aby, abz;
   if (rc.diag_inertia) {
     abx = rc.ib_inv[0] * mbx; aby = rc.ib_inv[1] * mby; abz = rc.ib_inv[2] * mbz;

@@ -96,11 +96,9 @@ __device__ __forceinline__ void fast_step(const StepArgs &A, FastState &S, doubl
       if (STEADY || ((primed >> c) & 1u)) {  // Pid.cpp:127-187
         const double prev_ierr = ierr[c];
         double ie = fma(dt, e, prev_ierr);
-        double iterm = pc.ki * ie;
-        // i_min = -i_max, cmd_min = -cmd_max by construction (Pid.cpp:70-73): one compare per clamp
-        const bool isat = fabs(iterm) > pc.i_max;
-        iterm = isat ? copysign(pc.i_max, iterm) : iterm;
-        ie = isat ? copysign(pc.i_max_over_ki, iterm) : ie;  // i_gain >= 0 in this variant
+        // integral clamp with back-calculation (Pid.cpp:143-150) applied to the integral itself:
+        // |Ki * Ierr| > Imax  <=>  |Ierr| > Imax / Ki (Ki >= 0 in this variant), clamped term = Ki * (Imax / Ki)
+        ie = (fabs(ie) > pc.i_max_over_ki) ? copysign(pc.i_max_over_ki, ie) : ie;
         // derive(): push the sample, least-squares derivative at `now` (Pid.cpp:193-217)
         double derr;
         if (DMOM) {
@@ -126,7 +124,7 @@ __device__ __forceinline__ void fast_step(const StepArgs &A, FastState &S, doubl
           missing[c] -= (missing[c] > 0u) ? 1u : 0u;
           if (missing[c] != 0u) derr = 0.0;
         }
-        const double cmd_raw = fma(pc.kd, derr, fma(pc.kp, e, pc.kf * tg) + iterm);
+        const double cmd_raw = fma(pc.ki, ie, fma(pc.kd, derr, fma(pc.kp, e, tgts[(NC + c) * FastCfg<NC>::tpb])));
         // clamp + anti-windup (Pid.cpp:175-184): mCmd != cmd  <=>  |cmd| > cmdMax
         const bool csat = fabs(cmd_raw) > pc.cmd_max;
         force = cmd_raw;
@@ -184,9 +182,10 @@ __device__ __forceinline__ void resync_moments(double (&mom)[NC][3], const doubl
   }
 }
 
-// shared memory per block: ring [LEN][NC][tpb], targets [NC][tpb], sine parameters [3][tpb] (doubles)
+// shared memory per block (doubles): ring [LEN][NC][tpb], targets [NC][tpb], feed-forward terms Kf*target [NC][tpb],
+// sine parameters [3][tpb]
 template <int NC, int LEN>
-constexpr size_t fast_smem_bytes() { return sizeof(double) * (size_t)FastCfg<NC>::tpb * (LEN * NC + NC + 3); }
+constexpr size_t fast_smem_bytes() { return sizeof(double) * (size_t)FastCfg<NC>::tpb * (LEN * NC + 2 * NC + 3); }
 
 template <int NC, int LEN, int MODE, bool DMOM>
 __global__ void __launch_bounds__(FastCfg<NC>::tpb, FastCfg<NC>::blocks) k_step_fast(const __grid_constant__ StepArgs A) {
@@ -201,7 +200,7 @@ __global__ void __launch_bounds__(FastCfg<NC>::tpb, FastCfg<NC>::blocks) k_step_
   const int live = A.live_idx;
   double *mywin = smem + tid;                          // [LEN][NC][tpb]
   double *mytgt = smem + LEN * NC * kTpbL + tid;       // [NC][tpb]
-  double *mysine = mytgt + NC * kTpbL;                 // [3][tpb]: amp, freq, phase
+  double *mysine = mytgt + 2 * NC * kTpbL;             // [3][tpb]: amp, freq, phase (after targets and feed-forward terms)
 
   FastState S;
   load_plat(A.L, i, S);
@@ -215,6 +214,7 @@ __global__ void __launch_bounds__(FastCfg<NC>::tpb, FastCfg<NC>::blocks) k_step_
   for (int c = 0; c < NC; ++c) {
     ierr[c] = A.L.pid[pid_off(A.L, c, live, PID_I_ERR) + i];
     mytgt[c * kTpbL] = A.L.cab[cab_off(A.L, c, tgt_field) + i];
+    mytgt[(NC + c) * kTpbL] = A.live.kf * mytgt[c * kTpbL];
     const unsigned ctl = A.L.ctl[(long long)c * np + i];
     primed |= ((ctl >> live) & 1u) << c;
     missing[c] = (ctl >> (8 + 8 * live)) & 0xffu;
@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(FastCfg<NC>::tpb, FastCfg<NC>::blocks) k_step_
         const double arg = __dadd_rn(__dmul_rn(__dmul_rn(__dmul_rn(sine_time, freq), 2.0), 3.14159265358979323846), phase);
         const double vel = (double)(float)__dmul_rn(amp, sin(arg));
 #pragma unroll
-        for (int c = 0; c < NC; ++c) mytgt[c * kTpbL] = vel;
+        for (int c = 0; c < NC; ++c) { mytgt[c * kTpbL] = vel; mytgt[(NC + c) * kTpbL] = A.live.kf * vel; }
         sine_time = __dadd_rn(sine_time, A.sine_pub_dt);
       }
       sine_ctr = (sine_ctr + 1 == A.sine_period) ? 0 : sine_ctr + 1;
@@ -274,7 +274,10 @@ __global__ void __launch_bounds__(FastCfg<NC>::tpb, FastCfg<NC>::blocks) k_step_
     if (cmd_row) {
       if (cmd_ctr == 0 && cmd_idx < A.n_cmd) {
 #pragma unroll
-        for (int c = 0; c < NC; ++c) mytgt[c * kTpbL] = (double)cmd_row[cmd_idx * NC + c];
+        for (int c = 0; c < NC; ++c) {
+          const double v = (double)cmd_row[cmd_idx * NC + c];
+          mytgt[c * kTpbL] = v; mytgt[(NC + c) * kTpbL] = A.live.kf * v;
+        }
         ++cmd_idx;
       }
       cmd_ctr = (cmd_ctr + 1 == A.steps_per_cmd) ? 0 : cmd_ctr + 1;
