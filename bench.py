@@ -36,9 +36,14 @@ def flops_per_instance_step(nc: int) -> int:
 
 
 def state_bytes_per_instance(nc: int) -> int:
-    # what the persistent kernel reads + writes per instance and launch: platform 13, per cable i_err, target,
-    # window 11, ctl (4 B) in; platform 13, per cable i_err, last_time, window 11, ctl, 6 telemetry columns out
-    return 8 * (13 + nc * 13 + 3) + 4 * nc + 8 * (13 + nc * 19) + 4 * nc
+    # what the persistent kernel reads + writes per instance and LAUNCH: in: platform 13, per cable
+    # i_err, target, window 11, moments 3, ctl (4 B), sine 3; out: platform 13, per cable i_err, last_time, window 11,
+    # moments 3, 6 telemetry columns, vel_target, ctl (read-modify-write: 8 B)
+    return 8 * (13 + 16 * nc + 3) + 4 * nc + 8 * (13 + 23 * nc) + 8 * nc
+
+
+def ik_bytes_per_pose(nc: int) -> int:
+    return 104 + 64 * nc   # 13 doubles in, (L, dL/dt, W[6]) per cable out
 
 
 class ClockSampler:
@@ -265,6 +270,7 @@ def own_arm(args):
                     "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
                     "note": "state is read and written once per launch of 1000 steps: the kernel is FP64-issue bound, not HBM bound"},
         }
+        extra = side_measurements(cb, wl, torch, local_rank, hbm_peak, fp64_peak) if (world == 1 and not args.no_extras) else None
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             v, sample, _ = cpu_arm("port", nc, k_sim, args.cpu_seconds, 1, host_cores())
@@ -285,11 +291,42 @@ def own_arm(args):
             "gpu_launches": int(launches),
             "roofline": roofline,
             "cpu_baseline": cpu,
+            "extra": extra,
         }
         print(json.dumps(line), flush=True)
     batch.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def side_measurements(cb, wl, torch, device, hbm_peak, fp64_peak):
+    """Not the headline: the reference's own 4-cable robot on the same workload, and the config-2 kinematics sweep."""
+    out = {}
+    n, k = 1 << 20, 1000
+    amp, freq, phase, pose7, twist6 = wl.c3_instances(n, seed=1)
+    with cb.CdprBatch(cb.default_config(4), n, device=device) as g:
+        g.set_platform_state(pose7, twist6); g.set_sine_cmd(amp, freq, phase)
+        ms = []
+        for _ in range(4):
+            g.step(k); ms.append(g.last_kernel_ms)
+        t = float(np.mean(ms[1:]))
+        out["nc4_reference_robot"] = {"value": n * k / (t * 1e-3), "unit": UNIT, "kernel_ms": t,
+                                      "fp64_frac": flops_per_instance_step(4) * n * k / (t * 1e-3) / 1e12 / fp64_peak}
+    for nc in (4, 8):
+        for npose in (65536, 1 << 22):
+            p7, t6 = wl.c2_poses(npose, seed=0)
+            st = np.ascontiguousarray(np.concatenate([p7[:, :3], p7[:, 6:7], p7[:, 3:6], t6], axis=1).T)
+            d_in = torch.from_numpy(st).cuda(device)
+            d_out = torch.empty((nc, 8, npose), dtype=torch.float64, device=f"cuda:{device}")
+            with cb.CdprBatch(cb.default_config(nc), 1, device=device) as g:
+                ms = []
+                for _ in range(12):
+                    g.ik_device(npose, d_in.data_ptr(), d_out.data_ptr()); ms.append(g.last_kernel_ms)
+                t = float(np.median(ms[2:]))
+            gbs = ik_bytes_per_pose(nc) * npose / (t * 1e-3) / 1e9
+            out[f"ik_sweep_nc{nc}_{npose}"] = {"poses_per_s": npose / (t * 1e-3), "kernel_us": t * 1e3, "GBps": gbs, "hbm_frac": gbs / hbm_peak,
+                                               "note": "one launch, single-shot timing; 65,536 poses (config 2) is launch-latency scale" if npose == 65536 else "one launch, inputs+outputs > L2"}
+    return out
 
 
 def batch_state_gb(batch) -> float:
@@ -310,6 +347,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--ref-seconds", type=float, default=6.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "own":
         args.warmup = 3

@@ -33,6 +33,23 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+HOST_DIR = os.path.join(HERE, "host")
+HOST_BIN = os.path.join(HOST_DIR, "cdpr_sinevelocitytest")
+
+
+def build_host(force: bool = False) -> str:
+    """The plugin-shaped C++ host shim + the headless sinevelocitytest driver, linked against the C ABI only."""
+    srcs = [os.path.join(HOST_DIR, f) for f in ("CdprBatchPlugin.cpp", "sinevelocitytest_main.cpp")]
+    deps = srcs + [os.path.join(HOST_DIR, "CdprBatchPlugin.h"), build()]
+    if force or not os.path.exists(HOST_BIN) or any(os.path.getmtime(d) > os.path.getmtime(HOST_BIN) for d in deps):
+        cmd = ["g++", "-O2", "-std=c++17", "-o", HOST_BIN] + srcs + ["-L" + HERE, "-lcdpr_b200", "-Wl,-rpath,$ORIGIN/.."]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("host shim build failed:\n" + r.stdout + r.stderr)
+    return HOST_BIN
+
+
 if __name__ == "__main__":
     import sys
     print(build(force=True, verbose="-v" in sys.argv))
+    print(build_host(force=True))

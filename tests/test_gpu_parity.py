@@ -284,3 +284,26 @@ def test_full_size_properties(built_lib):
     assert np.max(np.abs(np.linalg.norm(pose[:, 3:], axis=1) - 1.0)) < 1e-14
     assert np.all(np.abs(pose[:, :2]) < 0.3) and np.all((pose[:, 2] > 0.0) & (pose[:, 2] < 0.6))
     assert abs(np.median(eff.sum(axis=1)) - 4 * 3.9657) < 1.5
+
+
+def test_cpp_host_shim_runs_the_sine_driver(built_lib):
+    """The plugin-shaped C++ shim (Load / callbacks / update / publish*) driven by the restated sinevelocitytest loop,
+    against the oracle running the same schedule.  The shim publishes like the plugin: the pose BEFORE step k with the
+    effort OF step k."""
+    import subprocess
+    from cdpr_simulation_b200 import build as b
+    exe = b.build_host()
+    out = subprocess.run([exe, "3", "600", "0"], capture_output=True, text=True, check=True).stdout.strip().splitlines()
+    rows = np.array([[float(x) for x in line.split()] for line in out])
+    assert rows.shape == (6, 5)
+    cfg = ob.default_config(4)
+    o = ob.Batch(cfg, 1, amp=[0.05], freq=[0.1], phase=[0.0])
+    done = 0
+    for k, x, y, z, eff in rows:
+        o.step(int(k) - 1 - done)
+        pose, _ = o.platform_state()
+        o.step(1)
+        done = int(k)
+        effort = o.last_outputs()[3]
+        assert abs(pose[0, 2] - z) < 1e-9 * 0.3 and abs(pose[0, 0] - x) < 1e-12 and abs(pose[0, 1] - y) < 1e-12
+        assert abs(effort[0, 0] - eff) < 1e-8
