@@ -161,10 +161,10 @@ static void fir_weights(int degree, int len, double dt, double *w) {
   }
 }
 
-// The FIR weights of a degree <= 2 fit are a quadratic in the centred sample position k = j - (len-1)/2.
+// The FIR weights of a degree <= 2 fit are a quadratic in the sample position p = j + 1 (oldest 1 .. newest len).
 // Returns false when they are not (degree > 2): the kernel then keeps the plain FIR.
 static bool fir_as_quadratic(const double *w, int len, double *abc) {
-  const long double K = 0.5L * (len - 1);
+  const long double K = -1.0L;  // position = j - K = j + 1
   // least-squares quadratic through (k_j, w_j) via normal equations in long double, then check the residual
   long double s[5] = {0, 0, 0, 0, 0}, t[3] = {0, 0, 0};
   for (int j = 0; j < len; ++j) {

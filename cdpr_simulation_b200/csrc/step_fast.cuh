@@ -16,9 +16,12 @@
 // evaluates its derivative at `now` (Pid.cpp:193-247).  With uniform time stamps that is a fixed FIR
 // sum_j w_j y_j whose weights are a degree-d polynomial in the sample position.  Two forms:
 //   DMOM = false  plain FIR: LEN-1 shared-memory reads + LEN DFMA per cable and step (any degree);
-//   DMOM = true   (degree <= 2) sliding moments S_m = sum_j k_j^m y_j, m = 0,1,2, k_j = j - (LEN-1)/2:
-//                 the slide needs only the sample that leaves the window, so 1 read + 1 write per cable
-//                 and step; D = a*S0 + b*S1 + c*S2.  Every kResync steps (global step index, so results
+//   DMOM = true   (degree <= 2) sliding moments S_m = sum_j p_j^m y_j, m = 0,1,2, with positions p_j = j + 1
+//                 (oldest sample 1, newest LEN): after a slide every kept sample moves to p - 1 and the sample
+//                 that leaves sits at 0, so it drops out of S1, S2 by itself:
+//                   S0' = S0 - y_old + y_new,  S1' = S1 - S0 + LEN y_new,  S2' = S2 - 2 S1 + S0 + LEN^2 y_new
+//                 (old S0, S1 on the right): 1 read + 1 write of shared memory and 7 FP64 instructions per
+//                 cable and step; D = a*S0 + b*S1 + c*S2.  Every kResync steps (global step index, so results
 //                 do not depend on how steps are split into launches) the moments are re-summed from
 //                 the ring, which bounds the rounding drift of the recursion.
 #pragma once
@@ -66,8 +69,6 @@ __device__ __forceinline__ void fast_step(const StepArgs &A, FastState &S, doubl
     s += (s < 0) ? LEN : 0;
     slot[a] = s * (NC * FastCfg<NC>::tpb);
   }
-  constexpr double K = 0.5 * (LEN - 1);
-
 #pragma unroll
   for (int c = 0; c < NC; ++c) {
     // ---- inverse kinematics (a7): r = R b, d = a - p - r, L, u, r x u, joint rate
@@ -106,8 +107,8 @@ __device__ __forceinline__ void fast_step(const StepArgs &A, FastState &S, doubl
           w[slot[0]] = e;
           const double s0 = mom[c][0], s1 = mom[c][1], s2 = mom[c][2];
           const double n0 = (s0 - y_old) + e;
-          const double n1 = fma(K, e, fma(K + 1.0, y_old, s1 - s0));
-          const double n2 = fma(K * K, e, fma(-(K + 1.0) * (K + 1.0), y_old, fma(-2.0, s1, s2) + s0));
+          const double n1 = fma((double)LEN, e, s1 - s0);
+          const double n2 = fma((double)(LEN * LEN), e, fma(-2.0, s1, s2) + s0);
           mom[c][0] = n0; mom[c][1] = n1; mom[c][2] = n2;
           derr = fma(A.dmom[2], n2, fma(A.dmom[1], n1, A.dmom[0] * n0));
         } else {
@@ -161,22 +162,22 @@ __device__ __forceinline__ void fast_step(const StepArgs &A, FastState &S, doubl
   rigid_body_step(rc, S, R, fx, fy, fz, mx, my, mz);
 }
 
-// exact re-summation of the window moments from the ring (newest sample in slot `head`)
+// exact re-summation of the window moments from the ring (newest sample in slot `head`); rare, kept small
 template <int NC, int LEN>
 __device__ __forceinline__ void resync_moments(double (&mom)[NC][3], const double *__restrict__ win, int head) {
-  constexpr double K = 0.5 * (LEN - 1);
 #pragma unroll
   for (int c = 0; c < NC; ++c) {
     double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-#pragma unroll
-    for (int j = 0; j < LEN; ++j) {  // logical position j: oldest first
-      int sl = head + 1 + j;
+    int sl = head + 1;  // oldest sample
+#pragma unroll 1
+    for (int j = 0; j < LEN; ++j) {
       sl -= (sl >= LEN) ? LEN : 0;
       const double y = win[(sl * NC + c) * FastCfg<NC>::tpb];
-      const double k = (double)j - K;
+      const double p = (double)(j + 1);
       s0 += y;
-      s1 = fma(k, y, s1);
-      s2 = fma(k * k, y, s2);
+      s1 = fma(p, y, s1);
+      s2 = fma(p * p, y, s2);
+      ++sl;
     }
     mom[c][0] = s0; mom[c][1] = s1; mom[c][2] = s2;
   }
