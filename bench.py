@@ -312,6 +312,30 @@ def side_measurements(cb, wl, torch, device, hbm_peak, fp64_peak):
         t = float(np.mean(ms[1:]))
         out["nc4_reference_robot"] = {"value": n * k / (t * 1e-3), "unit": UNIT, "kernel_ms": t,
                                       "fp64_frac": flops_per_instance_step(4) * n * k / (t * 1e-3) / 1e12 / fp64_peak}
+    # config 5: 4096 command sequences x 256 steps per robot, 64 robots on this GPU (262,144 rollouts), cost reduced per sequence
+    n_seq, n_cmd, spc, n_rob = 4096, 26, 10, 64
+    cmds = wl.c5_rollouts(n_seq, n_cmd, 8)
+    _, _, _, rp, rt = wl.c3_instances(n_rob, seed=5)
+    with cb.CdprBatch(cb.default_config(8), n_rob * n_seq, device=device) as g:
+        cost = torch.zeros(n_seq, dtype=torch.float64, device=f"cuda:{device}")
+        ms = []
+        for _ in range(3):
+            g.rollout(n_rob, n_seq, cmds, spc, [0.0, 0.0, 0.32], 0.05, rp, rt, dev_cost_seq=cost.data_ptr(), want_host_cost=False)
+            ms.append(g.last_kernel_ms)
+        t = float(np.mean(ms[1:]))
+        out["rollouts_c5_nc8"] = {"value": n_rob * n_seq * n_cmd * spc / (t * 1e-3), "unit": UNIT, "kernel_ms": t,
+                                  "what": f"{n_rob} robots x {n_seq} sequences x {n_cmd * spc} steps, in-kernel cost + per-sequence reduction"}
+    # the catch-all kernel (hold + biquad cascades enabled): HBM/L2-bound fallback, reported for completeness
+    gcfg = cb.default_config(8)
+    gcfg.velocity_epsilon = 0.02; gcfg.vel_pid.p_cascade = 1; gcfg.vel_pid.d_cascade = 1
+    ng = 1 << 18
+    with cb.CdprBatch(gcfg, ng, device=device) as g:
+        g.set_platform_state(pose7[:ng], twist6[:ng]); g.set_sine_cmd(amp[:ng], freq[:ng], phase[:ng])
+        ms = []
+        for _ in range(3):
+            g.step(200); ms.append(g.last_kernel_ms)
+        t = float(np.mean(ms[1:]))
+        out["general_variant_nc8"] = {"value": ng * 200 / (t * 1e-3), "unit": UNIT, "kernel_ms": t, "variant": g.kernel_variant}
     for nc in (4, 8):
         for npose in (65536, 1 << 22):
             p7, t6 = wl.c2_poses(npose, seed=0)

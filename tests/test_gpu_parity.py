@@ -307,3 +307,42 @@ def test_cpp_host_shim_runs_the_sine_driver(built_lib):
         effort = o.last_outputs()[3]
         assert abs(pose[0, 2] - z) < 1e-9 * 0.3 and abs(pose[0, 0] - x) < 1e-12 and abs(pose[0, 1] - y) < 1e-12
         assert abs(effort[0, 0] - eff) < 1e-8
+
+
+@pytest.mark.parametrize("n", [1, 2, 127, 129])
+def test_ragged_batch_sizes(built_lib, n):
+    """Batches that do not fill a block (the reference's own case is ONE robot): tail threads never store."""
+    cfg, gpu, orc = make_pair(4, n, seed=21)
+    gpu.step(90); orc.step(90)
+    pg, tg = gpu.platform_state(); po, to = orc.platform_state()
+    assert pg.shape == (n, 7) and state_rel_err(pg, tg, po, to) < PER_STEP_TOL
+    gpu.close()
+
+
+def test_reference_single_robot_config1(built_lib):
+    """BASELINE.json configs[0]: ONE 4-cable robot from cdpr_gazebo.launch under sinevelocitytest's default command
+    (0.05 m/s, 0.1 Hz), 3 s of simulated time."""
+    cfg = cb.default_config(4)
+    with cb.CdprBatch(cfg, 1) as g:
+        g.set_sine_cmd(0.05, 0.1, 0.0)
+        o = ob.Batch(to_oracle_config(cfg), 1, amp=[0.05], freq=[0.1], phase=[0.0])
+        for _ in range(3):
+            g.step(1000); o.step(1000)
+            pg, tg = g.platform_state(); po, to = o.platform_state()
+            assert state_rel_err(pg, tg, po, to) < DIVERGENCE_TOL_1000
+        assert abs(g.sim_time - 3.0) < 1e-12
+
+
+def test_reset_restores_post_load_state(built_lib):
+    _, a, _ = make_pair(4, 70)
+    first = None
+    for _ in range(2):
+        a.step(123)
+        out = a.platform_state()
+        if first is None:
+            first = out
+            a.reset()
+            amp, freq, phase, pose7, twist6 = wl.c3_instances(70, 1)
+            a.set_platform_state(pose7, twist6)
+    assert np.array_equal(first[0], out[0]) and np.array_equal(first[1], out[1])
+    a.close()
