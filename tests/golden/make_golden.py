@@ -60,6 +60,8 @@ def main():
         src = open(os.path.join(REF, f"src/{name}.cpp")).read()
         drivers[name] = {m.group(1): float(m.group(2)) for m in re.finditer(r"const double (c\w+)\s*=\s*([0-9.eE+-]+);", src)}
     g["drivers"] = drivers
+    import yaml
+    g["cube_yaml"] = yaml.safe_load(open(os.path.join(REF, "sdf/cube.yaml")))
     json.dump(g, open(OUT, "w"), indent=1, sort_keys=True)
     print("wrote", OUT, "cables:", len(cables))
 

@@ -1,0 +1,65 @@
+"""CPU-only: the restated command drivers against the constants in the reference's driver sources, and the
+description -> config loader against the reference's cube.yaml / cube.sdf literals (all via tests/golden)."""
+import json
+import math
+import os
+
+import numpy as np
+
+import cdpr_simulation_b200 as cb
+from cdpr_simulation_b200 import drivers, model
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_constants.json")))
+
+
+def test_driver_defaults_match_reference_sources():
+    d = G["drivers"]
+    s = drivers.SineVelocity()
+    assert (s.amp, s.freq, s.publish_hz) == (d["sinevelocitytest"]["cVelocityAmplitude"], d["sinevelocitytest"]["cVelocityFrequency"], d["sinevelocitytest"]["cPublishFrequency"])
+    v = drivers.SquareVelocity()
+    assert (v.amp, v.freq, v.publish_hz) == (d["squarevelocitytest"]["cVelocityAmplitude"], d["squarevelocitytest"]["cVelocityFrequency"], d["squarevelocitytest"]["cPublishFrequency"])
+    p = drivers.SquarePosition()
+    assert (p.amp, p.bias, p.freq, p.publish_hz) == (d["squarepositiontest"]["cPositionAmplitude"], d["squarepositiontest"]["cPositionBias"],
+                                                     d["squarepositiontest"]["cPositionFrequency"], d["squarepositiontest"]["cPublishFrequency"])
+
+
+def test_driver_waveforms():
+    v = drivers.SquareVelocity()
+    vals = [float(v.publish()) for _ in range(200)]                 # one 20 s period at 10 Hz
+    assert set(np.round(vals, 6)) == {0.0, 0.06, -0.06}
+    assert vals[0] == 0.0 and vals[25] == np.float32(0.06)          # dead band until |sin| >= sqrt(1/2): t = 2.5 s
+    assert abs(v.time - 20.0) < 1e-9
+    p = drivers.SquarePosition()
+    pv = [float(p.publish()) for _ in range(100)]
+    assert pv[0] == np.float32(0.05) and pv[60] == np.float32(-0.05)   # copysign(amp, sin(0)) = +amp, as in the source
+    s = drivers.SineVelocity()
+    sv = [s.publish() for _ in range(3)]
+    assert sv[0] == 0.0 and sv[1] == np.float32(0.05 * math.sin(0.01 * 0.1 * 2 * math.pi)) and sv[1].dtype == np.float32
+
+
+def test_config_from_reference_yaml_matches_sdf(built_lib):
+    desc = G["cube_yaml"]
+    stale = model.config_from_description(desc)
+    assert list(stale.home_pos) == [0.0, 0.0, 2.0]                  # cube.yaml is stale ...
+    cfg = model.config_from_description(desc, home_xyz=G["platform_pose"][:3])   # ... cube.sdf:310 is authoritative
+    ref = cb.default_config(4)
+    assert bytes(cfg) == bytes(ref)
+    assert cfg.cable_damping == desc["joints"]["actuated"]["damping"] and cfg.effort_limit == desc["joints"]["actuated"]["effort"]
+
+
+def test_launch_params_round_trip(built_lib):
+    cfg = cb.default_config(4)
+    cfg.vel_pid.p_gain = 1.0; cfg.pos_pid.i_gain = 2.0; cfg.velocity_epsilon = 9.0
+    model.apply_launch_params(cfg, G["launch_params"])
+    assert bytes(cfg) == bytes(cb.default_config(4))
+    # the commented Ziegler-Nichols alternative (launch/cdpr_gazebo.launch:40-45)
+    model.apply_launch_params(cfg, {"positionControllerP": 20.0, "positionControllerI": 100, "positionControllerD": 2.666666666})
+    assert (cfg.pos_pid.p_gain, cfg.pos_pid.i_gain, cfg.pos_pid.d_gain) == (20.0, 100.0, 2.666666666)
+
+
+def test_eight_cable_description(built_lib):
+    desc = json.loads(json.dumps(G["cube_yaml"]))
+    desc["points"] = desc["points"] + [{"frame": [p["frame"][0], p["frame"][1], 0.0], "platform": p["platform"]} for p in desc["points"]]
+    cfg = model.config_from_description(desc, home_xyz=[0, 0, 0.3])
+    assert bytes(cfg) == bytes(cb.default_config(8))                # SURVEY.md App. A.2 synthetic extension

@@ -346,3 +346,30 @@ def test_reset_restores_post_load_state(built_lib):
             a.set_platform_state(pose7, twist6)
     assert np.array_equal(first[0], out[0]) and np.array_equal(first[1], out[1])
     a.close()
+
+
+class _OracleTarget:
+    """Adapter so cdpr_simulation_b200.drivers.run can play a driver against the oracle."""
+    def __init__(self, batch): self.b = batch
+    def set_velocity_cmd(self, axes): self.b.velocity_cmd(axes)
+    def set_position_cmd(self, axes): self.b.position_cmd(axes)
+    def step(self, k): self.b.step(k)
+
+
+@pytest.mark.parametrize("driver_name,eps,variant", [("SquareVelocity", -0.001, "fast"), ("SquareVelocity", 0.001, "general"),
+                                                     ("SquarePosition", -0.001, "fast"), ("SineVelocity", -0.001, "fast")])
+def test_reference_drivers_against_oracle(built_lib, driver_name, eps, variant):
+    """The reference's three manual test drivers (square velocity with dead band -> hold when eps > 0, square position,
+    sine velocity) played headless against the CUDA batch and the oracle."""
+    from cdpr_simulation_b200 import drivers
+    n, nc, steps = 96, 4, 3200
+    def edit(cfg): cfg.velocity_epsilon = eps
+    cfg, gpu, orc = make_pair(nc, n, seed=13, cfg_edit=edit, sine=False)
+    assert gpu.kernel_variant == variant
+    drivers.run(gpu, getattr(drivers, driver_name)(), n, nc, steps, cfg.dt)
+    drivers.run(_OracleTarget(orc), getattr(drivers, driver_name)(), n, nc, steps, cfg.dt)
+    pg, tg = gpu.platform_state(); po, to = orc.platform_state()
+    assert state_rel_err(pg, tg, po, to) < 1e-7
+    for a, b in zip(gpu.joint_states(), orc.joint_states()):
+        assert np.max(np.abs(a - b)) < 1e-7
+    gpu.close()
