@@ -6,7 +6,7 @@
 
 Every driver stores a double into float32 Joy.axes (the same value on all cables) and accumulates its publisher time
 with `time += 1.0 / publish_frequency`.  `run` plays a driver against anything with set_velocity_cmd /
-set_position_cmd / step (the CUDA batch, or an oracle batch adapter in the tests)."""
+set_position_cmd / step (the CUDA batch, or any adapter with the same three methods)."""
 from __future__ import annotations
 
 import math

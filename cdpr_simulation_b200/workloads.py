@@ -1,5 +1,5 @@
 """Synthetic inputs of SURVEY.md 8(d) (C2, C3/C4, C5), numpy only, seeded: the same arrays feed the
-CUDA path, the CPU oracle in the tests and the CPU baseline in bench.py."""
+CUDA path, the CPU checker in the tests and the CPU baseline in bench.py."""
 from __future__ import annotations
 
 import numpy as np

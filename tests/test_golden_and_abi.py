@@ -153,4 +153,4 @@ def test_product_never_touches_the_oracle():
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
-                assert "oracle" not in text.lower() or f == "workloads.py" and "CPU oracle in the tests" in text, os.path.join(dirpath, f)
+                assert "oracle" not in text.lower(), os.path.join(dirpath, f)
