@@ -71,17 +71,18 @@ __device__ __forceinline__ void fast_step(const StepArgs &A, FastState &S, doubl
   }
 #pragma unroll
   for (int c = 0; c < NC; ++c) {
-    // ---- inverse kinematics (a7): r = R b, d = a - p - r, L, u, r x u, joint rate
+    // ---- inverse kinematics (a7).  With g = a - p (anchor seen from the platform origin): d = g - R b = L u, and
+    // r x u = (g - d) x u = g x u because d is parallel to u -- so neither r nor u is formed:
+    //   m = g x d = L (r x u),  joint rate = (d.v + m.w) / L,  and the wrench below scales d and m by tension / L.
     const double bx = rc.b[c][0], by = rc.b[c][1], bz = rc.b[c][2];
-    const double rx = fma(r00, bx, fma(r01, by, r02 * bz));
-    const double ry = fma(r10, bx, fma(r11, by, r12 * bz));
-    const double rz = fma(r20, bx, fma(r21, by, r22 * bz));
-    const double dx = (rc.a[c][0] - S.px) - rx, dy = (rc.a[c][1] - S.py) - ry, dz = (rc.a[c][2] - S.pz) - rz;
+    const double gx = rc.a[c][0] - S.px, gy = rc.a[c][1] - S.py, gz = rc.a[c][2] - S.pz;
+    const double dx = fma(-r00, bx, fma(-r01, by, fma(-r02, bz, gx)));
+    const double dy = fma(-r10, bx, fma(-r11, by, fma(-r12, bz, gy)));
+    const double dz = fma(-r20, bx, fma(-r21, by, fma(-r22, bz, gz)));
     const double l2 = fma(dx, dx, fma(dy, dy, dz * dz));
     const double il = rsqrt_nr(l2);
-    const double ux = dx * il, uy = dy * il, uz = dz * il;
-    const double cx = fma(ry, uz, -(rz * uy)), cy = fma(rz, ux, -(rx * uz)), cz = fma(rx, uy, -(ry * ux));
-    const double qd = fma(ux, S.vx, fma(uy, S.vy, uz * S.vz)) + fma(cx, S.wx, fma(cy, S.wy, cz * S.wz));
+    const double cx = fma(gy, dz, -(gz * dy)), cy = fma(gz, dx, -(gx * dz)), cz = fma(gx, dy, -(gy * dx));
+    const double qd = (fma(dx, S.vx, fma(dy, S.vy, dz * S.vz)) + fma(cx, S.wx, fma(cy, S.wy, cz * S.wz))) * il;
     double qp = 0.0;
     if (MODE == MODE_POSITION || LAST) qp = rc.home_len[c] - l2 * il;
 
@@ -154,9 +155,9 @@ __device__ __forceinline__ void fast_step(const StepArgs &A, FastState &S, doubl
       A.L.cab[cab_off(A.L, c, CAB_PID_FORCE) + i] = force;
     }
     // ---- explicit joint damping, wrench (a8)
-    const double tau = fma(-rc.cdamp, qd, eff);
-    fx = fma(tau, ux, fx); fy = fma(tau, uy, fy); fz = fma(tau, uz, fz);
-    mx = fma(tau, cx, mx); my = fma(tau, cy, my); mz = fma(tau, cz, mz);
+    const double tl = fma(-rc.cdamp, qd, eff) * il;  // tension / L
+    fx = fma(tl, dx, fx); fy = fma(tl, dy, fy); fz = fma(tl, dz, fz);
+    mx = fma(tl, cx, mx); my = fma(tl, cy, my); mz = fma(tl, cz, mz);
   }
 
   rigid_body_step(rc, S, R, fx, fy, fz, mx, my, mz);
