@@ -228,6 +228,12 @@ static int make_robot_consts(const cdpr_config &c, RobotConsts &o, std::string &
   o.ib_inv[0] = (b * cc - f * f) / det; o.ib_inv[1] = (a * cc - e * e) / det; o.ib_inv[2] = (a * b - d * d) / det;
   o.ib_inv[3] = (e * f - d * cc) / det; o.ib_inv[4] = (d * f - e * b) / det; o.ib_inv[5] = (d * e - a * f) / det;
   o.diag_inertia = (d == 0.0 && e == 0.0 && f == 0.0) ? 1 : 0;
+  o.spec = 0;
+  if (o.diag_inertia) o.spec |= SPEC_DIAG;
+  if (o.diag_inertia && I[0] == I[1] && I[1] == I[2]) o.spec |= SPEC_ISO;
+  bool bz0 = true;
+  for (int i = 0; i < c.n_cables; ++i) bz0 = bz0 && (c.platform_anchor[i][2] == 0.0);
+  if (bz0) o.spec |= SPEC_BZ0;
   o.cdamp = c.cable_damping; o.effort_limit = c.effort_limit; o.vel_eps = c.velocity_epsilon;
   o.effort_limit_abs = c.effort_limit >= 0.0 ? c.effort_limit : INFINITY;
   return CDPR_OK;
@@ -350,12 +356,18 @@ extern "C" int cdpr_create(const cdpr_config *cfg, int64_t n_instances, int devi
       cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
       cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     };
+#define CDPR_PREP1(NC_, SM_, SP_)                                                                                        \
+    prep((const void *)k_step_fast<NC_, 11, MODE_FORCE, false, SP_>, SM_); prep((const void *)k_step_fast<NC_, 11, MODE_POSITION, false, SP_>, SM_); \
+    prep((const void *)k_step_fast<NC_, 11, MODE_POSITION, true, SP_>, SM_); prep((const void *)k_step_fast<NC_, 11, MODE_VELOCITY, false, SP_>, SM_); \
+    prep((const void *)k_step_fast<NC_, 11, MODE_VELOCITY, true, SP_>, SM_)
 #define CDPR_PREP(NC_, SM_)                                                                                              \
-    prep((const void *)k_step_fast<NC_, 11, MODE_FORCE, false>, SM_); prep((const void *)k_step_fast<NC_, 11, MODE_POSITION, false>, SM_); \
-    prep((const void *)k_step_fast<NC_, 11, MODE_POSITION, true>, SM_); prep((const void *)k_step_fast<NC_, 11, MODE_VELOCITY, false>, SM_); \
-    prep((const void *)k_step_fast<NC_, 11, MODE_VELOCITY, true>, SM_)
+    CDPR_PREP1(NC_, SM_, 0); CDPR_PREP1(NC_, SM_, SPEC_DIAG);                                                            \
+    prep((const void *)k_step_fast<NC_, 11, MODE_VELOCITY, true, SPEC_DIAG | SPEC_BZ0>, SM_);                            \
+    prep((const void *)k_step_fast<NC_, 11, MODE_VELOCITY, true, SPEC_DIAG | SPEC_ISO>, SM_);                            \
+    prep((const void *)k_step_fast<NC_, 11, MODE_VELOCITY, true, SPEC_DIAG | SPEC_ISO | SPEC_BZ0>, SM_)
     CDPR_PREP(4, smem4);
     CDPR_PREP(8, smem8);
+#undef CDPR_PREP1
 #undef CDPR_PREP
   }
   if (cudaStreamSynchronize(h->stream) != cudaSuccess) { h->err = "initialisation kernels failed"; return bail(CDPR_ERR_CUDA); }
@@ -493,18 +505,27 @@ static int launch_step(cdpr_handle h, const StepArgs &A) {
     k_step_general<<<grid, kTpb, 0, h->stream>>>(A);
   } else {
     const bool dm = h->dmom_ok[A.live_idx];
-#define CDPR_LAUNCH(NC_, MODE_, DM_)                                                                   \
-  k_step_fast<NC_, 11, MODE_, DM_><<<(unsigned)(h->np / FastCfg<NC_>::tpb), FastCfg<NC_>::tpb,        \
-                                     fast_smem_bytes<NC_, 11>(), h->stream>>>(A)
-    if (h->L.nc == 4) {
-      if (A.mode == MODE_FORCE) CDPR_LAUNCH(4, MODE_FORCE, false);
-      else if (A.mode == MODE_POSITION) { if (dm) CDPR_LAUNCH(4, MODE_POSITION, true); else CDPR_LAUNCH(4, MODE_POSITION, false); }
-      else { if (dm) CDPR_LAUNCH(4, MODE_VELOCITY, true); else CDPR_LAUNCH(4, MODE_VELOCITY, false); }
-    } else {
-      if (A.mode == MODE_FORCE) CDPR_LAUNCH(8, MODE_FORCE, false);
-      else if (A.mode == MODE_POSITION) { if (dm) CDPR_LAUNCH(8, MODE_POSITION, true); else CDPR_LAUNCH(8, MODE_POSITION, false); }
-      else { if (dm) CDPR_LAUNCH(8, MODE_VELOCITY, true); else CDPR_LAUNCH(8, MODE_VELOCITY, false); }
-    }
+    // the velocity mode with the moment D-term (the headline path) is specialised on the robot constants; every
+    // other combination runs the diagonal-inertia or fully general instance
+    const int spec_full = h->rc.spec, spec_base = h->rc.spec & SPEC_DIAG;
+#define CDPR_LAUNCH(NC_, MODE_, DM_, SP_)                                                              \
+  k_step_fast<NC_, 11, MODE_, DM_, SP_><<<(unsigned)(h->np / FastCfg<NC_>::tpb), FastCfg<NC_>::tpb,   \
+                                          fast_smem_bytes<NC_, 11>(), h->stream>>>(A)
+#define CDPR_LAUNCH_BASE(NC_, MODE_, DM_) \
+  do { if (spec_base) CDPR_LAUNCH(NC_, MODE_, DM_, SPEC_DIAG); else CDPR_LAUNCH(NC_, MODE_, DM_, 0); } while (0)
+#define CDPR_LAUNCH_NC(NC_)                                                                            \
+  do {                                                                                                 \
+    if (A.mode == MODE_FORCE) CDPR_LAUNCH_BASE(NC_, MODE_FORCE, false);                                \
+    else if (A.mode == MODE_POSITION) { if (dm) CDPR_LAUNCH_BASE(NC_, MODE_POSITION, true); else CDPR_LAUNCH_BASE(NC_, MODE_POSITION, false); } \
+    else if (!dm) CDPR_LAUNCH_BASE(NC_, MODE_VELOCITY, false);                                         \
+    else if (spec_full == (SPEC_DIAG | SPEC_ISO | SPEC_BZ0)) CDPR_LAUNCH(NC_, MODE_VELOCITY, true, SPEC_DIAG | SPEC_ISO | SPEC_BZ0); \
+    else if (spec_full == (SPEC_DIAG | SPEC_ISO)) CDPR_LAUNCH(NC_, MODE_VELOCITY, true, SPEC_DIAG | SPEC_ISO); \
+    else if (spec_full == (SPEC_DIAG | SPEC_BZ0)) CDPR_LAUNCH(NC_, MODE_VELOCITY, true, SPEC_DIAG | SPEC_BZ0); \
+    else CDPR_LAUNCH_BASE(NC_, MODE_VELOCITY, true);                                                   \
+  } while (0)
+    if (h->L.nc == 4) CDPR_LAUNCH_NC(4); else CDPR_LAUNCH_NC(8);
+#undef CDPR_LAUNCH_NC
+#undef CDPR_LAUNCH_BASE
 #undef CDPR_LAUNCH
   }
   CK(h, cudaGetLastError());

@@ -63,6 +63,7 @@ struct RobotConsts {
   double h, h_over_m, half_h;
   double ib[6], ib_inv[6];  // xx yy zz xy xz yz
   int diag_inertia;
+  int spec;                 // SPEC_* bits (physics.cuh) that hold for this robot
   double cdamp, effort_limit;  // effort_limit < 0: no truncation
   double effort_limit_abs;     // effort_limit, or +inf when truncation is off
   double vel_eps;

@@ -52,39 +52,52 @@ __device__ __forceinline__ void store_plat(double *p, long long stride, const Fa
   p[10 * stride] = S.wx; p[11 * stride] = S.wy; p[12 * stride] = S.wz;
 }
 
+// Compile-time specialisations of the robot constants (detected at cdpr_create, never assumed):
+//   SPEC_DIAG  body inertia is diagonal (products of inertia are 0), as in sdf/cube.sdf:331-338
+//   SPEC_ISO   ... and ixx == iyy == izz: the gyroscopic torque vanishes and I_w^-1 is a scalar
+//   SPEC_BZ0   every platform anchor has b_z == 0 (anchors in the platform's xy plane, cube.yaml:21-29)
+enum { SPEC_DIAG = 1, SPEC_ISO = 2, SPEC_BZ0 = 4 };
+
 // (fx..fz, mx..mz) = net force / torque about the COM in frame axes, gravity included
+template <int SPEC>
 __device__ __forceinline__ void rigid_body_step(const RobotConsts &rc, FastState &S, const Rot &R, double fx, double fy, double fz,
                                                 double mx, double my, double mz) {
   const double r00 = R.r00, r01 = R.r01, r02 = R.r02, r10 = R.r10, r11 = R.r11, r12 = R.r12, r20 = R.r20, r21 = R.r21, r22 = R.r22;
   // ---- rigid-body step, ODE order (a9): I_w = R I_b R^T, explicit gyroscopic torque
-  // angular part in the body frame: alpha = R I_b^-1 (R^T M - w_b x (I_b w_b)); identical to ODE's world-frame
-  // form M - w x (R I_b R^T w) because rotations preserve cross products
-  const double wbx = fma(r00, S.wx, fma(r10, S.wy, r20 * S.wz));
-  const double wby = fma(r01, S.wx, fma(r11, S.wy, r21 * S.wz));
-  const double wbz = fma(r02, S.wx, fma(r12, S.wy, r22 * S.wz));
-  double lbx, lby, lbz;
-  if (rc.diag_inertia) {
-    lbx = rc.ib[0] * wbx; lby = rc.ib[1] * wby; lbz = rc.ib[2] * wbz;
+  double alx, aly, alz;
+  if (SPEC & SPEC_ISO) {
+    // I_b = k * identity: w x (I w) = 0 and I_w^-1 = 1/k
+    alx = rc.ib_inv[0] * mx; aly = rc.ib_inv[0] * my; alz = rc.ib_inv[0] * mz;
   } else {
-    lbx = fma(rc.ib[0], wbx, fma(rc.ib[3], wby, rc.ib[4] * wbz));
-    lby = fma(rc.ib[3], wbx, fma(rc.ib[1], wby, rc.ib[5] * wbz));
-    lbz = fma(rc.ib[4], wbx, fma(rc.ib[5], wby, rc.ib[2] * wbz));
-  }
-  const double mbx = fma(r00, mx, fma(r10, my, r20 * mz)) - fma(wby, lbz, -(wbz * lby));
-  const double mby = fma(r01, mx, fma(r11, my, r21 * mz)) - fma(wbz, lbx, -(wbx * lbz));
-  const double mbz = fma(r02, mx, fma(r12, my, r22 * mz)) - fma(wbx, lby, -(wby * lbx));
-  double abx, aby, abz;
-  if (rc.diag_inertia) {
-    abx = rc.ib_inv[0] * mbx; aby = rc.ib_inv[1] * mby; abz = rc.ib_inv[2] * mbz;
-  } else {
-    abx = fma(rc.ib_inv[0], mbx, fma(rc.ib_inv[3], mby, rc.ib_inv[4] * mbz));
-    aby = fma(rc.ib_inv[3], mbx, fma(rc.ib_inv[1], mby, rc.ib_inv[5] * mbz));
-    abz = fma(rc.ib_inv[4], mbx, fma(rc.ib_inv[5], mby, rc.ib_inv[2] * mbz));
-  }
-  const double alx = fma(r00, abx, fma(r01, aby, r02 * abz));
-  const double aly = fma(r10, abx, fma(r11, aby, r12 * abz));
-  const double alz = fma(r20, abx, fma(r21, aby, r22 * abz));
+    // angular part in the body frame: alpha = R I_b^-1 (R^T M - w_b x (I_b w_b)); identical to ODE's world-frame
+    // form M - w x (R I_b R^T w) because rotations preserve cross products
+    const double wbx = fma(r00, S.wx, fma(r10, S.wy, r20 * S.wz));
+    const double wby = fma(r01, S.wx, fma(r11, S.wy, r21 * S.wz));
+    const double wbz = fma(r02, S.wx, fma(r12, S.wy, r22 * S.wz));
+    double lbx, lby, lbz;
+    if (SPEC & SPEC_DIAG) {
+      lbx = rc.ib[0] * wbx; lby = rc.ib[1] * wby; lbz = rc.ib[2] * wbz;
+    } else {
+      lbx = fma(rc.ib[0], wbx, fma(rc.ib[3], wby, rc.ib[4] * wbz));
+      lby = fma(rc.ib[3], wbx, fma(rc.ib[1], wby, rc.ib[5] * wbz));
+      lbz = fma(rc.ib[4], wbx, fma(rc.ib[5], wby, rc.ib[2] * wbz));
+    }
+    const double mbx = fma(r00, mx, fma(r10, my, r20 * mz)) - fma(wby, lbz, -(wbz * lby));
+    const double mby = fma(r01, mx, fma(r11, my, r21 * mz)) - fma(wbz, lbx, -(wbx * lbz));
+    const double mbz = fma(r02, mx, fma(r12, my, r22 * mz)) - fma(wbx, lby, -(wby * lbx));
+    double abx, aby, abz;
+    if (SPEC & SPEC_DIAG) {
+      abx = rc.ib_inv[0] * mbx; aby = rc.ib_inv[1] * mby; abz = rc.ib_inv[2] * mbz;
+    } else {
+      abx = fma(rc.ib_inv[0], mbx, fma(rc.ib_inv[3], mby, rc.ib_inv[4] * mbz));
+      aby = fma(rc.ib_inv[3], mbx, fma(rc.ib_inv[1], mby, rc.ib_inv[5] * mbz));
+      abz = fma(rc.ib_inv[4], mbx, fma(rc.ib_inv[5], mby, rc.ib_inv[2] * mbz));
+    }
+    alx = fma(r00, abx, fma(r01, aby, r02 * abz));
+    aly = fma(r10, abx, fma(r11, aby, r12 * abz));
+    alz = fma(r20, abx, fma(r21, aby, r22 * abz));
 
+  }
   S.vx = fma(rc.h_over_m, fx, S.vx); S.vy = fma(rc.h_over_m, fy, S.vy); S.vz = fma(rc.h_over_m, fz, S.vz);
   S.wx = fma(rc.h, alx, S.wx); S.wy = fma(rc.h, aly, S.wy); S.wz = fma(rc.h, alz, S.wz);
   S.px = fma(rc.h, S.vx, S.px); S.py = fma(rc.h, S.vy, S.py); S.pz = fma(rc.h, S.vz, S.pz);

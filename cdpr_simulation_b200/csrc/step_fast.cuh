@@ -32,7 +32,7 @@ namespace cdpr {
 
 constexpr int kResync = 64;
 #ifndef CDPR_NC4_BLOCKS
-#define CDPR_NC4_BLOCKS 2
+#define CDPR_NC4_BLOCKS 4
 #endif
 #ifndef CDPR_NC8_BLOCKS
 #define CDPR_NC8_BLOCKS 2
@@ -49,7 +49,7 @@ template <int NC> struct FastCfg { static constexpr int tpb = (NC <= 4) ? CDPR_N
 //   STEADY: every live Pid is primed and its window is full (mWasLastTime && mDbufferMissing == 0)
 //   LAST:   last step of the launch: also writes the telemetry columns
 //   MODE:   batch-uniform JointForceCalculator::UpdateMode
-template <int NC, int LEN, bool STEADY, bool LAST, int MODE, bool DMOM>
+template <int NC, int LEN, bool STEADY, bool LAST, int MODE, bool DMOM, int SPEC>
 __device__ __forceinline__ void fast_step(const StepArgs &A, FastState &S, double (&ierr)[NC], const double *__restrict__ tgts,
                                           double (&mom)[NC][3], unsigned &primed, unsigned (&missing)[NC],
                                           double *__restrict__ win, int head, double dt, long long i) {
@@ -76,9 +76,9 @@ __device__ __forceinline__ void fast_step(const StepArgs &A, FastState &S, doubl
     //   m = g x d = L (r x u),  joint rate = (d.v + m.w) / L,  and the wrench below scales d and m by tension / L.
     const double bx = rc.b[c][0], by = rc.b[c][1], bz = rc.b[c][2];
     const double gx = rc.a[c][0] - S.px, gy = rc.a[c][1] - S.py, gz = rc.a[c][2] - S.pz;
-    const double dx = fma(-r00, bx, fma(-r01, by, fma(-r02, bz, gx)));
-    const double dy = fma(-r10, bx, fma(-r11, by, fma(-r12, bz, gy)));
-    const double dz = fma(-r20, bx, fma(-r21, by, fma(-r22, bz, gz)));
+    const double dx = fma(-r00, bx, fma(-r01, by, (SPEC & SPEC_BZ0) ? gx : fma(-r02, bz, gx)));
+    const double dy = fma(-r10, bx, fma(-r11, by, (SPEC & SPEC_BZ0) ? gy : fma(-r12, bz, gy)));
+    const double dz = fma(-r20, bx, fma(-r21, by, (SPEC & SPEC_BZ0) ? gz : fma(-r22, bz, gz)));
     const double l2 = fma(dx, dx, fma(dy, dy, dz * dz));
     const double il = rsqrt_nr(l2);
     const double cx = fma(gy, dz, -(gz * dy)), cy = fma(gz, dx, -(gx * dz)), cz = fma(gx, dy, -(gy * dx));
@@ -160,7 +160,7 @@ __device__ __forceinline__ void fast_step(const StepArgs &A, FastState &S, doubl
     mx = fma(tl, cx, mx); my = fma(tl, cy, my); mz = fma(tl, cz, mz);
   }
 
-  rigid_body_step(rc, S, R, fx, fy, fz, mx, my, mz);
+  rigid_body_step<SPEC>(rc, S, R, fx, fy, fz, mx, my, mz);
 }
 
 // exact re-summation of the window moments from the ring (newest sample in slot `head`); rare, kept small
@@ -189,7 +189,7 @@ __device__ __forceinline__ void resync_moments(double (&mom)[NC][3], const doubl
 template <int NC, int LEN>
 constexpr size_t fast_smem_bytes() { return sizeof(double) * (size_t)FastCfg<NC>::tpb * (LEN * NC + 2 * NC + 3); }
 
-template <int NC, int LEN, int MODE, bool DMOM>
+template <int NC, int LEN, int MODE, bool DMOM, int SPEC>
 __global__ void __launch_bounds__(FastCfg<NC>::tpb, FastCfg<NC>::blocks) k_step_fast(const __grid_constant__ StepArgs A) {
   extern __shared__ double smem[];
   constexpr int kTpbL = FastCfg<NC>::tpb;
@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(FastCfg<NC>::tpb, FastCfg<NC>::blocks) k_step_
   for (; s + 1 < A.k_steps && !warp_steady; ++s) {
     double dt;
     pre_step(dt);
-    fast_step<NC, LEN, false, false, MODE, DMOM>(A, S, ierr, mytgt, mom, primed, missing, mywin, head, dt, i);
+    fast_step<NC, LEN, false, false, MODE, DMOM, SPEC>(A, S, ierr, mytgt, mom, primed, missing, mywin, head, dt, i);
     bool st = true;
 #pragma unroll
     for (int c = 0; c < NC; ++c) st = st && ((primed >> c) & 1u) && missing[c] == 0u;
@@ -327,7 +327,7 @@ __global__ void __launch_bounds__(FastCfg<NC>::tpb, FastCfg<NC>::blocks) k_step_
     for (; s + 1 < A.k_steps; ++s) {
       double dt;
       pre_step(dt);
-      fast_step<NC, LEN, true, false, MODE, DMOM>(A, S, ierr, mytgt, mom, primed, missing, mywin, head, dt, i);
+      fast_step<NC, LEN, true, false, MODE, DMOM, SPEC>(A, S, ierr, mytgt, mom, primed, missing, mywin, head, dt, i);
       post_step();
     }
   }
@@ -336,8 +336,8 @@ __global__ void __launch_bounds__(FastCfg<NC>::tpb, FastCfg<NC>::blocks) k_step_
     double dt;
     pre_step(dt);
     if (valid) {
-      if (warp_steady) fast_step<NC, LEN, true, true, MODE, DMOM>(A, S, ierr, mytgt, mom, primed, missing, mywin, head, dt, i);
-      else fast_step<NC, LEN, false, true, MODE, DMOM>(A, S, ierr, mytgt, mom, primed, missing, mywin, head, dt, i);
+      if (warp_steady) fast_step<NC, LEN, true, true, MODE, DMOM, SPEC>(A, S, ierr, mytgt, mom, primed, missing, mywin, head, dt, i);
+      else fast_step<NC, LEN, false, true, MODE, DMOM, SPEC>(A, S, ierr, mytgt, mom, primed, missing, mywin, head, dt, i);
     }
     post_step();
   }

@@ -213,7 +213,8 @@ __global__ void __launch_bounds__(kTpb) k_step_general(const __grid_constant__ S
       fx += tau * ux; fy += tau * uy; fz += tau * uz;
       mx += tau * cx; my += tau * cy; mz += tau * cz;
     }
-    rigid_body_step(rc, S, R, fx, fy, fz, mx, my, mz);
+    if (rc.diag_inertia) rigid_body_step<SPEC_DIAG>(rc, S, R, fx, fy, fz, mx, my, mz);
+    else rigid_body_step<0>(rc, S, R, fx, fy, fz, mx, my, mz);
     if (A.cost) {
       const double ex = S.px - A.target[0], ey = S.py - A.target[1], ez = S.pz - A.target[2];
       cost += fma(ex, ex, fma(ey, ey, ez * ez)) + A.lambda * fma(S.wx, S.wx, fma(S.wy, S.wy, S.wz * S.wz));

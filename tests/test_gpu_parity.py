@@ -373,3 +373,40 @@ def test_reference_drivers_against_oracle(built_lib, driver_name, eps, variant):
     for a, b in zip(gpu.joint_states(), orc.joint_states()):
         assert np.max(np.abs(a - b)) < 1e-7
     gpu.close()
+
+
+def _inertia_general(cfg):
+    for k, v in enumerate([1.0, 2.0, 3.0, 0.1, 0.05, -0.02]):
+        cfg.inertia[k] = v
+    for c in range(cfg.n_cables):
+        cfg.platform_anchor[c][2] = 0.004 * (c - 1.5)      # anchors off the platform's xy plane
+
+def _inertia_diag(cfg):
+    cfg.inertia[0], cfg.inertia[1], cfg.inertia[2] = 0.8, 1.7, 2.9
+
+def _inertia_diag_bz(cfg):
+    _inertia_diag(cfg)
+    cfg.platform_anchor[2][2] = -0.01
+
+def _iso_bz(cfg):
+    cfg.platform_anchor[1][2] = 0.02
+
+
+@pytest.mark.parametrize("edit", [_inertia_general, _inertia_diag, _inertia_diag_bz, _iso_bz])
+@pytest.mark.parametrize("nc", [4, 8])
+def test_robot_constant_specialisations(built_lib, nc, edit):
+    """Every compile-time specialisation of the step kernel (general / diagonal / isotropic inertia, anchors in or
+    off the platform plane) against the oracle, with an initial spin so the gyroscopic term matters."""
+    cfg = cb.default_config(nc)
+    edit(cfg)
+    n = 160
+    amp, freq, phase, pose7, twist6 = wl.c3_instances(n, 17)
+    twist6[:, 3:] = np.random.default_rng(3).uniform(-1.0, 1.0, (n, 3))
+    gpu = cb.CdprBatch(cfg, n)
+    gpu.set_platform_state(pose7, twist6); gpu.set_sine_cmd(amp, freq, phase)
+    orc = ob.Batch(to_oracle_config(cfg), n, pose7, twist6, amp, freq, phase)
+    assert gpu.kernel_variant == "fast"
+    gpu.step(250); orc.step(250)
+    pg, tg = gpu.platform_state(); po, to = orc.platform_state()
+    assert state_rel_err(pg, tg, po, to) < 1e-8
+    gpu.close()
