@@ -24,7 +24,7 @@ ERR_BAD_ARG, ERR_BAD_CABLE_COUNT, ERR_BAD_LENGTH, ERR_NO_DEVICE, ERR_CUDA, ERR_U
 
 # every symbol include/cdpr_b200.h declares (checked by tests/test_abi.py)
 EXPORTS = [
-    "cdpr_config_default", "cdpr_create", "cdpr_destroy", "cdpr_reset", "cdpr_last_error", "cdpr_set_stream", "cdpr_synchronize",
+    "cdpr_config_default", "cdpr_create", "cdpr_destroy", "cdpr_reset", "cdpr_last_error", "cdpr_set_stream", "cdpr_synchronize", "cdpr_set_async",
     "cdpr_set_velocity_cmd", "cdpr_set_position_cmd", "cdpr_set_effort_cmd", "cdpr_set_sine_cmd",
     "cdpr_step", "cdpr_step_count", "cdpr_sim_time",
     "cdpr_get_joint_states", "cdpr_get_platform_state", "cdpr_set_platform_state", "cdpr_get_pid_state",
@@ -96,6 +96,7 @@ def load():
     L.cdpr_last_error.argtypes = [vp]; L.cdpr_last_error.restype = C.c_char_p
     L.cdpr_set_stream.argtypes = [vp, vp]
     L.cdpr_synchronize.argtypes = [vp]
+    L.cdpr_set_async.argtypes = [vp, C.c_int]
     for f in (L.cdpr_set_velocity_cmd, L.cdpr_set_position_cmd, L.cdpr_set_effort_cmd):
         f.argtypes = [vp, vp, i64, C.c_int]
     L.cdpr_set_sine_cmd.argtypes = [vp, vp, vp, vp, i64]
@@ -185,6 +186,10 @@ class CdprBatch:
     def set_stream(self, cuda_stream: int):
         self._ck(self._L.cdpr_set_stream(self._h, C.c_void_p(cuda_stream)))
 
+    def set_async(self, on: bool = True):
+        """Host-buffer calls only enqueue; keep the (pinned) buffers alive until synchronize()."""
+        self._ck(self._L.cdpr_set_async(self._h, 1 if on else 0))
+
     def synchronize(self):
         self._ck(self._L.cdpr_synchronize(self._h))
 
@@ -209,10 +214,16 @@ class CdprBatch:
         if amp is None:
             self._ck(self._L.cdpr_set_sine_cmd(self._h, None, None, None, 0))
             return
-        amp = np.broadcast_to(_f64(amp), (self.n,)).copy()
-        freq = None if freq is None else np.broadcast_to(_f64(freq), (self.n,)).copy()
-        phase = None if phase is None else np.broadcast_to(_f64(phase), (self.n,)).copy()
-        self._ck(self._L.cdpr_set_sine_cmd(self._h, _ptr(amp), _ptr(freq), _ptr(phase), self.n))
+        def col(a):
+            if a is None:
+                return None
+            a = np.asarray(a)
+            if a.dtype == np.float64 and a.shape == (self.n,) and a.flags.c_contiguous:
+                return a                      # used in place (async mode: the caller keeps it alive)
+            return np.broadcast_to(_f64(a), (self.n,)).copy()
+        cols = [col(amp), col(freq), col(phase)]
+        self._keep = cols                     # temporaries must outlive an enqueued copy
+        self._ck(self._L.cdpr_set_sine_cmd(self._h, _ptr(cols[0]), _ptr(cols[1]), _ptr(cols[2]), self.n))
 
     # -- stepping ----------------------------------------------------------------------------
     def step(self, k_steps: int = 1):

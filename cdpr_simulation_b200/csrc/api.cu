@@ -41,6 +41,7 @@ struct cdpr_batch {
   bool own_stream = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool timed = false;
+  bool async_copies = false;  // host-buffer calls only enqueue; the caller synchronises (pinned buffers)
   long long launches = 0;
   void *stage = nullptr;
   size_t stage_bytes = 0;
@@ -259,6 +260,8 @@ static int ensure_stage(cdpr_handle h, size_t bytes) {
   return CDPR_OK;
 }
 
+static inline cudaError_t sync_unless_async(cdpr_handle h) { return h->async_copies ? cudaSuccess : cudaStreamSynchronize(h->stream); }
+
 static inline unsigned grid_for(long long n, int tpb) { return (unsigned)((n + tpb - 1) / tpb); }
 
 static int reset_to_load_state(cdpr_handle h) {
@@ -412,6 +415,12 @@ extern "C" int cdpr_set_stream(cdpr_handle h, void *cuda_stream) {
   return CDPR_OK;
 }
 
+extern "C" int cdpr_set_async(cdpr_handle h, int on) {
+  if (!h) return CDPR_ERR_BAD_ARG;
+  h->async_copies = on != 0;
+  return CDPR_OK;
+}
+
 extern "C" int cdpr_synchronize(cdpr_handle h) {
   if (!h) return CDPR_ERR_BAD_ARG;
   cudaSetDevice(h->device);
@@ -435,7 +444,7 @@ static int scatter_cmd(cdpr_handle h, const T *host, int64_t n_instances, int n_
   CK(h, cudaMemcpyAsync(h->stage, host, bytes, cudaMemcpyHostToDevice, h->stream));
   k_scatter_cab<T><<<grid_for(h->n, 256), 256, 0, h->stream>>>(h->L, field, (const T *)h->stage);
   CK(h, cudaGetLastError());
-  CK(h, cudaStreamSynchronize(h->stream));  // the caller may reuse its buffer
+  CK(h, sync_unless_async(h));  // the caller may reuse its buffer
   return CDPR_OK;
 }
 
@@ -466,8 +475,9 @@ extern "C" int cdpr_set_sine_cmd(cdpr_handle h, const double *amp, const double 
   const double defaults[3] = {0.05, 0.1, 0.0};  // sinevelocitytest.cpp:8-9
   for (int k = 0; k < 3; ++k) {
     if (!src[k]) { def.assign((size_t)h->n, defaults[k]); src[k] = def.data(); }
+    const bool temporary = (src[k] == def.data());
     CK(h, cudaMemcpyAsync(h->L.sine + (size_t)k * h->L.np, src[k], bytes, cudaMemcpyHostToDevice, h->stream));
-    CK(h, cudaStreamSynchronize(h->stream));
+    if (temporary) CK(h, cudaStreamSynchronize(h->stream)); else CK(h, sync_unless_async(h));
   }
   h->sine_on = true;
   h->sine_time = 0.0;
@@ -603,7 +613,7 @@ extern "C" int cdpr_get_platform_state(cdpr_handle h, double *pose7, double *twi
   CK(h, cudaGetLastError());
   if (pose7) CK(h, cudaMemcpyAsync(pose7, dp, nb * 7, cudaMemcpyDeviceToHost, h->stream));
   if (twist6) CK(h, cudaMemcpyAsync(twist6, dt, nb * 6, cudaMemcpyDeviceToHost, h->stream));
-  CK(h, cudaStreamSynchronize(h->stream));
+  CK(h, sync_unless_async(h));
   return CDPR_OK;
 }
 
@@ -618,7 +628,7 @@ extern "C" int cdpr_set_platform_state(cdpr_handle h, const double *pose7, const
   if (twist6) CK(h, cudaMemcpyAsync(dt, twist6, nb * 6, cudaMemcpyHostToDevice, h->stream));
   k_unpack_platform<<<grid_for(h->n, 256), 256, 0, h->stream>>>(h->L, pose7 ? dp : nullptr, twist6 ? dt : nullptr, 1);
   CK(h, cudaGetLastError());
-  CK(h, cudaStreamSynchronize(h->stream));
+  CK(h, sync_unless_async(h));
   return CDPR_OK;
 }
 
@@ -635,7 +645,7 @@ extern "C" int cdpr_get_joint_states(cdpr_handle h, double *position, double *ve
   if (position) CK(h, cudaMemcpyAsync(position, d0, nb, cudaMemcpyDeviceToHost, h->stream));
   if (velocity) CK(h, cudaMemcpyAsync(velocity, d1, nb, cudaMemcpyDeviceToHost, h->stream));
   if (effort) CK(h, cudaMemcpyAsync(effort, d2, nb, cudaMemcpyDeviceToHost, h->stream));
-  CK(h, cudaStreamSynchronize(h->stream));
+  CK(h, sync_unless_async(h));
   return CDPR_OK;
 }
 
@@ -648,7 +658,7 @@ extern "C" int cdpr_get_pid_state(cdpr_handle h, double *out) {
   k_pid_state<<<grid_for(h->n, 256), 256, 0, h->stream>>>(h->L, h->mode, (double *)h->stage);
   CK(h, cudaGetLastError());
   CK(h, cudaMemcpyAsync(out, h->stage, nb, cudaMemcpyDeviceToHost, h->stream));
-  CK(h, cudaStreamSynchronize(h->stream));
+  CK(h, sync_unless_async(h));
   return CDPR_OK;
 }
 

@@ -97,6 +97,9 @@ const char *cdpr_last_error(cdpr_handle h);
 /* Kernels run on this cudaStream_t (default: a stream owned by the handle). */
 int cdpr_set_stream(cdpr_handle h, void *cuda_stream);
 int cdpr_synchronize(cdpr_handle h);
+/* on != 0: calls that take host buffers only ENQUEUE their copies/kernels on the handle's stream and return; the
+ * caller keeps the (pinned) buffers alive and untouched until cdpr_synchronize. Default off (every call completes). */
+int cdpr_set_async(cdpr_handle h, int on);
 
 /* ---- commands (topics jointVelocities / jointPositions, CdprGazeboPlugin.cpp:67-83,206-219;
  *      JointForceCalculator::setForce, JointForceCalculator.h:92-95) ------------------------
