@@ -159,7 +159,7 @@ def own_arm(args):
     import torch.distributed as dist
     import cdpr_simulation_b200 as cb
     from cdpr_simulation_b200 import workloads as wl
-    from cdpr_simulation_b200.distributed import TrajectoryGather
+    from cdpr_simulation_b200.distributed import make_trajectory_gather
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -186,7 +186,8 @@ def own_arm(args):
     batch = cb.CdprBatch(cfg, n, device=local_rank)
     batch.set_stream(stream.cuda_stream)
     assert batch.kernel_variant == "fast"
-    gather = TrajectoryGather(batch, every=args.snapshot_every, steps_per_pass=k_sim, stream=stream) if world > 1 else None
+    gather, gather_kind = (make_trajectory_gather(batch, args.snapshot_every, k_sim, stream, prefer_fused=(args.gather == "fused"))
+                           if world > 1 else (None, None))
 
     def load_inputs():
         batch.set_platform_state(pin_in[3].numpy(), pin_in[4].numpy())
@@ -316,7 +317,7 @@ def own_arm(args):
                                    f"NC={nc} ({'synthetic 8-cable extension' if nc == 8 else 'reference 4-cable robot'})",
                        "instances_per_gpu": n, "sim_steps_per_pass": k_sim, "n_cables": nc,
                        "l2": "resident state per GPU (%.1f GB) is larger than L2; no flush needed" % (batch_state_gb(batch)),
-                       "multi_gpu": None if world == 1 else f"snapshot every {args.snapshot_every} steps all-gathered over NCCL on a side stream"},
+                       "multi_gpu": None if world == 1 else f"snapshot every {args.snapshot_every} steps gathered to every rank -- {gather_kind}"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / args.steps,
@@ -351,6 +352,7 @@ def side_measurements(cb, wl, torch, device, hbm_peak, fp64_peak):
     _, _, _, rp, rt = wl.c3_instances(n_rob, seed=5)
     with cb.CdprBatch(cb.default_config(8), n_rob * n_seq, device=device) as g:
         cost = torch.zeros(n_seq, dtype=torch.float64, device=f"cuda:{device}")
+        torch.cuda.synchronize()
         ms = []
         for _ in range(3):
             g.rollout(n_rob, n_seq, cmds, spc, [0.0, 0.0, 0.32], 0.05, rp, rt, dev_cost_seq=cost.data_ptr(), want_host_cost=False)
@@ -375,6 +377,7 @@ def side_measurements(cb, wl, torch, device, hbm_peak, fp64_peak):
             st = np.ascontiguousarray(np.concatenate([p7[:, :3], p7[:, 6:7], p7[:, 3:6], t6], axis=1).T)
             d_in = torch.from_numpy(st).cuda(device)
             d_out = torch.empty((nc, 8, npose), dtype=torch.float64, device=f"cuda:{device}")
+            torch.cuda.synchronize()
             with cb.CdprBatch(cb.default_config(nc), 1, device=device) as g:
                 ms = []
                 for _ in range(12):
@@ -401,6 +404,7 @@ def main():
     ap.add_argument("--instances", type=int, default=1 << 20, help="instances per GPU")
     ap.add_argument("--sim-steps", type=int, default=1000, help="physics steps per pass (one kernel launch)")
     ap.add_argument("--snapshot-every", type=int, default=100)
+    ap.add_argument("--gather", default="fused", choices=["fused", "nccl"], help="multi-GPU trajectory gather implementation")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--ref-seconds", type=float, default=6.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -29,7 +29,7 @@ EXPORTS = [
     "cdpr_step", "cdpr_step_count", "cdpr_sim_time",
     "cdpr_get_joint_states", "cdpr_get_platform_state", "cdpr_set_platform_state", "cdpr_get_pid_state",
     "cdpr_state_bytes", "cdpr_get_state", "cdpr_set_state",
-    "cdpr_set_snapshots", "cdpr_snapshot_count",
+    "cdpr_set_snapshots", "cdpr_set_snapshot_peers", "cdpr_set_snapshot_multicast", "cdpr_snapshot_count",
     "cdpr_ik", "cdpr_ik_device", "cdpr_rollout",
     "cdpr_padded_instances", "cdpr_device_platform_state",
     "cdpr_measure_fp64_tflops", "cdpr_last_kernel_ms", "cdpr_launch_count", "cdpr_kernel_variant",
@@ -111,6 +111,8 @@ def load():
     L.cdpr_get_state.argtypes = [vp, vp, C.c_size_t]
     L.cdpr_set_state.argtypes = [vp, vp, C.c_size_t]
     L.cdpr_set_snapshots.argtypes = [vp, i64, vp, i64]
+    L.cdpr_set_snapshot_peers.argtypes = [vp, i64, C.POINTER(vp), C.c_int, i64, i64, i64]
+    L.cdpr_set_snapshot_multicast.argtypes = [vp, i64, vp, i64, i64, i64]
     L.cdpr_snapshot_count.argtypes = [vp]; L.cdpr_snapshot_count.restype = i64
     L.cdpr_ik.argtypes = [vp, i64, vp, vp, vp, vp, vp]
     L.cdpr_ik_device.argtypes = [vp, i64, vp, vp]
@@ -271,6 +273,15 @@ class CdprBatch:
     # -- snapshots ---------------------------------------------------------------------------
     def set_snapshots(self, every: int, dev_ptr: int | None, capacity: int):
         self._ck(self._L.cdpr_set_snapshots(self._h, int(every), C.c_void_p(dev_ptr) if dev_ptr else None, int(capacity)))
+
+    def set_snapshot_peers(self, every: int, peer_ptrs, instance_offset: int, total_instances: int, capacity: int):
+        """Fused all-gather: snapshots go straight into every rank's gather buffer (NVLink-mapped pointers)."""
+        arr = (C.c_void_p * len(peer_ptrs))(*[int(p) for p in peer_ptrs])
+        self._ck(self._L.cdpr_set_snapshot_peers(self._h, int(every), arr, len(peer_ptrs), int(instance_offset), int(total_instances), int(capacity)))
+
+    def set_snapshot_multicast(self, every: int, multicast_ptr: int, instance_offset: int, total_instances: int, capacity: int):
+        """Fused all-gather through one NVLS multicast address (multimem.st)."""
+        self._ck(self._L.cdpr_set_snapshot_multicast(self._h, int(every), C.c_void_p(int(multicast_ptr)), int(instance_offset), int(total_instances), int(capacity)))
 
     @property
     def snapshot_count(self) -> int:

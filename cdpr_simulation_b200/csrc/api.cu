@@ -35,7 +35,10 @@ struct cdpr_batch {
   bool sine_on = false;
   int sine_period = 10;
   double sine_time = 0.0, sine_pub_dt = 0.01;
-  double *snap = nullptr;
+  double *snap_peers[8] = {nullptr};
+  int n_snap_peers = 0;
+  bool snap_multimem = false;
+  long long snap_stride = 0, snap_offset = 0;
   long long snap_every = 0, snap_written = 0, snap_capacity = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
@@ -506,7 +509,10 @@ static void fill_args(cdpr_handle h, StepArgs &A, int k_steps, bool sine) {
   A.mode = h->mode; A.k_steps = k_steps; A.n0 = h->step_count;
   A.sec0 = h->sec; A.nsec0 = h->nsec; A.dt_ns = h->dt_ns; A.t0 = time_double(h->sec, h->nsec);
   A.sine_on = sine ? 1 : 0; A.sine_period = h->sine_period; A.sine_time0 = h->sine_time; A.sine_pub_dt = h->sine_pub_dt;
-  A.snap = h->snap; A.snap_every = h->snap ? h->snap_every : 0; A.snap_written0 = h->snap_written; A.snap_capacity = h->snap_capacity;
+  for (int p = 0; p < 8; ++p) A.snap_peers[p] = h->snap_peers[p];
+  A.snap_multimem = (h->snap_multimem && !h->general) ? 1 : 0;
+  A.n_snap_peers = h->n_snap_peers; A.snap_stride = h->snap_stride; A.snap_offset = h->snap_offset;
+  A.snap_every = h->n_snap_peers > 0 ? h->snap_every : 0; A.snap_written0 = h->snap_written; A.snap_capacity = h->snap_capacity;
 }
 
 static int launch_step(cdpr_handle h, const StepArgs &A) {
@@ -548,7 +554,7 @@ static void advance_host_clock(cdpr_handle h, long long k, bool sine) {
     for (long long n = h->step_count + 1; n <= h->step_count + k; ++n)
       if ((n - 1) % h->sine_period == 0) h->sine_time = h->sine_time + h->sine_pub_dt;
   }
-  if (h->snap && h->snap_every > 0) h->snap_written += (h->step_count + k) / h->snap_every - h->step_count / h->snap_every;
+  if (h->n_snap_peers > 0 && h->snap_every > 0) h->snap_written += (h->step_count + k) / h->snap_every - h->step_count / h->snap_every;
   long long ns = (long long)h->nsec + (long long)h->dt_ns * k;
   h->sec += (int)(ns / 1000000000LL);
   h->nsec = (int)(ns % 1000000000LL);
@@ -735,11 +741,35 @@ extern "C" int cdpr_set_state(cdpr_handle h, const void *blob, size_t bytes) {
 // ---------------------------------------------------------------------------------------------
 // snapshots
 // ---------------------------------------------------------------------------------------------
-extern "C" int cdpr_set_snapshots(cdpr_handle h, int64_t every, void *dev_buf, int64_t capacity) {
-  if (!h || every < 0 || capacity < 0) return CDPR_ERR_BAD_ARG;
-  if (every == 0 || !dev_buf) { h->snap = nullptr; h->snap_every = 0; h->snap_written = 0; h->snap_capacity = 0; return CDPR_OK; }
-  h->snap = (double *)dev_buf; h->snap_every = every; h->snap_capacity = capacity; h->snap_written = 0;
+extern "C" int cdpr_set_snapshot_peers(cdpr_handle h, int64_t every, void *const *peer_bufs, int n_peers, int64_t instance_offset,
+                                       int64_t total_instances, int64_t capacity) {
+  if (!h || every < 0 || capacity < 0 || n_peers < 0 || n_peers > 8) return CDPR_ERR_BAD_ARG;
+  h->n_snap_peers = 0; h->snap_every = 0; h->snap_written = 0; h->snap_capacity = 0; h->snap_multimem = false;
+  if (every == 0 || n_peers == 0 || !peer_bufs) return CDPR_OK;
+  if (instance_offset < 0 || instance_offset + h->n > total_instances) return fail(h, CDPR_ERR_BAD_ARG, "instance range outside the gather buffer");
+  for (int p = 0; p < n_peers; ++p) {
+    if (!peer_bufs[p]) return fail(h, CDPR_ERR_BAD_ARG, "null peer buffer");
+    h->snap_peers[p] = (double *)peer_bufs[p];
+  }
+  h->n_snap_peers = n_peers; h->snap_stride = total_instances; h->snap_offset = instance_offset;
+  h->snap_every = every; h->snap_capacity = capacity;
   return CDPR_OK;
+}
+
+extern "C" int cdpr_set_snapshot_multicast(cdpr_handle h, int64_t every, void *multicast_buf, int64_t instance_offset,
+                                           int64_t total_instances, int64_t capacity) {
+  if (!h) return CDPR_ERR_BAD_ARG;
+  if (h->general) return fail(h, CDPR_ERR_UNSUPPORTED, "multicast snapshots need the fast kernel variant");
+  void *one[1] = {multicast_buf};
+  int rc = cdpr_set_snapshot_peers(h, multicast_buf ? every : 0, one, multicast_buf ? 1 : 0, instance_offset, total_instances, capacity);
+  if (rc == CDPR_OK && multicast_buf && every > 0) h->snap_multimem = true;
+  return rc;
+}
+
+extern "C" int cdpr_set_snapshots(cdpr_handle h, int64_t every, void *dev_buf, int64_t capacity) {
+  if (!h) return CDPR_ERR_BAD_ARG;
+  void *one[1] = {dev_buf};
+  return cdpr_set_snapshot_peers(h, dev_buf ? every : 0, one, dev_buf ? 1 : 0, 0, h->n, capacity);
 }
 extern "C" int64_t cdpr_snapshot_count(cdpr_handle h) { return h ? std::min(h->snap_written, h->snap_capacity) : -1; }
 
@@ -831,7 +861,7 @@ extern "C" int cdpr_rollout(cdpr_handle h, int64_t n_robots, int64_t n_seq, cons
   h->mode = MODE_VELOCITY;
   StepArgs A;
   fill_args(h, A, (int)(n_cmd * steps_per_cmd), false);
-  A.snap = nullptr; A.snap_every = 0;
+  A.n_snap_peers = 0; A.snap_every = 0;
   A.cmd_table = h->cmd_dev; A.n_seq = (int)n_seq; A.n_cmd = (int)n_cmd; A.steps_per_cmd = (int)steps_per_cmd;
   A.cost = h->cost_dev; A.target[0] = target_pos[0]; A.target[1] = target_pos[1]; A.target[2] = target_pos[2]; A.lambda = lambda;
   CK(h, cudaEventRecord(h->ev0, h->stream));
@@ -843,10 +873,10 @@ extern "C" int cdpr_rollout(cdpr_handle h, int64_t n_robots, int64_t n_seq, cons
   }
   CK(h, cudaEventRecord(h->ev1, h->stream));
   h->timed = true;
-  const bool snap_keep = h->snap != nullptr;
-  double *snap_saved = h->snap; h->snap = nullptr;
+  const int peers_saved = h->n_snap_peers;
+  h->n_snap_peers = 0;  // rollouts write no snapshots
   advance_host_clock(h, n_cmd * steps_per_cmd, false);
-  if (snap_keep) h->snap = snap_saved;
+  h->n_snap_peers = peers_saved;
   if (host_cost) {
     CK(h, cudaMemcpyAsync(host_cost, h->cost_dev, sizeof(double) * (size_t)h->n, cudaMemcpyDeviceToHost, h->stream));
     CK(h, cudaStreamSynchronize(h->stream));

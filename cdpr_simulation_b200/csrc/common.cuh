@@ -87,7 +87,12 @@ struct StepArgs {
   int sine_on, sine_period;
   double sine_time0, sine_pub_dt;
   // snapshots
-  double *snap;
+  // snapshots: every peer buffer is [capacity][13][snap_stride]; this handle's instances start at column snap_offset.
+  // One local buffer (stride n, offset 0), or the gather buffers of ALL ranks mapped over NVLink (fused all-gather).
+  double *snap_peers[8];
+  int n_snap_peers;
+  int snap_multimem;  // snap_peers[0] is an NVLS multicast address: one multimem.st reaches every rank's buffer
+  long long snap_stride, snap_offset;
   long long snap_every, snap_written0, snap_capacity;
   // rollout mode (cdpr_rollout)
   const float *cmd_table;  // [n_seq][n_cmd][NC]

@@ -58,6 +58,15 @@ __device__ __forceinline__ void store_plat(double *p, long long stride, const Fa
 //   SPEC_BZ0   every platform anchor has b_z == 0 (anchors in the platform's xy plane, cube.yaml:21-29)
 enum { SPEC_DIAG = 1, SPEC_ISO = 2, SPEC_BZ0 = 4 };
 
+// NVLS multicast store: one store, replicated by the NVSwitch into the mapped buffer of every rank
+__device__ __forceinline__ void mc_store(double *p, double v) { asm volatile("multimem.st.weak.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory"); }
+__device__ __forceinline__ void store_plat_multicast(double *p, long long stride, const FastState &S) {
+  mc_store(p, S.px); mc_store(p + stride, S.py); mc_store(p + 2 * stride, S.pz);
+  mc_store(p + 3 * stride, S.qw); mc_store(p + 4 * stride, S.qx); mc_store(p + 5 * stride, S.qy); mc_store(p + 6 * stride, S.qz);
+  mc_store(p + 7 * stride, S.vx); mc_store(p + 8 * stride, S.vy); mc_store(p + 9 * stride, S.vz);
+  mc_store(p + 10 * stride, S.wx); mc_store(p + 11 * stride, S.wy); mc_store(p + 12 * stride, S.wz);
+}
+
 // (fx..fz, mx..mz) = net force / torque about the COM in frame axes, gravity included
 template <int SPEC>
 __device__ __forceinline__ void rigid_body_step(const RobotConsts &rc, FastState &S, const Rot &R, double fx, double fy, double fz,

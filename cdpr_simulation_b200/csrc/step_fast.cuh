@@ -300,7 +300,13 @@ __global__ void __launch_bounds__(FastCfg<NC>::tpb, FastCfg<NC>::blocks) k_step_
     if (A.snap_every > 0) {
       if (++snap_ctr == A.snap_every) {
         snap_ctr = 0;
-        if (valid && snap_idx < A.snap_capacity) store_plat(A.snap + snap_idx * 13 * (long long)A.L.n + i, A.L.n, S);
+        if (valid && snap_idx < A.snap_capacity) {
+          const long long o = snap_idx * 13 * A.snap_stride + A.snap_offset + i;
+          if (A.snap_multimem) store_plat_multicast(A.snap_peers[0] + o, A.snap_stride, S);
+          else
+            for (int p = 0; p < A.n_snap_peers; ++p)  // plain stores; peer buffers are NVLink-mapped device memory
+              store_plat(A.snap_peers[p] + o, A.snap_stride, S);
+        }
         ++snap_idx;
       }
     }

@@ -222,7 +222,8 @@ __global__ void __launch_bounds__(kTpb) k_step_general(const __grid_constant__ S
     if (A.snap_every > 0) {
       if (++snap_ctr == A.snap_every) {
         snap_ctr = 0;
-        if (snap_idx < A.snap_capacity) store_plat(A.snap + snap_idx * 13 * (long long)L.n + i, L.n, S);
+        if (snap_idx < A.snap_capacity)
+          for (int p = 0; p < A.n_snap_peers; ++p) store_plat(A.snap_peers[p] + snap_idx * 13 * A.snap_stride + A.snap_offset + i, A.snap_stride, S);
         ++snap_idx;
       }
     }

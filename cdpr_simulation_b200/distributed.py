@@ -84,4 +84,66 @@ class TrajectoryGather:
         self.stream.wait_stream(self.comm)
 
 
-__all__ = ["shard_range", "gather_trajectory", "allreduce_cost", "global_trajectory_to_instance_major", "TrajectoryGather", "world"]
+class FusedTrajectoryGather:
+    """The trajectory all-gather fused into the step kernel over NVLink peer memory (no collective call).
+
+    Every rank allocates the FULL gather buffer [n_snap][13][N_total] in symmetric memory (double-buffered) and maps
+    all peers' buffers (torch.distributed._symmetric_memory rendezvous). The step kernel stores each snapshot of its
+    own instances into column range [rank*n, (rank+1)*n) of EVERY rank's buffer with plain stores -- the transfer
+    rides along with the compute, snapshot by snapshot. after_pass() enqueues a cross-rank barrier on the compute
+    stream: once it passes, every peer's kernel has finished, so this rank's buffer holds the whole trajectory in
+    global instance order."""
+
+    def __init__(self, batch, every: int, steps_per_pass: int, stream: torch.cuda.Stream, multicast: bool = True):
+        import torch.distributed._symmetric_memory as symm
+        self.batch, self.every, self.stream = batch, int(every), stream
+        self.n_snap = steps_per_pass // self.every
+        self.rank, self.ws = world()
+        if self.ws > 8:
+            raise RuntimeError("cdpr_set_snapshot_peers takes at most 8 peers")
+        dev = torch.device("cuda", batch.device)
+        self.total = batch.n * self.ws
+        self.bufs, self.hdls = [], []
+        for _ in range(2):
+            t = symm.empty((self.n_snap, 13, self.total), dtype=torch.float64, device=dev)
+            self.bufs.append(t)
+            self.hdls.append(symm.rendezvous(t, dist.group.WORLD))
+        # NVLS: one multimem.st per value instead of one store per rank, when the switch supports it
+        self.multicast = bool(multicast) and all(getattr(h, "has_multicast_support", False) and int(h.multicast_ptr) != 0 for h in self.hdls)
+        self.i = 0
+
+    def before_pass(self):
+        slot = self.i % 2
+        if self.multicast:
+            self.batch.set_snapshot_multicast(self.every, int(self.hdls[slot].multicast_ptr), self.rank * self.batch.n, self.total, self.n_snap)
+            return
+        self.batch.set_snapshot_peers(self.every, [int(p) for p in self.hdls[slot].buffer_ptrs], self.rank * self.batch.n, self.total, self.n_snap)
+
+    def after_pass(self):
+        slot = self.i % 2
+        with torch.cuda.stream(self.stream):
+            self.hdls[slot].barrier(channel=slot)
+        self.i += 1
+
+    def finish(self):
+        pass
+
+    def latest(self) -> torch.Tensor:
+        """[n_snap][13][N_total] of the last completed pass (valid after the stream reached its barrier)."""
+        return self.bufs[(self.i - 1) % 2]
+
+
+def make_trajectory_gather(batch, every, steps_per_pass, stream, prefer_fused: bool = True):
+    """Fused peer-memory gather when symmetric memory is available on this box, else NCCL all-gather on a side stream."""
+    if prefer_fused:
+        try:
+            g = FusedTrajectoryGather(batch, every, steps_per_pass, stream)
+            how = "one NVLS multimem.st per value" if g.multicast else "one NVLink peer store per rank and value"
+            return g, f"fused: step kernel stores snapshots into every rank's symmetric-memory buffer ({how})"
+        except Exception as e:  # no symmetric memory / no P2P on this box
+            reason = f"{type(e).__name__}: {e}"
+            return TrajectoryGather(batch, every, steps_per_pass, stream), f"NCCL all-gather on a side stream (fused path unavailable: {reason[:120]})"
+    return TrajectoryGather(batch, every, steps_per_pass, stream), "NCCL all-gather on a side stream"
+
+
+__all__ = ["FusedTrajectoryGather", "make_trajectory_gather", "shard_range", "gather_trajectory", "allreduce_cost", "global_trajectory_to_instance_major", "TrajectoryGather", "world"]

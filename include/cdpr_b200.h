@@ -16,6 +16,9 @@
  *   Cable index c is the numeric suffix of the reference joint name "cable<c>"
  *   (CdprGazeboPlugin.cpp:150-157); instance index i is the caller's, never permuted.
  *
+ * Device buffers handed to the library must be ready when the call is made (or the handle must share the producer's
+ * stream, cdpr_set_stream): the handle's own stream does not synchronise with the legacy default stream.
+ *
  * Every function returns CDPR_OK (0) or a negative error code and never throws.
  * A handle is not thread-safe; distinct handles are independent (no globals).
  * There is NO CPU fallback: cdpr_create fails with CDPR_ERR_NO_DEVICE without a CUDA device.
@@ -137,6 +140,16 @@ int cdpr_set_state(cdpr_handle h, const void *blob, size_t bytes);
  * laid out [capacity][13][n_instances] = px py pz qw qx qy qz vx vy vz wx wy wz; the write index
  * restarts at 0 on every call of this function. every == 0 disables. */
 int cdpr_set_snapshots(cdpr_handle h, int64_t every, void *dev_buf, int64_t capacity);
+/* Fused all-gather: the same snapshots, written by the step kernel into the gather buffer of EVERY rank. peer_bufs[p]
+ * (p < n_peers <= 8) is rank p's buffer [capacity][13][total_instances] as mapped into this process (NVLink peer /
+ * symmetric memory); this handle's instances occupy columns [instance_offset, instance_offset + N). After the step
+ * and a cross-rank barrier every buffer holds the whole trajectory in global instance order -- no collective call. */
+int cdpr_set_snapshot_peers(cdpr_handle h, int64_t every, void *const *peer_bufs, int n_peers, int64_t instance_offset,
+                            int64_t total_instances, int64_t capacity);
+/* Same, through ONE NVLS multicast address covering all ranks' buffers: each snapshot value is a single
+ * multimem.st that the NVSwitch replicates to every rank (fast kernel variant only). */
+int cdpr_set_snapshot_multicast(cdpr_handle h, int64_t every, void *multicast_buf, int64_t instance_offset,
+                                int64_t total_instances, int64_t capacity);
 int64_t cdpr_snapshot_count(cdpr_handle h);
 
 /* ---- kinematics only (Joint::Position/GetVelocity read-backs + the wrench Jacobian) ------- */

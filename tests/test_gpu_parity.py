@@ -214,6 +214,7 @@ def test_snapshots_match_stepwise_states(built_lib):
     n, every, k = 190, 25, 200
     _, a, _ = make_pair(4, n)
     buf = torch.zeros((k // every, 13, n), dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()   # the handle runs on its own stream: buffers handed to it must be ready
     a.set_snapshots(every, buf.data_ptr(), buf.shape[0])
     a.step(k)
     a.synchronize()
@@ -254,6 +255,7 @@ def test_rollout_costs_match_oracle(built_lib):
     target, lam = np.array([0.0, 0.0, 0.31]), 0.1
     with cb.CdprBatch(cfg, n_robots * n_seq) as g:
         dev = torch.zeros(n_seq, dtype=torch.float64, device="cuda")
+        torch.cuda.synchronize()
         cost = g.rollout(n_robots, n_seq, cmds, spc, target, lam, pose7, twist6, dev_cost_seq=dev.data_ptr())
         g.synchronize()
         cost_seq = dev.cpu().numpy()
