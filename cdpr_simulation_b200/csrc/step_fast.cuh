@@ -32,7 +32,7 @@ namespace cdpr {
 
 constexpr int kResync = 64;
 #ifndef CDPR_NC4_BLOCKS
-#define CDPR_NC4_BLOCKS 4
+#define CDPR_NC4_BLOCKS 2
 #endif
 #ifndef CDPR_NC8_BLOCKS
 #define CDPR_NC8_BLOCKS 2
@@ -184,6 +184,16 @@ __device__ __forceinline__ void resync_moments(double (&mom)[NC][3], const doubl
   }
 }
 
+// rare path (every snap_every steps), kept out of line so the hot loop's register allocation does not see it
+__device__ __noinline__ void write_snapshot(const StepArgs &A, FastState S, long long o) {
+  if (A.snap_multimem) {
+    store_plat_multicast(A.snap_peers[0] + o, A.snap_stride, S);
+  } else {
+    for (int p = 0; p < A.n_snap_peers; ++p)  // plain stores; peer buffers are NVLink-mapped device memory
+      store_plat(A.snap_peers[p] + o, A.snap_stride, S);
+  }
+}
+
 // shared memory per block (doubles): ring [LEN][NC][tpb], targets [NC][tpb], feed-forward terms Kf*target [NC][tpb],
 // sine parameters [3][tpb]
 template <int NC, int LEN>
@@ -252,100 +262,120 @@ __global__ void __launch_bounds__(FastCfg<NC>::tpb, FastCfg<NC>::blocks) k_step_
   int resync_ctr = (int)(A.n0 % kResync);
   long long snap_idx = A.snap_written0;
   long long snap_ctr = A.snap_every > 0 ? (A.n0 % A.snap_every) : 0;
-  int s = 0;
-
-  // everything of a step except the force law / physics: clock, command sources
-  auto pre_step = [&](double &dt) {
+  // The K steps run as short inner loops between EVENTS, so the hot loop body holds nothing but the clock, the force
+  // law and the physics.  Events before a step: a new command (sine publisher, command table).  Events after a step:
+  // moment re-summation, snapshot.  All event schedules depend on the global step index only.
+  auto clock_tick = [&](double &dt) {
     // World::Step: simTime += dt, then the plugin callback
     nsec += A.dt_ns;
     if (nsec >= 1000000000) { nsec -= 1000000000; ++sec; }
     const double t = time_double(sec, nsec);
     dt = __dsub_rn(t, tprev);
     tprev = t;
-    if (A.sine_on) {  // sinevelocitytest.cpp:35-38,48: float32 axes, accumulated publisher time
-      if (sine_ctr == 0) {
-        const double amp = mysine[0], freq = mysine[kTpbL], phase = mysine[2 * kTpbL];
-        const double arg = __dadd_rn(__dmul_rn(__dmul_rn(__dmul_rn(sine_time, freq), 2.0), 3.14159265358979323846), phase);
-        const double vel = (double)(float)__dmul_rn(amp, sin(arg));
-#pragma unroll
-        for (int c = 0; c < NC; ++c) { mytgt[c * kTpbL] = vel; mytgt[(NC + c) * kTpbL] = A.live.kf * vel; }
-        sine_time = __dadd_rn(sine_time, A.sine_pub_dt);
-      }
-      sine_ctr = (sine_ctr + 1 == A.sine_period) ? 0 : sine_ctr + 1;
-    }
-    if (cmd_row) {
-      if (cmd_ctr == 0 && cmd_idx < A.n_cmd) {
-#pragma unroll
-        for (int c = 0; c < NC; ++c) {
-          const double v = (double)cmd_row[cmd_idx * NC + c];
-          mytgt[c * kTpbL] = v; mytgt[(NC + c) * kTpbL] = A.live.kf * v;
-        }
-        ++cmd_idx;
-      }
-      cmd_ctr = (cmd_ctr + 1 == A.steps_per_cmd) ? 0 : cmd_ctr + 1;
-    }
     head = (head + 1 == LEN) ? 0 : head + 1;
   };
-  auto post_step = [&]() {
-    if (DMOM && PIDMODE) {
-      if (++resync_ctr == kResync) {
-        resync_ctr = 0;
-        resync_moments<NC, LEN>(mom, mywin, head);
-      }
+  auto events_before = [&]() {
+    if (A.sine_on && sine_ctr == 0) {  // sinevelocitytest.cpp:35-38,48: float32 axes, accumulated publisher time
+      const double amp = mysine[0], freq = mysine[kTpbL], phase = mysine[2 * kTpbL];
+      const double arg = __dadd_rn(__dmul_rn(__dmul_rn(__dmul_rn(sine_time, freq), 2.0), 3.14159265358979323846), phase);
+      const double vel = (double)(float)__dmul_rn(amp, sin(arg));
+#pragma unroll
+      for (int c = 0; c < NC; ++c) { mytgt[c * kTpbL] = vel; mytgt[(NC + c) * kTpbL] = A.live.kf * vel; }
+      sine_time = __dadd_rn(sine_time, A.sine_pub_dt);
     }
-    if (A.cost) {
-      const double ex = S.px - A.target[0], ey = S.py - A.target[1], ez = S.pz - A.target[2];
-      cost += fma(ex, ex, fma(ey, ey, ez * ez)) + A.lambda * fma(S.wx, S.wx, fma(S.wy, S.wy, S.wz * S.wz));
-    }
-    if (A.snap_every > 0) {
-      if (++snap_ctr == A.snap_every) {
-        snap_ctr = 0;
-        if (valid && snap_idx < A.snap_capacity) {
-          const long long o = snap_idx * 13 * A.snap_stride + A.snap_offset + i;
-          if (A.snap_multimem) store_plat_multicast(A.snap_peers[0] + o, A.snap_stride, S);
-          else
-            for (int p = 0; p < A.n_snap_peers; ++p)  // plain stores; peer buffers are NVLink-mapped device memory
-              store_plat(A.snap_peers[p] + o, A.snap_stride, S);
-        }
-        ++snap_idx;
+    if (cmd_row && cmd_ctr == 0 && cmd_idx < A.n_cmd) {
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        const double v = (double)cmd_row[cmd_idx * NC + c];
+        mytgt[c * kTpbL] = v; mytgt[(NC + c) * kTpbL] = A.live.kf * v;
       }
+      ++cmd_idx;
     }
   };
-
-  // phase 1 (at most LEN + 1 steps after a Pid reset): some live Pid of the warp is un-primed or its window is not full
-  for (; s + 1 < A.k_steps && !warp_steady; ++s) {
-    double dt;
-    pre_step(dt);
-    fast_step<NC, LEN, false, false, MODE, DMOM, SPEC>(A, S, ierr, mytgt, mom, primed, missing, mywin, head, dt, i);
-    bool st = true;
-#pragma unroll
-    for (int c = 0; c < NC; ++c) st = st && ((primed >> c) & 1u) && missing[c] == 0u;
-    warp_steady = __all_sync(0xffffffffu, st);
-    post_step();
-  }
-  if (warp_steady && PIDMODE) {  // the flags are constants from here on: keep them out of the hot loop's registers
-    primed = (1u << NC) - 1u;
-#pragma unroll
-    for (int c = 0; c < NC; ++c) missing[c] = 0u;
-  }
-  // phase 2: the hot loop
-  if (warp_steady) {
-    for (; s + 1 < A.k_steps; ++s) {
-      double dt;
-      pre_step(dt);
-      fast_step<NC, LEN, true, false, MODE, DMOM, SPEC>(A, S, ierr, mytgt, mom, primed, missing, mywin, head, dt, i);
-      post_step();
+  // how many steps may run before the next event of any kind (at least 1)
+  auto run_length = [&](int remaining) {
+    int run = remaining;
+    if (A.sine_on) run = min(run, A.sine_period - sine_ctr);
+    if (cmd_row) run = min(run, A.steps_per_cmd - cmd_ctr);
+    if (DMOM && PIDMODE) run = min(run, kResync - resync_ctr);
+    if (A.snap_every > 0) run = (int)min((long long)run, A.snap_every - snap_ctr);
+    return run;
+  };
+  auto advance_counters = [&](int run) {
+    if (A.sine_on) { sine_ctr += run; if (sine_ctr >= A.sine_period) sine_ctr = 0; }
+    if (cmd_row) { cmd_ctr += run; if (cmd_ctr >= A.steps_per_cmd) cmd_ctr = 0; }
+    if (DMOM && PIDMODE) resync_ctr += run;
+    if (A.snap_every > 0) snap_ctr += run;
+  };
+  auto events_after = [&]() {
+    if (DMOM && PIDMODE && resync_ctr >= kResync) {
+      resync_ctr = 0;
+      resync_moments<NC, LEN>(mom, mywin, head);
     }
+    if (A.snap_every > 0 && snap_ctr >= A.snap_every) {
+      snap_ctr = 0;
+      if (valid && snap_idx < A.snap_capacity) write_snapshot(A, S, snap_idx * 13 * A.snap_stride + A.snap_offset + i);
+      ++snap_idx;
+    }
+  };
+  auto add_cost = [&]() {
+    const double ex = S.px - A.target[0], ey = S.py - A.target[1], ez = S.pz - A.target[2];
+    cost += fma(ex, ex, fma(ey, ey, ez * ez)) + A.lambda * fma(S.wx, S.wx, fma(S.wy, S.wy, S.wz * S.wz));
+  };
+
+  int s = 0;
+  const int k_body = A.k_steps - 1;  // the last step runs separately (it also publishes telemetry)
+  while (s < k_body) {
+    events_before();
+    if (!warp_steady) {
+      // warm-up (at most LEN + 1 steps after a Pid reset): some live Pid of the warp is un-primed or its window is not full
+      double dt;
+      clock_tick(dt);
+      fast_step<NC, LEN, false, false, MODE, DMOM, SPEC>(A, S, ierr, mytgt, mom, primed, missing, mywin, head, dt, i);
+      if (A.cost) add_cost();
+      bool st = true;
+#pragma unroll
+      for (int c = 0; c < NC; ++c) st = st && ((primed >> c) & 1u) && missing[c] == 0u;
+      warp_steady = __all_sync(0xffffffffu, st);
+      if (warp_steady && PIDMODE) {  // the flags are constants from here on: keep them out of the hot loop's registers
+        primed = (1u << NC) - 1u;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) missing[c] = 0u;
+      }
+      advance_counters(1);
+      ++s;
+    } else {
+      const int run = run_length(k_body - s);
+      if (A.cost) {
+        for (int r = 0; r < run; ++r) {
+          double dt;
+          clock_tick(dt);
+          fast_step<NC, LEN, true, false, MODE, DMOM, SPEC>(A, S, ierr, mytgt, mom, primed, missing, mywin, head, dt, i);
+          add_cost();
+        }
+      } else {
+        for (int r = 0; r < run; ++r) {  // the hot loop
+          double dt;
+          clock_tick(dt);
+          fast_step<NC, LEN, true, false, MODE, DMOM, SPEC>(A, S, ierr, mytgt, mom, primed, missing, mywin, head, dt, i);
+        }
+      }
+      advance_counters(run);
+      s += run;
+    }
+    events_after();
   }
-  // last step of the launch: also publishes the effort / Pid telemetry columns
-  if (s < A.k_steps) {
+  if (A.k_steps > 0) {  // last step of the launch
+    events_before();
     double dt;
-    pre_step(dt);
+    clock_tick(dt);
     if (valid) {
       if (warp_steady) fast_step<NC, LEN, true, true, MODE, DMOM, SPEC>(A, S, ierr, mytgt, mom, primed, missing, mywin, head, dt, i);
       else fast_step<NC, LEN, false, true, MODE, DMOM, SPEC>(A, S, ierr, mytgt, mom, primed, missing, mywin, head, dt, i);
     }
-    post_step();
+    if (A.cost) add_cost();
+    advance_counters(1);
+    events_after();
   }
 
   if (!valid) return;
