@@ -412,3 +412,25 @@ def test_robot_constant_specialisations(built_lib, nc, edit):
     pg, tg = gpu.platform_state(); po, to = orc.platform_state()
     assert state_rel_err(pg, tg, po, to) < 1e-8
     gpu.close()
+
+
+@pytest.mark.parametrize("nc", [4, 8])
+@pytest.mark.parametrize("n", [65536, (1 << 19) + 77])
+def test_ik_device_soa(built_lib, nc, n):
+    """The device (SoA) kinematics sweep at config-2 size and at a ragged large size."""
+    import torch
+    cfg = cb.default_config(nc)
+    pose7, twist6 = wl.c2_poses(n, seed=0)
+    st = np.ascontiguousarray(np.concatenate([pose7[:, :3], pose7[:, 6:7], pose7[:, 3:6], twist6], axis=1).T)
+    d_in = torch.from_numpy(st).cuda(); d_out = torch.empty((nc, 8, n), dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    with cb.CdprBatch(cfg, 1) as g:
+        g.ik_device(n, d_in.data_ptr(), d_out.data_ptr()); g.synchronize()
+    out = d_out.cpu().numpy()
+    sub = slice(0, 20000)
+    oln, olr, ow = ob.ik(to_oracle_config(cfg), pose7[sub], twist6[sub])
+    assert np.max(np.abs(out[:, 0, sub].T - oln) / oln) < 1e-14 and np.max(np.abs(out[:, 1, sub].T - olr)) < 1e-14
+    assert np.max(np.abs(np.transpose(out[:, 2:8, sub], (2, 0, 1)) - ow)) < 1e-14
+    tail = slice(n - 500, n)
+    oln, _, _ = ob.ik(to_oracle_config(cfg), pose7[tail], twist6[tail])
+    assert np.max(np.abs(out[:, 0, tail].T - oln) / oln) < 1e-14
