@@ -60,7 +60,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -291,10 +291,19 @@ def own_arm(args):
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         hbm_bytes = state_bytes_per_instance(nc) * float(n)
+        traffic, traffic_src = None, None
+        try:   # DRAM bytes of this kernel from the committed `ncu --set full` capture of the same launch shape
+            prof = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_summary.json")))[f"step_fast_nc{nc}"]
+            if n == (1 << 20) and k_sim == 1000:
+                scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+                traffic = sum(float(prof[m]["value"]) * scale[prof[m]["unit"]] for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+                traffic_src = "profiles/r1_ncu_summary.json (ncu --set full, one launch of 2^20 instances x 1000 steps)"
+        except Exception:
+            pass
         roofline = {
             "bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak if fp64_peak > 0 else None,
-            "traffic": None,
-            "kernel": f"k_step_fast<{nc},11>", "kernel_ms": kms,
+            "traffic": traffic, "traffic_unit": "bytes per launch", "traffic_source": traffic_src, "algorithmic_bytes_per_launch": hbm_bytes,
+            "kernel": f"k_step_fast<{nc},11,VELOCITY,moments,spec>", "kernel_ms": kms,
             "flops_per_instance_step": flops_per_instance_step(nc),
             "flops_note": "count for this robot (isotropic inertia, anchors in the platform plane: 115 + 92 NC); a general robot is 244 + 98 NC",
             "peak_source": "DFMA issue rate measured in this run by cdpr_measure_fp64_tflops (MEASURED_PEAKS.json has no FP64 entry; "
