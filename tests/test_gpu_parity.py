@@ -434,3 +434,50 @@ def test_ik_device_soa(built_lib, nc, n):
     tail = slice(n - 500, n)
     oln, _, _ = ob.ik(to_oracle_config(cfg), pose7[tail], twist6[tail])
     assert np.max(np.abs(out[:, 0, tail].T - oln) / oln) < 1e-14
+
+
+def test_api_edge_cases(built_lib):
+    import torch
+    n = 50
+    cfg, g, _ = make_pair(4, n)
+    g.step(0)
+    assert g.step_count == 0
+    with pytest.raises(cb.CdprError):
+        g.step(-1)
+    # snapshot buffer smaller than the number of snapshots produced: the first `capacity` are written, the rest dropped
+    buf = torch.full((2, 13, n), -7.0, dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    g.set_snapshots(10, buf.data_ptr(), 2)
+    g.step(55); g.synchronize()
+    assert g.snapshot_count == 2 and not bool((buf == -7.0).any())
+    # a checkpoint of another shape is refused and leaves the state alone
+    other = cb.CdprBatch(cfg, n + 1)
+    before = g.platform_state()
+    with pytest.raises(cb.CdprError):
+        g.set_state(other.get_state())
+    after = g.platform_state()
+    assert np.array_equal(before[0], after[0])
+    other.close(); g.close()
+
+
+def test_async_mode_and_external_stream_match_sync(built_lib):
+    import torch
+    n = 300
+    amp, freq, phase, pose7, twist6 = wl.c3_instances(n, 4)
+    cfg = cb.default_config(8)
+    with cb.CdprBatch(cfg, n) as a:
+        a.set_platform_state(pose7, twist6); a.set_sine_cmd(amp, freq, phase); a.step(77)
+        ref = a.platform_state(); refj = a.joint_states()
+    s = torch.cuda.Stream()
+    pin = lambda x: torch.from_numpy(np.ascontiguousarray(x)).pin_memory()
+    p_in = [pin(x) for x in (pose7, twist6, amp, freq, phase)]
+    outs = [torch.empty(sh, dtype=torch.float64).pin_memory() for sh in ((n, 7), (n, 6), (n, 8), (n, 8), (n, 8))]
+    with cb.CdprBatch(cfg, n) as b:
+        b.set_stream(s.cuda_stream); b.set_async(True)
+        b.set_platform_state(p_in[0].numpy(), p_in[1].numpy()); b.set_sine_cmd(p_in[2].numpy(), p_in[3].numpy(), p_in[4].numpy())
+        b.step(77)
+        b.platform_state((outs[0].numpy(), outs[1].numpy())); b.joint_states(tuple(o.numpy() for o in outs[2:]))
+        b.synchronize()
+    assert np.array_equal(outs[0].numpy(), ref[0]) and np.array_equal(outs[1].numpy(), ref[1])
+    for o, r in zip(outs[2:], refj):
+        assert np.array_equal(o.numpy(), r)
