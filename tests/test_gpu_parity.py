@@ -481,3 +481,27 @@ def test_async_mode_and_external_stream_match_sync(built_lib):
     assert np.array_equal(outs[0].numpy(), ref[0]) and np.array_equal(outs[1].numpy(), ref[1])
     for o, r in zip(outs[2:], refj):
         assert np.array_equal(o.numpy(), r)
+
+
+@pytest.mark.skipif(not ob.ref_available(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("nc", [4, 8])
+def test_gpu_against_the_references_own_force_law(built_lib, nc):
+    """CUDA path vs the reduced model driven by the REFERENCE's compiled Pid.cpp / JointForceCalculator.cpp (oracle L0).
+    The only difference allowed is the reference's own D-term conditioning noise (absolute-time normal equations,
+    SURVEY.md F5): ~1e-7 on the pose after 1.5 s, against 1e-14 when the same fit is done in window-relative time."""
+    n = 48
+    cfg = cb.default_config(nc)
+    amp, freq, phase, pose7, twist6 = wl.c3_instances(n, 23)
+    with cb.CdprBatch(cfg, n) as g:
+        g.set_platform_state(pose7, twist6); g.set_sine_cmd(amp, freq, phase)
+        g.step(1500)
+        pg, tg = g.platform_state()
+        _, _, eg = g.joint_states()
+    o = ob.Batch(to_oracle_config(cfg), n, pose7, twist6, amp, freq, phase)
+    o.step_reference_forcelaw(1500)
+    po, to = o.platform_state()
+    eo = o.last_outputs()[3]
+    assert np.max(np.abs(pg - po)) < 1e-6 and np.max(np.abs(tg - to)) < 1e-4
+    assert np.max(np.abs(eg - eo)) < 1e-2          # forces: the D gain multiplies the reference's derivative noise
+    # and it is NOT trivially satisfied: the platforms moved by centimetres
+    assert np.max(np.abs(pg[:, :3] - pose7[:, :3])) > 1e-2
