@@ -278,7 +278,7 @@ static int reset_to_load_state(cdpr_handle h) {
   const cdpr_config &c = h->cfg;
   k_init_state<<<grid_for(L.np, 256), 256, 0, h->stream>>>(L, h->rc, c.home_pos[0], c.home_pos[1], c.home_pos[2], c.home_quat[0],
                                                            c.home_quat[1], c.home_quat[2], c.home_quat[3],
-                                                           (unsigned)c.vel_pid.d_buffer_length, (unsigned)c.pos_pid.d_buffer_length);
+                                                           (unsigned)c.vel_pid.d_buffer_length, (unsigned)c.pos_pid.d_buffer_length, h->general ? 1 : 0);
   CK(h, cudaGetLastError());
   h->mode = MODE_POSITION;  // CdprGazeboPlugin.cpp:154
   h->vel_pending = h->pos_pending = false;
@@ -492,7 +492,7 @@ extern "C" int cdpr_set_sine_cmd(cdpr_handle h, const double *amp, const double 
 // ---------------------------------------------------------------------------------------------
 static int reset_pid(cdpr_handle h, int k) {
   const unsigned len = (unsigned)(k == PID_VEL ? h->cfg.vel_pid.d_buffer_length : h->cfg.pos_pid.d_buffer_length);
-  k_reset_pid<<<grid_for(h->L.np, 256), 256, 0, h->stream>>>(h->L, k, len);
+  k_reset_pid<<<grid_for(h->L.np, 256), 256, 0, h->stream>>>(h->L, k, len, h->general ? 1 : 0);
   CK(h, cudaGetLastError());
   ++h->launches;
   return CDPR_OK;

@@ -7,7 +7,8 @@
 //   pid   [NC][2][PID_F][Np]      last_time, p_err, i_err, d_err, cmd      (pid 0 = velocity, 1 = position)
 //   win_y [NC][2][LEN][Np]        D-term error window, logical order (oldest first) = Pid::mDbufferY
 //   mom   [NC][2][3][Np]          window moments S0 S1 S2 of the fast variant's D-term (see step_fast.cuh)
-//   win_x [NC][2][LEN][Np]        D-term time stamps = Pid::mDbufferX      (general variant only)
+//   win_x [NC][2][LEN][Np]        D-term time stamps = Pid::mDbufferX      (general variant only; there win_x/win_y are
+//                                 rings whose head lives in ctl, see step_general.cuh)
 //   filt  [NC][2][2][CASC][4][Np] biquad x1 x2 y1 y2 (P filter, D filter)  (general variant only)
 //   ctl   [NC][Np] uint32         bit0 vel.wasLast, bit1 pos.wasLast, bits8-15 vel.missing, 16-23 pos.missing
 //   sine  [3][Np]                 amp, freq, phase of the in-kernel sinevelocitytest generator

@@ -69,18 +69,20 @@ __global__ void __launch_bounds__(256) k_ik(const __grid_constant__ IkArgs A) {
 // state after CdprGazeboPlugin::Load: platform at home and at rest; every cable in Position mode,
 // target 0, both Pids reset (wasLast = false, missing = bufferLength); everything else is memset 0.
 __global__ void k_init_state(DevLayout L, RobotConsts rc, double hx, double hy, double hz, double qw, double qx, double qy, double qz,
-                             unsigned vel_len, unsigned pos_len) {
+                             unsigned vel_len, unsigned pos_len, int general) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= L.np) return;
   double *p = L.plat + i;
   p[0] = hx; p[L.np] = hy; p[2 * L.np] = hz;
   p[3 * L.np] = qw; p[4 * L.np] = qx; p[5 * L.np] = qy; p[6 * L.np] = qz;
   for (int k = 7; k < 13; ++k) p[k * L.np] = 0.0;
-  for (int c = 0; c < L.nc; ++c) L.ctl[(long long)c * L.np + i] = (vel_len << 8) | (pos_len << 16);
+  // control word: fast variant = wasLast bits 0-1, missing counters in bytes 1-2; general variant: see step_general.cuh
+  const unsigned ctl0 = general ? ((vel_len << 2) | (pos_len << 8)) : ((vel_len << 8) | (pos_len << 16));
+  for (int c = 0; c < L.nc; ++c) L.ctl[(long long)c * L.np + i] = ctl0;
 }
 
 // Pid::reset (Pid.cpp:100-115) for pid k of every cable of every instance; mLastTime is kept.
-__global__ void k_reset_pid(DevLayout L, int k, unsigned len_k) {
+__global__ void k_reset_pid(DevLayout L, int k, unsigned len_k, int general) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= L.np) return;
   for (int c = 0; c < L.nc; ++c) {
@@ -99,8 +101,13 @@ __global__ void k_reset_pid(DevLayout L, int k, unsigned len_k) {
         for (int s = 0; s < L.casc; ++s)
           for (int f = 0; f < 4; ++f) L.filt[filt_off(L, c, k, pd, s, f) + i] = 0.0;
     unsigned ctl = L.ctl[(long long)c * L.np + i];
-    ctl &= ~((1u << k) | (0xffu << (8 + 8 * k)));
-    ctl |= len_k << (8 + 8 * k);
+    if (general) {  // wasLast = false, missing = bufferLength, ring head = 0
+      ctl &= ~((1u << k) | (0x3fu << (2 + 6 * k)) | (0x1fu << (14 + 5 * k)));
+      ctl |= len_k << (2 + 6 * k);
+    } else {
+      ctl &= ~((1u << k) | (0xffu << (8 + 8 * k)));
+      ctl |= len_k << (8 + 8 * k);
+    }
     L.ctl[(long long)c * L.np + i] = ctl;
   }
 }

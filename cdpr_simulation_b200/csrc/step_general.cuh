@@ -6,7 +6,7 @@
 //
 // One thread per instance; the platform state lives in registers for the K steps, the per-cable
 // controller state is read-modify-written in HBM/L2 every step (coalesced: consecutive threads,
-// consecutive addresses).  This variant is HBM/L2-bound, not FP64-bound; the reference's launch
+// consecutive addresses); the D windows are rings there, so a push is one store and the fit one pass.  This variant is HBM/L2-bound, not FP64-bound; the reference's launch
 // configuration never needs it (see step_fast.cuh).
 #pragma once
 #include "common.cuh"
@@ -27,66 +27,106 @@ __device__ inline double cascade_update(const DevLayout &L, int c, int k, int pd
   return out;
 }
 
-// Pid::derive (Pid.cpp:193-217): shift the window, append, and once full return the derivative at
-// `now` of the least-squares polynomial through it.  The fit runs in window-relative, span-scaled
-// time (same polynomial as the reference's absolute-time fit, but well conditioned).
-__device__ inline double derive_general(const DevLayout &L, const PidConsts &pc, int c, int k, unsigned &missing, double value,
-                                        double now, long long i) {
-  const int len = pc.len;
-  double xs[kMaxDbuf], ys[kMaxDbuf];
-  for (int j = 1; j < len; ++j) {
-    xs[j - 1] = L.win_x[win_off(L, c, k, j) + i];
-    ys[j - 1] = L.win_y[win_off(L, c, k, j) + i];
-  }
-  xs[len - 1] = now;
-  ys[len - 1] = value;
+// Control word of the general variant, one per (instance, cable):
+//   bit 0 / 1      velocity / position Pid: mWasLastTime
+//   bits 2-7, 8-13 mDbufferMissing of the two Pids (0..32)
+//   bits 14-18, 19-23 ring head of the two Pids = slot of the OLDEST window sample = next slot to overwrite
+// The D windows of this variant are rings in HBM (no shifting through memory, Pid.cpp:194-199 restated).
+__host__ __device__ inline unsigned gctl_pack(unsigned vel_len, unsigned pos_len) { return (vel_len << 2) | (pos_len << 8); }
+__device__ __forceinline__ unsigned gctl_missing(unsigned ctl, int k) { return (ctl >> (2 + 6 * k)) & 0x3fu; }
+__device__ __forceinline__ unsigned gctl_head(unsigned ctl, int k) { return (ctl >> (14 + 5 * k)) & 0x1fu; }
+__device__ __forceinline__ unsigned gctl_set(unsigned ctl, int k, unsigned missing, unsigned head) {
+  ctl &= ~((0x3fu << (2 + 6 * k)) | (0x1fu << (14 + 5 * k)));
+  return ctl | (missing << (2 + 6 * k)) | (head << (14 + 5 * k));
+}
+
+// Derivative at `now` of the degree-D least-squares polynomial through the window (Pid.cpp:203-212 + 219-247), fitted
+// in window-relative, span-scaled time (same polynomial as the reference's absolute-time fit, but well conditioned):
+// one pass over the ring accumulates the normal equations, Gaussian elimination with partial pivoting solves them.
+template <int D>
+__device__ __forceinline__ double ls_derivative(const DevLayout &L, int c, int k, int len, unsigned oldest, double now, long long i) {
+  constexpr int M = D + 1;
+  const double span = now - L.win_x[win_off(L, c, k, (int)oldest) + i];
+  const double inv_span = 1.0 / span;
+  double sx[2 * D + 1], sy[M];
+#pragma unroll
+  for (int p = 0; p <= 2 * D; ++p) sx[p] = 0.0;
+#pragma unroll
+  for (int p = 0; p < M; ++p) sy[p] = 0.0;
+#pragma unroll 4
   for (int j = 0; j < len; ++j) {
-    L.win_x[win_off(L, c, k, j) + i] = xs[j];
-    L.win_y[win_off(L, c, k, j) + i] = ys[j];
-  }
-  missing -= (missing > 0u) ? 1u : 0u;
-  if (missing != 0u || pc.degree < 1) return 0.0;
-  const int m = pc.degree + 1;
-  const double span = now - xs[0];
-  double sx[2 * kMaxDegree + 1], M[kMaxDegree + 1][kMaxDegree + 2];
-  for (int p = 0; p <= 2 * pc.degree; ++p) sx[p] = 0.0;
-  for (int r = 0; r < m; ++r) M[r][m] = 0.0;
-  for (int j = 0; j < len; ++j) {
-    const double x = (xs[j] - now) / span;
+    const double x = (L.win_x[win_off(L, c, k, j) + i] - now) * inv_span;
+    const double y = L.win_y[win_off(L, c, k, j) + i];
     double pw = 1.0;
-    for (int p = 0; p <= 2 * pc.degree; ++p) {
+#pragma unroll
+    for (int p = 0; p <= 2 * D; ++p) {
       sx[p] += pw;
-      if (p < m) M[p][m] += pw * ys[j];
+      if (p < M) sy[p] = fma(pw, y, sy[p]);
       pw *= x;
     }
   }
-  for (int r = 0; r < m; ++r)
-    for (int q = 0; q < m; ++q) M[r][q] = sx[r + q];
-  // Gaussian elimination with partial pivoting on the (degree+1)^2 normal equations
-  for (int col = 0; col < m; ++col) {
-    int piv = col;
-    for (int r = col + 1; r < m; ++r)
-      if (fabs(M[r][col]) > fabs(M[piv][col])) piv = r;
-    if (M[piv][col] == 0.0) return 0.0;
-    if (piv != col)
-      for (int q = col; q <= m; ++q) { const double t = M[col][q]; M[col][q] = M[piv][q]; M[piv][q] = t; }
-    for (int r = col + 1; r < m; ++r) {
-      const double f = M[r][col] / M[col][col];
-      for (int q = col; q <= m; ++q) M[r][q] -= f * M[col][q];
+  double A[M][M + 1];
+#pragma unroll
+  for (int r = 0; r < M; ++r) {
+#pragma unroll
+    for (int q = 0; q < M; ++q) A[r][q] = sx[r + q];
+    A[r][M] = sy[r];
+  }
+#pragma unroll
+  for (int col = 0; col < M; ++col) {
+#pragma unroll
+    for (int r = col + 1; r < M; ++r) {  // partial pivoting by compare-and-swap keeps every index static
+      const bool sw = fabs(A[r][col]) > fabs(A[col][col]);
+#pragma unroll
+      for (int q = col; q <= M; ++q) {
+        const double a = A[col][q], b = A[r][q];
+        A[col][q] = sw ? b : a;
+        A[r][q] = sw ? a : b;
+      }
+    }
+    if (A[col][col] == 0.0) return 0.0;
+    const double inv = 1.0 / A[col][col];
+#pragma unroll
+    for (int r = col + 1; r < M; ++r) {
+      const double f = A[r][col] * inv;
+#pragma unroll
+      for (int q = col + 1; q <= M; ++q) A[r][q] = fma(-f, A[col][q], A[r][q]);
     }
   }
-  double coef[kMaxDegree + 1];
-  for (int r = m - 1; r >= 0; --r) {
-    double s = M[r][m];
-    for (int q = r + 1; q < m; ++q) s -= M[r][q] * coef[q];
-    coef[r] = s / M[r][r];
+  double coef[M];
+#pragma unroll
+  for (int r = M - 1; r >= 1; --r) {  // coef[0] is not needed
+    double s = A[r][M];
+#pragma unroll
+    for (int q = r + 1; q < M; ++q) s = fma(-A[r][q], coef[q], s);
+    coef[r] = s / A[r][r];
   }
-  return coef[1] / span;
+  return coef[1] * inv_span;
+}
+
+// Pid::derive (Pid.cpp:193-217): overwrite the oldest sample, then the fit once the window is full
+__device__ __forceinline__ double derive_general(const DevLayout &L, const PidConsts &pc, int c, int k, unsigned &ctl, double value,
+                                                 double now, long long i) {
+  const int len = pc.len;
+  unsigned head = gctl_head(ctl, k), missing = gctl_missing(ctl, k);
+  L.win_x[win_off(L, c, k, (int)head) + i] = now;
+  L.win_y[win_off(L, c, k, (int)head) + i] = value;
+  head = (head + 1u == (unsigned)len) ? 0u : head + 1u;
+  missing -= (missing > 0u) ? 1u : 0u;
+  ctl = gctl_set(ctl, k, missing, head);
+  if (missing != 0u) return 0.0;
+  switch (pc.degree) {
+    case 1: return ls_derivative<1>(L, c, k, len, head, now, i);
+    case 2: return ls_derivative<2>(L, c, k, len, head, now, i);
+    case 3: return ls_derivative<3>(L, c, k, len, head, now, i);
+    case 4: return ls_derivative<4>(L, c, k, len, head, now, i);
+    default: return 0.0;  // degree 0: derivative of a constant
+  }
 }
 
 // Pid::update (Pid.cpp:122-191) on the state columns of (cable c, pid k)
-__device__ inline double pid_update_general(const DevLayout &L, const PidConsts &pc, int c, int k, unsigned &ctl, double desired,
-                                            double actual, double now, long long i) {
+__device__ __forceinline__ double pid_update_general(const DevLayout &L, const PidConsts &pc, int c, int k, unsigned &ctl, double desired,
+                                                     double actual, double now, long long i) {
   double *last_time = L.pid + pid_off(L, c, k, PID_LAST_TIME) + i;
   double *cmdp = L.pid + pid_off(L, c, k, PID_CMD) + i;
   double cmd_out;
@@ -108,18 +148,19 @@ __device__ inline double pid_update_general(const DevLayout &L, const PidConsts 
     double i_term = pc.ki * ie;
     if (i_term > pc.i_max) { i_term = pc.i_max; ie = pc.i_max_over_ki; }
     else if (i_term < pc.i_min) { i_term = pc.i_min; ie = pc.i_min_over_ki; }
-    double de = *d_err;
+    double de;
     if (dt > 0.0) {
-      unsigned missing = (ctl >> (8 + 8 * k)) & 0xffu;
-      const double derived = derive_general(L, pc, c, k, missing, error, now, i);
-      ctl = (ctl & ~(0xffu << (8 + 8 * k))) | (missing << (8 + 8 * k));
+      const double derived = derive_general(L, pc, c, k, ctl, error, now, i);
       de = cascade_update(L, c, k, 1, pc.d_casc, pc.df, derived, i);
       *d_err = de;
+    } else {
+      de = *d_err;
     }
     const double d_term = pc.kd * de;
     const double cmd_raw = f_term + p_term + i_term + d_term;
-    double cmd = *cmdp;
+    double cmd;
     if (pc.cmd_max > pc.cmd_min) cmd = clampd(cmd_raw, pc.cmd_min, pc.cmd_max);
+    else cmd = *cmdp;  // cmdLimit == 0: mCmd keeps its previous value (Pid.cpp:175-179)
     if (cmd != cmd_raw) {
       ie = prev_ierr;
       cmd += dt * error * pc.ki;
@@ -132,7 +173,7 @@ __device__ inline double pid_update_general(const DevLayout &L, const PidConsts 
   return cmd_out;
 }
 
-__global__ void __launch_bounds__(kTpb) k_step_general(const __grid_constant__ StepArgs A) {
+__global__ void __launch_bounds__(kTpb, 4) k_step_general(const __grid_constant__ StepArgs A) {
   const long long i = (long long)blockIdx.x * kTpb + threadIdx.x;
   if (i >= A.L.n) return;
   const DevLayout &L = A.L;
@@ -177,15 +218,15 @@ __global__ void __launch_bounds__(kTpb) k_step_general(const __grid_constant__ S
     double fx = rc.mg[0], fy = rc.mg[1], fz = rc.mg[2], mx = 0.0, my = 0.0, mz = 0.0;
     for (int c = 0; c < nc; ++c) {
       const double bx = rc.b[c][0], by = rc.b[c][1], bz = rc.b[c][2];
-      const double rx = R.r00 * bx + R.r01 * by + R.r02 * bz;
-      const double ry = R.r10 * bx + R.r11 * by + R.r12 * bz;
-      const double rz = R.r20 * bx + R.r21 * by + R.r22 * bz;
-      const double dx = (rc.a[c][0] - S.px) - rx, dy = (rc.a[c][1] - S.py) - ry, dz = (rc.a[c][2] - S.pz) - rz;
-      const double len = sqrt(dx * dx + dy * dy + dz * dz);
-      const double ux = dx / len, uy = dy / len, uz = dz / len;
-      const double cx = ry * uz - rz * uy, cy = rz * ux - rx * uz, cz = rx * uy - ry * ux;
-      const double qd = ux * S.vx + uy * S.vy + uz * S.vz + cx * S.wx + cy * S.wy + cz * S.wz;
-      const double qp = rc.home_len[c] - len;
+      const double gx = rc.a[c][0] - S.px, gy = rc.a[c][1] - S.py, gz = rc.a[c][2] - S.pz;
+      const double dx = fma(-R.r00, bx, fma(-R.r01, by, fma(-R.r02, bz, gx)));
+      const double dy = fma(-R.r10, bx, fma(-R.r11, by, fma(-R.r12, bz, gy)));
+      const double dz = fma(-R.r20, bx, fma(-R.r21, by, fma(-R.r22, bz, gz)));
+      const double l2 = fma(dx, dx, fma(dy, dy, dz * dz));
+      const double il = rsqrt_nr(l2);
+      const double cx = fma(gy, dz, -(gz * dy)), cy = fma(gz, dx, -(gx * dz)), cz = fma(gx, dy, -(gy * dx));  // L (r x u), see step_fast.cuh
+      const double qd = (fma(dx, S.vx, fma(dy, S.vy, dz * S.vz)) + fma(cx, S.wx, fma(cy, S.wy, cz * S.wz))) * il;
+      const double qp = rc.home_len[c] - l2 * il;
 
       unsigned ctl = L.ctl[(long long)c * np + i];
       double *last_pos = L.cab + cab_off(L, c, CAB_LAST_POS) + i;
@@ -209,9 +250,9 @@ __global__ void __launch_bounds__(kTpb) k_step_general(const __grid_constant__ S
       const double eff = (rc.effort_limit >= 0.0) ? clampd(force, -rc.effort_limit, rc.effort_limit) : force;
       L.cab[cab_off(L, c, CAB_EFFORT) + i] = eff;
       L.cab[cab_off(L, c, CAB_PID_FORCE) + i] = force;
-      const double tau = eff - rc.cdamp * qd;
-      fx += tau * ux; fy += tau * uy; fz += tau * uz;
-      mx += tau * cx; my += tau * cy; mz += tau * cz;
+      const double tl = fma(-rc.cdamp, qd, eff) * il;  // tension / L
+      fx = fma(tl, dx, fx); fy = fma(tl, dy, fy); fz = fma(tl, dz, fz);
+      mx = fma(tl, cx, mx); my = fma(tl, cy, my); mz = fma(tl, cz, mz);
     }
     if (rc.diag_inertia) rigid_body_step<SPEC_DIAG>(rc, S, R, fx, fy, fz, mx, my, mz);
     else rigid_body_step<0>(rc, S, R, fx, fy, fz, mx, my, mz);
