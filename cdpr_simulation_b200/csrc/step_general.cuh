@@ -173,7 +173,10 @@ __device__ __forceinline__ double pid_update_general(const DevLayout &L, const P
   return cmd_out;
 }
 
-__global__ void __launch_bounds__(kTpb, 4) k_step_general(const __grid_constant__ StepArgs A) {
+#ifndef CDPR_GEN_BLOCKS
+#define CDPR_GEN_BLOCKS 8
+#endif
+__global__ void __launch_bounds__(kTpb, CDPR_GEN_BLOCKS) k_step_general(const __grid_constant__ StepArgs A) {
   const long long i = (long long)blockIdx.x * kTpb + threadIdx.x;
   if (i >= A.L.n) return;
   const DevLayout &L = A.L;
