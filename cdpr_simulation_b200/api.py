@@ -31,7 +31,7 @@ EXPORTS = [
     "cdpr_state_bytes", "cdpr_get_state", "cdpr_set_state",
     "cdpr_set_snapshots", "cdpr_set_snapshot_peers", "cdpr_set_snapshot_multicast", "cdpr_snapshot_count",
     "cdpr_ik", "cdpr_ik_device", "cdpr_rollout",
-    "cdpr_padded_instances", "cdpr_device_platform_state",
+    "cdpr_dterm_weights", "cdpr_padded_instances", "cdpr_device_platform_state",
     "cdpr_measure_fp64_tflops", "cdpr_last_kernel_ms", "cdpr_launch_count", "cdpr_kernel_variant",
 ]
 
@@ -117,6 +117,7 @@ def load():
     L.cdpr_ik.argtypes = [vp, i64, vp, vp, vp, vp, vp]
     L.cdpr_ik_device.argtypes = [vp, i64, vp, vp]
     L.cdpr_rollout.argtypes = [vp, i64, i64, vp, vp, vp, i64, i64, C.POINTER(dbl * 3), dbl, vp, vp]
+    L.cdpr_dterm_weights.argtypes = [C.POINTER(PidParams), dbl, vp, vp, C.POINTER(C.c_int)]
     L.cdpr_padded_instances.argtypes = [vp]; L.cdpr_padded_instances.restype = i64
     L.cdpr_device_platform_state.argtypes = [vp]; L.cdpr_device_platform_state.restype = vp
     L.cdpr_measure_fp64_tflops.argtypes = [C.c_int, C.c_int]; L.cdpr_measure_fp64_tflops.restype = dbl
@@ -330,6 +331,15 @@ class CdprBatch:
     @property
     def kernel_variant(self) -> str:
         return self._L.cdpr_kernel_variant(self._h).decode()
+
+
+def dterm_weights(pid: PidParams, dt: float):
+    """(fir[len], quadratic[3], is_quadratic) of the D-term for uniform time stamps; host only."""
+    fir = np.zeros(int(pid.d_buffer_length)); quad = np.zeros(3); flag = C.c_int(0)
+    rc = load().cdpr_dterm_weights(C.byref(pid), float(dt), _ptr(fir), _ptr(quad), C.byref(flag))
+    if rc != OK:
+        raise CdprError(rc, "cdpr_dterm_weights")
+    return fir, quad, bool(flag.value)
 
 
 def measure_fp64_tflops(device: int = 0, iters: int = 8192) -> float:

@@ -887,6 +887,20 @@ extern "C" int cdpr_rollout(cdpr_handle h, int64_t n_robots, int64_t n_seq, cons
 // ---------------------------------------------------------------------------------------------
 // raw device access, measurement helpers
 // ---------------------------------------------------------------------------------------------
+// Host-side constants of the D-term, computable without a device (used by the CPU tests)
+extern "C" int cdpr_dterm_weights(const cdpr_pid_params *pid, double dt, double *fir, double *quadratic, int *is_quadratic) {
+  if (!pid || !fir || pid->d_buffer_length < 2 || pid->d_buffer_length > CDPR_MAX_DBUF || pid->d_degree < 0 ||
+      pid->d_degree > CDPR_MAX_DEGREE || !(dt > 0.0))
+    return CDPR_ERR_BAD_ARG;
+  double w[kMaxDbuf], abc[3] = {0, 0, 0};
+  fir_weights(pid->d_degree, pid->d_buffer_length, dt, w);
+  for (int j = 0; j < pid->d_buffer_length; ++j) fir[j] = w[j];
+  const bool ok = fir_as_quadratic(w, pid->d_buffer_length, abc);
+  if (quadratic) for (int q = 0; q < 3; ++q) quadratic[q] = abc[q];
+  if (is_quadratic) *is_quadratic = ok ? 1 : 0;
+  return CDPR_OK;
+}
+
 extern "C" int64_t cdpr_padded_instances(cdpr_handle h) { return h ? h->np : -1; }
 extern "C" void *cdpr_device_platform_state(cdpr_handle h) { return h ? h->L.plat : nullptr; }
 extern "C" int64_t cdpr_launch_count(cdpr_handle h) { return h ? h->launches : -1; }

@@ -169,6 +169,12 @@ int cdpr_rollout(cdpr_handle h, int64_t n_robots, int64_t n_seq, const double *p
                  const float *cmds, int64_t n_cmd, int64_t steps_per_cmd, const double target_pos[3], double lambda,
                  void *dev_cost_seq, double *host_cost /* [N] or NULL */);
 
+/* ---- D-term constants (host only, no device needed) ---------------------------------------- */
+/* With uniform time stamps Pid::derive (Pid.cpp:193-247) is a fixed FIR: derivative = sum_j fir[j] * y[j], j = 0
+ * oldest. fir: [d_buffer_length]. quadratic[3] (may be NULL): fir[j] = q0 + q1 p + q2 p^2 with p = j + 1, valid when
+ * *is_quadratic = 1 (degree <= 2): the coefficients of the sliding-moment form used by the step kernel. */
+int cdpr_dterm_weights(const cdpr_pid_params *pid, double dt, double *fir, double *quadratic, int *is_quadratic);
+
 /* ---- raw device access for zero-copy callers (torch.distributed gathers) ----------------- */
 int64_t cdpr_padded_instances(cdpr_handle h);
 void *cdpr_device_platform_state(cdpr_handle h); /* [13][padded] float64, same order as snapshots */

@@ -63,3 +63,34 @@ def test_eight_cable_description(built_lib):
     desc["points"] = desc["points"] + [{"frame": [p["frame"][0], p["frame"][1], 0.0], "platform": p["platform"]} for p in desc["points"]]
     cfg = model.config_from_description(desc, home_xyz=[0, 0, 0.3])
     assert bytes(cfg) == bytes(cb.default_config(8))                # SURVEY.md App. A.2 synthetic extension
+
+
+def test_dterm_fir_weights_against_numpy_least_squares(built_lib):
+    """Host logic of the step kernel's D-term: the FIR weights equal the derivative-at-the-end row of the least-squares
+    polynomial fit (numpy), for every degree / window length; for degree <= 2 they are an exact quadratic in the sample
+    position (the sliding-moment form); the reference's launch values give the classic 11-point end-point weights."""
+    import cdpr_simulation_b200 as cb
+    cfg = cb.default_config(4)
+    dt = 0.001
+    for deg, ln in [(1, 2), (1, 5), (2, 11), (2, 3), (3, 9), (4, 32), (2, 20), (0, 4)]:
+        pid = cb.PidParams.from_buffer_copy(bytes(cfg.vel_pid))
+        pid.d_degree, pid.d_buffer_length = deg, ln
+        fir, quad, is_quad = cb.dterm_weights(pid, dt)
+        t = (np.arange(ln) - (ln - 1)) * dt                       # window-relative times, newest = 0
+        if deg == 0:
+            assert np.all(fir == 0)
+            continue
+        V = np.vander(t / (dt * (ln - 1)), deg + 1, increasing=True)
+        row = np.linalg.pinv(V)[1] / (dt * (ln - 1))              # d/dt of the fitted polynomial at t = 0
+        assert np.max(np.abs(fir - row)) < 1e-9 * np.max(np.abs(row)), (deg, ln)
+        assert abs(fir.sum()) < 1e-9 * np.abs(fir).sum()          # a constant signal has zero derivative
+        assert abs(fir @ t - 1.0) < 1e-10                         # a unit ramp has derivative 1
+        assert is_quad == (deg <= 2)
+        if is_quad:
+            p = np.arange(1, ln + 1)
+            assert np.max(np.abs(quad[0] + quad[1] * p + quad[2] * p * p - fir)) < 1e-12 * np.max(np.abs(fir))
+    pid = cb.PidParams.from_buffer_copy(bytes(cfg.vel_pid))
+    fir, _, _ = cb.dterm_weights(pid, dt)
+    # 11-point quadratic fit, derivative at the last point: closed form (3 j^2 ... ) / h -- check two known entries
+    ref = np.linalg.pinv(np.vander(np.arange(-10.0, 1.0), 3, increasing=True))[1] / dt
+    assert np.allclose(fir, ref, rtol=1e-10)
