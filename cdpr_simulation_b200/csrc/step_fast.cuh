@@ -107,11 +107,12 @@ __device__ __forceinline__ void fast_step(const StepArgs &A, FastState &S, doubl
           const double y_old = w[slot[0]];
           w[slot[0]] = e;
           const double s0 = mom[c][0], s1 = mom[c][1], s2 = mom[c][2];
-          const double n0 = (s0 - y_old) + e;
+          // y_old (a shared-memory read) enters last, so its latency hides behind the rest of the chain
           const double n1 = fma((double)LEN, e, s1 - s0);
           const double n2 = fma((double)(LEN * LEN), e, fma(-2.0, s1, s2) + s0);
+          const double n0 = (s0 + e) - y_old;
           mom[c][0] = n0; mom[c][1] = n1; mom[c][2] = n2;
-          derr = fma(A.dmom[2], n2, fma(A.dmom[1], n1, A.dmom[0] * n0));
+          derr = fma(A.dmom[0], n0, fma(A.dmom[1], n1, A.dmom[2] * n2));
         } else {
           w[slot[0]] = e;
           double d0 = A.fir[LEN - 1] * e, d1 = 0.0;
