@@ -45,6 +45,7 @@ struct cdpr_batch {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool timed = false;
   bool async_copies = false;  // host-buffer calls only enqueue; the caller synchronises (pinned buffers)
+  bool targets_uniform = false;  // all cables of an instance hold the same velocity target (zeros after Load, or written by the sine publisher)
   long long launches = 0;
   void *stage = nullptr;
   size_t stage_bytes = 0;
@@ -285,6 +286,7 @@ static int reset_to_load_state(cdpr_handle h) {
   h->sec = h->nsec = 0;
   h->step_count = 0;
   h->sine_time = 0.0;
+  h->targets_uniform = true;
   return CDPR_OK;
 }
 
@@ -370,7 +372,8 @@ extern "C" int cdpr_create(const cdpr_config *cfg, int64_t n_instances, int devi
     CDPR_PREP1(NC_, SM_, 0); CDPR_PREP1(NC_, SM_, SPEC_DIAG);                                                            \
     prep((const void *)k_step_fast<NC_, 11, MODE_VELOCITY, true, SPEC_DIAG | SPEC_BZ0>, SM_);                            \
     prep((const void *)k_step_fast<NC_, 11, MODE_VELOCITY, true, SPEC_DIAG | SPEC_ISO>, SM_);                            \
-    prep((const void *)k_step_fast<NC_, 11, MODE_VELOCITY, true, SPEC_DIAG | SPEC_ISO | SPEC_BZ0>, SM_)
+    prep((const void *)k_step_fast<NC_, 11, MODE_VELOCITY, true, SPEC_DIAG | SPEC_ISO | SPEC_BZ0>, SM_);                  \
+    prep((const void *)k_step_fast<NC_, 11, MODE_VELOCITY, true, SPEC_DIAG | SPEC_ISO | SPEC_BZ0 | SPEC_NOFF | SPEC_UTGT>, SM_)
     CDPR_PREP(4, smem4);
     CDPR_PREP(8, smem8);
 #undef CDPR_PREP1
@@ -453,7 +456,7 @@ static int scatter_cmd(cdpr_handle h, const T *host, int64_t n_instances, int n_
 
 extern "C" int cdpr_set_velocity_cmd(cdpr_handle h, const float *axes, int64_t n_instances, int n_axes) {
   int rc = scatter_cmd<float>(h, axes, n_instances, n_axes, CAB_VEL_TARGET);
-  if (rc == CDPR_OK) h->vel_pending = true;
+  if (rc == CDPR_OK) { h->vel_pending = true; h->targets_uniform = false; }
   return rc;
 }
 extern "C" int cdpr_set_position_cmd(cdpr_handle h, const float *axes, int64_t n_instances, int n_axes) {
@@ -524,6 +527,8 @@ static int launch_step(cdpr_handle h, const StepArgs &A) {
     // the velocity mode with the moment D-term (the headline path) is specialised on the robot constants; every
     // other combination runs the diagonal-inertia or fully general instance
     const int spec_full = h->rc.spec, spec_base = h->rc.spec & SPEC_DIAG;
+    // one target for all cables (the sine publisher) and no feed-forward term: targets live in a register
+    const bool uniform_noff = A.sine_on && !A.cmd_table && A.live.kf == 0.0 && h->targets_uniform;
 #define CDPR_LAUNCH(NC_, MODE_, DM_, SP_)                                                              \
   k_step_fast<NC_, 11, MODE_, DM_, SP_><<<(unsigned)(h->np / FastCfg<NC_>::tpb), FastCfg<NC_>::tpb,   \
                                           fast_smem_bytes<NC_, 11>(), h->stream>>>(A)
@@ -534,6 +539,8 @@ static int launch_step(cdpr_handle h, const StepArgs &A) {
     if (A.mode == MODE_FORCE) CDPR_LAUNCH_BASE(NC_, MODE_FORCE, false);                                \
     else if (A.mode == MODE_POSITION) { if (dm) CDPR_LAUNCH_BASE(NC_, MODE_POSITION, true); else CDPR_LAUNCH_BASE(NC_, MODE_POSITION, false); } \
     else if (!dm) CDPR_LAUNCH_BASE(NC_, MODE_VELOCITY, false);                                         \
+    else if (spec_full == (SPEC_DIAG | SPEC_ISO | SPEC_BZ0) && uniform_noff)                           \
+      CDPR_LAUNCH(NC_, MODE_VELOCITY, true, SPEC_DIAG | SPEC_ISO | SPEC_BZ0 | SPEC_NOFF | SPEC_UTGT);  \
     else if (spec_full == (SPEC_DIAG | SPEC_ISO | SPEC_BZ0)) CDPR_LAUNCH(NC_, MODE_VELOCITY, true, SPEC_DIAG | SPEC_ISO | SPEC_BZ0); \
     else if (spec_full == (SPEC_DIAG | SPEC_ISO)) CDPR_LAUNCH(NC_, MODE_VELOCITY, true, SPEC_DIAG | SPEC_ISO); \
     else if (spec_full == (SPEC_DIAG | SPEC_BZ0)) CDPR_LAUNCH(NC_, MODE_VELOCITY, true, SPEC_DIAG | SPEC_BZ0); \
@@ -594,6 +601,10 @@ extern "C" int cdpr_step(cdpr_handle h, int64_t k_steps) {
     fill_args(h, A, (int)seg, sine);
     int rc = launch_step(h, A);
     if (rc) return rc;
+    if (sine) {  // did the publisher write a command in this segment? then every cable holds that one value
+      const long long first = ((h->step_count + h->sine_period - 1) / h->sine_period) * h->sine_period;  // first n0' >= step_count with n0' % period == 0
+      if (first < h->step_count + seg) h->targets_uniform = true;
+    }
     advance_host_clock(h, seg, sine);
     remaining -= seg;
   }
@@ -733,6 +744,7 @@ extern "C" int cdpr_set_state(cdpr_handle h, const void *blob, size_t bytes) {
     o += s.bytes;
   }
   CK(h, cudaStreamSynchronize(h->stream));
+  h->targets_uniform = false;
   h->mode = hd.mode; h->vel_pending = hd.vel_pending; h->pos_pending = hd.pos_pending; h->sec = hd.sec; h->nsec = hd.nsec;
   h->sine_on = hd.sine_on; h->step_count = hd.step_count; h->sine_time = hd.sine_time;
   return CDPR_OK;
@@ -873,6 +885,7 @@ extern "C" int cdpr_rollout(cdpr_handle h, int64_t n_robots, int64_t n_seq, cons
   }
   CK(h, cudaEventRecord(h->ev1, h->stream));
   h->timed = true;
+  h->targets_uniform = false;
   const int peers_saved = h->n_snap_peers;
   h->n_snap_peers = 0;  // rollouts write no snapshots
   advance_host_clock(h, n_cmd * steps_per_cmd, false);

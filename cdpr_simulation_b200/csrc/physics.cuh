@@ -56,7 +56,9 @@ __device__ __forceinline__ void store_plat(double *p, long long stride, const Fa
 //   SPEC_DIAG  body inertia is diagonal (products of inertia are 0), as in sdf/cube.sdf:331-338
 //   SPEC_ISO   ... and ixx == iyy == izz: the gyroscopic torque vanishes and I_w^-1 is a scalar
 //   SPEC_BZ0   every platform anchor has b_z == 0 (anchors in the platform's xy plane, cube.yaml:21-29)
-enum { SPEC_DIAG = 1, SPEC_ISO = 2, SPEC_BZ0 = 4 };
+//   SPEC_NOFF  the live Pid has no feed-forward gain (velocityControllerForward = 0, launch:19)
+//   SPEC_UTGT  every cable has the same target (the sine publisher writes one value to all axes, sinevelocitytest.cpp:36-38)
+enum { SPEC_DIAG = 1, SPEC_ISO = 2, SPEC_BZ0 = 4, SPEC_NOFF = 8, SPEC_UTGT = 16 };
 
 // NVLS multicast store: one store, replicated by the NVSwitch into the mapped buffer of every rank
 __device__ __forceinline__ void mc_store(double *p, double v) { asm volatile("multimem.st.weak.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory"); }

@@ -50,7 +50,7 @@ template <int NC> struct FastCfg { static constexpr int tpb = (NC <= 4) ? CDPR_N
 //   LAST:   last step of the launch: also writes the telemetry columns
 //   MODE:   batch-uniform JointForceCalculator::UpdateMode
 template <int NC, int LEN, bool STEADY, bool LAST, int MODE, bool DMOM, int SPEC>
-__device__ __forceinline__ void fast_step(const StepArgs &A, FastState &S, double (&ierr)[NC], const double *__restrict__ tgts,
+__device__ __forceinline__ void fast_step(const StepArgs &A, FastState &S, double (&ierr)[NC], const double *__restrict__ tgts, const double tgu,
                                           double (&mom)[NC][3], unsigned &primed, unsigned (&missing)[NC],
                                           double *__restrict__ win, int head, double dt, long long i) {
   const RobotConsts &rc = A.rc;
@@ -92,7 +92,7 @@ __device__ __forceinline__ void fast_step(const StepArgs &A, FastState &S, doubl
       force = tgts[c * FastCfg<NC>::tpb];  // JointForceCalculator.cpp:67-70
       eff = (fabs(force) > rc.effort_limit_abs) ? copysign(rc.effort_limit_abs, force) : force;
     } else {
-      const double tg = tgts[c * FastCfg<NC>::tpb];
+      const double tg = (SPEC & SPEC_UTGT) ? tgu : tgts[c * FastCfg<NC>::tpb];
       const double e = tg - ((MODE == MODE_VELOCITY) ? qd : qp);
       double *w = win + c * FastCfg<NC>::tpb;
       if (STEADY || ((primed >> c) & 1u)) {  // Pid.cpp:127-187
@@ -127,7 +127,8 @@ __device__ __forceinline__ void fast_step(const StepArgs &A, FastState &S, doubl
           missing[c] -= (missing[c] > 0u) ? 1u : 0u;
           if (missing[c] != 0u) derr = 0.0;
         }
-        const double cmd_raw = fma(pc.ki, ie, fma(pc.kd, derr, fma(pc.kp, e, tgts[(NC + c) * FastCfg<NC>::tpb])));
+        const double cmd_raw = (SPEC & SPEC_NOFF) ? fma(pc.ki, ie, fma(pc.kd, derr, pc.kp * e))
+                                                  : fma(pc.ki, ie, fma(pc.kd, derr, fma(pc.kp, e, tgts[(NC + c) * FastCfg<NC>::tpb])));
         // clamp + anti-windup (Pid.cpp:175-184): mCmd != cmd  <=>  |cmd| > cmdMax
         const bool csat = fabs(cmd_raw) > pc.cmd_max;
         force = cmd_raw;
@@ -254,6 +255,7 @@ __global__ void __launch_bounds__(FastCfg<NC>::tpb, FastCfg<NC>::blocks) k_step_
   const float *cmd_row = nullptr;
   if (A.cmd_table) cmd_row = A.cmd_table + (size_t)(i % A.n_seq) * A.n_cmd * NC;
   double cost = 0.0;
+  double tgu = mytgt[0];  // SPEC_UTGT: the one target shared by all cables, kept in a register
 
   bool warp_steady = __all_sync(0xffffffffu, steady || !PIDMODE);
   int sec = A.sec0, nsec = A.nsec0, head = head0;
@@ -282,6 +284,7 @@ __global__ void __launch_bounds__(FastCfg<NC>::tpb, FastCfg<NC>::blocks) k_step_
       const double vel = (double)(float)__dmul_rn(amp, sin(arg));
 #pragma unroll
       for (int c = 0; c < NC; ++c) { mytgt[c * kTpbL] = vel; mytgt[(NC + c) * kTpbL] = A.live.kf * vel; }
+      tgu = vel;
       sine_time = __dadd_rn(sine_time, A.sine_pub_dt);
     }
     if (cmd_row && cmd_ctr == 0 && cmd_idx < A.n_cmd) {
@@ -332,7 +335,7 @@ __global__ void __launch_bounds__(FastCfg<NC>::tpb, FastCfg<NC>::blocks) k_step_
       // warm-up (at most LEN + 1 steps after a Pid reset): some live Pid of the warp is un-primed or its window is not full
       double dt;
       clock_tick(dt);
-      fast_step<NC, LEN, false, false, MODE, DMOM, SPEC>(A, S, ierr, mytgt, mom, primed, missing, mywin, head, dt, i);
+      fast_step<NC, LEN, false, false, MODE, DMOM, SPEC>(A, S, ierr, mytgt, tgu, mom, primed, missing, mywin, head, dt, i);
       if (A.cost) add_cost();
       bool st = true;
 #pragma unroll
@@ -351,14 +354,14 @@ __global__ void __launch_bounds__(FastCfg<NC>::tpb, FastCfg<NC>::blocks) k_step_
         for (int r = 0; r < run; ++r) {
           double dt;
           clock_tick(dt);
-          fast_step<NC, LEN, true, false, MODE, DMOM, SPEC>(A, S, ierr, mytgt, mom, primed, missing, mywin, head, dt, i);
+          fast_step<NC, LEN, true, false, MODE, DMOM, SPEC>(A, S, ierr, mytgt, tgu, mom, primed, missing, mywin, head, dt, i);
           add_cost();
         }
       } else {
         for (int r = 0; r < run; ++r) {  // the hot loop
           double dt;
           clock_tick(dt);
-          fast_step<NC, LEN, true, false, MODE, DMOM, SPEC>(A, S, ierr, mytgt, mom, primed, missing, mywin, head, dt, i);
+          fast_step<NC, LEN, true, false, MODE, DMOM, SPEC>(A, S, ierr, mytgt, tgu, mom, primed, missing, mywin, head, dt, i);
         }
       }
       advance_counters(run);
@@ -371,8 +374,8 @@ __global__ void __launch_bounds__(FastCfg<NC>::tpb, FastCfg<NC>::blocks) k_step_
     double dt;
     clock_tick(dt);
     if (valid) {
-      if (warp_steady) fast_step<NC, LEN, true, true, MODE, DMOM, SPEC>(A, S, ierr, mytgt, mom, primed, missing, mywin, head, dt, i);
-      else fast_step<NC, LEN, false, true, MODE, DMOM, SPEC>(A, S, ierr, mytgt, mom, primed, missing, mywin, head, dt, i);
+      if (warp_steady) fast_step<NC, LEN, true, true, MODE, DMOM, SPEC>(A, S, ierr, mytgt, tgu, mom, primed, missing, mywin, head, dt, i);
+      else fast_step<NC, LEN, false, true, MODE, DMOM, SPEC>(A, S, ierr, mytgt, tgu, mom, primed, missing, mywin, head, dt, i);
     }
     if (A.cost) add_cost();
     advance_counters(1);
