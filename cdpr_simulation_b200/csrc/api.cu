@@ -359,23 +359,24 @@ extern "C" int cdpr_create(const cdpr_config *cfg, int64_t n_instances, int devi
   if (cudaMemsetAsync(L.sine, 0, col * 3, h->stream) != cudaSuccess) { h->err = "memset failed"; return bail(CDPR_ERR_CUDA); }
   if ((rc = reset_to_load_state(h))) return bail(rc);
   if (!h->general) {
-    const int smem4 = (int)fast_smem_bytes<4, 11>(), smem8 = (int)fast_smem_bytes<8, 11>();
-    auto prep = [](const void *f, int smem) {
-      cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    auto prep = [](const void *f, size_t smem) {
+      cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     };
-#define CDPR_PREP1(NC_, SM_, SP_)                                                                                        \
-    prep((const void *)k_step_fast<NC_, 11, MODE_FORCE, false, SP_>, SM_); prep((const void *)k_step_fast<NC_, 11, MODE_POSITION, false, SP_>, SM_); \
-    prep((const void *)k_step_fast<NC_, 11, MODE_POSITION, true, SP_>, SM_); prep((const void *)k_step_fast<NC_, 11, MODE_VELOCITY, false, SP_>, SM_); \
-    prep((const void *)k_step_fast<NC_, 11, MODE_VELOCITY, true, SP_>, SM_)
-#define CDPR_PREP(NC_, SM_)                                                                                              \
-    CDPR_PREP1(NC_, SM_, 0); CDPR_PREP1(NC_, SM_, SPEC_DIAG);                                                            \
-    prep((const void *)k_step_fast<NC_, 11, MODE_VELOCITY, true, SPEC_DIAG | SPEC_BZ0>, SM_);                            \
-    prep((const void *)k_step_fast<NC_, 11, MODE_VELOCITY, true, SPEC_DIAG | SPEC_ISO>, SM_);                            \
-    prep((const void *)k_step_fast<NC_, 11, MODE_VELOCITY, true, SPEC_DIAG | SPEC_ISO | SPEC_BZ0>, SM_);                  \
-    prep((const void *)k_step_fast<NC_, 11, MODE_VELOCITY, true, SPEC_DIAG | SPEC_ISO | SPEC_BZ0 | SPEC_NOFF | SPEC_UTGT>, SM_)
-    CDPR_PREP(4, smem4);
-    CDPR_PREP(8, smem8);
+#define CDPR_PREP_ONE(NC_, MODE_, DM_, SP_) prep((const void *)k_step_fast<NC_, 11, MODE_, DM_, SP_>, fast_smem_bytes<NC_, 11, SP_>())
+#define CDPR_PREP1(NC_, SP_)                                                                                   \
+    CDPR_PREP_ONE(NC_, MODE_FORCE, false, SP_); CDPR_PREP_ONE(NC_, MODE_POSITION, false, SP_);                 \
+    CDPR_PREP_ONE(NC_, MODE_POSITION, true, SP_); CDPR_PREP_ONE(NC_, MODE_VELOCITY, false, SP_);               \
+    CDPR_PREP_ONE(NC_, MODE_VELOCITY, true, SP_)
+#define CDPR_PREP(NC_)                                                                                         \
+    CDPR_PREP1(NC_, 0); CDPR_PREP1(NC_, SPEC_DIAG);                                                            \
+    CDPR_PREP_ONE(NC_, MODE_VELOCITY, true, SPEC_DIAG | SPEC_BZ0);                                             \
+    CDPR_PREP_ONE(NC_, MODE_VELOCITY, true, SPEC_DIAG | SPEC_ISO);                                             \
+    CDPR_PREP_ONE(NC_, MODE_VELOCITY, true, SPEC_DIAG | SPEC_ISO | SPEC_BZ0);                                  \
+    CDPR_PREP_ONE(NC_, MODE_VELOCITY, true, SPEC_DIAG | SPEC_ISO | SPEC_BZ0 | SPEC_NOFF | SPEC_UTGT)
+    CDPR_PREP(4);
+    CDPR_PREP(8);
+#undef CDPR_PREP_ONE
 #undef CDPR_PREP1
 #undef CDPR_PREP
   }
@@ -530,8 +531,8 @@ static int launch_step(cdpr_handle h, const StepArgs &A) {
     // one target for all cables (the sine publisher) and no feed-forward term: targets live in a register
     const bool uniform_noff = A.sine_on && !A.cmd_table && A.live.kf == 0.0 && h->targets_uniform;
 #define CDPR_LAUNCH(NC_, MODE_, DM_, SP_)                                                              \
-  k_step_fast<NC_, 11, MODE_, DM_, SP_><<<(unsigned)(h->np / FastCfg<NC_>::tpb), FastCfg<NC_>::tpb,   \
-                                          fast_smem_bytes<NC_, 11>(), h->stream>>>(A)
+  k_step_fast<NC_, 11, MODE_, DM_, SP_><<<grid_for(h->np, FastCfg<NC_, SP_>::tpb), FastCfg<NC_, SP_>::tpb, \
+                                          fast_smem_bytes<NC_, 11, SP_>(), h->stream>>>(A)
 #define CDPR_LAUNCH_BASE(NC_, MODE_, DM_) \
   do { if (spec_base) CDPR_LAUNCH(NC_, MODE_, DM_, SPEC_DIAG); else CDPR_LAUNCH(NC_, MODE_, DM_, 0); } while (0)
 #define CDPR_LAUNCH_NC(NC_)                                                                            \

@@ -43,7 +43,18 @@ constexpr int kResync = 64;
 #ifndef CDPR_NC8_TPB
 #define CDPR_NC8_TPB 128
 #endif
-template <int NC> struct FastCfg { static constexpr int tpb = (NC <= 4) ? CDPR_NC4_TPB : CDPR_NC8_TPB; static constexpr int blocks = (NC <= 4) ? CDPR_NC4_BLOCKS : CDPR_NC8_BLOCKS; };
+#ifndef CDPR_NC8_LEAN_TPB
+#define CDPR_NC8_LEAN_TPB 128
+#endif
+#ifndef CDPR_NC8_LEAN_BLOCKS
+#define CDPR_NC8_LEAN_BLOCKS 2
+#endif
+// "lean" = SPEC_UTGT | SPEC_NOFF: the one target lives in a register, so no target / feed-forward arrays in shared memory
+template <int NC, int SPEC = 0> struct FastCfg {
+  static constexpr bool lean = (SPEC & (8 | 16)) == (8 | 16);
+  static constexpr int tpb = (NC <= 4) ? CDPR_NC4_TPB : (lean ? CDPR_NC8_LEAN_TPB : CDPR_NC8_TPB);
+  static constexpr int blocks = (NC <= 4) ? CDPR_NC4_BLOCKS : (lean ? CDPR_NC8_LEAN_BLOCKS : CDPR_NC8_BLOCKS);
+};
 
 // One physics step for one instance.
 //   STEADY: every live Pid is primed and its window is full (mWasLastTime && mDbufferMissing == 0)
@@ -67,7 +78,7 @@ __device__ __forceinline__ void fast_step(const StepArgs &A, FastState &S, doubl
   for (int a = 0; a < (DMOM ? 1 : LEN); ++a) {
     int s = head - a;
     s += (s < 0) ? LEN : 0;
-    slot[a] = s * (NC * FastCfg<NC>::tpb);
+    slot[a] = s * (NC * FastCfg<NC, SPEC>::tpb);
   }
 #pragma unroll
   for (int c = 0; c < NC; ++c) {
@@ -89,12 +100,12 @@ __device__ __forceinline__ void fast_step(const StepArgs &A, FastState &S, doubl
     // ---- force law (a3, a4, a5)
     double force, eff;
     if (MODE == MODE_FORCE) {
-      force = tgts[c * FastCfg<NC>::tpb];  // JointForceCalculator.cpp:67-70
+      force = tgts[c * FastCfg<NC, SPEC>::tpb];  // JointForceCalculator.cpp:67-70
       eff = (fabs(force) > rc.effort_limit_abs) ? copysign(rc.effort_limit_abs, force) : force;
     } else {
-      const double tg = (SPEC & SPEC_UTGT) ? tgu : tgts[c * FastCfg<NC>::tpb];
+      const double tg = (SPEC & SPEC_UTGT) ? tgu : tgts[c * FastCfg<NC, SPEC>::tpb];
       const double e = tg - ((MODE == MODE_VELOCITY) ? qd : qp);
-      double *w = win + c * FastCfg<NC>::tpb;
+      double *w = win + c * FastCfg<NC, SPEC>::tpb;
       if (STEADY || ((primed >> c) & 1u)) {  // Pid.cpp:127-187
         const double prev_ierr = ierr[c];
         double ie = fma(dt, e, prev_ierr);
@@ -128,7 +139,7 @@ __device__ __forceinline__ void fast_step(const StepArgs &A, FastState &S, doubl
           if (missing[c] != 0u) derr = 0.0;
         }
         const double cmd_raw = (SPEC & SPEC_NOFF) ? fma(pc.ki, ie, fma(pc.kd, derr, pc.kp * e))
-                                                  : fma(pc.ki, ie, fma(pc.kd, derr, fma(pc.kp, e, tgts[(NC + c) * FastCfg<NC>::tpb])));
+                                                  : fma(pc.ki, ie, fma(pc.kd, derr, fma(pc.kp, e, tgts[(NC + c) * FastCfg<NC, SPEC>::tpb])));
         // clamp + anti-windup (Pid.cpp:175-184): mCmd != cmd  <=>  |cmd| > cmdMax
         const bool csat = fabs(cmd_raw) > pc.cmd_max;
         force = cmd_raw;
@@ -166,7 +177,7 @@ __device__ __forceinline__ void fast_step(const StepArgs &A, FastState &S, doubl
 }
 
 // exact re-summation of the window moments from the ring (newest sample in slot `head`); rare, kept small
-template <int NC, int LEN>
+template <int NC, int LEN, int SPEC>
 __device__ __forceinline__ void resync_moments(double (&mom)[NC][3], const double *__restrict__ win, int head) {
 #pragma unroll
   for (int c = 0; c < NC; ++c) {
@@ -175,7 +186,7 @@ __device__ __forceinline__ void resync_moments(double (&mom)[NC][3], const doubl
 #pragma unroll 1
     for (int j = 0; j < LEN; ++j) {
       sl -= (sl >= LEN) ? LEN : 0;
-      const double y = win[(sl * NC + c) * FastCfg<NC>::tpb];
+      const double y = win[(sl * NC + c) * FastCfg<NC, SPEC>::tpb];
       const double p = (double)(j + 1);
       s0 += y;
       s1 = fma(p, y, s1);
@@ -198,13 +209,13 @@ __device__ __noinline__ void write_snapshot(const StepArgs &A, FastState S, long
 
 // shared memory per block (doubles): ring [LEN][NC][tpb], targets [NC][tpb], feed-forward terms Kf*target [NC][tpb],
 // sine parameters [3][tpb]
-template <int NC, int LEN>
-constexpr size_t fast_smem_bytes() { return sizeof(double) * (size_t)FastCfg<NC>::tpb * (LEN * NC + 2 * NC + 3); }
+template <int NC, int LEN, int SPEC>
+constexpr size_t fast_smem_bytes() { return sizeof(double) * (size_t)FastCfg<NC, SPEC>::tpb * (LEN * NC + (FastCfg<NC, SPEC>::lean ? 0 : 2 * NC) + 3); }
 
 template <int NC, int LEN, int MODE, bool DMOM, int SPEC>
-__global__ void __launch_bounds__(FastCfg<NC>::tpb, FastCfg<NC>::blocks) k_step_fast(const __grid_constant__ StepArgs A) {
+__global__ void __launch_bounds__(FastCfg<NC, SPEC>::tpb, FastCfg<NC, SPEC>::blocks) k_step_fast(const __grid_constant__ StepArgs A) {
   extern __shared__ double smem[];
-  constexpr int kTpbL = FastCfg<NC>::tpb;
+  constexpr int kTpbL = FastCfg<NC, SPEC>::tpb;
   constexpr bool PIDMODE = (MODE != MODE_FORCE);
   const int tid = threadIdx.x;
   const long long gi = (long long)blockIdx.x * kTpbL + tid;
@@ -214,7 +225,8 @@ __global__ void __launch_bounds__(FastCfg<NC>::tpb, FastCfg<NC>::blocks) k_step_
   const int live = A.live_idx;
   double *mywin = smem + tid;                          // [LEN][NC][tpb]
   double *mytgt = smem + LEN * NC * kTpbL + tid;       // [NC][tpb]
-  double *mysine = mytgt + 2 * NC * kTpbL;             // [3][tpb]: amp, freq, phase (after targets and feed-forward terms)
+  constexpr bool kLean = FastCfg<NC, SPEC>::lean;       // no target arrays: mytgt is never dereferenced
+  double *mysine = mytgt + (kLean ? 0 : 2 * NC * kTpbL);  // [3][tpb]: amp, freq, phase
 
   FastState S;
   load_plat(A.L, i, S);
@@ -227,8 +239,10 @@ __global__ void __launch_bounds__(FastCfg<NC>::tpb, FastCfg<NC>::blocks) k_step_
 #pragma unroll
   for (int c = 0; c < NC; ++c) {
     ierr[c] = A.L.pid[pid_off(A.L, c, live, PID_I_ERR) + i];
-    mytgt[c * kTpbL] = A.L.cab[cab_off(A.L, c, tgt_field) + i];
-    mytgt[(NC + c) * kTpbL] = A.live.kf * mytgt[c * kTpbL];
+    if (!kLean) {
+      mytgt[c * kTpbL] = A.L.cab[cab_off(A.L, c, tgt_field) + i];
+      mytgt[(NC + c) * kTpbL] = A.live.kf * mytgt[c * kTpbL];
+    }
     const unsigned ctl = A.L.ctl[(long long)c * np + i];
     primed |= ((ctl >> live) & 1u) << c;
     missing[c] = (ctl >> (8 + 8 * live)) & 0xffu;
@@ -255,7 +269,7 @@ __global__ void __launch_bounds__(FastCfg<NC>::tpb, FastCfg<NC>::blocks) k_step_
   const float *cmd_row = nullptr;
   if (A.cmd_table) cmd_row = A.cmd_table + (size_t)(i % A.n_seq) * A.n_cmd * NC;
   double cost = 0.0;
-  double tgu = mytgt[0];  // SPEC_UTGT: the one target shared by all cables, kept in a register
+  double tgu = A.L.cab[cab_off(A.L, 0, tgt_field) + i];  // SPEC_UTGT: the one target shared by all cables, kept in a register
 
   bool warp_steady = __all_sync(0xffffffffu, steady || !PIDMODE);
   int sec = A.sec0, nsec = A.nsec0, head = head0;
@@ -283,7 +297,10 @@ __global__ void __launch_bounds__(FastCfg<NC>::tpb, FastCfg<NC>::blocks) k_step_
       const double arg = __dadd_rn(__dmul_rn(__dmul_rn(__dmul_rn(sine_time, freq), 2.0), 3.14159265358979323846), phase);
       const double vel = (double)(float)__dmul_rn(amp, sin(arg));
 #pragma unroll
-      for (int c = 0; c < NC; ++c) { mytgt[c * kTpbL] = vel; mytgt[(NC + c) * kTpbL] = A.live.kf * vel; }
+      if (!kLean) {
+#pragma unroll
+        for (int c = 0; c < NC; ++c) { mytgt[c * kTpbL] = vel; mytgt[(NC + c) * kTpbL] = A.live.kf * vel; }
+      }
       tgu = vel;
       sine_time = __dadd_rn(sine_time, A.sine_pub_dt);
     }
@@ -314,7 +331,7 @@ __global__ void __launch_bounds__(FastCfg<NC>::tpb, FastCfg<NC>::blocks) k_step_
   auto events_after = [&]() {
     if (DMOM && PIDMODE && resync_ctr >= kResync) {
       resync_ctr = 0;
-      resync_moments<NC, LEN>(mom, mywin, head);
+      resync_moments<NC, LEN, SPEC>(mom, mywin, head);
     }
     if (A.snap_every > 0 && snap_ctr >= A.snap_every) {
       snap_ctr = 0;
@@ -390,7 +407,7 @@ __global__ void __launch_bounds__(FastCfg<NC>::tpb, FastCfg<NC>::blocks) k_step_
   for (int c = 0; c < NC; ++c) {
     A.L.pid[pid_off(A.L, c, live, PID_I_ERR) + i] = ierr[c];
     A.L.pid[pid_off(A.L, c, live, PID_LAST_TIME) + i] = tprev;
-    if (A.sine_on || A.cmd_table) A.L.cab[cab_off(A.L, c, CAB_VEL_TARGET) + i] = mytgt[c * kTpbL];
+    if (A.sine_on || A.cmd_table) A.L.cab[cab_off(A.L, c, CAB_VEL_TARGET) + i] = kLean ? tgu : mytgt[c * kTpbL];
     unsigned ctl = A.L.ctl[(long long)c * np + i];
     ctl &= ~((1u << live) | (0xffu << (8 + 8 * live)));
     ctl |= (((primed >> c) & 1u) << live) | (missing[c] << (8 + 8 * live));
