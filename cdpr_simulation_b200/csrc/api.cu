@@ -43,6 +43,11 @@ struct cdpr_batch {
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // async mode: everything that is not a step kernel (reset, uploads, layout kernels, downloads) runs on a
+  // high-priority stream of its own, so it is not starved behind step kernels that fill every SM (another handle's)
+  cudaStream_t io_stream = nullptr;
+  cudaEvent_t io_done = nullptr, main_done = nullptr;
+  bool io_pending = false, main_pending = false;
   bool timed = false;
   bool async_copies = false;  // host-buffer calls only enqueue; the caller synchronises (pinned buffers)
   bool targets_uniform = false;  // all cables of an instance hold the same velocity target (zeros after Load, or written by the sine publisher)
@@ -266,18 +271,39 @@ static int ensure_stage(cdpr_handle h, size_t bytes) {
 
 static inline cudaError_t sync_unless_async(cdpr_handle h) { return h->async_copies ? cudaSuccess : cudaStreamSynchronize(h->stream); }
 
+// Stream for a non-step operation: the handle's stream, or in async mode the io stream ordered after the last step
+static cudaStream_t io_begin(cdpr_handle h) {
+  if (!h->async_copies) return h->stream;
+  if (h->main_pending) { cudaStreamWaitEvent(h->io_stream, h->main_done, 0); h->main_pending = false; }
+  return h->io_stream;
+}
+static void io_end(cdpr_handle h) {
+  if (!h->async_copies) return;
+  cudaEventRecord(h->io_done, h->io_stream);
+  h->io_pending = true;
+}
+// before / after work on the handle's own stream that touches the state (step kernels, checkpoints, rollouts)
+static void main_begin(cdpr_handle h) {
+  if (h->io_pending) { cudaStreamWaitEvent(h->stream, h->io_done, 0); h->io_pending = false; }
+}
+static void main_end(cdpr_handle h) {
+  if (!h->async_copies) return;
+  cudaEventRecord(h->main_done, h->stream);
+  h->main_pending = true;
+}
+
 static inline unsigned grid_for(long long n, int tpb) { return (unsigned)((n + tpb - 1) / tpb); }
 
-static int reset_to_load_state(cdpr_handle h) {
+static int reset_to_load_state(cdpr_handle h, cudaStream_t st) {
   const DevLayout &L = h->L;
-  CK(h, cudaMemsetAsync(L.cab, 0, sizeof(double) * L.nc * CAB_F * L.np, h->stream));
-  CK(h, cudaMemsetAsync(L.pid, 0, sizeof(double) * L.nc * 2 * PID_F * L.np, h->stream));
-  CK(h, cudaMemsetAsync(L.win_y, 0, sizeof(double) * L.nc * 2 * L.len * L.np, h->stream));
-  if (L.mom) CK(h, cudaMemsetAsync(L.mom, 0, sizeof(double) * L.nc * 2 * 3 * L.np, h->stream));
-  if (L.win_x) CK(h, cudaMemsetAsync(L.win_x, 0, sizeof(double) * L.nc * 2 * L.len * L.np, h->stream));
-  if (L.filt) CK(h, cudaMemsetAsync(L.filt, 0, sizeof(double) * L.nc * 2 * 2 * L.casc * 4 * L.np, h->stream));
+  CK(h, cudaMemsetAsync(L.cab, 0, sizeof(double) * L.nc * CAB_F * L.np, st));
+  CK(h, cudaMemsetAsync(L.pid, 0, sizeof(double) * L.nc * 2 * PID_F * L.np, st));
+  CK(h, cudaMemsetAsync(L.win_y, 0, sizeof(double) * L.nc * 2 * L.len * L.np, st));
+  if (L.mom) CK(h, cudaMemsetAsync(L.mom, 0, sizeof(double) * L.nc * 2 * 3 * L.np, st));
+  if (L.win_x) CK(h, cudaMemsetAsync(L.win_x, 0, sizeof(double) * L.nc * 2 * L.len * L.np, st));
+  if (L.filt) CK(h, cudaMemsetAsync(L.filt, 0, sizeof(double) * L.nc * 2 * 2 * L.casc * 4 * L.np, st));
   const cdpr_config &c = h->cfg;
-  k_init_state<<<grid_for(L.np, 256), 256, 0, h->stream>>>(L, h->rc, c.home_pos[0], c.home_pos[1], c.home_pos[2], c.home_quat[0],
+  k_init_state<<<grid_for(L.np, 256), 256, 0, st>>>(L, h->rc, c.home_pos[0], c.home_pos[1], c.home_pos[2], c.home_quat[0],
                                                            c.home_quat[1], c.home_quat[2], c.home_quat[3],
                                                            (unsigned)c.vel_pid.d_buffer_length, (unsigned)c.pos_pid.d_buffer_length, h->general ? 1 : 0);
   CK(h, cudaGetLastError());
@@ -338,6 +364,13 @@ extern "C" int cdpr_create(const cdpr_config *cfg, int64_t n_instances, int devi
   h->own_stream = true;
   cudaEventCreate(&h->ev0);
   cudaEventCreate(&h->ev1);
+  {
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);  // hi = numerically lowest = highest priority
+    cudaStreamCreateWithPriority(&h->io_stream, cudaStreamNonBlocking, hi);
+    cudaEventCreateWithFlags(&h->io_done, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->main_done, cudaEventDisableTiming);
+  }
   h->n = n_instances;
   h->np = (n_instances + kTpb - 1) / kTpb * kTpb;
   DevLayout &L = h->L;
@@ -357,7 +390,7 @@ extern "C" int cdpr_create(const cdpr_config *cfg, int64_t n_instances, int devi
   if ((rc = dev_alloc(h, (void **)&L.ctl, sizeof(uint32_t) * (size_t)L.np * L.nc))) return bail(rc);
   if ((rc = dev_alloc(h, (void **)&L.sine, col * 3))) return bail(rc);
   if (cudaMemsetAsync(L.sine, 0, col * 3, h->stream) != cudaSuccess) { h->err = "memset failed"; return bail(CDPR_ERR_CUDA); }
-  if ((rc = reset_to_load_state(h))) return bail(rc);
+  if ((rc = reset_to_load_state(h, h->stream))) return bail(rc);
   if (!h->general) {
     auto prep = [](const void *f, size_t smem) {
       cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -395,6 +428,9 @@ extern "C" int cdpr_destroy(cdpr_handle h) {
   if (h->cmd_dev) cudaFree(h->cmd_dev);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->io_stream) { cudaStreamSynchronize(h->io_stream); cudaStreamDestroy(h->io_stream); }
+  if (h->io_done) cudaEventDestroy(h->io_done);
+  if (h->main_done) cudaEventDestroy(h->main_done);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return CDPR_OK;
@@ -403,7 +439,8 @@ extern "C" int cdpr_destroy(cdpr_handle h) {
 extern "C" int cdpr_reset(cdpr_handle h) {
   if (!h) return CDPR_ERR_BAD_ARG;
   cudaSetDevice(h->device);
-  int rc = reset_to_load_state(h);
+  int rc = reset_to_load_state(h, io_begin(h));
+  io_end(h);
   if (rc) return rc;
   h->snap_written = 0;
   h->launches += 1;
@@ -416,6 +453,8 @@ extern "C" int cdpr_set_stream(cdpr_handle h, void *cuda_stream) {
   if (!h) return CDPR_ERR_BAD_ARG;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->io_stream) cudaStreamSynchronize(h->io_stream);
+  h->io_pending = h->main_pending = false;
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   h->stream = (cudaStream_t)cuda_stream;
   h->own_stream = false;
@@ -424,6 +463,10 @@ extern "C" int cdpr_set_stream(cdpr_handle h, void *cuda_stream) {
 
 extern "C" int cdpr_set_async(cdpr_handle h, int on) {
   if (!h) return CDPR_ERR_BAD_ARG;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  cudaStreamSynchronize(h->io_stream);
+  h->io_pending = h->main_pending = false;
   h->async_copies = on != 0;
   return CDPR_OK;
 }
@@ -432,6 +475,7 @@ extern "C" int cdpr_synchronize(cdpr_handle h) {
   if (!h) return CDPR_ERR_BAD_ARG;
   cudaSetDevice(h->device);
   CK(h, cudaStreamSynchronize(h->stream));
+  CK(h, cudaStreamSynchronize(h->io_stream));
   return CDPR_OK;
 }
 
@@ -448,9 +492,11 @@ static int scatter_cmd(cdpr_handle h, const T *host, int64_t n_instances, int n_
   const size_t bytes = sizeof(T) * (size_t)h->n * h->L.nc;
   int rc = ensure_stage(h, bytes);
   if (rc) return rc;
-  CK(h, cudaMemcpyAsync(h->stage, host, bytes, cudaMemcpyHostToDevice, h->stream));
-  k_scatter_cab<T><<<grid_for(h->n, 256), 256, 0, h->stream>>>(h->L, field, (const T *)h->stage);
+  cudaStream_t st = io_begin(h);
+  CK(h, cudaMemcpyAsync(h->stage, host, bytes, cudaMemcpyHostToDevice, st));
+  k_scatter_cab<T><<<grid_for(h->n, 256), 256, 0, st>>>(h->L, field, (const T *)h->stage);
   CK(h, cudaGetLastError());
+  io_end(h);
   CK(h, sync_unless_async(h));  // the caller may reuse its buffer
   return CDPR_OK;
 }
@@ -483,8 +529,10 @@ extern "C" int cdpr_set_sine_cmd(cdpr_handle h, const double *amp, const double 
   for (int k = 0; k < 3; ++k) {
     if (!src[k]) { def.assign((size_t)h->n, defaults[k]); src[k] = def.data(); }
     const bool temporary = (src[k] == def.data());
-    CK(h, cudaMemcpyAsync(h->L.sine + (size_t)k * h->L.np, src[k], bytes, cudaMemcpyHostToDevice, h->stream));
-    if (temporary) CK(h, cudaStreamSynchronize(h->stream)); else CK(h, sync_unless_async(h));
+    cudaStream_t st = io_begin(h);
+    CK(h, cudaMemcpyAsync(h->L.sine + (size_t)k * h->L.np, src[k], bytes, cudaMemcpyHostToDevice, st));
+    io_end(h);
+    if (temporary) CK(h, cudaStreamSynchronize(st)); else CK(h, sync_unless_async(h));
   }
   h->sine_on = true;
   h->sine_time = 0.0;
@@ -573,6 +621,7 @@ extern "C" int cdpr_step(cdpr_handle h, int64_t k_steps) {
   if (!h || k_steps < 0) return CDPR_ERR_BAD_ARG;
   if (k_steps == 0) return CDPR_OK;
   cudaSetDevice(h->device);
+  main_begin(h);
   CK(h, cudaEventRecord(h->ev0, h->stream));
   long long remaining = k_steps;
   while (remaining > 0) {
@@ -611,6 +660,7 @@ extern "C" int cdpr_step(cdpr_handle h, int64_t k_steps) {
   }
   CK(h, cudaEventRecord(h->ev1, h->stream));
   h->timed = true;
+  main_end(h);
   return CDPR_OK;
 }
 
@@ -627,10 +677,12 @@ extern "C" int cdpr_get_platform_state(cdpr_handle h, double *pose7, double *twi
   int rc = ensure_stage(h, nb * 13);
   if (rc) return rc;
   double *dp = (double *)h->stage, *dt = dp + 7 * h->n;
-  k_pack_platform<<<grid_for(h->n, 256), 256, 0, h->stream>>>(h->L, pose7 ? dp : nullptr, twist6 ? dt : nullptr);
+  cudaStream_t st = io_begin(h);
+  k_pack_platform<<<grid_for(h->n, 256), 256, 0, st>>>(h->L, pose7 ? dp : nullptr, twist6 ? dt : nullptr);
   CK(h, cudaGetLastError());
-  if (pose7) CK(h, cudaMemcpyAsync(pose7, dp, nb * 7, cudaMemcpyDeviceToHost, h->stream));
-  if (twist6) CK(h, cudaMemcpyAsync(twist6, dt, nb * 6, cudaMemcpyDeviceToHost, h->stream));
+  if (pose7) CK(h, cudaMemcpyAsync(pose7, dp, nb * 7, cudaMemcpyDeviceToHost, st));
+  if (twist6) CK(h, cudaMemcpyAsync(twist6, dt, nb * 6, cudaMemcpyDeviceToHost, st));
+  io_end(h);
   CK(h, sync_unless_async(h));
   return CDPR_OK;
 }
@@ -642,10 +694,12 @@ extern "C" int cdpr_set_platform_state(cdpr_handle h, const double *pose7, const
   int rc = ensure_stage(h, nb * 13);
   if (rc) return rc;
   double *dp = (double *)h->stage, *dt = dp + 7 * h->n;
-  if (pose7) CK(h, cudaMemcpyAsync(dp, pose7, nb * 7, cudaMemcpyHostToDevice, h->stream));
-  if (twist6) CK(h, cudaMemcpyAsync(dt, twist6, nb * 6, cudaMemcpyHostToDevice, h->stream));
-  k_unpack_platform<<<grid_for(h->n, 256), 256, 0, h->stream>>>(h->L, pose7 ? dp : nullptr, twist6 ? dt : nullptr, 1);
+  cudaStream_t st = io_begin(h);
+  if (pose7) CK(h, cudaMemcpyAsync(dp, pose7, nb * 7, cudaMemcpyHostToDevice, st));
+  if (twist6) CK(h, cudaMemcpyAsync(dt, twist6, nb * 6, cudaMemcpyHostToDevice, st));
+  k_unpack_platform<<<grid_for(h->n, 256), 256, 0, st>>>(h->L, pose7 ? dp : nullptr, twist6 ? dt : nullptr, 1);
   CK(h, cudaGetLastError());
+  io_end(h);
   CK(h, sync_unless_async(h));
   return CDPR_OK;
 }
@@ -657,12 +711,13 @@ extern "C" int cdpr_get_joint_states(cdpr_handle h, double *position, double *ve
   int rc = ensure_stage(h, nb * 3);
   if (rc) return rc;
   double *d0 = (double *)h->stage, *d1 = d0 + h->n * h->L.nc, *d2 = d1 + h->n * h->L.nc;
-  k_joint_states<<<grid_for(h->n, 256), 256, 0, h->stream>>>(h->L, h->rc, position ? d0 : nullptr, velocity ? d1 : nullptr,
-                                                             effort ? d2 : nullptr);
+  cudaStream_t st = io_begin(h);
+  k_joint_states<<<grid_for(h->n, 256), 256, 0, st>>>(h->L, h->rc, position ? d0 : nullptr, velocity ? d1 : nullptr, effort ? d2 : nullptr);
   CK(h, cudaGetLastError());
-  if (position) CK(h, cudaMemcpyAsync(position, d0, nb, cudaMemcpyDeviceToHost, h->stream));
-  if (velocity) CK(h, cudaMemcpyAsync(velocity, d1, nb, cudaMemcpyDeviceToHost, h->stream));
-  if (effort) CK(h, cudaMemcpyAsync(effort, d2, nb, cudaMemcpyDeviceToHost, h->stream));
+  if (position) CK(h, cudaMemcpyAsync(position, d0, nb, cudaMemcpyDeviceToHost, st));
+  if (velocity) CK(h, cudaMemcpyAsync(velocity, d1, nb, cudaMemcpyDeviceToHost, st));
+  if (effort) CK(h, cudaMemcpyAsync(effort, d2, nb, cudaMemcpyDeviceToHost, st));
+  io_end(h);
   CK(h, sync_unless_async(h));
   return CDPR_OK;
 }
@@ -673,9 +728,11 @@ extern "C" int cdpr_get_pid_state(cdpr_handle h, double *out) {
   const size_t nb = sizeof(double) * (size_t)h->n * h->L.nc * 6;
   int rc = ensure_stage(h, nb);
   if (rc) return rc;
-  k_pid_state<<<grid_for(h->n, 256), 256, 0, h->stream>>>(h->L, h->mode, (double *)h->stage);
+  cudaStream_t st = io_begin(h);
+  k_pid_state<<<grid_for(h->n, 256), 256, 0, st>>>(h->L, h->mode, (double *)h->stage);
   CK(h, cudaGetLastError());
-  CK(h, cudaMemcpyAsync(out, h->stage, nb, cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaMemcpyAsync(out, h->stage, nb, cudaMemcpyDeviceToHost, st));
+  io_end(h);
   CK(h, sync_unless_async(h));
   return CDPR_OK;
 }
@@ -716,6 +773,7 @@ extern "C" size_t cdpr_state_bytes(cdpr_handle h) {
 extern "C" int cdpr_get_state(cdpr_handle h, void *blob, size_t bytes) {
   if (!h || !blob || bytes < cdpr_state_bytes(h)) return CDPR_ERR_BAD_ARG;
   cudaSetDevice(h->device);
+  main_begin(h);
   BlobHeader hd;
   std::memset(&hd, 0, sizeof(hd));
   hd.magic = kMagic; hd.n = h->n; hd.np = h->np; hd.nc = h->L.nc; hd.len = h->L.len; hd.casc = h->L.casc; hd.general = h->general;
@@ -739,6 +797,7 @@ extern "C" int cdpr_set_state(cdpr_handle h, const void *blob, size_t bytes) {
       hd.general != (int)h->general)
     return fail(h, CDPR_ERR_BAD_ARG, "checkpoint does not match this handle's shape");
   cudaSetDevice(h->device);
+  main_begin(h);
   const uint8_t *o = (const uint8_t *)blob + sizeof(hd);
   for (auto &s : sections(h)) {
     CK(h, cudaMemcpyAsync(s.ptr, o, s.bytes, cudaMemcpyHostToDevice, h->stream));
@@ -802,6 +861,7 @@ static int launch_ik(cdpr_handle h, const IkArgs &A, bool aos) {
 extern "C" int cdpr_ik_device(cdpr_handle h, int64_t n, const void *dev_state13, void *dev_out) {
   if (!h || n < 1 || !dev_state13 || !dev_out) return CDPR_ERR_BAD_ARG;
   cudaSetDevice(h->device);
+  main_begin(h);
   IkArgs A;
   std::memset(&A, 0, sizeof(A));
   A.rc = h->rc; A.nc = h->L.nc; A.n = n; A.state13 = (const double *)dev_state13; A.out = (double *)dev_out;
@@ -820,6 +880,7 @@ extern "C" int cdpr_ik(cdpr_handle h, int64_t n, const double *pose7, const doub
   const size_t in_b = sizeof(double) * (size_t)n * 13, out_b = sizeof(double) * (size_t)n * nc * 8;
   int rc = ensure_stage(h, in_b + out_b);
   if (rc) return rc;
+  main_begin(h);
   double *dp = (double *)h->stage, *dt = dp + 7 * n, *dl = dt + 6 * n, *dr = dl + n * nc, *dw = dr + n * nc;
   CK(h, cudaMemcpyAsync(dp, pose7, sizeof(double) * n * 7, cudaMemcpyHostToDevice, h->stream));
   CK(h, cudaMemcpyAsync(dt, twist6, sizeof(double) * n * 6, cudaMemcpyHostToDevice, h->stream));
@@ -848,7 +909,8 @@ extern "C" int cdpr_rollout(cdpr_handle h, int64_t n_robots, int64_t n_seq, cons
   if (n_robots * n_seq != h->n) return fail(h, CDPR_ERR_BAD_ARG, "n_robots * n_seq must equal the handle's instance count");
   if (n_cmd * steps_per_cmd > (1 << 30)) return fail(h, CDPR_ERR_BAD_ARG, "rollout too long");
   cudaSetDevice(h->device);
-  int rc = reset_to_load_state(h);
+  main_begin(h);
+  int rc = reset_to_load_state(h, h->stream);
   if (rc) return rc;
   if (pose7 || twist6) {
     const size_t nb = sizeof(double) * (size_t)n_robots;
@@ -891,6 +953,7 @@ extern "C" int cdpr_rollout(cdpr_handle h, int64_t n_robots, int64_t n_seq, cons
   h->n_snap_peers = 0;  // rollouts write no snapshots
   advance_host_clock(h, n_cmd * steps_per_cmd, false);
   h->n_snap_peers = peers_saved;
+  main_end(h);
   if (host_cost) {
     CK(h, cudaMemcpyAsync(host_cost, h->cost_dev, sizeof(double) * (size_t)h->n, cudaMemcpyDeviceToHost, h->stream));
     CK(h, cudaStreamSynchronize(h->stream));

@@ -100,8 +100,11 @@ const char *cdpr_last_error(cdpr_handle h);
 /* Kernels run on this cudaStream_t (default: a stream owned by the handle). */
 int cdpr_set_stream(cdpr_handle h, void *cuda_stream);
 int cdpr_synchronize(cdpr_handle h);
-/* on != 0: calls that take host buffers only ENQUEUE their copies/kernels on the handle's stream and return; the
- * caller keeps the (pinned) buffers alive and untouched until cdpr_synchronize. Default off (every call completes). */
+/* on != 0: calls that take host buffers only ENQUEUE their copies/kernels and return; the caller keeps the (pinned)
+ * buffers alive and untouched until cdpr_synchronize. In this mode everything that is not a step kernel (reset,
+ * uploads, layout kernels, downloads) runs on a high-priority stream owned by the handle, ordered against the step
+ * kernels by events, so the I/O of one handle is not starved behind step kernels of another handle that fill every SM.
+ * Default off (every call completes on the handle's stream). */
 int cdpr_set_async(cdpr_handle h, int on);
 
 /* ---- commands (topics jointVelocities / jointPositions, CdprGazeboPlugin.cpp:67-83,206-219;
