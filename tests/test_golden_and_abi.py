@@ -144,6 +144,12 @@ def test_create_argument_checks(built_lib):
     assert L.cdpr_create(C.byref(cfg), 4, 0, C.byref(h)) == cb.api.ERR_BAD_ARG
     bad = cb.Config()
     assert L.cdpr_config_default(C.byref(bad), 0) == cb.api.ERR_BAD_ARG
+    cfg = cb.default_config(4)
+    assert L.cdpr_create(C.byref(cfg), 0, 0, C.byref(h)) == cb.api.ERR_BAD_ARG          # empty batch
+    assert L.cdpr_create(C.byref(cfg), 1 << 40, 0, C.byref(h)) == cb.api.ERR_BAD_ARG    # beyond the 2^31 index range
+    cfg.vel_pid.d_buffer_length = 40
+    assert L.cdpr_create(C.byref(cfg), 4, 0, C.byref(h)) == cb.api.ERR_BAD_ARG          # window longer than CDPR_MAX_DBUF
+    assert not h.value
 
 
 def test_product_never_touches_the_oracle():

@@ -274,7 +274,7 @@ def test_rollout_costs_match_oracle(built_lib):
 def test_full_size_properties(built_lib):
     """At a size the oracle cannot follow: unit quaternions, finite state, platform stays inside the frame,
     static-equilibrium tension near m g / (4 * 0.617802) for slow commands."""
-    n = 1 << 16
+    n = 1 << 20                       # BASELINE.json configs[2]: 2^20 instances x 1000 steps
     cfg = cb.default_config(4)
     amp, freq, phase, pose7, twist6 = wl.c3_instances(n, 1)
     with cb.CdprBatch(cfg, n) as g:
@@ -286,6 +286,12 @@ def test_full_size_properties(built_lib):
     assert np.max(np.abs(np.linalg.norm(pose[:, 3:], axis=1) - 1.0)) < 1e-14
     assert np.all(np.abs(pose[:, :2]) < 0.3) and np.all((pose[:, 2] > 0.0) & (pose[:, 2] < 0.6))
     assert abs(np.median(eff.sum(axis=1)) - 4 * 3.9657) < 1.5
+    # the first 512 instances of the full-size batch are exactly what a 512-instance batch computes (no cross-talk)
+    with cb.CdprBatch(cfg, 512) as g:
+        g.set_platform_state(pose7[:512], twist6[:512]); g.set_sine_cmd(amp[:512], freq[:512], phase[:512])
+        g.step(1000)
+        p2, t2 = g.platform_state()
+    assert np.array_equal(p2, pose[:512]) and np.array_equal(t2, twist[:512])
 
 
 def test_cpp_host_shim_runs_the_sine_driver(built_lib):
