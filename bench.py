@@ -355,6 +355,27 @@ def side_measurements(cb, wl, torch, device, hbm_peak, fp64_peak):
         t = float(np.mean(ms[1:]))
         out["nc4_reference_robot"] = {"value": n * k / (t * 1e-3), "unit": UNIT, "kernel_ms": t,
                                       "fp64_frac": flops_per_instance_step(4) * n * k / (t * 1e-3) / 1e12 / fp64_peak}
+    # config 1 (the reference's own operating point): ONE 4-cable robot stepped like the plugin does it -- one update() per
+    # physics step: command in, one step, joint states + platform state out (the Gazebo path is capped at ~1e3 steps/s)
+    with cb.CdprBatch(cb.default_config(4), 1, device=device) as g:
+        axes = np.full((1, 4), 0.01, dtype=np.float32)
+        for _ in range(50):
+            g.step(1)
+        t0 = time.perf_counter()
+        reps = 2000
+        for k in range(reps):
+            if k % 10 == 0:
+                g.set_velocity_cmd(axes)
+            g.step(1)
+            g.joint_states(); g.platform_state()
+        dt1 = (time.perf_counter() - t0) / reps
+        t0 = time.perf_counter()
+        for k in range(reps):
+            g.step(1)
+        g.synchronize()
+        dt2 = (time.perf_counter() - t0) / reps
+        out["plugin_style_single_robot"] = {"updates_per_s_with_readback": 1.0 / dt1, "steps_per_s_no_readback": 1.0 / dt2,
+                                            "what": "N=1, NC=4, k=1 per call through the C ABI; with readback = set command every 10 steps + step + joint states + platform state (host buffers, synchronous)"}
     # config 5: 4096 command sequences x 256 steps per robot, 64 robots on this GPU (262,144 rollouts), cost reduced per sequence
     n_seq, n_cmd, spc, n_rob = 4096, 26, 10, 64
     cmds = wl.c5_rollouts(n_seq, n_cmd, 8)
