@@ -570,7 +570,8 @@ static void fill_args(cdpr_handle h, StepArgs &A, int k_steps, bool sine) {
 static int launch_step(cdpr_handle h, const StepArgs &A) {
   const unsigned grid = (unsigned)(h->np / kTpb);
   if (h->general) {
-    k_step_general<<<grid, kTpb, 0, h->stream>>>(A);
+    if (std::max(h->pc[PID_VEL].degree, h->pc[PID_POS].degree) <= 2) k_step_general<2><<<grid, kTpb, 0, h->stream>>>(A);
+    else k_step_general<4><<<grid, kTpb, 0, h->stream>>>(A);
   } else {
     const bool dm = h->dmom_ok[A.live_idx];
     // the velocity mode with the moment D-term (the headline path) is specialised on the robot constants; every

@@ -105,6 +105,7 @@ __device__ __forceinline__ double ls_derivative(const DevLayout &L, int c, int k
 }
 
 // Pid::derive (Pid.cpp:193-217): overwrite the oldest sample, then the fit once the window is full
+template <int DMAX>
 __device__ __forceinline__ double derive_general(const DevLayout &L, const PidConsts &pc, int c, int k, unsigned &ctl, double value,
                                                  double now, long long i) {
   const int len = pc.len;
@@ -115,16 +116,17 @@ __device__ __forceinline__ double derive_general(const DevLayout &L, const PidCo
   missing -= (missing > 0u) ? 1u : 0u;
   ctl = gctl_set(ctl, k, missing, head);
   if (missing != 0u) return 0.0;
-  switch (pc.degree) {
-    case 1: return ls_derivative<1>(L, c, k, len, head, now, i);
-    case 2: return ls_derivative<2>(L, c, k, len, head, now, i);
-    case 3: return ls_derivative<3>(L, c, k, len, head, now, i);
-    case 4: return ls_derivative<4>(L, c, k, len, head, now, i);
-    default: return 0.0;  // degree 0: derivative of a constant
-  }
+  // DMAX bounds the degrees compiled into this instance (the 5 x 6 system of degree 4 would set the register budget
+  // of the common degree-2 case otherwise)
+  if (pc.degree == 1) return ls_derivative<1>(L, c, k, len, head, now, i);
+  if (pc.degree == 2) return ls_derivative<2>(L, c, k, len, head, now, i);
+  if (DMAX >= 3 && pc.degree == 3) return ls_derivative<3>(L, c, k, len, head, now, i);
+  if (DMAX >= 4 && pc.degree == 4) return ls_derivative<4>(L, c, k, len, head, now, i);
+  return 0.0;  // degree 0: derivative of a constant
 }
 
 // Pid::update (Pid.cpp:122-191) on the state columns of (cable c, pid k)
+template <int DMAX>
 __device__ __forceinline__ double pid_update_general(const DevLayout &L, const PidConsts &pc, int c, int k, unsigned &ctl, double desired,
                                                      double actual, double now, long long i) {
   double *last_time = L.pid + pid_off(L, c, k, PID_LAST_TIME) + i;
@@ -150,7 +152,7 @@ __device__ __forceinline__ double pid_update_general(const DevLayout &L, const P
     else if (i_term < pc.i_min) { i_term = pc.i_min; ie = pc.i_min_over_ki; }
     double de;
     if (dt > 0.0) {
-      const double derived = derive_general(L, pc, c, k, ctl, error, now, i);
+      const double derived = derive_general<DMAX>(L, pc, c, k, ctl, error, now, i);
       de = cascade_update(L, c, k, 1, pc.d_casc, pc.df, derived, i);
       *d_err = de;
     } else {
@@ -174,8 +176,9 @@ __device__ __forceinline__ double pid_update_general(const DevLayout &L, const P
 }
 
 #ifndef CDPR_GEN_BLOCKS
-#define CDPR_GEN_BLOCKS 8
+#define CDPR_GEN_BLOCKS 6
 #endif
+template <int DMAX>
 __global__ void __launch_bounds__(kTpb, CDPR_GEN_BLOCKS) k_step_general(const __grid_constant__ StepArgs A) {
   const long long i = (long long)blockIdx.x * kTpb + threadIdx.x;
   if (i >= A.L.n) return;
@@ -233,21 +236,22 @@ __global__ void __launch_bounds__(kTpb, CDPR_GEN_BLOCKS) k_step_general(const __
 
       unsigned ctl = L.ctl[(long long)c * np + i];
       double *last_pos = L.cab + cab_off(L, c, CAB_LAST_POS) + i;
+      // JointForceCalculator::update (.cpp:59-96): pick the Pid, its set point and its measurement, then ONE Pid update
       double force;
       if (A.mode == MODE_FORCE) {
         *last_pos = qp;
         force = L.cab[cab_off(L, c, CAB_FORCE_CMD) + i];
-      } else if (A.mode == MODE_VELOCITY) {
-        const double vt = L.cab[cab_off(L, c, CAB_VEL_TARGET) + i];
-        if (fabs(vt) > rc.vel_eps) {
-          *last_pos = qp;
-          force = pid_update_general(L, A.pc[PID_VEL], c, PID_VEL, ctl, vt, qd, now, i);
-        } else {  // hold the last position with the position Pid
-          force = pid_update_general(L, A.pc[PID_POS], c, PID_POS, ctl, *last_pos, qp, now, i);
-        }
       } else {
-        *last_pos = qp;
-        force = pid_update_general(L, A.pc[PID_POS], c, PID_POS, ctl, L.cab[cab_off(L, c, CAB_POS_TARGET) + i], qp, now, i);
+        int k;
+        double desired, actual;
+        if (A.mode == MODE_VELOCITY) {
+          const double vt = L.cab[cab_off(L, c, CAB_VEL_TARGET) + i];
+          if (fabs(vt) > rc.vel_eps) { *last_pos = qp; k = PID_VEL; desired = vt; actual = qd; }
+          else { k = PID_POS; desired = *last_pos; actual = qp; }  // hold the last position with the position Pid
+        } else {
+          *last_pos = qp; k = PID_POS; desired = L.cab[cab_off(L, c, CAB_POS_TARGET) + i]; actual = qp;
+        }
+        force = pid_update_general<DMAX>(L, A.pc[k], c, k, ctl, desired, actual, now, i);
       }
       L.ctl[(long long)c * np + i] = ctl;
       const double eff = (rc.effort_limit >= 0.0) ? clampd(force, -rc.effort_limit, rc.effort_limit) : force;
