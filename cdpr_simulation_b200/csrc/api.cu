@@ -556,6 +556,7 @@ static void fill_args(cdpr_handle h, StepArgs &A, int k_steps, bool sine) {
   A.live_idx = (h->mode == MODE_POSITION) ? PID_POS : PID_VEL;
   A.live = h->pc[A.live_idx];
   std::memcpy(A.fir, h->fir[A.live_idx], sizeof(A.fir));
+  std::memcpy(A.fir2, h->fir, sizeof(A.fir2));
   std::memcpy(A.dmom, h->dmom[A.live_idx], sizeof(A.dmom));
   A.effort_ge_cmd = h->rc.effort_limit_abs >= A.live.cmd_max ? 1 : 0;
   A.mode = h->mode; A.k_steps = k_steps; A.n0 = h->step_count;

@@ -77,6 +77,7 @@ struct StepArgs {
   PidConsts live;      // copy of pc[live_idx]: the Pid the fast kernel runs
   int live_idx;
   double fir[kMaxDbuf];  // D-term FIR weights of the LIVE pid, logical order, already divided by the window span
+  double fir2[2][kMaxDbuf];  // FIR weights of BOTH pids (general variant: used whenever a window's time stamps are uniform)
   double dmom[3];        // the same weights as a quadratic in the centred sample position: w_j = dmom[0] + dmom[1] k + dmom[2] k^2
   int effort_ge_cmd;     // effort limit >= cmdMax of the live pid: truncation can only bite on a saturated command
   int mode;            // batch-uniform JointForceCalculator::UpdateMode

@@ -106,8 +106,8 @@ __device__ __forceinline__ double ls_derivative(const DevLayout &L, int c, int k
 
 // Pid::derive (Pid.cpp:193-217): overwrite the oldest sample, then the fit once the window is full
 template <int DMAX>
-__device__ __forceinline__ double derive_general(const DevLayout &L, const PidConsts &pc, int c, int k, unsigned &ctl, double value,
-                                                 double now, long long i) {
+__device__ __forceinline__ double derive_general(const StepArgs &A, const DevLayout &L, const PidConsts &pc, int c, int k, unsigned &ctl,
+                                                 double value, double now, long long i) {
   const int len = pc.len;
   unsigned head = gctl_head(ctl, k), missing = gctl_missing(ctl, k);
   L.win_x[win_off(L, c, k, (int)head) + i] = now;
@@ -116,6 +116,22 @@ __device__ __forceinline__ double derive_general(const DevLayout &L, const PidCo
   missing -= (missing > 0u) ? 1u : 0u;
   ctl = gctl_set(ctl, k, missing, head);
   if (missing != 0u) return 0.0;
+  if (pc.degree < 1) return 0.0;  // degree 0: derivative of a constant
+  // Common case: the window holds the last `len` CONSECUTIVE steps (span == (len-1) dt): the fit is the fixed FIR of
+  // step_fast.cuh -- one pass over the error ring, no time stamps, no solve.  Gaps (hold phases, stale windows) take
+  // the general fit below.
+  const double span = now - L.win_x[win_off(L, c, k, (int)head) + i];
+  if (fabs(span - (len - 1) * A.rc.h) < 0.25 * A.rc.h) {
+    double d0 = 0.0, d1 = 0.0;
+    int sl = (int)head;  // oldest sample = logical position 0
+#pragma unroll 2
+    for (int j = 0; j < len; ++j) {
+      const double y = L.win_y[win_off(L, c, k, sl) + i];
+      if (j & 1) d1 = fma(A.fir2[k][j], y, d1); else d0 = fma(A.fir2[k][j], y, d0);
+      sl = (sl + 1 == len) ? 0 : sl + 1;
+    }
+    return d0 + d1;
+  }
   // DMAX bounds the degrees compiled into this instance (the 5 x 6 system of degree 4 would set the register budget
   // of the common degree-2 case otherwise)
   if (pc.degree == 1) return ls_derivative<1>(L, c, k, len, head, now, i);
@@ -127,7 +143,7 @@ __device__ __forceinline__ double derive_general(const DevLayout &L, const PidCo
 
 // Pid::update (Pid.cpp:122-191) on the state columns of (cable c, pid k)
 template <int DMAX>
-__device__ __forceinline__ double pid_update_general(const DevLayout &L, const PidConsts &pc, int c, int k, unsigned &ctl, double desired,
+__device__ __forceinline__ double pid_update_general(const StepArgs &A, const DevLayout &L, const PidConsts &pc, int c, int k, unsigned &ctl, double desired,
                                                      double actual, double now, long long i) {
   double *last_time = L.pid + pid_off(L, c, k, PID_LAST_TIME) + i;
   double *cmdp = L.pid + pid_off(L, c, k, PID_CMD) + i;
@@ -152,7 +168,7 @@ __device__ __forceinline__ double pid_update_general(const DevLayout &L, const P
     else if (i_term < pc.i_min) { i_term = pc.i_min; ie = pc.i_min_over_ki; }
     double de;
     if (dt > 0.0) {
-      const double derived = derive_general<DMAX>(L, pc, c, k, ctl, error, now, i);
+      const double derived = derive_general<DMAX>(A, L, pc, c, k, ctl, error, now, i);
       de = cascade_update(L, c, k, 1, pc.d_casc, pc.df, derived, i);
       *d_err = de;
     } else {
@@ -251,7 +267,7 @@ __global__ void __launch_bounds__(kTpb, CDPR_GEN_BLOCKS) k_step_general(const __
         } else {
           *last_pos = qp; k = PID_POS; desired = L.cab[cab_off(L, c, CAB_POS_TARGET) + i]; actual = qp;
         }
-        force = pid_update_general<DMAX>(L, A.pc[k], c, k, ctl, desired, actual, now, i);
+        force = pid_update_general<DMAX>(A, L, A.pc[k], c, k, ctl, desired, actual, now, i);
       }
       L.ctl[(long long)c * np + i] = ctl;
       const double eff = (rc.effort_limit >= 0.0) ? clampd(force, -rc.effort_limit, rc.effort_limit) : force;
