@@ -196,3 +196,58 @@ def test_reduced_model_trajectory_l1_vs_l0_force_law():
     a.step(1500); b.step_reference_forcelaw(1500)
     pa, ta = a.platform_state(); pb, tb = b.platform_state()
     assert np.max(np.abs(pa - pb)) < 1e-7 and np.max(np.abs(ta - tb)) < 1e-5
+
+
+# ---- randomised pinning (hypothesis): any gains / limits / cascades / epsilon, any command script ---------------------
+from hypothesis import given, settings, strategies as st, HealthCheck
+
+_gain = st.floats(min_value=0.0, max_value=500.0, allow_nan=False)
+_limit = st.one_of(st.just(0.0), st.floats(min_value=0.05, max_value=200.0, allow_nan=False), st.floats(min_value=-50.0, max_value=-0.05))
+
+
+@settings(max_examples=40, deadline=None, suppress_health_check=[HealthCheck.too_slow])
+@given(kp=_gain, ki=st.floats(min_value=0.01, max_value=300.0), kf=st.floats(min_value=-2.0, max_value=2.0), i_limit=_limit, cmd_limit=_limit,
+       p_cascade=st.integers(0, 3), cutoff=st.floats(min_value=0.01, max_value=0.45), quality=st.floats(min_value=0.3, max_value=2.0),
+       eps=st.floats(min_value=-0.01, max_value=0.06), seed=st.integers(0, 2**16),
+       script=st.lists(st.tuples(st.sampled_from(["vel", "pos", "eff"]), st.integers(1, 119),
+                                 st.lists(st.floats(min_value=-0.0625, max_value=0.0625, width=32), min_size=4, max_size=4)), min_size=1, max_size=6))
+def test_force_law_bit_exact_for_random_parameters(kp, ki, kf, i_limit, cmd_limit, p_cascade, cutoff, quality, eps, seed, script):
+    """D gain 0 (the derivative is pinned separately): for ANY parameter set and command script the oracle's forces equal
+    the reference's compiled JointForceCalculator/Pid forces bit for bit -- negative limits (abs() in the ctor),
+    cmdLimit == 0 (frozen command), biquad cascades on the P input, hold above/below epsilon, mode switches."""
+    L, R = ob.lib(), ob.ref()
+    cfg = ob.default_config(4)
+    cfg.velocity_epsilon = eps
+    for pid in (cfg.vel_pid, cfg.pos_pid):
+        pid.p_gain, pid.i_gain, pid.d_gain, pid.i_limit, pid.cmd_limit = kp, ki, 0.0, i_limit, cmd_limit
+    cfg.vel_pid.forward_gain = kf
+    cfg.vel_pid.p_cascade, cfg.vel_pid.p_cutoff, cfg.vel_pid.p_quality = p_cascade, cutoff, quality
+    ref = R.ref_plugin_create(4, C.byref(cfg.vel_pid), C.byref(cfg.pos_pid), eps)
+    cables = [L.orc_cable_new(C.byref(cfg)) for _ in range(4)]
+    rng = np.random.default_rng(seed)
+    q = np.zeros(4)
+    try:
+        for step in range(1, 121):
+            ns = step * 1_000_000
+            R.ref_plugin_set_time(ref, 0, ns)
+            for kind, at, val in script:
+                if at == step:
+                    if kind == "vel":
+                        axes = np.asarray(val, dtype=np.float32)
+                        R.ref_plugin_velocity_cmd(ref, axes); [L.orc_cable_set_velocity_target(c, float(a)) for c, a in zip(cables, axes)]
+                    elif kind == "pos":
+                        axes = np.asarray(val, dtype=np.float32)
+                        R.ref_plugin_position_cmd(ref, axes); [L.orc_cable_set_position_target(c, float(a)) for c, a in zip(cables, axes)]
+                    else:
+                        f = np.asarray(val, dtype=np.float64) * 50.0
+                        R.ref_plugin_effort_cmd(ref, f); [L.orc_cable_set_force(c, float(a)) for c, a in zip(cables, f)]
+            qd = 0.05 * rng.normal(size=4)
+            q = q + 1e-3 * qd
+            for c in range(4):
+                R.ref_plugin_set_joint(ref, c, q[c], qd[c])
+                fr = R.ref_plugin_update_cable(ref, c, None)
+                fo = L.orc_cable_update(cables[c], 0, ns, q[c], qd[c])
+                assert fr == fo or (np.isnan(fr) and np.isnan(fo)), (step, c, fr, fo)
+    finally:
+        R.ref_plugin_destroy(ref)
+        [L.orc_cable_free(c) for c in cables]
