@@ -511,3 +511,29 @@ def test_gpu_against_the_references_own_force_law(built_lib, nc):
     assert np.max(np.abs(eg - eo)) < 1e-2          # forces: the D gain multiplies the reference's derivative noise
     # and it is NOT trivially satisfied: the platforms moved by centimetres
     assert np.max(np.abs(pg[:, :3] - pose7[:, :3])) > 1e-2
+
+
+@pytest.mark.parametrize("nc", [4, 8])
+@pytest.mark.parametrize("limits", [(0.5, 100.0, 100.0), (100.0, 3.0, 100.0), (0.3, 1.5, 100.0), (100.0, 100.0, 2.0), (100.0, 6.0, 4.0)])
+def test_fast_variant_saturation_paths(built_lib, nc, limits):
+    """Integral clamp with back-calculation, command clamp + anti-windup (which may exceed the clamp, Pid.cpp:181-184)
+    and the joint's effort truncation, all inside the FAST kernel: small limits so that every path fires."""
+    i_limit, cmd_limit, effort = limits
+    def edit(cfg):
+        for pid in (cfg.vel_pid, cfg.pos_pid):
+            pid.i_limit, pid.cmd_limit = i_limit, cmd_limit
+        cfg.effort_limit = effort
+    cfg, gpu, orc = make_pair(nc, 140, seed=31, cfg_edit=edit)
+    assert gpu.kernel_variant == "fast"
+    saw_sat = False
+    for k in (3, 30, 200, 700):
+        gpu.step(k); orc.step(k)
+        pg, tg = gpu.platform_state(); po, to = orc.platform_state()
+        assert state_rel_err(pg, tg, po, to) < 1e-8, (limits, k)
+        eff = orc.last_outputs()[3]
+        saw_sat = saw_sat or bool(np.any(np.abs(eff) >= min(cmd_limit, effort) * 0.999))
+        for a, b in zip(gpu.joint_states(), orc.joint_states()):
+            assert np.max(np.abs(a - b)) < 1e-8
+    if min(cmd_limit, effort) < 10:
+        assert saw_sat, "the test is meant to saturate"
+    gpu.close()
