@@ -559,6 +559,7 @@ static void fill_args(cdpr_handle h, StepArgs &A, int k_steps, bool sine) {
   std::memcpy(A.fir2, h->fir, sizeof(A.fir2));
   std::memcpy(A.dmom, h->dmom[A.live_idx], sizeof(A.dmom));
   A.effort_ge_cmd = h->rc.effort_limit_abs >= A.live.cmd_max ? 1 : 0;
+  A.sat_thr = fmin(A.live.cmd_max, h->rc.effort_limit_abs);
   A.mode = h->mode; A.k_steps = k_steps; A.n0 = h->step_count;
   A.sec0 = h->sec; A.nsec0 = h->nsec; A.dt_ns = h->dt_ns; A.t0 = time_double(h->sec, h->nsec);
   A.sine_on = sine ? 1 : 0; A.sine_period = h->sine_period; A.sine_time0 = h->sine_time; A.sine_pub_dt = h->sine_pub_dt;

@@ -80,6 +80,7 @@ struct StepArgs {
   double fir2[2][kMaxDbuf];  // FIR weights of BOTH pids (general variant: used whenever a window's time stamps are uniform)
   double dmom[3];        // the same weights as a quadratic in the centred sample position: w_j = dmom[0] + dmom[1] k + dmom[2] k^2
   int effort_ge_cmd;     // effort limit >= cmdMax of the live pid: truncation can only bite on a saturated command
+  double sat_thr;        // min(cmdMax, effort limit): an unclamped command within it passes every clamp unchanged
   int mode;            // batch-uniform JointForceCalculator::UpdateMode
   int k_steps;
   long long n0;        // physics steps done before this launch

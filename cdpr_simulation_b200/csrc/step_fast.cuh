@@ -52,9 +52,94 @@ constexpr int kResync = 64;
 // "lean" = SPEC_UTGT | SPEC_NOFF: the one target lives in a register, so no target / feed-forward arrays in shared memory
 template <int NC, int SPEC = 0> struct FastCfg {
   static constexpr bool lean = (SPEC & (8 | 16)) == (8 | 16);
+  // optimistic saturation handling parks the pre-update integrals in [NC][tpb] doubles of scratch; the non-lean
+  // 8-cable layout has no room for it and commits the integrals after the vote instead (one more LDS + DFMA per cable)
+  static constexpr bool scratch = (NC <= 4) || lean;
   static constexpr int tpb = (NC <= 4) ? CDPR_NC4_TPB : (lean ? CDPR_NC8_LEAN_TPB : CDPR_NC8_TPB);
   static constexpr int blocks = (NC <= 4) ? CDPR_NC4_BLOCKS : (lean ? CDPR_NC8_LEAN_BLOCKS : CDPR_NC8_BLOCKS);
 };
+
+// ---- inverse kinematics of one cable (a7).  With g = a - p (anchor seen from the platform origin): d = g - R b = L u,
+// and r x u = (g - d) x u = g x u because d is parallel to u -- so neither r nor u is formed:
+//   m = g x d = L (r x u),  joint rate = (d.v + m.w) / L,  and the wrench scales d and m by tension / L.
+struct CableKin { double dx, dy, dz, cx, cy, cz, il, qd, qp; };
+template <int SPEC, bool WANT_QP>
+__device__ __forceinline__ CableKin cable_kin(const RobotConsts &rc, const FastState &S, const Rot &R, int c) {
+  CableKin k;
+  const double bx = rc.b[c][0], by = rc.b[c][1], bz = rc.b[c][2];
+  const double gx = rc.a[c][0] - S.px, gy = rc.a[c][1] - S.py, gz = rc.a[c][2] - S.pz;
+  k.dx = fma(-R.r00, bx, fma(-R.r01, by, (SPEC & SPEC_BZ0) ? gx : fma(-R.r02, bz, gx)));
+  k.dy = fma(-R.r10, bx, fma(-R.r11, by, (SPEC & SPEC_BZ0) ? gy : fma(-R.r12, bz, gy)));
+  k.dz = fma(-R.r20, bx, fma(-R.r21, by, (SPEC & SPEC_BZ0) ? gz : fma(-R.r22, bz, gz)));
+  const double l2 = fma(k.dx, k.dx, fma(k.dy, k.dy, k.dz * k.dz));
+  k.il = rsqrt_nr(l2);
+  k.cx = fma(gy, k.dz, -(gz * k.dy)); k.cy = fma(gz, k.dx, -(gx * k.dz)); k.cz = fma(gx, k.dy, -(gy * k.dx));
+  k.qd = (fma(k.dx, S.vx, fma(k.dy, S.vy, k.dz * S.vz)) + fma(k.cx, S.wx, fma(k.cy, S.wy, k.cz * S.wz))) * k.il;
+  k.qp = 0.0;
+  if (WANT_QP) k.qp = rc.home_len[c] - l2 * k.il;
+  return k;
+}
+
+// P + I + D (+ feed-forward `ff`) before any clamp (Pid.cpp:140-172)
+template <int SPEC>
+__device__ __forceinline__ double pid_command(const PidConsts &pc, double e, double ie, double derr, double ff) {
+  return (SPEC & SPEC_NOFF) ? fma(pc.ki, ie, fma(pc.kd, derr, pc.kp * e)) : fma(pc.ki, ie, fma(pc.kd, derr, fma(pc.kp, e, ff)));
+}
+
+// The exact clamping chain, from the integrated-but-unclamped integral `ie1`.
+template <int SPEC>
+__device__ __forceinline__ void pid_clamped(const StepArgs &A, double dt, double e, double derr, double ff, double ie1, double prev_ierr,
+                                            double &force, double &eff, double &ie) {
+  const PidConsts &pc = A.live;
+  // integral clamp with back-calculation (Pid.cpp:143-150) applied to the integral itself:
+  // |Ki * Ierr| > Imax  <=>  |Ierr| > Imax / Ki (Ki >= 0 in this variant), clamped term = Ki * (Imax / Ki)
+  ie = (fabs(ie1) > pc.i_max_over_ki) ? copysign(pc.i_max_over_ki, ie1) : ie1;
+  const double cmd_raw = pid_command<SPEC>(pc, e, ie, derr, ff);
+  // clamp + anti-windup (Pid.cpp:175-184): mCmd != cmd  <=>  |cmd| > cmdMax
+  const bool csat = fabs(cmd_raw) > pc.cmd_max;
+  force = cmd_raw;
+  if (csat) {  // rare: saturated command
+    force = fma(dt * e, pc.ki, copysign(pc.cmd_max, cmd_raw));
+    ie = prev_ierr;
+  }
+  // Joint::SetForce truncation can only bite on a saturated command when effortLimit >= cmdMax
+  eff = force;
+  if (csat || !A.effort_ge_cmd) eff = (fabs(force) > A.rc.effort_limit_abs) ? copysign(A.rc.effort_limit_abs, force) : force;
+}
+
+// Saturation (Pid.cpp:143-150 integral clamp, :175-184 command clamp + anti-windup, Joint::SetForce truncation) is
+// rare, and handling it inline costs ~10 non-FP64 issue slots per cable.  The steady, non-last body (the hot loop)
+// therefore runs OPTIMISTICALLY: it integrates and applies the unclamped command, and only accumulates one predicate
+// "something in this step would have clamped".  One warp vote per step; if it fires, saturated_pass() recomputes every
+// cable's force with the exact clamping chain and rebuilds the wrench from scratch in cable order.  That pass is
+// bit-identical to the inline code the other bodies run, so a step's result does not depend on which body ran it.
+// The integral before the update, needed by the anti-windup restore, is parked in shared memory (`prv`) where the
+// layout has room (FastCfg::scratch); otherwise the integrals are committed after the vote from the ring's newest slot.
+// Out of line and by value, so the hot loop's register allocation does not see it.
+template <int NC, bool SCR> struct SatIn { FastState S; double ie1[NC], derr[NC]; double prev[SCR ? 1 : NC]; double tgu, dt; };
+template <int NC> struct SatOut { double ierr[NC]; double fx, fy, fz, mx, my, mz; };
+template <int NC, int MODE, int SPEC>
+__device__ __noinline__ SatOut<NC> saturated_pass(const StepArgs &A, SatIn<NC, FastCfg<NC, SPEC>::scratch> in, const double *tgts, const double *prv) {
+  constexpr int kT = FastCfg<NC, SPEC>::tpb;
+  const RobotConsts &rc = A.rc;
+  const Rot R = make_rot(in.S);
+  SatOut<NC> o;
+  o.fx = rc.mg[0]; o.fy = rc.mg[1]; o.fz = rc.mg[2];
+  o.mx = 0.0; o.my = 0.0; o.mz = 0.0;
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    const CableKin k = cable_kin<SPEC, MODE == MODE_POSITION>(rc, in.S, R, c);
+    const double tg = (SPEC & SPEC_UTGT) ? in.tgu : tgts[c * kT];
+    const double ff = (SPEC & SPEC_NOFF) ? 0.0 : tgts[(NC + c) * kT];
+    const double e = tg - ((MODE == MODE_VELOCITY) ? k.qd : k.qp);
+    double force, eff;
+    pid_clamped<SPEC>(A, in.dt, e, in.derr[c], ff, in.ie1[c], FastCfg<NC, SPEC>::scratch ? prv[c * kT] : in.prev[c], force, eff, o.ierr[c]);
+    const double tl = fma(-rc.cdamp, k.qd, eff) * k.il;
+    o.fx = fma(tl, k.dx, o.fx); o.fy = fma(tl, k.dy, o.fy); o.fz = fma(tl, k.dz, o.fz);
+    o.mx = fma(tl, k.cx, o.mx); o.my = fma(tl, k.cy, o.my); o.mz = fma(tl, k.cz, o.mz);
+  }
+  return o;
+}
 
 // One physics step for one instance.
 //   STEADY: every live Pid is primed and its window is full (mWasLastTime && mDbufferMissing == 0)
@@ -63,11 +148,13 @@ template <int NC, int SPEC = 0> struct FastCfg {
 template <int NC, int LEN, bool STEADY, bool LAST, int MODE, bool DMOM, int SPEC>
 __device__ __forceinline__ void fast_step(const StepArgs &A, FastState &S, double (&ierr)[NC], const double *__restrict__ tgts, const double tgu,
                                           double (&mom)[NC][3], unsigned &primed, unsigned (&missing)[NC],
-                                          double *__restrict__ win, int head, double dt, long long i) {
+                                          double *__restrict__ win, double *__restrict__ prv, int head, double dt, long long i) {
+  constexpr int kT = FastCfg<NC, SPEC>::tpb;
+  constexpr bool OPT = STEADY && !LAST && MODE != MODE_FORCE;
+  constexpr bool SCR = FastCfg<NC, SPEC>::scratch;
   const RobotConsts &rc = A.rc;
   const PidConsts &pc = A.live;
   const Rot R = make_rot(S);
-  const double r00 = R.r00, r01 = R.r01, r02 = R.r02, r10 = R.r10, r11 = R.r11, r12 = R.r12, r20 = R.r20, r21 = R.r21, r22 = R.r22;
 
   double fx = rc.mg[0], fy = rc.mg[1], fz = rc.mg[2];
   double mx = 0.0, my = 0.0, mz = 0.0;
@@ -78,79 +165,65 @@ __device__ __forceinline__ void fast_step(const StepArgs &A, FastState &S, doubl
   for (int a = 0; a < (DMOM ? 1 : LEN); ++a) {
     int s = head - a;
     s += (s < 0) ? LEN : 0;
-    slot[a] = s * (NC * FastCfg<NC, SPEC>::tpb);
+    slot[a] = s * (NC * kT);
   }
+  // least-squares derivative at `now` from the window state AFTER this step's sample went in (Pid.cpp:193-217)
+  auto dterm = [&](int c, double e, const double *w) {
+    if (DMOM) return fma(A.dmom[0], mom[c][0], fma(A.dmom[1], mom[c][1], A.dmom[2] * mom[c][2]));
+    double d0 = A.fir[LEN - 1] * e, d1 = 0.0;
+#pragma unroll
+    for (int a = 1; a < LEN; ++a) {
+      if (a & 1) d1 = fma(A.fir[LEN - 1 - a], w[slot[a]], d1);
+      else d0 = fma(A.fir[LEN - 1 - a], w[slot[a]], d0);
+    }
+    return d0 + d1;
+  };
+
+  bool sat = false;
 #pragma unroll
   for (int c = 0; c < NC; ++c) {
-    // ---- inverse kinematics (a7).  With g = a - p (anchor seen from the platform origin): d = g - R b = L u, and
-    // r x u = (g - d) x u = g x u because d is parallel to u -- so neither r nor u is formed:
-    //   m = g x d = L (r x u),  joint rate = (d.v + m.w) / L,  and the wrench below scales d and m by tension / L.
-    const double bx = rc.b[c][0], by = rc.b[c][1], bz = rc.b[c][2];
-    const double gx = rc.a[c][0] - S.px, gy = rc.a[c][1] - S.py, gz = rc.a[c][2] - S.pz;
-    const double dx = fma(-r00, bx, fma(-r01, by, (SPEC & SPEC_BZ0) ? gx : fma(-r02, bz, gx)));
-    const double dy = fma(-r10, bx, fma(-r11, by, (SPEC & SPEC_BZ0) ? gy : fma(-r12, bz, gy)));
-    const double dz = fma(-r20, bx, fma(-r21, by, (SPEC & SPEC_BZ0) ? gz : fma(-r22, bz, gz)));
-    const double l2 = fma(dx, dx, fma(dy, dy, dz * dz));
-    const double il = rsqrt_nr(l2);
-    const double cx = fma(gy, dz, -(gz * dy)), cy = fma(gz, dx, -(gx * dz)), cz = fma(gx, dy, -(gy * dx));
-    const double qd = (fma(dx, S.vx, fma(dy, S.vy, dz * S.vz)) + fma(cx, S.wx, fma(cy, S.wy, cz * S.wz))) * il;
-    double qp = 0.0;
-    if (MODE == MODE_POSITION || LAST) qp = rc.home_len[c] - l2 * il;
+    const CableKin k = cable_kin<SPEC, MODE == MODE_POSITION || LAST>(rc, S, R, c);
 
     // ---- force law (a3, a4, a5)
     double force, eff;
     if (MODE == MODE_FORCE) {
-      force = tgts[c * FastCfg<NC, SPEC>::tpb];  // JointForceCalculator.cpp:67-70
+      force = tgts[c * kT];  // JointForceCalculator.cpp:67-70
       eff = (fabs(force) > rc.effort_limit_abs) ? copysign(rc.effort_limit_abs, force) : force;
     } else {
-      const double tg = (SPEC & SPEC_UTGT) ? tgu : tgts[c * FastCfg<NC, SPEC>::tpb];
-      const double e = tg - ((MODE == MODE_VELOCITY) ? qd : qp);
-      double *w = win + c * FastCfg<NC, SPEC>::tpb;
+      const double tg = (SPEC & SPEC_UTGT) ? tgu : tgts[c * kT];
+      const double e = tg - ((MODE == MODE_VELOCITY) ? k.qd : k.qp);
+      double *w = win + c * kT;
       if (STEADY || ((primed >> c) & 1u)) {  // Pid.cpp:127-187
         const double prev_ierr = ierr[c];
-        double ie = fma(dt, e, prev_ierr);
-        // integral clamp with back-calculation (Pid.cpp:143-150) applied to the integral itself:
-        // |Ki * Ierr| > Imax  <=>  |Ierr| > Imax / Ki (Ki >= 0 in this variant), clamped term = Ki * (Imax / Ki)
-        ie = (fabs(ie) > pc.i_max_over_ki) ? copysign(pc.i_max_over_ki, ie) : ie;
-        // derive(): push the sample, least-squares derivative at `now` (Pid.cpp:193-217)
-        double derr;
+        const double ie1 = fma(dt, e, prev_ierr);
+        // derive(): push the sample
         if (DMOM) {
           const double y_old = w[slot[0]];
           w[slot[0]] = e;
           const double s0 = mom[c][0], s1 = mom[c][1], s2 = mom[c][2];
           // y_old (a shared-memory read) enters last, so its latency hides behind the rest of the chain
-          const double n1 = fma((double)LEN, e, s1 - s0);
-          const double n2 = fma((double)(LEN * LEN), e, fma(-2.0, s1, s2) + s0);
-          const double n0 = (s0 + e) - y_old;
-          mom[c][0] = n0; mom[c][1] = n1; mom[c][2] = n2;
-          derr = fma(A.dmom[0], n0, fma(A.dmom[1], n1, A.dmom[2] * n2));
+          mom[c][1] = fma((double)LEN, e, s1 - s0);
+          mom[c][2] = fma((double)(LEN * LEN), e, fma(-2.0, s1, s2) + s0);
+          mom[c][0] = (s0 + e) - y_old;
         } else {
           w[slot[0]] = e;
-          double d0 = A.fir[LEN - 1] * e, d1 = 0.0;
-#pragma unroll
-          for (int a = 1; a < LEN; ++a) {
-            if (a & 1) d1 = fma(A.fir[LEN - 1 - a], w[slot[a]], d1);
-            else d0 = fma(A.fir[LEN - 1 - a], w[slot[a]], d0);
-          }
-          derr = d0 + d1;
         }
+        double derr = dterm(c, e, w);
         if (!STEADY) {
           missing[c] -= (missing[c] > 0u) ? 1u : 0u;
           if (missing[c] != 0u) derr = 0.0;
         }
-        const double cmd_raw = (SPEC & SPEC_NOFF) ? fma(pc.ki, ie, fma(pc.kd, derr, pc.kp * e))
-                                                  : fma(pc.ki, ie, fma(pc.kd, derr, fma(pc.kp, e, tgts[(NC + c) * FastCfg<NC, SPEC>::tpb])));
-        // clamp + anti-windup (Pid.cpp:175-184): mCmd != cmd  <=>  |cmd| > cmdMax
-        const bool csat = fabs(cmd_raw) > pc.cmd_max;
-        force = cmd_raw;
-        if (csat) {  // rare: saturated command
-          force = fma(dt * e, pc.ki, copysign(pc.cmd_max, cmd_raw));
-          ie = prev_ierr;
+        const double ff = (SPEC & SPEC_NOFF) ? 0.0 : tgts[(NC + c) * kT];
+        if (OPT) {
+          force = pid_command<SPEC>(pc, e, ie1, derr, ff);
+          eff = force;
+          sat = sat || (fabs(ie1) > pc.i_max_over_ki) || (fabs(force) > A.sat_thr);
+          if (SCR) { prv[c * kT] = prev_ierr; ierr[c] = ie1; }
+        } else {
+          double ie;
+          pid_clamped<SPEC>(A, dt, e, derr, ff, ie1, prev_ierr, force, eff, ie);
+          ierr[c] = ie;
         }
-        // Joint::SetForce truncation can only bite on a saturated command when effortLimit >= cmdMax
-        eff = force;
-        if (csat || !A.effort_ge_cmd) eff = (fabs(force) > rc.effort_limit_abs) ? copysign(rc.effort_limit_abs, force) : force;
-        ierr[c] = ie;
         if (LAST) {
           A.L.pid[pid_off(A.L, c, A.live_idx, PID_P_ERR) + i] = e;
           A.L.pid[pid_off(A.L, c, A.live_idx, PID_D_ERR) + i] = derr;
@@ -163,14 +236,36 @@ __device__ __forceinline__ void fast_step(const StepArgs &A, FastState &S, doubl
       if (LAST) A.L.pid[pid_off(A.L, c, A.live_idx, PID_CMD) + i] = force;
     }
     if (LAST) {
-      A.L.cab[cab_off(A.L, c, CAB_LAST_POS) + i] = qp;
+      A.L.cab[cab_off(A.L, c, CAB_LAST_POS) + i] = k.qp;
       A.L.cab[cab_off(A.L, c, CAB_EFFORT) + i] = eff;
       A.L.cab[cab_off(A.L, c, CAB_PID_FORCE) + i] = force;
     }
     // ---- explicit joint damping, wrench (a8)
-    const double tl = fma(-rc.cdamp, qd, eff) * il;  // tension / L
-    fx = fma(tl, dx, fx); fy = fma(tl, dy, fy); fz = fma(tl, dz, fz);
-    mx = fma(tl, cx, mx); my = fma(tl, cy, my); mz = fma(tl, cz, mz);
+    const double tl = fma(-rc.cdamp, k.qd, eff) * k.il;  // tension / L
+    fx = fma(tl, k.dx, fx); fy = fma(tl, k.dy, fy); fz = fma(tl, k.dz, fz);
+    mx = fma(tl, k.cx, mx); my = fma(tl, k.cy, my); mz = fma(tl, k.cz, mz);
+  }
+
+  if (OPT) {
+    // the ring's newest slot holds this step's error of every cable
+    if (__any_sync(0xffffffffu, sat)) {  // rare: redo the force law of this step with the clamps
+      SatIn<NC, SCR> in;
+      in.S = S; in.tgu = tgu; in.dt = dt;
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        const double e = win[c * kT + slot[0]];
+        if (!SCR) in.prev[c] = ierr[c];
+        in.ie1[c] = SCR ? ierr[c] : fma(dt, e, ierr[c]);
+        in.derr[c] = dterm(c, e, win + c * kT);
+      }
+      const SatOut<NC> o = saturated_pass<NC, MODE, SPEC>(A, in, tgts, prv);
+#pragma unroll
+      for (int c = 0; c < NC; ++c) ierr[c] = o.ierr[c];
+      fx = o.fx; fy = o.fy; fz = o.fz; mx = o.mx; my = o.my; mz = o.mz;
+    } else if (!SCR) {
+#pragma unroll
+      for (int c = 0; c < NC; ++c) ierr[c] = fma(dt, win[c * kT + slot[0]], ierr[c]);
+    }
   }
 
   rigid_body_step<SPEC>(rc, S, R, fx, fy, fz, mx, my, mz);
@@ -208,9 +303,9 @@ __device__ __noinline__ void write_snapshot(const StepArgs &A, FastState S, long
 }
 
 // shared memory per block (doubles): ring [LEN][NC][tpb], targets [NC][tpb], feed-forward terms Kf*target [NC][tpb],
-// sine parameters [3][tpb]
+// sine parameters [3][tpb], pre-update integrals [NC][tpb] (optimistic variants)
 template <int NC, int LEN, int SPEC>
-constexpr size_t fast_smem_bytes() { return sizeof(double) * (size_t)FastCfg<NC, SPEC>::tpb * (LEN * NC + (FastCfg<NC, SPEC>::lean ? 0 : 2 * NC) + 3); }
+constexpr size_t fast_smem_bytes() { return sizeof(double) * (size_t)FastCfg<NC, SPEC>::tpb * (LEN * NC + (FastCfg<NC, SPEC>::lean ? 0 : 2 * NC) + 3 + (FastCfg<NC, SPEC>::scratch ? NC : 0)); }
 
 template <int NC, int LEN, int MODE, bool DMOM, int SPEC>
 __global__ void __launch_bounds__(FastCfg<NC, SPEC>::tpb, FastCfg<NC, SPEC>::blocks) k_step_fast(const __grid_constant__ StepArgs A) {
@@ -227,6 +322,7 @@ __global__ void __launch_bounds__(FastCfg<NC, SPEC>::tpb, FastCfg<NC, SPEC>::blo
   double *mytgt = smem + LEN * NC * kTpbL + tid;       // [NC][tpb]
   constexpr bool kLean = FastCfg<NC, SPEC>::lean;       // no target arrays: mytgt is never dereferenced
   double *mysine = mytgt + (kLean ? 0 : 2 * NC * kTpbL);  // [3][tpb]: amp, freq, phase
+  double *myprv = mysine + 3 * kTpbL;                      // [NC][tpb], optimistic variants only
 
   FastState S;
   load_plat(A.L, i, S);
@@ -352,7 +448,7 @@ __global__ void __launch_bounds__(FastCfg<NC, SPEC>::tpb, FastCfg<NC, SPEC>::blo
       // warm-up (at most LEN + 1 steps after a Pid reset): some live Pid of the warp is un-primed or its window is not full
       double dt;
       clock_tick(dt);
-      fast_step<NC, LEN, false, false, MODE, DMOM, SPEC>(A, S, ierr, mytgt, tgu, mom, primed, missing, mywin, head, dt, i);
+      fast_step<NC, LEN, false, false, MODE, DMOM, SPEC>(A, S, ierr, mytgt, tgu, mom, primed, missing, mywin, myprv, head, dt, i);
       if (A.cost) add_cost();
       bool st = true;
 #pragma unroll
@@ -371,14 +467,14 @@ __global__ void __launch_bounds__(FastCfg<NC, SPEC>::tpb, FastCfg<NC, SPEC>::blo
         for (int r = 0; r < run; ++r) {
           double dt;
           clock_tick(dt);
-          fast_step<NC, LEN, true, false, MODE, DMOM, SPEC>(A, S, ierr, mytgt, tgu, mom, primed, missing, mywin, head, dt, i);
+          fast_step<NC, LEN, true, false, MODE, DMOM, SPEC>(A, S, ierr, mytgt, tgu, mom, primed, missing, mywin, myprv, head, dt, i);
           add_cost();
         }
       } else {
         for (int r = 0; r < run; ++r) {  // the hot loop
           double dt;
           clock_tick(dt);
-          fast_step<NC, LEN, true, false, MODE, DMOM, SPEC>(A, S, ierr, mytgt, tgu, mom, primed, missing, mywin, head, dt, i);
+          fast_step<NC, LEN, true, false, MODE, DMOM, SPEC>(A, S, ierr, mytgt, tgu, mom, primed, missing, mywin, myprv, head, dt, i);
         }
       }
       advance_counters(run);
@@ -391,8 +487,8 @@ __global__ void __launch_bounds__(FastCfg<NC, SPEC>::tpb, FastCfg<NC, SPEC>::blo
     double dt;
     clock_tick(dt);
     if (valid) {
-      if (warp_steady) fast_step<NC, LEN, true, true, MODE, DMOM, SPEC>(A, S, ierr, mytgt, tgu, mom, primed, missing, mywin, head, dt, i);
-      else fast_step<NC, LEN, false, true, MODE, DMOM, SPEC>(A, S, ierr, mytgt, tgu, mom, primed, missing, mywin, head, dt, i);
+      if (warp_steady) fast_step<NC, LEN, true, true, MODE, DMOM, SPEC>(A, S, ierr, mytgt, tgu, mom, primed, missing, mywin, myprv, head, dt, i);
+      else fast_step<NC, LEN, false, true, MODE, DMOM, SPEC>(A, S, ierr, mytgt, tgu, mom, primed, missing, mywin, myprv, head, dt, i);
     }
     if (A.cost) add_cost();
     advance_counters(1);

@@ -537,3 +537,67 @@ def test_fast_variant_saturation_paths(built_lib, nc, limits):
     if min(cmd_limit, effort) < 10:
         assert saw_sat, "the test is meant to saturate"
     gpu.close()
+
+
+@pytest.mark.parametrize("nc", [4, 8])
+@pytest.mark.parametrize("limits", [(0.3, 1.5, 100.0), (100.0, 6.0, 4.0), (0.5, 100.0, 100.0)])
+def test_saturated_steps_do_not_depend_on_the_launch_split(built_lib, nc, limits):
+    """The hot loop handles saturation optimistically (one vote per step, out-of-line exact pass when it fires); the
+    first-steps and last-step bodies clamp inline.  Both must give the same bits, so how K steps are cut into launches
+    cannot show in the state, the integrals or the telemetry."""
+    i_limit, cmd_limit, effort = limits
+    def edit(cfg):
+        for pid in (cfg.vel_pid, cfg.pos_pid):
+            pid.i_limit, pid.cmd_limit = i_limit, cmd_limit
+        cfg.effort_limit = effort
+    _, a, _ = make_pair(nc, 160, seed=32, cfg_edit=edit)
+    _, b, _ = make_pair(nc, 160, seed=32, cfg_edit=edit)
+    a.step(300)
+    for k in (1, 2, 10, 11, 13, 100, 163):
+        b.step(k)
+    pa, ta = a.platform_state(); pb, tb = b.platform_state()
+    assert np.array_equal(pa, pb) and np.array_equal(ta, tb)
+    for x, y in zip(a.joint_states(), b.joint_states()):
+        assert np.array_equal(x, y)
+    assert np.array_equal(a.pid_state(), b.pid_state())
+    a.close(); b.close()
+
+
+@pytest.mark.parametrize("nc", [4, 8])
+@pytest.mark.parametrize("shape", ["per_cable_velocity", "position", "cubic_fir_feedforward"])
+def test_saturation_with_per_cable_commands(built_lib, nc, shape):
+    """The same saturation paths in the layouts that keep per-cable targets (and feed-forward terms) in shared memory,
+    in Position mode, and with the FIR form of the D-term (cubic fit): against the oracle, and bitwise against a
+    different launch split."""
+    def edit(cfg):
+        for pid in (cfg.vel_pid, cfg.pos_pid):
+            pid.i_limit, pid.cmd_limit = 0.4, 5.0
+            if shape == "cubic_fir_feedforward":
+                pid.d_degree, pid.forward_gain = 3, 2.5
+        cfg.effort_limit = 4.0
+    n = 150
+    rng = np.random.default_rng(77)
+    v = rng.uniform(-0.3, 0.3, (n, nc)).astype(np.float32)
+    p = rng.uniform(-0.05, 0.05, (n, nc)).astype(np.float32)
+    runs = []
+    for split in ((260,), (1, 12, 47, 200)):
+        cfg, gpu, orc = make_pair(nc, n, seed=41, cfg_edit=edit, sine=False)
+        assert gpu.kernel_variant == "fast"
+        if shape == "position":
+            gpu.step(20); orc.step(20)
+            gpu.set_position_cmd(p); orc.position_cmd(p)
+        else:
+            gpu.set_velocity_cmd(v); orc.velocity_cmd(v)
+        for k in split:
+            gpu.step(k); orc.step(k)
+        pg, tg = gpu.platform_state(); po, to = orc.platform_state()
+        assert state_rel_err(pg, tg, po, to) < 1e-8, (shape, split)
+        for a, b in zip(gpu.joint_states(), orc.joint_states()):
+            assert np.max(np.abs(a - b)) < 1e-8
+        assert np.any(np.abs(orc.last_outputs()[3]) >= 4.0 * 0.999), "the test is meant to saturate"
+        runs.append((pg, tg, gpu.joint_states(), gpu.pid_state()))
+        gpu.close()
+    a, b = runs
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[3], b[3])
+    for x, y in zip(a[2], b[2]):
+        assert np.array_equal(x, y)
