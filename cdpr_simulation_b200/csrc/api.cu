@@ -558,6 +558,13 @@ static void fill_args(cdpr_handle h, StepArgs &A, int k_steps, bool sine) {
   std::memcpy(A.fir, h->fir[A.live_idx], sizeof(A.fir));
   std::memcpy(A.fir2, h->fir, sizeof(A.fir2));
   std::memcpy(A.dmom, h->dmom[A.live_idx], sizeof(A.dmom));
+  {  // D = a S0 + b S1 + c S2 over positions 1..LEN; one slide of the window, substituted into Kd * D
+    const double a = A.dmom[0], b = A.dmom[1], c = A.dmom[2], kd = A.live.kd, len = (double)A.live.len;
+    A.dk[0] = kd * (a + len * b + len * len * c);
+    A.dk[1] = kd * (c - b);
+    A.dk[2] = -2.0 * kd * c;
+    A.dk[3] = -kd * a;
+  }
   A.effort_ge_cmd = h->rc.effort_limit_abs >= A.live.cmd_max ? 1 : 0;
   A.sat_thr = fmin(A.live.cmd_max, h->rc.effort_limit_abs);
   A.mode = h->mode; A.k_steps = k_steps; A.n0 = h->step_count;

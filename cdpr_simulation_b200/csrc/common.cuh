@@ -6,7 +6,7 @@
 //   cab   [NC][CAB_F][Np]         last_pos, force_cmd, pos_target, vel_target, effort, pid_force
 //   pid   [NC][2][PID_F][Np]      last_time, p_err, i_err, d_err, cmd      (pid 0 = velocity, 1 = position)
 //   win_y [NC][2][LEN][Np]        D-term error window, logical order (oldest first) = Pid::mDbufferY
-//   mom   [NC][2][3][Np]          window moments S0 S1 S2 of the fast variant's D-term (see step_fast.cuh)
+//   mom   [NC][2][3][Np]          window state S0, S1, Kd*D of the fast variant's D-term (see step_fast.cuh)
 //   win_x [NC][2][LEN][Np]        D-term time stamps = Pid::mDbufferX      (general variant only; there win_x/win_y are
 //                                 rings whose head lives in ctl, see step_general.cuh)
 //   filt  [NC][2][2][CASC][4][Np] biquad x1 x2 y1 y2 (P filter, D filter)  (general variant only)
@@ -79,6 +79,7 @@ struct StepArgs {
   double fir[kMaxDbuf];  // D-term FIR weights of the LIVE pid, logical order, already divided by the window span
   double fir2[2][kMaxDbuf];  // FIR weights of BOTH pids (general variant: used whenever a window's time stamps are uniform)
   double dmom[3];        // the same weights as a quadratic in the centred sample position: w_j = dmom[0] + dmom[1] k + dmom[2] k^2
+  double dk[4];          // Kd * D recursion of the fast variant (step_fast.cuh): coefficients of y_new, S0, S1, y_old
   int effort_ge_cmd;     // effort limit >= cmdMax of the live pid: truncation can only bite on a saturated command
   double sat_thr;        // min(cmdMax, effort limit): an unclamped command within it passes every clamp unchanged
   int mode;            // batch-uniform JointForceCalculator::UpdateMode

@@ -20,10 +20,13 @@
 //                 (oldest sample 1, newest LEN): after a slide every kept sample moves to p - 1 and the sample
 //                 that leaves sits at 0, so it drops out of S1, S2 by itself:
 //                   S0' = S0 - y_old + y_new,  S1' = S1 - S0 + LEN y_new,  S2' = S2 - 2 S1 + S0 + LEN^2 y_new
-//                 (old S0, S1 on the right): 1 read + 1 write of shared memory and 7 FP64 instructions per
-//                 cable and step; D = a*S0 + b*S1 + c*S2.  Every kResync steps (global step index, so results
-//                 do not depend on how steps are split into launches) the moments are re-summed from
-//                 the ring, which bounds the rounding drift of the recursion.
+//                 (old S0, S1 on the right) and D = a S0 + b S1 + c S2.  S2 is only ever needed inside D, so the
+//                 kernel carries (S0, S1, Kd D) instead: substituting the slide into D gives
+//                   Kd D' = Kd D + Kd (a + LEN b + LEN^2 c) y_new - Kd a y_old + Kd (c - b) S0 - 2 Kd c S1
+//                 -- 1 read + 1 write of shared memory and 8 FP64 instructions per cable and step, and the command
+//                 is Ki Ierr + (Kp e + Kd D): 2 more.  Every kResync steps (global step index, so results do not
+//                 depend on how steps are split into launches) S0, S1, S2 are re-summed from the ring and D rebuilt,
+//                 which bounds the rounding drift of the recursion.
 #pragma once
 #include "common.cuh"
 #include "physics.cuh"
@@ -80,21 +83,22 @@ __device__ __forceinline__ CableKin cable_kin(const RobotConsts &rc, const FastS
   return k;
 }
 
-// P + I + D (+ feed-forward `ff`) before any clamp (Pid.cpp:140-172)
-template <int SPEC>
-__device__ __forceinline__ double pid_command(const PidConsts &pc, double e, double ie, double derr, double ff) {
-  return (SPEC & SPEC_NOFF) ? fma(pc.ki, ie, fma(pc.kd, derr, pc.kp * e)) : fma(pc.ki, ie, fma(pc.kd, derr, fma(pc.kp, e, ff)));
+// P + I + D (+ feed-forward `ff`) before any clamp (Pid.cpp:140-172).  DMOM: `d` is Kd * dErr already.
+template <int SPEC, bool DMOM>
+__device__ __forceinline__ double pid_command(const PidConsts &pc, double e, double ie, double d, double ff) {
+  if (DMOM) return fma(pc.ki, ie, fma(pc.kp, e, (SPEC & SPEC_NOFF) ? d : d + ff));
+  return (SPEC & SPEC_NOFF) ? fma(pc.ki, ie, fma(pc.kd, d, pc.kp * e)) : fma(pc.ki, ie, fma(pc.kd, d, fma(pc.kp, e, ff)));
 }
 
 // The exact clamping chain, from the integrated-but-unclamped integral `ie1`.
-template <int SPEC>
+template <int SPEC, bool DMOM>
 __device__ __forceinline__ void pid_clamped(const StepArgs &A, double dt, double e, double derr, double ff, double ie1, double prev_ierr,
                                             double &force, double &eff, double &ie) {
   const PidConsts &pc = A.live;
   // integral clamp with back-calculation (Pid.cpp:143-150) applied to the integral itself:
   // |Ki * Ierr| > Imax  <=>  |Ierr| > Imax / Ki (Ki >= 0 in this variant), clamped term = Ki * (Imax / Ki)
   ie = (fabs(ie1) > pc.i_max_over_ki) ? copysign(pc.i_max_over_ki, ie1) : ie1;
-  const double cmd_raw = pid_command<SPEC>(pc, e, ie, derr, ff);
+  const double cmd_raw = pid_command<SPEC, DMOM>(pc, e, ie, derr, ff);
   // clamp + anti-windup (Pid.cpp:175-184): mCmd != cmd  <=>  |cmd| > cmdMax
   const bool csat = fabs(cmd_raw) > pc.cmd_max;
   force = cmd_raw;
@@ -118,7 +122,7 @@ __device__ __forceinline__ void pid_clamped(const StepArgs &A, double dt, double
 // Out of line and by value, so the hot loop's register allocation does not see it.
 template <int NC, bool SCR> struct SatIn { FastState S; double ie1[NC], derr[NC]; double prev[SCR ? 1 : NC]; double tgu, dt; };
 template <int NC> struct SatOut { double ierr[NC]; double fx, fy, fz, mx, my, mz; };
-template <int NC, int MODE, int SPEC>
+template <int NC, int MODE, bool DMOM, int SPEC>
 __device__ __noinline__ SatOut<NC> saturated_pass(const StepArgs &A, SatIn<NC, FastCfg<NC, SPEC>::scratch> in, const double *tgts, const double *prv) {
   constexpr int kT = FastCfg<NC, SPEC>::tpb;
   const RobotConsts &rc = A.rc;
@@ -133,7 +137,7 @@ __device__ __noinline__ SatOut<NC> saturated_pass(const StepArgs &A, SatIn<NC, F
     const double ff = (SPEC & SPEC_NOFF) ? 0.0 : tgts[(NC + c) * kT];
     const double e = tg - ((MODE == MODE_VELOCITY) ? k.qd : k.qp);
     double force, eff;
-    pid_clamped<SPEC>(A, in.dt, e, in.derr[c], ff, in.ie1[c], FastCfg<NC, SPEC>::scratch ? prv[c * kT] : in.prev[c], force, eff, o.ierr[c]);
+    pid_clamped<SPEC, DMOM>(A, in.dt, e, in.derr[c], ff, in.ie1[c], FastCfg<NC, SPEC>::scratch ? prv[c * kT] : in.prev[c], force, eff, o.ierr[c]);
     const double tl = fma(-rc.cdamp, k.qd, eff) * k.il;
     o.fx = fma(tl, k.dx, o.fx); o.fy = fma(tl, k.dy, o.fy); o.fz = fma(tl, k.dz, o.fz);
     o.mx = fma(tl, k.cx, o.mx); o.my = fma(tl, k.cy, o.my); o.mz = fma(tl, k.cz, o.mz);
@@ -167,9 +171,10 @@ __device__ __forceinline__ void fast_step(const StepArgs &A, FastState &S, doubl
     s += (s < 0) ? LEN : 0;
     slot[a] = s * (NC * kT);
   }
-  // least-squares derivative at `now` from the window state AFTER this step's sample went in (Pid.cpp:193-217)
+  // least-squares derivative at `now` from the window state AFTER this step's sample went in (Pid.cpp:193-217);
+  // DMOM: times Kd
   auto dterm = [&](int c, double e, const double *w) {
-    if (DMOM) return fma(A.dmom[0], mom[c][0], fma(A.dmom[1], mom[c][1], A.dmom[2] * mom[c][2]));
+    if (DMOM) return mom[c][2];
     double d0 = A.fir[LEN - 1] * e, d1 = 0.0;
 #pragma unroll
     for (int a = 1; a < LEN; ++a) {
@@ -200,10 +205,10 @@ __device__ __forceinline__ void fast_step(const StepArgs &A, FastState &S, doubl
         if (DMOM) {
           const double y_old = w[slot[0]];
           w[slot[0]] = e;
-          const double s0 = mom[c][0], s1 = mom[c][1], s2 = mom[c][2];
+          const double s0 = mom[c][0], s1 = mom[c][1];
           // y_old (a shared-memory read) enters last, so its latency hides behind the rest of the chain
+          mom[c][2] = fma(A.dk[3], y_old, fma(A.dk[2], s1, fma(A.dk[1], s0, fma(A.dk[0], e, mom[c][2]))));
           mom[c][1] = fma((double)LEN, e, s1 - s0);
-          mom[c][2] = fma((double)(LEN * LEN), e, fma(-2.0, s1, s2) + s0);
           mom[c][0] = (s0 + e) - y_old;
         } else {
           w[slot[0]] = e;
@@ -215,18 +220,30 @@ __device__ __forceinline__ void fast_step(const StepArgs &A, FastState &S, doubl
         }
         const double ff = (SPEC & SPEC_NOFF) ? 0.0 : tgts[(NC + c) * kT];
         if (OPT) {
-          force = pid_command<SPEC>(pc, e, ie1, derr, ff);
+          force = pid_command<SPEC, DMOM>(pc, e, ie1, derr, ff);
           eff = force;
           sat = sat || (fabs(ie1) > pc.i_max_over_ki) || (fabs(force) > A.sat_thr);
           if (SCR) { prv[c * kT] = prev_ierr; ierr[c] = ie1; }
         } else {
           double ie;
-          pid_clamped<SPEC>(A, dt, e, derr, ff, ie1, prev_ierr, force, eff, ie);
+          pid_clamped<SPEC, DMOM>(A, dt, e, derr, ff, ie1, prev_ierr, force, eff, ie);
           ierr[c] = ie;
         }
         if (LAST) {
           A.L.pid[pid_off(A.L, c, A.live_idx, PID_P_ERR) + i] = e;
-          A.L.pid[pid_off(A.L, c, A.live_idx, PID_D_ERR) + i] = derr;
+          double derr_out = derr;
+          if (DMOM) {  // the carried value is Kd * dErr (and Kd may be 0): publish the FIR over the ring instead
+            derr_out = 0.0;
+            if (STEADY || missing[c] == 0u) {
+#pragma unroll
+              for (int a = 0; a < LEN; ++a) {
+                int sl = head - a;
+                sl += (sl < 0) ? LEN : 0;
+                derr_out = fma(A.fir[LEN - 1 - a], w[sl * (NC * kT)], derr_out);
+              }
+            }
+          }
+          A.L.pid[pid_off(A.L, c, A.live_idx, PID_D_ERR) + i] = derr_out;
         }
       } else {  // first update after a reset: Pid.cpp:123-126
         primed |= 1u << c;
@@ -258,7 +275,7 @@ __device__ __forceinline__ void fast_step(const StepArgs &A, FastState &S, doubl
         in.ie1[c] = SCR ? ierr[c] : fma(dt, e, ierr[c]);
         in.derr[c] = dterm(c, e, win + c * kT);
       }
-      const SatOut<NC> o = saturated_pass<NC, MODE, SPEC>(A, in, tgts, prv);
+      const SatOut<NC> o = saturated_pass<NC, MODE, DMOM, SPEC>(A, in, tgts, prv);
 #pragma unroll
       for (int c = 0; c < NC; ++c) ierr[c] = o.ierr[c];
       fx = o.fx; fy = o.fy; fz = o.fz; mx = o.mx; my = o.my; mz = o.mz;
@@ -273,7 +290,7 @@ __device__ __forceinline__ void fast_step(const StepArgs &A, FastState &S, doubl
 
 // exact re-summation of the window moments from the ring (newest sample in slot `head`); rare, kept small
 template <int NC, int LEN, int SPEC>
-__device__ __forceinline__ void resync_moments(double (&mom)[NC][3], const double *__restrict__ win, int head) {
+__device__ __forceinline__ void resync_moments(const StepArgs &A, double (&mom)[NC][3], const double *__restrict__ win, int head) {
 #pragma unroll
   for (int c = 0; c < NC; ++c) {
     double s0 = 0.0, s1 = 0.0, s2 = 0.0;
@@ -288,7 +305,8 @@ __device__ __forceinline__ void resync_moments(double (&mom)[NC][3], const doubl
       s2 = fma(p * p, y, s2);
       ++sl;
     }
-    mom[c][0] = s0; mom[c][1] = s1; mom[c][2] = s2;
+    mom[c][0] = s0; mom[c][1] = s1;
+    mom[c][2] = A.live.kd * fma(A.dmom[0], s0, fma(A.dmom[1], s1, A.dmom[2] * s2));
   }
 }
 
@@ -427,7 +445,7 @@ __global__ void __launch_bounds__(FastCfg<NC, SPEC>::tpb, FastCfg<NC, SPEC>::blo
   auto events_after = [&]() {
     if (DMOM && PIDMODE && resync_ctr >= kResync) {
       resync_ctr = 0;
-      resync_moments<NC, LEN, SPEC>(mom, mywin, head);
+      resync_moments<NC, LEN, SPEC>(A, mom, mywin, head);
     }
     if (A.snap_every > 0 && snap_ctr >= A.snap_every) {
       snap_ctr = 0;
