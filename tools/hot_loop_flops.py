@@ -21,7 +21,7 @@ for nc in (8, 4):
         body = [(a, t) for a, t in ins if lo <= a <= hi]
         for j, (a, t) in enumerate(body):
             if t.startswith("VOTE.ANY"):
-                for a2, t2 in body[j + 1:j + 20]:
+                for a2, t2 in body[j + 1:j + 60]:
                     m2 = re.match(r"@!?P\d+\s+BRA\s+0x([0-9a-f]+)", t2)
                     if m2:
                         cold = (a2 + 1, int(m2.group(1), 16))
