@@ -34,6 +34,7 @@
 namespace cdpr {
 
 constexpr int kResync = 64;
+constexpr int kSatHold = 32;  // clean steps before a warp that saw a clamp fire returns to the optimistic body
 #ifndef CDPR_NC4_BLOCKS
 #define CDPR_NC4_BLOCKS 2
 #endif
@@ -149,12 +150,14 @@ __device__ __noinline__ SatOut<NC> saturated_pass(const StepArgs &A, SatIn<NC, F
 //   STEADY: every live Pid is primed and its window is full (mWasLastTime && mDbufferMissing == 0)
 //   LAST:   last step of the launch: also writes the telemetry columns
 //   MODE:   batch-uniform JointForceCalculator::UpdateMode
-template <int NC, int LEN, bool STEADY, bool LAST, int MODE, bool DMOM, int SPEC>
-__device__ __forceinline__ void fast_step(const StepArgs &A, FastState &S, double (&ierr)[NC], const double *__restrict__ tgts, const double tgu,
+//   OPT:    optimistic saturation handling (steady, non-last steps only); returns the warp's vote "a clamp fired in
+//           this step".  The clamping steady body (OPT = false, VOTE = true) returns the same vote, computed inline.
+template <int NC, int LEN, bool STEADY, bool LAST, bool OPT, bool VOTE, int MODE, bool DMOM, int SPEC>
+__device__ __forceinline__ bool fast_step(const StepArgs &A, FastState &S, double (&ierr)[NC], const double *__restrict__ tgts, const double tgu,
                                           double (&mom)[NC][3], unsigned &primed, unsigned (&missing)[NC],
                                           double *__restrict__ win, double *__restrict__ prv, int head, double dt, long long i) {
   constexpr int kT = FastCfg<NC, SPEC>::tpb;
-  constexpr bool OPT = STEADY && !LAST && MODE != MODE_FORCE;
+  static_assert(!OPT || (STEADY && !LAST && MODE != MODE_FORCE), "optimistic steps are steady, non-last Pid steps");
   constexpr bool SCR = FastCfg<NC, SPEC>::scratch;
   const RobotConsts &rc = A.rc;
   const PidConsts &pc = A.live;
@@ -227,6 +230,7 @@ __device__ __forceinline__ void fast_step(const StepArgs &A, FastState &S, doubl
         } else {
           double ie;
           pid_clamped<SPEC, DMOM>(A, dt, e, derr, ff, ie1, prev_ierr, force, eff, ie);
+          if (VOTE) sat = sat || (ie != ie1) || (fabs(force) > A.sat_thr);  // some clamp changed the integral or the force
           ierr[c] = ie;
         }
         if (LAST) {
@@ -263,9 +267,12 @@ __device__ __forceinline__ void fast_step(const StepArgs &A, FastState &S, doubl
     mx = fma(tl, k.cx, mx); my = fma(tl, k.cy, my); mz = fma(tl, k.cz, mz);
   }
 
+  bool fired = false;
+  if (VOTE && !OPT) fired = __any_sync(0xffffffffu, sat);
   if (OPT) {
     // the ring's newest slot holds this step's error of every cable
-    if (__any_sync(0xffffffffu, sat)) {  // rare: redo the force law of this step with the clamps
+    fired = __any_sync(0xffffffffu, sat);
+    if (fired) {  // rare: redo the force law of this step with the clamps
       SatIn<NC, SCR> in;
       in.S = S; in.tgu = tgu; in.dt = dt;
 #pragma unroll
@@ -286,6 +293,7 @@ __device__ __forceinline__ void fast_step(const StepArgs &A, FastState &S, doubl
   }
 
   rigid_body_step<SPEC>(rc, S, R, fx, fy, fz, mx, my, mz);
+  return fired;
 }
 
 // exact re-summation of the window moments from the ring (newest sample in slot `head`); rare, kept small
@@ -458,7 +466,7 @@ __global__ void __launch_bounds__(FastCfg<NC, SPEC>::tpb, FastCfg<NC, SPEC>::blo
     cost += fma(ex, ex, fma(ey, ey, ez * ez)) + A.lambda * fma(S.wx, S.wx, fma(S.wy, S.wy, S.wz * S.wz));
   };
 
-  int s = 0;
+  int s = 0, sat_hold = 0;
   const int k_body = A.k_steps - 1;  // the last step runs separately (it also publishes telemetry)
   while (s < k_body) {
     events_before();
@@ -466,7 +474,7 @@ __global__ void __launch_bounds__(FastCfg<NC, SPEC>::tpb, FastCfg<NC, SPEC>::blo
       // warm-up (at most LEN + 1 steps after a Pid reset): some live Pid of the warp is un-primed or its window is not full
       double dt;
       clock_tick(dt);
-      fast_step<NC, LEN, false, false, MODE, DMOM, SPEC>(A, S, ierr, mytgt, tgu, mom, primed, missing, mywin, myprv, head, dt, i);
+      fast_step<NC, LEN, false, false, false, false, MODE, DMOM, SPEC>(A, S, ierr, mytgt, tgu, mom, primed, missing, mywin, myprv, head, dt, i);
       if (A.cost) add_cost();
       bool st = true;
 #pragma unroll
@@ -481,18 +489,43 @@ __global__ void __launch_bounds__(FastCfg<NC, SPEC>::tpb, FastCfg<NC, SPEC>::blo
       ++s;
     } else {
       const int run = run_length(k_body - s);
-      if (A.cost) {
-        for (int r = 0; r < run; ++r) {
-          double dt;
-          clock_tick(dt);
-          fast_step<NC, LEN, true, false, MODE, DMOM, SPEC>(A, S, ierr, mytgt, tgu, mom, primed, missing, mywin, myprv, head, dt, i);
-          add_cost();
-        }
-      } else {
-        for (int r = 0; r < run; ++r) {  // the hot loop
-          double dt;
-          clock_tick(dt);
-          fast_step<NC, LEN, true, false, MODE, DMOM, SPEC>(A, S, ierr, mytgt, tgu, mom, primed, missing, mywin, myprv, head, dt, i);
+      // Two interchangeable steady bodies (same bits out): the optimistic one, and -- while clamps keep firing -- the
+      // one that clamps inline.  sat_hold counts down the clean steps left before the warp goes back to optimistic.
+      int r = 0;
+      while (r < run) {
+        if (!PIDMODE) {
+          for (; r < run; ++r) {
+            double dt;
+            clock_tick(dt);
+            fast_step<NC, LEN, true, false, false, false, MODE, DMOM, SPEC>(A, S, ierr, mytgt, tgu, mom, primed, missing, mywin, myprv, head, dt, i);
+            if (A.cost) add_cost();
+          }
+        } else if (sat_hold > 0) {
+          for (; r < run && sat_hold > 0; ++r) {
+            double dt;
+            clock_tick(dt);
+            const bool fired = fast_step<NC, LEN, true, false, false, true, PIDMODE ? MODE : MODE_VELOCITY, DMOM, SPEC>(A, S, ierr, mytgt, tgu, mom, primed, missing, mywin, myprv, head, dt, i);
+            sat_hold = fired ? kSatHold : sat_hold - 1;
+            if (A.cost) add_cost();
+          }
+        } else if (A.cost) {
+          for (; r < run;) {
+            double dt;
+            clock_tick(dt);
+            const bool fired = fast_step<NC, LEN, true, false, true, true, PIDMODE ? MODE : MODE_VELOCITY, DMOM, SPEC>(A, S, ierr, mytgt, tgu, mom, primed, missing, mywin, myprv, head, dt, i);
+            add_cost();
+            ++r;
+            if (fired) { sat_hold = kSatHold; break; }
+          }
+        } else {
+          bool fired;
+          do {  // the hot loop
+            double dt;
+            clock_tick(dt);
+            fired = fast_step<NC, LEN, true, false, true, true, PIDMODE ? MODE : MODE_VELOCITY, DMOM, SPEC>(A, S, ierr, mytgt, tgu, mom, primed, missing, mywin, myprv, head, dt, i);
+            ++r;
+          } while (!fired && r < run);
+          if (fired) sat_hold = kSatHold;
         }
       }
       advance_counters(run);
@@ -505,8 +538,8 @@ __global__ void __launch_bounds__(FastCfg<NC, SPEC>::tpb, FastCfg<NC, SPEC>::blo
     double dt;
     clock_tick(dt);
     if (valid) {
-      if (warp_steady) fast_step<NC, LEN, true, true, MODE, DMOM, SPEC>(A, S, ierr, mytgt, tgu, mom, primed, missing, mywin, myprv, head, dt, i);
-      else fast_step<NC, LEN, false, true, MODE, DMOM, SPEC>(A, S, ierr, mytgt, tgu, mom, primed, missing, mywin, myprv, head, dt, i);
+      if (warp_steady) fast_step<NC, LEN, true, true, false, false, MODE, DMOM, SPEC>(A, S, ierr, mytgt, tgu, mom, primed, missing, mywin, myprv, head, dt, i);
+      else fast_step<NC, LEN, false, true, false, false, MODE, DMOM, SPEC>(A, S, ierr, mytgt, tgu, mom, primed, missing, mywin, myprv, head, dt, i);
     }
     if (A.cost) add_cost();
     advance_counters(1);

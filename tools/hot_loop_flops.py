@@ -27,7 +27,11 @@ for nc in (8, 4):
                         cold = (a2 + 1, int(m2.group(1), 16))
                         break
         c = collections.Counter(re.sub(r"^@!?U?P\d+\s+", "", t).split()[0].split(".")[0] for a, t in body if not (cold[0] <= a < cold[1]))
-        if best is None or c["DFMA"] > best[1]["DFMA"]:
+        # the hot loop = the smallest big loop that calls the out-of-line saturated pass (the optimistic body without
+        # the rollout cost); the body that clamps inline has no call
+        if c["DFMA"] < 100 or not any("CALL" in t for a, t in body):
+            continue
+        if best is None or sum(c.values()) < best[2]:
             best = ((lo, hi), c, sum(c.values()))
     (lo, hi), c, nb = best
     other = nb - (c["DFMA"] + c["DMUL"] + c["DADD"] + c["DSETP"])

@@ -13,8 +13,13 @@ ap.add_argument("--instances", type=int, default=1 << 20)
 ap.add_argument("--sim-steps", type=int, default=1000)
 ap.add_argument("--launches", type=int, default=3)
 ap.add_argument("--ik", action="store_true")
+ap.add_argument("--cmd-limit", type=float, default=None, help="shrink the command clamp so that steps saturate")
+ap.add_argument("--i-limit", type=float, default=None)
 a = ap.parse_args()
 cfg = cb.default_config(a.nc)
+for pid in (cfg.vel_pid, cfg.pos_pid):
+    if a.cmd_limit is not None: pid.cmd_limit = a.cmd_limit
+    if a.i_limit is not None: pid.i_limit = a.i_limit
 if a.ik:
     import torch
     pose7, twist6 = wl.c2_poses(a.instances, 0)
