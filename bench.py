@@ -29,7 +29,8 @@ sys.path.insert(0, ROOT)
 METRIC = "CDPR instance-steps/sec"
 UNIT = "instance-steps/s"
 # Algorithmic FP64 work per instance-step (FMA = 2 flop, sqrt = div = 1):
-#   platform: 244 general inertia | 196 diagonal | 115 isotropic (no gyroscopic torque, scalar inverse inertia)
+#   platform: 244 general inertia | 196 diagonal | 93 isotropic (no gyroscopic torque, scalar inverse inertia; App. D's
+#             estimate for it is 115, the kernel needs 93)
 #   per cable: kinematics 52 (46 when every platform anchor has b_z = 0: R b needs 6 mul + 3 add instead of 9 + 6),
 #              force law 25 (error 1, integral 2, sliding-window D-term 13 in its (S0, S1, Kd D) form, command 4 ... the
 #              clamps are compares and the back-calculation arithmetic only runs on saturated steps: neither is
@@ -37,7 +38,7 @@ UNIT = "instance-steps/s"
 # The reference robot (sdf/cube.sdf) has isotropic inertia diag(1,1,1) and anchors in the platform plane, and the
 # kernel is specialised on exactly those properties, so the roofline uses the SMALLER count that matches it.
 def flops_per_instance_step(nc: int, inertia: str = "iso", bz0: bool = True) -> int:
-    platform = {"general": 244, "diag": 196, "iso": 115}[inertia]
+    platform = {"general": 244, "diag": 196, "iso": 93}[inertia]   # iso: counted from the kernel's SASS (App. D estimates 115)
     return platform + nc * ((46 if bz0 else 52) + 25 + 14)
 
 
@@ -307,7 +308,7 @@ def own_arm(args):
             "traffic": traffic, "traffic_unit": "bytes per launch", "traffic_source": traffic_src, "algorithmic_bytes_per_launch": hbm_bytes,
             "kernel": f"k_step_fast<{nc},11,VELOCITY,moments,spec>", "kernel_ms": kms,
             "flops_per_instance_step": flops_per_instance_step(nc),
-            "flops_note": "count for this robot (isotropic inertia, anchors in the platform plane: 115 + 85 NC; SASS count of the hot loop: 789 @NC=8, profiles/r1_hot_loop_flops.txt); a general robot is 244 + 91 NC; SURVEY 8(d)'s FIR-form count is 244 + 98 NC",
+            "flops_note": "count for this robot (isotropic inertia, anchors in the platform plane: 93 + 85 NC = the SASS count of the hot loop, 773 @NC=8, profiles/r1_hot_loop_flops.txt); a general robot is 244 + 91 NC; SURVEY 8(d)'s FIR-form count is 244 + 98 NC",
             "peak_source": "DFMA issue rate measured in this run by cdpr_measure_fp64_tflops (MEASURED_PEAKS.json has no FP64 entry; "
                            "nominal B200 FP64 is 37 TFLOP/s)",
             "hbm": {"achieved": hbm_bytes / (kms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
