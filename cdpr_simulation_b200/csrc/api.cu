@@ -406,6 +406,7 @@ extern "C" int cdpr_create(const cdpr_config *cfg, int64_t n_instances, int devi
     CDPR_PREP_ONE(NC_, MODE_VELOCITY, true, SPEC_DIAG | SPEC_BZ0);                                             \
     CDPR_PREP_ONE(NC_, MODE_VELOCITY, true, SPEC_DIAG | SPEC_ISO);                                             \
     CDPR_PREP_ONE(NC_, MODE_VELOCITY, true, SPEC_DIAG | SPEC_ISO | SPEC_BZ0);                                  \
+    CDPR_PREP_ONE(NC_, MODE_POSITION, true, SPEC_DIAG | SPEC_ISO | SPEC_BZ0);                                  \
     CDPR_PREP_ONE(NC_, MODE_VELOCITY, true, SPEC_DIAG | SPEC_ISO | SPEC_BZ0 | SPEC_NOFF | SPEC_UTGT)
     CDPR_PREP(4);
     CDPR_PREP(8);
@@ -583,7 +584,7 @@ static int launch_step(cdpr_handle h, const StepArgs &A) {
     else k_step_general<4><<<grid, kTpb, 0, h->stream>>>(A);
   } else {
     const bool dm = h->dmom_ok[A.live_idx];
-    // the velocity mode with the moment D-term (the headline path) is specialised on the robot constants; every
+    // the velocity and position modes with the moment D-term are specialised on the robot constants; every
     // other combination runs the diagonal-inertia or fully general instance
     const int spec_full = h->rc.spec, spec_base = h->rc.spec & SPEC_DIAG;
     // one target for all cables (the sine publisher) and no feed-forward term: targets live in a register
@@ -596,7 +597,10 @@ static int launch_step(cdpr_handle h, const StepArgs &A) {
 #define CDPR_LAUNCH_NC(NC_)                                                                            \
   do {                                                                                                 \
     if (A.mode == MODE_FORCE) CDPR_LAUNCH_BASE(NC_, MODE_FORCE, false);                                \
-    else if (A.mode == MODE_POSITION) { if (dm) CDPR_LAUNCH_BASE(NC_, MODE_POSITION, true); else CDPR_LAUNCH_BASE(NC_, MODE_POSITION, false); } \
+    else if (A.mode == MODE_POSITION) {                                                                \
+      if (dm && spec_full == (SPEC_DIAG | SPEC_ISO | SPEC_BZ0)) CDPR_LAUNCH(NC_, MODE_POSITION, true, SPEC_DIAG | SPEC_ISO | SPEC_BZ0); \
+      else if (dm) CDPR_LAUNCH_BASE(NC_, MODE_POSITION, true); else CDPR_LAUNCH_BASE(NC_, MODE_POSITION, false);                      \
+    }                                                                                                  \
     else if (!dm) CDPR_LAUNCH_BASE(NC_, MODE_VELOCITY, false);                                         \
     else if (spec_full == (SPEC_DIAG | SPEC_ISO | SPEC_BZ0) && uniform_noff)                           \
       CDPR_LAUNCH(NC_, MODE_VELOCITY, true, SPEC_DIAG | SPEC_ISO | SPEC_BZ0 | SPEC_NOFF | SPEC_UTGT);  \

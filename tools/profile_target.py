@@ -15,6 +15,7 @@ ap.add_argument("--launches", type=int, default=3)
 ap.add_argument("--ik", action="store_true")
 ap.add_argument("--cmd-limit", type=float, default=None, help="shrink the command clamp so that steps saturate")
 ap.add_argument("--i-limit", type=float, default=None)
+ap.add_argument("--mode", default="sine", choices=["sine", "position", "velocity"], help="sine publisher | per-cable position targets | per-cable velocity targets")
 a = ap.parse_args()
 cfg = cb.default_config(a.nc)
 for pid in (cfg.vel_pid, cfg.pos_pid):
@@ -32,7 +33,11 @@ if a.ik:
 else:
     amp, freq, phase, pose7, twist6 = wl.c3_instances(a.instances, 1)
     with cb.CdprBatch(cfg, a.instances) as g:
-        g.set_platform_state(pose7, twist6); g.set_sine_cmd(amp, freq, phase)
+        g.set_platform_state(pose7, twist6)
+        rng = np.random.default_rng(3)
+        if a.mode == "sine": g.set_sine_cmd(amp, freq, phase)
+        elif a.mode == "position": g.set_position_cmd(rng.uniform(-0.02, 0.02, (a.instances, a.nc)).astype(np.float32))
+        else: g.set_velocity_cmd(rng.uniform(-0.05, 0.05, (a.instances, a.nc)).astype(np.float32))
         for _ in range(a.launches):
             g.step(a.sim_steps); g.synchronize()
             print("step ms", g.last_kernel_ms, "rate", a.instances * a.sim_steps / g.last_kernel_ms * 1e3)
