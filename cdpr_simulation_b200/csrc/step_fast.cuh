@@ -8,7 +8,7 @@
 //   - cmdLimit != 0, iGain >= 0, window length 11,
 // which is the reference's launch configuration.  Everything else runs in step_general.cuh.
 //
-// On-chip residency:  platform state, integral errors, targets, window moments, flags -> registers
+// On-chip residency:  platform state, integral errors, targets, window sums + Kd D, flags -> registers
 //                     D-term error windows (Pid::mDbufferY, LEN per cable)            -> shared memory,
 //                     a ring [slot][cable][thread]: a warp touches 256 contiguous bytes per access
 //
