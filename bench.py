@@ -358,6 +358,25 @@ def side_measurements(cb, wl, torch, device, hbm_peak, fp64_peak):
         t = float(np.mean(ms[1:]))
         out["nc4_reference_robot"] = {"value": n * k / (t * 1e-3), "unit": UNIT, "kernel_ms": t,
                                       "fp64_frac": flops_per_instance_step(4) * n * k / (t * 1e-3) / 1e12 / fp64_peak}
+    # the other shapes of the same kernel: per-cable position targets (Position mode), and a run whose command clamp
+    # fires on every step (the inline-clamping steady body instead of the optimistic one)
+    with cb.CdprBatch(cb.default_config(8), n, device=device) as g:
+        g.set_platform_state(pose7, twist6)
+        g.set_position_cmd(np.random.default_rng(3).uniform(-0.02, 0.02, (n, 8)).astype(np.float32))
+        ms = []
+        for _ in range(3):
+            g.step(k); ms.append(g.last_kernel_ms)
+        t = float(np.mean(ms[1:]))
+        out["position_mode_nc8"] = {"value": n * k / (t * 1e-3), "unit": UNIT, "kernel_ms": t}
+    sat_cfg = cb.default_config(8)
+    sat_cfg.vel_pid.cmd_limit = 3.5   # below the ~4 N equilibrium tension: saturated throughout
+    with cb.CdprBatch(sat_cfg, n, device=device) as g:
+        g.set_platform_state(pose7, twist6); g.set_sine_cmd(amp, freq, phase)
+        ms = []
+        for _ in range(3):
+            g.step(k); ms.append(g.last_kernel_ms)
+        t = float(np.mean(ms[1:]))
+        out["always_saturated_nc8"] = {"value": n * k / (t * 1e-3), "unit": UNIT, "kernel_ms": t}
     # config 1 (the reference's own operating point): ONE 4-cable robot stepped like the plugin does it -- one update() per
     # physics step: command in, one step, joint states + platform state out (the Gazebo path is capped at ~1e3 steps/s)
     with cb.CdprBatch(cb.default_config(4), 1, device=device) as g:
