@@ -296,26 +296,31 @@ __device__ __forceinline__ bool fast_step(const StepArgs &A, FastState &S, doubl
   return fired;
 }
 
-// exact re-summation of the window moments from the ring (newest sample in slot `head`); rare, kept small
+// exact re-summation of the window sums from the ring (newest sample in slot `head`), every kResync steps.  Sample-major
+// and fully unrolled: one slot address per sample age, NC independent accumulator triples -- a rolled per-cable loop
+// is a serial LDS -> FMA chain and cost 6 % of the whole kernel.
 template <int NC, int LEN, int SPEC>
 __device__ __forceinline__ void resync_moments(const StepArgs &A, double (&mom)[NC][3], const double *__restrict__ win, int head) {
+  double s2[NC];
 #pragma unroll
-  for (int c = 0; c < NC; ++c) {
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-    int sl = head + 1;  // oldest sample
-#pragma unroll 1
-    for (int j = 0; j < LEN; ++j) {
-      sl -= (sl >= LEN) ? LEN : 0;
-      const double y = win[(sl * NC + c) * FastCfg<NC, SPEC>::tpb];
-      const double p = (double)(j + 1);
-      s0 += y;
-      s1 = fma(p, y, s1);
-      s2 = fma(p * p, y, s2);
-      ++sl;
+  for (int c = 0; c < NC; ++c) { mom[c][0] = 0.0; mom[c][1] = 0.0; s2[c] = 0.0; }
+  int sl = head + 1;  // oldest sample
+#pragma unroll
+  for (int j = 0; j < LEN; ++j) {
+    sl -= (sl >= LEN) ? LEN : 0;
+    const double *w = win + sl * (NC * FastCfg<NC, SPEC>::tpb);
+    const double p = (double)(j + 1);
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const double y = w[c * FastCfg<NC, SPEC>::tpb];
+      mom[c][0] += y;
+      mom[c][1] = fma(p, y, mom[c][1]);
+      s2[c] = fma(p * p, y, s2[c]);
     }
-    mom[c][0] = s0; mom[c][1] = s1;
-    mom[c][2] = A.live.kd * fma(A.dmom[0], s0, fma(A.dmom[1], s1, A.dmom[2] * s2));
+    ++sl;
   }
+#pragma unroll
+  for (int c = 0; c < NC; ++c) mom[c][2] = A.live.kd * fma(A.dmom[0], mom[c][0], fma(A.dmom[1], mom[c][1], A.dmom[2] * s2[c]));
 }
 
 // rare path (every snap_every steps), kept out of line so the hot loop's register allocation does not see it

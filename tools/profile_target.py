@@ -15,9 +15,11 @@ ap.add_argument("--launches", type=int, default=3)
 ap.add_argument("--ik", action="store_true")
 ap.add_argument("--cmd-limit", type=float, default=None, help="shrink the command clamp so that steps saturate")
 ap.add_argument("--i-limit", type=float, default=None)
+ap.add_argument("--sine-hz", type=float, default=None, help="publisher rate of the in-kernel sine generator")
 ap.add_argument("--mode", default="sine", choices=["sine", "position", "velocity"], help="sine publisher | per-cable position targets | per-cable velocity targets")
 a = ap.parse_args()
 cfg = cb.default_config(a.nc)
+if a.sine_hz: cfg.sine_publish_hz = a.sine_hz
 for pid in (cfg.vel_pid, cfg.pos_pid):
     if a.cmd_limit is not None: pid.cmd_limit = a.cmd_limit
     if a.i_limit is not None: pid.i_limit = a.i_limit
