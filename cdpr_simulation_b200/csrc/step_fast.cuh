@@ -393,8 +393,12 @@ __global__ void __launch_bounds__(FastCfg<NC, SPEC>::tpb, FastCfg<NC, SPEC>::blo
 #pragma unroll
     for (int m = 0; m < 3; ++m) mysine[m * kTpbL] = A.L.sine[m * np + i];
   }
+  // the lean layout is only launched for the sine publisher without a command table or rollout cost (api.cu), so its
+  // event code drops those checks at compile time
   const float *cmd_row = nullptr;
-  if (A.cmd_table) cmd_row = A.cmd_table + (size_t)(i % A.n_seq) * A.n_cmd * NC;
+  if (!kLean && A.cmd_table) cmd_row = A.cmd_table + (size_t)(i % A.n_seq) * A.n_cmd * NC;
+  const bool sine_on = kLean || A.sine_on;
+  const bool want_cost = !kLean && A.cost != nullptr;
   double cost = 0.0;
   double tgu = A.L.cab[cab_off(A.L, 0, tgt_field) + i];  // SPEC_UTGT: the one target shared by all cables, kept in a register
 
@@ -419,7 +423,7 @@ __global__ void __launch_bounds__(FastCfg<NC, SPEC>::tpb, FastCfg<NC, SPEC>::blo
     head = (head + 1 == LEN) ? 0 : head + 1;
   };
   auto events_before = [&]() {
-    if (A.sine_on && sine_ctr == 0) {  // sinevelocitytest.cpp:35-38,48: float32 axes, accumulated publisher time
+    if (sine_on && sine_ctr == 0) {  // sinevelocitytest.cpp:35-38,48: float32 axes, accumulated publisher time
       const double amp = mysine[0], freq = mysine[kTpbL], phase = mysine[2 * kTpbL];
       const double arg = __dadd_rn(__dmul_rn(__dmul_rn(__dmul_rn(sine_time, freq), 2.0), 3.14159265358979323846), phase);
       const double vel = (double)(float)__dmul_rn(amp, sin(arg));
@@ -431,7 +435,7 @@ __global__ void __launch_bounds__(FastCfg<NC, SPEC>::tpb, FastCfg<NC, SPEC>::blo
       tgu = vel;
       sine_time = __dadd_rn(sine_time, A.sine_pub_dt);
     }
-    if (cmd_row && cmd_ctr == 0 && cmd_idx < A.n_cmd) {
+    if (!kLean && cmd_row && cmd_ctr == 0 && cmd_idx < A.n_cmd) {
 #pragma unroll
       for (int c = 0; c < NC; ++c) {
         const double v = (double)cmd_row[cmd_idx * NC + c];
@@ -443,15 +447,15 @@ __global__ void __launch_bounds__(FastCfg<NC, SPEC>::tpb, FastCfg<NC, SPEC>::blo
   // how many steps may run before the next event of any kind (at least 1)
   auto run_length = [&](int remaining) {
     int run = remaining;
-    if (A.sine_on) run = min(run, A.sine_period - sine_ctr);
-    if (cmd_row) run = min(run, A.steps_per_cmd - cmd_ctr);
+    if (sine_on) run = min(run, A.sine_period - sine_ctr);
+    if (!kLean && cmd_row) run = min(run, A.steps_per_cmd - cmd_ctr);
     if (DMOM && PIDMODE) run = min(run, kResync - resync_ctr);
     if (A.snap_every > 0) run = (int)min((long long)run, A.snap_every - snap_ctr);
     return run;
   };
   auto advance_counters = [&](int run) {
-    if (A.sine_on) { sine_ctr += run; if (sine_ctr >= A.sine_period) sine_ctr = 0; }
-    if (cmd_row) { cmd_ctr += run; if (cmd_ctr >= A.steps_per_cmd) cmd_ctr = 0; }
+    if (sine_on) { sine_ctr += run; if (sine_ctr >= A.sine_period) sine_ctr = 0; }
+    if (!kLean && cmd_row) { cmd_ctr += run; if (cmd_ctr >= A.steps_per_cmd) cmd_ctr = 0; }
     if (DMOM && PIDMODE) resync_ctr += run;
     if (A.snap_every > 0) snap_ctr += run;
   };
@@ -480,7 +484,7 @@ __global__ void __launch_bounds__(FastCfg<NC, SPEC>::tpb, FastCfg<NC, SPEC>::blo
       double dt;
       clock_tick(dt);
       fast_step<NC, LEN, false, false, false, false, MODE, DMOM, SPEC>(A, S, ierr, mytgt, tgu, mom, primed, missing, mywin, myprv, head, dt, i);
-      if (A.cost) add_cost();
+      if (want_cost) add_cost();
       bool st = true;
 #pragma unroll
       for (int c = 0; c < NC; ++c) st = st && ((primed >> c) & 1u) && missing[c] == 0u;
@@ -503,7 +507,7 @@ __global__ void __launch_bounds__(FastCfg<NC, SPEC>::tpb, FastCfg<NC, SPEC>::blo
             double dt;
             clock_tick(dt);
             fast_step<NC, LEN, true, false, false, false, MODE, DMOM, SPEC>(A, S, ierr, mytgt, tgu, mom, primed, missing, mywin, myprv, head, dt, i);
-            if (A.cost) add_cost();
+            if (want_cost) add_cost();
           }
         } else if (sat_hold > 0) {
           for (; r < run && sat_hold > 0; ++r) {
@@ -511,9 +515,9 @@ __global__ void __launch_bounds__(FastCfg<NC, SPEC>::tpb, FastCfg<NC, SPEC>::blo
             clock_tick(dt);
             const bool fired = fast_step<NC, LEN, true, false, false, true, PIDMODE ? MODE : MODE_VELOCITY, DMOM, SPEC>(A, S, ierr, mytgt, tgu, mom, primed, missing, mywin, myprv, head, dt, i);
             sat_hold = fired ? kSatHold : sat_hold - 1;
-            if (A.cost) add_cost();
+            if (want_cost) add_cost();
           }
-        } else if (A.cost) {
+        } else if (want_cost) {
           for (; r < run;) {
             double dt;
             clock_tick(dt);
@@ -546,20 +550,20 @@ __global__ void __launch_bounds__(FastCfg<NC, SPEC>::tpb, FastCfg<NC, SPEC>::blo
       if (warp_steady) fast_step<NC, LEN, true, true, false, false, MODE, DMOM, SPEC>(A, S, ierr, mytgt, tgu, mom, primed, missing, mywin, myprv, head, dt, i);
       else fast_step<NC, LEN, false, true, false, false, MODE, DMOM, SPEC>(A, S, ierr, mytgt, tgu, mom, primed, missing, mywin, myprv, head, dt, i);
     }
-    if (A.cost) add_cost();
+    if (want_cost) add_cost();
     advance_counters(1);
     events_after();
   }
 
   if (!valid) return;
   store_plat(A.L.plat + i, np, S);
-  if (A.cost) A.cost[i] = cost;
+  if (want_cost) A.cost[i] = cost;
   if (!PIDMODE) return;  // Force mode touches no Pid state
 #pragma unroll
   for (int c = 0; c < NC; ++c) {
     A.L.pid[pid_off(A.L, c, live, PID_I_ERR) + i] = ierr[c];
     A.L.pid[pid_off(A.L, c, live, PID_LAST_TIME) + i] = tprev;
-    if (A.sine_on || A.cmd_table) A.L.cab[cab_off(A.L, c, CAB_VEL_TARGET) + i] = kLean ? tgu : mytgt[c * kTpbL];
+    if (sine_on || cmd_row) A.L.cab[cab_off(A.L, c, CAB_VEL_TARGET) + i] = kLean ? tgu : mytgt[c * kTpbL];
     unsigned ctl = A.L.ctl[(long long)c * np + i];
     ctl &= ~((1u << live) | (0xffu << (8 + 8 * live)));
     ctl |= (((primed >> c) & 1u) << live) | (missing[c] << (8 + 8 * live));
