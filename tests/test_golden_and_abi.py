@@ -160,3 +160,26 @@ def test_product_never_touches_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "oracle" not in text.lower(), os.path.join(dirpath, f)
+
+
+def test_roofline_numerator_is_the_sass_count_of_the_hot_loop(built_lib):
+    """bench.py's flops per instance-step must be what the step kernel's hot loop really executes (FMA = 2, the other
+    FP64 instructions and the rsqrt seed = 1), read from the SASS of the library that is about to be measured."""
+    import shutil
+    import subprocess
+    import sys
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "hot_loop_flops.py"), built_lib],
+                         capture_output=True, text=True, check=True).stdout
+    sys.path.insert(0, root)
+    import bench
+    seen = {}
+    for line in out.splitlines():
+        m = re.match(r"NC=(\d+): .* (\d+) executed flops", line)
+        if m:
+            seen[int(m.group(1))] = int(m.group(2))
+    assert set(seen) == {4, 8}, out
+    for nc, flops in seen.items():
+        assert bench.flops_per_instance_step(nc) == flops, (nc, flops, bench.flops_per_instance_step(nc))
