@@ -94,3 +94,42 @@ def test_dterm_fir_weights_against_numpy_least_squares(built_lib):
     # 11-point quadratic fit, derivative at the last point: closed form (3 j^2 ... ) / h -- check two known entries
     ref = np.linalg.pinv(np.vander(np.arange(-10.0, 1.0), 3, increasing=True))[1] / dt
     assert np.allclose(fir, ref, rtol=1e-10)
+
+
+def test_sliding_window_recursion_of_the_step_kernel(built_lib):
+    """The step kernel carries (S0, S1, Kd*D) per cable instead of re-reading the 11-sample window (step_fast.cuh):
+    the recursion below is its update, statement by statement.  Algebra: exact in rational terms; in doubles it must
+    stay within ~1e-12 of the FIR over the 64 steps between two re-summations, and a re-summation must land on the
+    FIR again.  (Drift grows like n^2.5, which is why the kernel re-sums every 64 steps and not every 1000.)"""
+    cfg = cb.default_config(4)
+    dt, ln, kd = cfg.dt, 11, 1.0
+    pid = cb.PidParams.from_buffer_copy(bytes(cfg.vel_pid))
+    fir, (a, b, c), is_quad = cb.dterm_weights(pid, dt)
+    assert is_quad and len(fir) == ln
+    dk = (kd * (a + ln * b + ln * ln * c), kd * (c - b), -2.0 * kd * c, -kd * a)   # y_new, S0, S1, y_old (api.cu fill_args)
+    rng = np.random.default_rng(11)
+    t = np.arange(400) * dt
+    y = 0.05 * np.sin(2 * np.pi * 0.7 * t + 0.3) + 1e-3 * rng.standard_normal(t.size)   # velocity-error-like signal
+    ring = list(y[:ln])
+    p = np.arange(1, ln + 1, dtype=float)
+    def resum(w):
+        w = np.asarray(w)
+        s0 = 0.0; s1 = 0.0; s2 = 0.0
+        for j in range(ln):                      # same order as resync_moments
+            s0 += w[j]; s1 = p[j] * w[j] + s1; s2 = p[j] * p[j] * w[j] + s2
+        return s0, s1, kd * (a * s0 + (b * s1 + c * s2))
+    s0, s1, kdd = resum(ring)
+    assert abs(kdd - kd * float(fir @ np.asarray(ring))) < 1e-12 * np.abs(fir).sum() * 0.05
+    worst = 0.0
+    for n in range(ln, t.size):
+        e, y_old = y[n], ring.pop(0)
+        ring.append(e)
+        kdd = dk[3] * y_old + (dk[2] * s1 + (dk[1] * s0 + (dk[0] * e + kdd)))     # old S0, S1 on the right
+        s1 = ln * e + (s1 - s0)
+        s0 = (s0 + e) - y_old
+        exact = kd * float(fir @ np.asarray(ring))
+        worst = max(worst, abs(kdd - exact))
+        if (n - ln + 1) % 64 == 0:               # kResync
+            s0, s1, kdd = resum(ring)
+            assert abs(kdd - exact) < 1e-12
+    assert worst < 2e-11, worst                  # D itself is O(0.1 .. 1) here
