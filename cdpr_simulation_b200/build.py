@@ -8,9 +8,13 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 # CDPR_B200_LIB selects another build of the same library (kernel tuning experiments only)
 LIB = os.environ.get("CDPR_B200_LIB") or os.path.join(HERE, "libcdpr_b200.so")
-SOURCES = ["api.cu"]
-HEADERS = ["common.cuh", "physics.cuh", "step_fast.cuh", "step_general.cuh", "misc_kernels.cuh", "../../include/cdpr_b200.h"]
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-shared"]
+# one translation unit per group of kernel instances: they compile in parallel, then link into the one .so
+SOURCES = ["api.cu", "general.cu", "fast_nc4_base.cu", "fast_nc4_diag.cu", "fast_nc4_spec.cu", "fast_nc8_base.cu", "fast_nc8_diag.cu",
+           "fast_nc8_spec.cu"]
+HEADERS = ["common.cuh", "physics.cuh", "step_fast.cuh", "step_general.cuh", "misc_kernels.cuh", "launch.h", "fast_inst.cuh",
+           "../../include/cdpr_b200.h"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]
+OBJ_DIR = os.path.join(HERE, "build")
 
 
 def stale() -> bool:
@@ -20,16 +24,37 @@ def stale() -> bool:
     return any(os.path.exists(os.path.join(CSRC, f)) and os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
 
 
+def _compile_one(args):
+    cmd, src = args
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    return src, r.returncode, r.stdout + r.stderr
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
-    if force or stale():
-        nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-        extra = os.environ.get("CDPR_NVCC_EXTRA", "").split()
-        cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
-        r = subprocess.run(cmd, capture_output=True, text=True)
-        if r.returncode != 0:
-            raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
-        if verbose:
-            print(r.stderr)
+    """nvcc -c every unit that is older than its sources (in parallel), then one nvcc -shared link."""
+    if not (force or stale()):
+        return LIB
+    from concurrent.futures import ThreadPoolExecutor
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    extra = os.environ.get("CDPR_NVCC_EXTRA", "").split()
+    tag = ("_" + "".join(c if c.isalnum() else "_" for c in " ".join(extra))) if extra else ""
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    newest_header = max(os.path.getmtime(os.path.join(CSRC, f)) for f in HEADERS)
+    jobs, objs = [], []
+    for s in SOURCES:
+        src, obj = os.path.join(CSRC, s), os.path.join(OBJ_DIR, s[:-3] + tag + ".o")
+        objs.append(obj)
+        if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(newest_header, os.path.getmtime(src)):
+            jobs.append(([nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src], s))
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+        for src, rc, out in ex.map(_compile_one, jobs):
+            if rc != 0:
+                raise RuntimeError(f"nvcc failed on {src}:\n{out}")
+            if verbose:
+                print(out)
+    r = subprocess.run([nvcc, "-shared", "-o", LIB] + objs, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
     return LIB
 
 

@@ -9,13 +9,13 @@
 
 #include "../../include/cdpr_b200.h"
 #include "common.cuh"
+#include "launch.h"
 #include "misc_kernels.cuh"
-#include "step_fast.cuh"
-#include "step_general.cuh"
 
 using namespace cdpr;
 
 static thread_local std::string g_create_error;
+static const std::vector<FastEntry> &fast_table();
 
 struct cdpr_batch {
   cdpr_config cfg;
@@ -392,27 +392,11 @@ extern "C" int cdpr_create(const cdpr_config *cfg, int64_t n_instances, int devi
   if (cudaMemsetAsync(L.sine, 0, col * 3, h->stream) != cudaSuccess) { h->err = "memset failed"; return bail(CDPR_ERR_CUDA); }
   if ((rc = reset_to_load_state(h, h->stream))) return bail(rc);
   if (!h->general) {
-    auto prep = [](const void *f, size_t smem) {
-      cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    };
-#define CDPR_PREP_ONE(NC_, MODE_, DM_, SP_) prep((const void *)k_step_fast<NC_, 11, MODE_, DM_, SP_>, fast_smem_bytes<NC_, 11, SP_>())
-#define CDPR_PREP1(NC_, SP_)                                                                                   \
-    CDPR_PREP_ONE(NC_, MODE_FORCE, false, SP_); CDPR_PREP_ONE(NC_, MODE_POSITION, false, SP_);                 \
-    CDPR_PREP_ONE(NC_, MODE_POSITION, true, SP_); CDPR_PREP_ONE(NC_, MODE_VELOCITY, false, SP_);               \
-    CDPR_PREP_ONE(NC_, MODE_VELOCITY, true, SP_)
-#define CDPR_PREP(NC_)                                                                                         \
-    CDPR_PREP1(NC_, 0); CDPR_PREP1(NC_, SPEC_DIAG);                                                            \
-    CDPR_PREP_ONE(NC_, MODE_VELOCITY, true, SPEC_DIAG | SPEC_BZ0);                                             \
-    CDPR_PREP_ONE(NC_, MODE_VELOCITY, true, SPEC_DIAG | SPEC_ISO);                                             \
-    CDPR_PREP_ONE(NC_, MODE_VELOCITY, true, SPEC_DIAG | SPEC_ISO | SPEC_BZ0);                                  \
-    CDPR_PREP_ONE(NC_, MODE_POSITION, true, SPEC_DIAG | SPEC_ISO | SPEC_BZ0);                                  \
-    CDPR_PREP_ONE(NC_, MODE_VELOCITY, true, SPEC_DIAG | SPEC_ISO | SPEC_BZ0 | SPEC_NOFF | SPEC_UTGT)
-    CDPR_PREP(4);
-    CDPR_PREP(8);
-#undef CDPR_PREP_ONE
-#undef CDPR_PREP1
-#undef CDPR_PREP
+    for (const FastEntry &e : fast_table()) {
+      if (e.nc != cfg->n_cables) continue;
+      cudaFuncSetAttribute(e.func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e.smem);
+      cudaFuncSetAttribute(e.func, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    }
   }
   if (cudaStreamSynchronize(h->stream) != cudaSuccess) { h->err = "initialisation kernels failed"; return bail(CDPR_ERR_CUDA); }
   *out = h;
@@ -577,42 +561,39 @@ static void fill_args(cdpr_handle h, StepArgs &A, int k_steps, bool sine) {
   A.snap_every = h->n_snap_peers > 0 ? h->snap_every : 0; A.snap_written0 = h->snap_written; A.snap_capacity = h->snap_capacity;
 }
 
+// every k_step_fast instance of the library, collected once from the translation units that hold them
+static const std::vector<FastEntry> &fast_table() {
+  static const std::vector<FastEntry> table = [] {
+    std::vector<FastEntry> t;
+    fast_entries_nc4_base(t); fast_entries_nc4_diag(t); fast_entries_nc4_spec(t);
+    fast_entries_nc8_base(t); fast_entries_nc8_diag(t); fast_entries_nc8_spec(t);
+    return t;
+  }();
+  return table;
+}
+static const FastEntry *fast_find(int nc, int mode, bool dmom, int spec) {
+  for (const FastEntry &e : fast_table())
+    if (e.nc == nc && e.mode == mode && e.dmom == dmom && e.spec == spec) return &e;
+  return nullptr;
+}
+
 static int launch_step(cdpr_handle h, const StepArgs &A) {
-  const unsigned grid = (unsigned)(h->np / kTpb);
   if (h->general) {
-    if (std::max(h->pc[PID_VEL].degree, h->pc[PID_POS].degree) <= 2) k_step_general<2><<<grid, kTpb, 0, h->stream>>>(A);
-    else k_step_general<4><<<grid, kTpb, 0, h->stream>>>(A);
+    general_launch(std::max(h->pc[PID_VEL].degree, h->pc[PID_POS].degree), (unsigned)(h->np / kTpb), A, h->stream);
   } else {
-    const bool dm = h->dmom_ok[A.live_idx];
+    const bool dm = h->dmom_ok[A.live_idx] && A.mode != MODE_FORCE;
     // the velocity and position modes with the moment D-term are specialised on the robot constants; every
     // other combination runs the diagonal-inertia or fully general instance
     const int spec_full = h->rc.spec, spec_base = h->rc.spec & SPEC_DIAG;
     // one target for all cables (the sine publisher) and no feed-forward term: targets live in a register
     const bool uniform_noff = A.sine_on && !A.cmd_table && A.live.kf == 0.0 && h->targets_uniform;
-#define CDPR_LAUNCH(NC_, MODE_, DM_, SP_)                                                              \
-  k_step_fast<NC_, 11, MODE_, DM_, SP_><<<grid_for(h->np, FastCfg<NC_, SP_>::tpb), FastCfg<NC_, SP_>::tpb, \
-                                          fast_smem_bytes<NC_, 11, SP_>(), h->stream>>>(A)
-#define CDPR_LAUNCH_BASE(NC_, MODE_, DM_) \
-  do { if (spec_base) CDPR_LAUNCH(NC_, MODE_, DM_, SPEC_DIAG); else CDPR_LAUNCH(NC_, MODE_, DM_, 0); } while (0)
-#define CDPR_LAUNCH_NC(NC_)                                                                            \
-  do {                                                                                                 \
-    if (A.mode == MODE_FORCE) CDPR_LAUNCH_BASE(NC_, MODE_FORCE, false);                                \
-    else if (A.mode == MODE_POSITION) {                                                                \
-      if (dm && spec_full == (SPEC_DIAG | SPEC_ISO | SPEC_BZ0)) CDPR_LAUNCH(NC_, MODE_POSITION, true, SPEC_DIAG | SPEC_ISO | SPEC_BZ0); \
-      else if (dm) CDPR_LAUNCH_BASE(NC_, MODE_POSITION, true); else CDPR_LAUNCH_BASE(NC_, MODE_POSITION, false);                      \
-    }                                                                                                  \
-    else if (!dm) CDPR_LAUNCH_BASE(NC_, MODE_VELOCITY, false);                                         \
-    else if (spec_full == (SPEC_DIAG | SPEC_ISO | SPEC_BZ0) && uniform_noff)                           \
-      CDPR_LAUNCH(NC_, MODE_VELOCITY, true, SPEC_DIAG | SPEC_ISO | SPEC_BZ0 | SPEC_NOFF | SPEC_UTGT);  \
-    else if (spec_full == (SPEC_DIAG | SPEC_ISO | SPEC_BZ0)) CDPR_LAUNCH(NC_, MODE_VELOCITY, true, SPEC_DIAG | SPEC_ISO | SPEC_BZ0); \
-    else if (spec_full == (SPEC_DIAG | SPEC_ISO)) CDPR_LAUNCH(NC_, MODE_VELOCITY, true, SPEC_DIAG | SPEC_ISO); \
-    else if (spec_full == (SPEC_DIAG | SPEC_BZ0)) CDPR_LAUNCH(NC_, MODE_VELOCITY, true, SPEC_DIAG | SPEC_BZ0); \
-    else CDPR_LAUNCH_BASE(NC_, MODE_VELOCITY, true);                                                   \
-  } while (0)
-    if (h->L.nc == 4) CDPR_LAUNCH_NC(4); else CDPR_LAUNCH_NC(8);
-#undef CDPR_LAUNCH_NC
-#undef CDPR_LAUNCH_BASE
-#undef CDPR_LAUNCH
+    const FastEntry *e = nullptr;
+    if (dm && A.mode == MODE_VELOCITY && uniform_noff && spec_full == (SPEC_DIAG | SPEC_ISO | SPEC_BZ0))
+      e = fast_find(h->L.nc, A.mode, true, spec_full | SPEC_NOFF | SPEC_UTGT);
+    if (!e && dm) e = fast_find(h->L.nc, A.mode, true, spec_full);
+    if (!e) e = fast_find(h->L.nc, A.mode, dm, spec_base);
+    if (!e) return fail(h, CDPR_ERR_UNSUPPORTED, "no step kernel instance for this configuration");
+    e->launch(grid_for(h->np, e->tpb), A, h->stream);
   }
   CK(h, cudaGetLastError());
   ++h->launches;

@@ -1,0 +1,2 @@
+#include "fast_inst.cuh"
+namespace cdpr { void fast_entries_nc8_base(std::vector<FastEntry> &out) { fast_entries_all_modes<8, 0>(out); } }

@@ -324,7 +324,7 @@ __device__ __forceinline__ void resync_moments(const StepArgs &A, double (&mom)[
 }
 
 // rare path (every snap_every steps), kept out of line so the hot loop's register allocation does not see it
-__device__ __noinline__ void write_snapshot(const StepArgs &A, FastState S, long long o) {
+static __device__ __noinline__ void write_snapshot(const StepArgs &A, FastState S, long long o) {
   if (A.snap_multimem) {
     store_plat_multicast(A.snap_peers[0] + o, A.snap_stride, S);
   } else {

@@ -15,7 +15,7 @@
 namespace cdpr {
 
 // Pid::CascadeFilter::update (Pid.cpp:38-44) over BiQuad::process (Filter.h:152-165)
-__device__ inline double cascade_update(const DevLayout &L, int c, int k, int pd, int stages, const double *co, double x, long long i) {
+static __device__ inline double cascade_update(const DevLayout &L, int c, int k, int pd, int stages, const double *co, double x, long long i) {
   double out = x;
   for (int s = 0; s < stages; ++s) {
     double *x1 = L.filt + filt_off(L, c, k, pd, s, 0) + i, *x2 = L.filt + filt_off(L, c, k, pd, s, 1) + i;
