@@ -9,7 +9,10 @@ A bench "step" is one pass of the hot path over one batch: `instances` independe
 advanced `sim_steps` physics steps by ONE persistent kernel launch (BASELINE.json configs[2]: 2^20 instances x
 1000 steps under per-instance sine velocity commands, fp64; NC = 8 is the north_star's synthetic 8-cable
 extension of the 4-cable reference robot).  For N > 1 every rank owns its own 2^20 instances (configs[3]) and the
-decimated trajectory (a snapshot every 100 steps) is all-gathered over NCCL on a side stream inside the timed region.
+decimated trajectory (a snapshot every 100 steps) is gathered to every rank inside the timed region; after the timed
+regions the gathered trajectory is CHECKED (bitwise against an NCCL all-gather of the same pass and against a fresh
+single-GPU recompute of a sample of every rank's columns) and configs[4] -- the sampled-rollout batch with its
+cross-GPU cost all-reduce -- is run, timed and checked.  Both verdicts are part of the JSON line.
 """
 from __future__ import annotations
 
@@ -26,31 +29,35 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+from cdpr_simulation_b200.flops import frozen_flops_per_instance_step, frozen_ik_flops_per_pose, ik_bytes_per_pose  # noqa: E402
+
 METRIC = "CDPR instance-steps/sec"
 UNIT = "instance-steps/s"
-# Algorithmic FP64 work per instance-step (FMA = 2 flop, sqrt = div = 1):
-#   platform: 244 general inertia | 196 diagonal | 93 isotropic (no gyroscopic torque, scalar inverse inertia; App. D's
-#             estimate for it is 115, the kernel needs 93)
-#   per cable: kinematics 52 (46 when every platform anchor has b_z = 0: R b needs 6 mul + 3 add instead of 9 + 6),
-#              force law 25 (error 1, integral 2, sliding-window D-term 13 in its (S0, S1, Kd D) form, command 4 ... the
-#              clamps are compares and the back-calculation arithmetic only runs on saturated steps: neither is
-#              counted; App. D's FIR form of the same law is 32), damping + wrench 14
-# The reference robot (sdf/cube.sdf) has isotropic inertia diag(1,1,1) and anchors in the platform plane, and the
-# kernel is specialised on exactly those properties, so the roofline uses the SMALLER count that matches it.
-def flops_per_instance_step(nc: int, inertia: str = "iso", bz0: bool = True) -> int:
-    platform = {"general": 244, "diag": 196, "iso": 93}[inertia]   # iso: counted from the kernel's SASS (App. D estimates 115)
-    return platform + nc * ((46 if bz0 else 52) + 25 + 14)
+
+
+def flops_per_instance_step(nc: int) -> int:
+    """The roofline numerator: FROZEN algorithmic count (cdpr_simulation_b200/flops.py; 1028 @ NC=8, 636 @ NC=4)."""
+    return frozen_flops_per_instance_step(nc, "general")
+
+
+def executed_flops_per_instance_step(nc: int):
+    """What the built kernel's hot loop executes per step (SASS count; FMA = 2).  None when cuobjdump is unavailable."""
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import hot_loop_flops
+        return int(hot_loop_flops.count()[nc]["executed_flops"])
+    except Exception:
+        try:
+            return int(json.load(open(os.path.join(ROOT, "profiles", "hot_loop_flops.json")))[str(nc)]["executed_flops"])
+        except Exception:
+            return None
 
 
 def state_bytes_per_instance(nc: int) -> int:
     # what the persistent kernel reads + writes per instance and LAUNCH (DESIGN.md 4): in: platform 13, per cable
     # i_err, target, window 11, moments 3, ctl (4 B), sine 3; out: platform 13, per cable i_err, last_time, window 11,
-    # moments 3, 6 telemetry columns, vel_target, ctl (read-modify-write: 8 B)
-    return 8 * (13 + 16 * nc + 3) + 4 * nc + 8 * (13 + 23 * nc) + 8 * nc
-
-
-def ik_bytes_per_pose(nc: int) -> int:
-    return 104 + 64 * nc   # 13 doubles in, (L, dL/dt, W[6]) per cable out
+    # moments 3, 10 telemetry columns, vel_target, ctl (read-modify-write: 8 B)
+    return 8 * (13 + 16 * nc + 3) + 4 * nc + 8 * (13 + 27 * nc) + 8 * nc
 
 
 class ClockSampler:
@@ -146,17 +153,140 @@ def reference_arm(args):
     # K timed passes of a bounded sample; the sample shrinks with K so that the whole run stays around 1.5 minutes
     per_pass = max(0.5, min(args.ref_seconds, 90.0 / max(1, args.steps)))
     value, sample, ms = cpu_arm(kind, args.nc, args.sim_steps, per_pass, args.steps, cores)
+    law = ("the reference's own Pid.cpp/JointForceCalculator.cpp, compiled unmodified (oracle/_ref), as the force law" if kind == "reference"
+           else "FALLBACK: oracle/_ref is not built on this box, so the force law is the repository's C restatement (oracle port), not the reference's code")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"C3 sample: sine velocity commands, NC={args.nc}, {args.sim_steps} physics steps per pass, "
-                               "reduced model with the reference's Pid.cpp/JointForceCalculator.cpp as the force law, host cores only"},
+                               f"reduced model with {law}, host cores only"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "reference_code_ran": kind == "reference",
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# multi-GPU correctness, inside the bench (driver-visible): configs[3] gather and configs[4] rollouts + all-reduce
+# ------------------------------------------------------------------------------------------------------------------
+def gather_check(cb, wl, D, torch, dist, batch, gather, load_inputs, args, rank, world, local_rank, stream):
+    """After the timed region: one more pass through the FUSED gather, then the same pass again with local snapshots and
+    an NCCL all_gather; the two trajectories must be bitwise equal on every rank.  Rank 0 also recomputes, on a fresh
+    single-GPU handle, a sample of the instances of EVERY rank and compares those columns bitwise (a wrong column
+    offset in the fused stores cannot hide behind two equally wrong gathers)."""
+    n, k_sim, every = args.instances, args.sim_steps, args.snapshot_every
+    n_snap = k_sim // every
+    with torch.cuda.stream(stream):
+        batch.reset(); load_inputs()
+        gather.before_pass(); batch.step(k_sim); gather.after_pass(); gather.finish()
+        stream.synchronize()
+        if hasattr(gather, "latest"):
+            fused = gather.latest().clone()                                   # [n_snap][13][world * n]
+        else:
+            fused = D.global_trajectory_to_instance_major(gather.recv).clone()
+        local = torch.zeros((n_snap, 13, n), dtype=torch.float64, device=f"cuda:{local_rank}")
+        torch.cuda.synchronize()
+        batch.reset(); load_inputs()
+        batch.set_snapshots(every, local.data_ptr(), n_snap)
+        batch.step(k_sim); batch.synchronize()
+        batch.set_snapshots(0, None, 0)
+    gathered = D.gather_trajectory(local)
+    traj = D.global_trajectory_to_instance_major(gathered)
+    equal = bool(torch.equal(fused, traj))
+    # rank 0: fresh single-GPU recompute of the first `m` instances of every rank
+    m = min(n, 2048)
+    sample_ok = True
+    if rank == 0:
+        cfg = cb.default_config(args.nc)
+        for r in range(world):
+            amp, freq, phase, pose7, twist6 = wl.c3_instances(n, seed=1 + 1000 * r)
+            with cb.CdprBatch(cfg, m, device=local_rank) as g:
+                snaps = torch.zeros((n_snap, 13, m), dtype=torch.float64, device=f"cuda:{local_rank}")
+                torch.cuda.synchronize()
+                g.set_platform_state(pose7[:m], twist6[:m]); g.set_sine_cmd(amp[:m], freq[:m], phase[:m])
+                g.set_snapshots(every, snaps.data_ptr(), n_snap)
+                g.step(k_sim); g.synchronize()
+            sample_ok = sample_ok and bool(torch.equal(snaps, fused[:, :, r * n: r * n + m]))
+    flags = torch.tensor([1.0 if equal else 0.0, 1.0 if sample_ok else 0.0], dtype=torch.float64, device=f"cuda:{local_rank}")
+    dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+    del fused, traj, gathered, local
+    return {"ranks": world, "bitwise_equal": bool(flags[0] > 0.5), "sample_recompute_equal": bool(flags[1] > 0.5),
+            "snapshots": n_snap, "instances_total": world * n, "sample_instances_per_rank": m,
+            "what": "fused gather buffer of every rank == NCCL all_gather of the same pass (bitwise); rank 0: columns of every "
+                    "rank == fresh single-GPU recompute of that rank's first instances (bitwise)"}
+
+
+def rollouts_c5(cb, wl, D, torch, dist, args, rank, world, local_rank):
+    """configs[4]: 4096 command sequences x 256 steps per robot, robots sharded across the ranks (64 per GPU), in-kernel
+    tracking cost, per-sequence sums over this rank's robots, cost vector all-reduced across the GPUs."""
+    n_seq, n_cmd, spc, n_rob = 4096, 32, 8, args.rollout_robots          # 32 commands x 8 steps = 256 steps
+    nc = args.nc
+    cmds = wl.c5_rollouts(n_seq, n_cmd, nc)
+    _, _, _, rp_all, rt_all = wl.c3_instances(n_rob * world, seed=5)
+    lo, hi = rank * n_rob, (rank + 1) * n_rob                                 # contiguous robot range of this rank
+    dev = f"cuda:{local_rank}"
+    out = {}
+    with cb.CdprBatch(cb.default_config(nc), n_rob * n_seq, device=local_rank) as g:
+        cost = torch.zeros(n_seq, dtype=torch.float64, device=dev)
+        torch.cuda.synchronize()
+        ms = []
+        for _ in range(4):
+            g.rollout(n_rob, n_seq, cmds, spc, [0.0, 0.0, 0.32], 0.05, rp_all[lo:hi], rt_all[lo:hi], dev_cost_seq=cost.data_ptr(), want_host_cost=False)
+            g.synchronize()
+            ms.append(g.last_kernel_ms)
+        kernel_ms = float(np.mean(ms[1:]))
+        partial = cost.clone()
+        allreduce_us, check = None, None
+        if world > 1:
+            torch.cuda.synchronize(); dist.barrier()
+            work = partial.clone()
+            for _ in range(5):                                                # warm the communicator for this size
+                D.allreduce_cost(work)
+            reps = 50
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize(); dist.barrier()
+            e0.record()
+            for _ in range(reps):
+                D.allreduce_cost(work)
+            e1.record(); torch.cuda.synchronize()
+            t = torch.tensor([e0.elapsed_time(e1) / reps * 1e3], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            allreduce_us = float(t[0])
+            total = D.allreduce_cost(partial.clone())
+            # check: gather every rank's partial vector and add them up in rank order
+            parts = [torch.empty_like(partial) for _ in range(world)]
+            dist.all_gather(parts, partial)
+            expect = torch.zeros_like(partial)
+            for p_ in parts:
+                expect += p_
+            rel = float(((total - expect).abs() / expect.abs().clamp_min(1e-300)).max())
+            # and rank 0 re-runs the robots of the LAST rank on its own GPU: that partial vector must match bitwise
+            same = True
+            if rank == 0:
+                l2, h2 = (world - 1) * n_rob, world * n_rob
+                c2 = torch.zeros(n_seq, dtype=torch.float64, device=dev)
+                torch.cuda.synchronize()
+                g.rollout(n_rob, n_seq, cmds, spc, [0.0, 0.0, 0.32], 0.05, rp_all[l2:h2], rt_all[l2:h2], dev_cost_seq=c2.data_ptr(), want_host_cost=False)
+                g.synchronize()
+                same = bool(torch.equal(c2, parts[world - 1]))
+            f = torch.tensor([1.0 if rel < 1e-13 else 0.0, 1.0 if same else 0.0], dtype=torch.float64, device=dev)
+            dist.all_reduce(f, op=dist.ReduceOp.MIN)
+            check = {"allreduce_vs_rank_ordered_sum_max_rel": rel, "allreduce_ok": bool(f[0] > 0.5),
+                     "last_ranks_partial_recomputed_on_rank0_bitwise": bool(f[1] > 0.5)}
+        t = torch.tensor([kernel_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        kernel_ms = float(t[0])
+        steps = n_cmd * spc
+        out = {"value": world * n_rob * n_seq * steps / ((kernel_ms + (allreduce_us or 0.0) * 1e-3) * 1e-3), "unit": UNIT,
+               "kernel_ms": kernel_ms, "allreduce_us": allreduce_us, "ranks": world,
+               "robots_per_gpu": n_rob, "sequences": n_seq, "steps": steps, "n_cables": nc, "check": check,
+               "what": f"{world} x {n_rob} robots x {n_seq} sequences x {steps} steps; cost vector of {n_seq} float64 all-reduced (NCCL) across the ranks; "
+                       "value = rollout steps / (kernel + all-reduce time, max over ranks)"}
+    return out
 
 
 def own_arm(args):
@@ -164,6 +294,7 @@ def own_arm(args):
     import torch.distributed as dist
     import cdpr_simulation_b200 as cb
     from cdpr_simulation_b200 import workloads as wl
+    from cdpr_simulation_b200 import distributed as D
     from cdpr_simulation_b200.distributed import make_trajectory_gather
 
     rank = int(os.environ.get("RANK", "0"))
@@ -185,7 +316,8 @@ def own_arm(args):
         t.numpy()[...] = a
         return t
     pin_in = [pinned(a) for a in (amp, freq, phase, pose7, twist6)]
-    pin_out = [torch.empty(s, dtype=torch.float64, pin_memory=True) for s in ((n, 7), (n, 6), (n, nc), (n, nc), (n, nc))]
+    out_shapes = ((n, 7), (n, 6), (n, nc), (n, nc), (n, nc))
+    pin_out = [torch.empty(s, dtype=torch.float64, pin_memory=True) for s in out_shapes]
 
     stream = torch.cuda.Stream()
     batch = cb.CdprBatch(cfg, n, device=local_rank)
@@ -235,7 +367,12 @@ def own_arm(args):
         # ---------------- e2e: host buffers in, host buffers out, through the public API ----------------
         # Two handles (A/B) on two streams, each with its own pinned buffers: while pass k computes on one, the D2H of
         # pass k-1 and the H2D of pass k+1 run on the other (calls only enqueue: cdpr_set_async). Every pass still does
-        # its own reset + H2D of all inputs + step + D2H of all outputs.
+        # its own reset + H2D of all inputs + step + D2H of all outputs.  N > 1: every pass also runs the trajectory
+        # gather, and each rank delivers its share of the GATHERED trajectory to the host -- the whole global snapshots
+        # s with s % N == rank, read from its own copy of the gather buffer -- so the host receives the full decimated
+        # trajectory of all N x 2^20 instances once per pass, spread over the N PCIe links.
+        n_snap = k_sim // args.snapshot_every
+        my_snaps = [s for s in range(n_snap) if s % world == rank] if world > 1 else []
         lanes = []
         for lane in range(2):
             st = stream if lane == 0 else torch.cuda.Stream()
@@ -243,37 +380,63 @@ def own_arm(args):
             bt.set_stream(st.cuda_stream)
             bt.set_async(True)
             ins = pin_in if lane == 0 else [pinned(a) for a in (amp, freq, phase, pose7, twist6)]
-            outs = pin_out if lane == 0 else [torch.empty(s, dtype=torch.float64, pin_memory=True) for s in ((n, 7), (n, 6), (n, nc), (n, nc), (n, nc))]
-            lanes.append((bt, ins, outs))
+            outs = pin_out if lane == 0 else [torch.empty(s, dtype=torch.float64, pin_memory=True) for s in out_shapes]
+            gl = None
+            if world > 1:
+                gl = gather if lane == 0 else make_trajectory_gather(bt, args.snapshot_every, k_sim, st, prefer_fused=(args.gather == "fused"))[0]
+            traj_host = torch.empty((len(my_snaps), 13, world * n), dtype=torch.float64, pin_memory=True) if my_snaps else None
+            lanes.append((bt, ins, outs, gl, st, traj_host))
         if gather: gather.finish()
-        gather_e2e = None   # the trajectory gather is measured in the device-timed region; the e2e region returns final states
 
         def e2e_pass(k):
-            bt, ins, outs = lanes[k % 2]
+            bt, ins, outs, gl, st, traj_host = lanes[k % 2]
             bt.synchronize()                                   # the pinned buffers of this lane are free again
+            if gl is not None:
+                st.synchronize()
             bt.reset()
             bt.set_platform_state(ins[3].numpy(), ins[4].numpy())            # H2D
             bt.set_sine_cmd(ins[0].numpy(), ins[1].numpy(), ins[2].numpy())
+            if gl is not None: gl.before_pass()
             bt.step(k_sim)
+            if gl is not None:
+                gl.after_pass(); gl.finish()
+                src = gl.latest() if hasattr(gl, "latest") else None
+                with torch.cuda.stream(st):
+                    for j, s in enumerate(my_snaps):                        # D2H of this rank's share of the gathered trajectory
+                        if src is not None:
+                            traj_host[j].copy_(src[s], non_blocking=True)
+                        else:
+                            traj_host[j].copy_(D.global_trajectory_to_instance_major(gl.recv)[s], non_blocking=True)
             bt.platform_state((outs[0].numpy(), outs[1].numpy()))            # D2H
             bt.joint_states(tuple(t.numpy() for t in outs[2:]))
 
+        def lanes_sync():
+            for bt, _, _, _, st, _ in lanes:
+                bt.synchronize(); st.synchronize()
+
         for k in range(2):
             e2e_pass(k)                                        # warm both lanes
-        for bt, _, _ in lanes:
-            bt.synchronize()
+        lanes_sync()
         barrier()
         t0 = time.perf_counter()
         for k in range(args.steps):
             e2e_pass(k)
-        for bt, _, _ in lanes:
-            bt.synchronize()
+        lanes_sync()
         barrier()
         e2e_s = time.perf_counter() - t0
-        for bt, _, _ in lanes:
+        for bt, _, _, _, _, _ in lanes:
             bt.set_async(False)
+        traj_bytes = sum(t.numel() * t.element_size() for t in [lanes[0][5]] if t is not None)
         if lanes[1][0] is not batch:
             lanes[1][0].close()
+
+    # ---------------- multi-GPU correctness + configs[4], after the timed regions ----------------
+    gcheck = None
+    if world > 1:
+        gcheck = gather_check(cb, wl, D, torch, dist, batch, gather, load_inputs, args, rank, world, local_rank, stream)
+    c5 = None
+    if not args.no_rollouts:
+        c5 = rollouts_c5(cb, wl, D, torch, dist, args, rank, world, local_rank)
 
     t = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -283,12 +446,14 @@ def own_arm(args):
     value = total_units / (ms_total * 1e-3)
     e2e_value = total_units / (e2e_ms * 1e-3)
     h2d = sum(x.numel() * x.element_size() for x in pin_in)
-    d2h = sum(x.numel() * x.element_size() for x in pin_out)
+    d2h = sum(x.numel() * x.element_size() for x in pin_out) + traj_bytes
 
     if rank == 0:
         kms = float(np.mean(kernel_ms))
-        flops = flops_per_instance_step(nc) * float(n) * k_sim
-        achieved = flops / (kms * 1e-3) / 1e12
+        frozen = flops_per_instance_step(nc)
+        executed = executed_flops_per_instance_step(nc)
+        achieved = frozen * float(n) * k_sim / (kms * 1e-3) / 1e12
+        achieved_exec = executed * float(n) * k_sim / (kms * 1e-3) / 1e12 if executed else None
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -297,28 +462,41 @@ def own_arm(args):
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         hbm_bytes = state_bytes_per_instance(nc) * float(n)
         traffic, traffic_src = None, None
-        try:   # DRAM bytes of this kernel from the committed `ncu --set full` capture of the same launch shape
-            prof = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_summary.json")))[f"step_fast_nc{nc}"]
-            if n == (1 << 20) and k_sim == 1000:
-                scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
-                traffic = sum(float(prof[m]["value"]) * scale[prof[m]["unit"]] for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
-                traffic_src = "profiles/r1_ncu_summary.json (ncu --set full, one launch of 2^20 instances x 1000 steps)"
-        except Exception:
-            pass
+        for prof_name in ("r2_ncu_summary.json", "r1_ncu_summary.json"):
+            try:   # DRAM bytes of this kernel from the committed `ncu --set full` capture of the same launch shape
+                prof = json.load(open(os.path.join(ROOT, "profiles", prof_name)))[f"step_fast_nc{nc}"]
+                if n == (1 << 20) and k_sim == 1000:
+                    scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+                    traffic = sum(float(prof[m]["value"]) * scale[prof[m]["unit"]] for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+                    traffic_src = f"profiles/{prof_name} (ncu --set full, one launch of 2^20 instances x 1000 steps)"
+                    break
+            except Exception:
+                pass
+        fp64_src = ("MEASURED_PEAKS.json" if "fp64_tflops" in peaks else
+                    "DFMA issue rate measured in this run by cdpr_measure_fp64_tflops (MEASURED_PEAKS.json has no FP64 entry; nominal B200 FP64 = "
+                    "148 SM x 64 lanes x 2 x 1.965 GHz = 37.2 TFLOP/s; tools/ubench_dfma.cu output with clocks: profiles/r2_fp64_peak.txt)")
+        fp64_den = peaks.get("fp64_tflops", fp64_peak)
         roofline = {
-            "bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak if fp64_peak > 0 else None,
+            "bound": "fp64", "achieved": achieved, "peak": fp64_den, "unit": "TFLOP/s", "frac": achieved / fp64_den if fp64_den > 0 else None,
             "traffic": traffic, "traffic_unit": "bytes per launch", "traffic_source": traffic_src, "algorithmic_bytes_per_launch": hbm_bytes,
             "kernel": f"k_step_fast<{nc},11,VELOCITY,moments,spec>", "kernel_ms": kms,
-            "flops_per_instance_step": flops_per_instance_step(nc),
-            "flops_note": "count for this robot (isotropic inertia, anchors in the platform plane: 93 + 85 NC = the SASS count of the hot loop, 773 @NC=8, profiles/r1_hot_loop_flops.txt); a general robot is 244 + 91 NC; SURVEY 8(d)'s FIR-form count is 244 + 98 NC",
-            "peak_source": "DFMA issue rate measured in this run by cdpr_measure_fp64_tflops (MEASURED_PEAKS.json has no FP64 entry; "
-                           "nominal B200 FP64 is 37 TFLOP/s)",
+            "flops_per_instance_step": frozen,
+            "flops_note": "FROZEN algorithmic count (cdpr_simulation_b200/flops.py = BASELINE.md section 4 / SURVEY App. D: 244 + 98 NC, general inertia, "
+                          "FIR form of the D-term); it does not follow the kernel",
+            "executed_flops": executed,
+            "executed_flops_note": "FP64 work the built kernel's hot loop really issues per instance-step (SASS count, FMA = 2; tools/hot_loop_flops.py); "
+                                   "smaller than the frozen count because the kernel is specialised on this robot (isotropic inertia, anchors in the "
+                                   "platform plane) and carries the D-term as a 3-value recursion",
+            "achieved_executed": achieved_exec, "frac_executed": (achieved_exec / fp64_den) if (achieved_exec and fp64_den > 0) else None,
+            "peak_source": fp64_src, "peak_measured_in_run": fp64_peak,
             "hbm": {"achieved": hbm_bytes / (kms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                     "frac": hbm_bytes / (kms * 1e-3) / 1e9 / hbm_peak,
                     "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
                     "note": "state is read and written once per launch of 1000 steps: the kernel is FP64-issue bound, not HBM bound"},
         }
-        extra = side_measurements(cb, wl, torch, local_rank, hbm_peak, fp64_peak) if (world == 1 and not args.no_extras) else None
+        extra, ik_c2 = None, None
+        if world == 1 and not args.no_extras:
+            extra, ik_c2 = side_measurements(cb, wl, torch, local_rank, hbm_peak, fp64_den)
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             v, sample, _ = cpu_arm("port", nc, k_sim, args.cpu_seconds, 1, host_cores())
@@ -331,24 +509,108 @@ def own_arm(args):
                                    f"NC={nc} ({'synthetic 8-cable extension' if nc == 8 else 'reference 4-cable robot'})",
                        "instances_per_gpu": n, "sim_steps_per_pass": k_sim, "n_cables": nc,
                        "l2": "resident state per GPU (%.1f GB) is larger than L2; no flush needed" % (batch_state_gb(batch)),
-                       "multi_gpu": None if world == 1 else f"snapshot every {args.snapshot_every} steps gathered to every rank -- {gather_kind}"},
+                       "multi_gpu": None if world == 1 else f"C4: snapshot every {args.snapshot_every} steps gathered to every rank -- {gather_kind}"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / args.steps,
-                    "what": "per pass: reset + H2D(pose, twist, sine params) + step + D2H(platform pose/twist, joint states) through the C ABI, pinned host buffers, two handles double-buffered so copies overlap the other handle's kernel"},
+                    "what": "per pass and rank: reset + H2D(pose, twist, sine params) + step + D2H(platform pose/twist, joint states) through the C ABI, "
+                            "pinned host buffers, two handles double-buffered so copies overlap the other handle's kernel"
+                            + ("" if world == 1 else f"; plus the trajectory gather and the D2H of this rank's share of the gathered trajectory "
+                                                     f"({len(my_snaps)} of {n_snap} global snapshots x 13 x {world * n} float64)")},
             "gpu_launches": int(launches),
             "roofline": roofline,
             "cpu_baseline": cpu,
+            "gather_check": gcheck,
+            "rollouts_c5": c5,
+            "ik_c2": ik_c2,
             "extra": extra,
         }
         print(json.dumps(line), flush=True)
     batch.close()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
+def ik_c2_measurement(cb, wl, torch, device, hbm_peak, nc, npose):
+    """configs[1]: the kinematics sweep at its stated size, steady state through a CUDA graph (no launch gaps), with a
+    cudaMemcpyAsync device-to-device copy moving the SAME number of DRAM bytes timed the same way as the ceiling."""
+    p7, t6 = wl.c2_poses(npose, seed=0)
+    st = np.ascontiguousarray(np.concatenate([p7[:, :3], p7[:, 6:7], p7[:, 3:6], t6], axis=1).T)
+    nbytes = ik_bytes_per_pose(nc) * npose
+    # enough rotating buffer sets that consecutive launches cannot be served from the 126 MB L2
+    sets = max(2, int(np.ceil(3 * 126e6 / nbytes)))
+    dev = f"cuda:{device}"
+    d_in = [torch.from_numpy(st).to(dev) for _ in range(sets)]
+    d_out = [torch.empty((nc, 8, npose), dtype=torch.float64, device=dev) for _ in range(sets)]
+    # copy ceiling: a D2D copy of nbytes/2 reads nbytes/2 and writes nbytes/2 = the sweep's DRAM traffic
+    half = (nbytes // 2 + 255) // 256 * 256
+    c_src = [torch.empty(half, dtype=torch.uint8, device=dev) for _ in range(sets)]
+    c_dst = [torch.empty(half, dtype=torch.uint8, device=dev) for _ in range(sets)]
+    torch.cuda.synchronize()
+    res = {}
+    with cb.CdprBatch(cb.default_config(nc), 1, device=device) as g:
+        single = []
+        for k in range(12):
+            g.ik_device(npose, d_in[k % sets].data_ptr(), d_out[k % sets].data_ptr()); single.append(g.last_kernel_ms)
+        s = torch.cuda.Stream(device=device)
+        g.set_stream(s.cuda_stream)
+        g.set_option(cb.api.OPT_KERNEL_TIMING, 0)          # no event records: the launches go into a CUDA graph
+        reps = 10
+        def timed(fn_capture):
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.stream(s):
+                fn_capture()                                 # warm
+                s.synchronize()
+                with torch.cuda.graph(graph, stream=s):
+                    fn_capture()
+                graph.replay(); s.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(s)
+                for _ in range(reps):
+                    graph.replay()
+                e1.record(s)
+                s.synchronize()
+            return e0.elapsed_time(e1) / (reps * sets)
+        def sweep():
+            for k in range(sets):
+                g.ik_device(npose, d_in[k].data_ptr(), d_out[k].data_ptr())
+        def copies():
+            for k in range(sets):
+                c_dst[k].copy_(c_src[k], non_blocking=True)
+        try:
+            steady = timed(sweep)
+            how = f"CUDA graph of {sets} launches over {sets} rotating buffer sets (> L2 in total), {reps} replays"
+        except Exception as e:   # graph capture unavailable: plain back-to-back launches
+            how = f"{reps * sets} back-to-back launches (graph capture failed: {type(e).__name__})"
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(s):
+                sweep(); e0.record(s)
+                for _ in range(reps):
+                    sweep()
+                e1.record(s); s.synchronize()
+            steady = e0.elapsed_time(e1) / (reps * sets)
+        try:
+            copy_ms = timed(copies)
+        except Exception:
+            copy_ms = None
+        g.set_option(cb.api.OPT_KERNEL_TIMING, 1)
+    gbs = nbytes / (steady * 1e-3) / 1e9
+    copy_gbs = (2 * half) / (copy_ms * 1e-3) / 1e9 if copy_ms else None
+    res = {"poses": npose, "n_cables": nc, "poses_per_s": npose / (steady * 1e-3), "kernel_us_steady": steady * 1e3,
+           "kernel_us_single_shot": float(np.median(single[2:])) * 1e3, "how": how,
+           "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "traffic": None,
+                        "algorithmic_bytes_per_launch": nbytes, "flops_per_pose": frozen_ik_flops_per_pose(nc),
+                        "kernel": "k_ik_pair (one thread per cable and pose pair)"},
+           "copy_ceiling": {"us": copy_ms * 1e3 if copy_ms else None, "GBps": copy_gbs, "bytes_read_plus_written": 2 * half,
+                            "what": "cudaMemcpyAsync D2D moving the same DRAM bytes (read + write), same graph, same rotation"},
+           "frac_of_copy_ceiling": (gbs / copy_gbs) if copy_gbs else None}
+    return res
+
+
 def side_measurements(cb, wl, torch, device, hbm_peak, fp64_peak):
-    """Not the headline: the reference's own 4-cable robot on the same workload, and the config-2 kinematics sweep."""
+    """Not the headline: the reference's own 4-cable robot on the same workload, the other kernel shapes, plugin-style
+    stepping, the hold / filter variant, and the config-2 kinematics sweep (returned separately as `ik_c2`)."""
     out = {}
     n, k = 1 << 20, 1000
     amp, freq, phase, pose7, twist6 = wl.c3_instances(n, seed=1)
@@ -359,7 +621,8 @@ def side_measurements(cb, wl, torch, device, hbm_peak, fp64_peak):
             g.step(k); ms.append(g.last_kernel_ms)
         t = float(np.mean(ms[1:]))
         out["nc4_reference_robot"] = {"value": n * k / (t * 1e-3), "unit": UNIT, "kernel_ms": t,
-                                      "fp64_frac": flops_per_instance_step(4) * n * k / (t * 1e-3) / 1e12 / fp64_peak}
+                                      "fp64_frac": flops_per_instance_step(4) * n * k / (t * 1e-3) / 1e12 / fp64_peak,
+                                      "fp64_frac_executed": (executed_flops_per_instance_step(4) or 0) * n * k / (t * 1e-3) / 1e12 / fp64_peak}
     # the other shapes of the same kernel: per-cable position targets (Position mode), and a run whose command clamp
     # fires on every step (the inline-clamping steady body instead of the optimistic one)
     with cb.CdprBatch(cb.default_config(8), n, device=device) as g:
@@ -387,34 +650,22 @@ def side_measurements(cb, wl, torch, device, hbm_peak, fp64_peak):
             g.step(1)
         t0 = time.perf_counter()
         reps = 2000
-        for k in range(reps):
-            if k % 10 == 0:
+        for kk in range(reps):
+            if kk % 10 == 0:
                 g.set_velocity_cmd(axes)
             g.step(1)
             g.joint_states(); g.platform_state()
         dt1 = (time.perf_counter() - t0) / reps
         t0 = time.perf_counter()
-        for k in range(reps):
+        for kk in range(reps):
             g.step(1)
         g.synchronize()
         dt2 = (time.perf_counter() - t0) / reps
         out["plugin_style_single_robot"] = {"updates_per_s_with_readback": 1.0 / dt1, "steps_per_s_no_readback": 1.0 / dt2,
                                             "what": "N=1, NC=4, k=1 per call through the C ABI; with readback = set command every 10 steps + step + joint states + platform state (host buffers, synchronous)"}
-    # config 5: 4096 command sequences x 256 steps per robot, 64 robots on this GPU (262,144 rollouts), cost reduced per sequence
-    n_seq, n_cmd, spc, n_rob = 4096, 26, 10, 64
-    cmds = wl.c5_rollouts(n_seq, n_cmd, 8)
-    _, _, _, rp, rt = wl.c3_instances(n_rob, seed=5)
-    with cb.CdprBatch(cb.default_config(8), n_rob * n_seq, device=device) as g:
-        cost = torch.zeros(n_seq, dtype=torch.float64, device=f"cuda:{device}")
-        torch.cuda.synchronize()
-        ms = []
-        for _ in range(3):
-            g.rollout(n_rob, n_seq, cmds, spc, [0.0, 0.0, 0.32], 0.05, rp, rt, dev_cost_seq=cost.data_ptr(), want_host_cost=False)
-            ms.append(g.last_kernel_ms)
-        t = float(np.mean(ms[1:]))
-        out["rollouts_c5_nc8"] = {"value": n_rob * n_seq * n_cmd * spc / (t * 1e-3), "unit": UNIT, "kernel_ms": t,
-                                  "what": f"{n_rob} robots x {n_seq} sequences x {n_cmd * spc} steps, in-kernel cost + per-sequence reduction"}
-    # the catch-all kernel (hold + biquad cascades enabled): HBM/L2-bound fallback, reported for completeness
+        if hasattr(g, "update"):
+            out["plugin_style_single_robot"].update(plugin_update_rate(g, axes, reps))
+    # the hold / filter variant (velocity hold below 2 cm/s + one biquad stage on the P input and on the D output)
     gcfg = cb.default_config(8)
     gcfg.velocity_epsilon = 0.02; gcfg.vel_pid.p_cascade = 1; gcfg.vel_pid.d_cascade = 1
     ng = 1 << 18
@@ -425,42 +676,29 @@ def side_measurements(cb, wl, torch, device, hbm_peak, fp64_peak):
             g.step(200); ms.append(g.last_kernel_ms)
         t = float(np.mean(ms[1:]))
         out["general_variant_nc8"] = {"value": ng * 200 / (t * 1e-3), "unit": UNIT, "kernel_ms": t, "variant": g.kernel_variant}
+    ik_c2 = None
     for nc in (4, 8):
         for npose in (65536, 1 << 22):
-            p7, t6 = wl.c2_poses(npose, seed=0)
-            st = np.ascontiguousarray(np.concatenate([p7[:, :3], p7[:, 6:7], p7[:, 3:6], t6], axis=1).T)
-            # enough rotating buffer sets that consecutive launches cannot be served from the 126 MB L2
-            sets = max(2, int(np.ceil(3 * 126e6 / (ik_bytes_per_pose(nc) * npose))))
-            d_in = [torch.from_numpy(st).cuda(device) for _ in range(sets)]
-            d_out = [torch.empty((nc, 8, npose), dtype=torch.float64, device=f"cuda:{device}") for _ in range(sets)]
-            torch.cuda.synchronize()
-            with cb.CdprBatch(cb.default_config(nc), 1, device=device) as g:
-                single = []
-                for k in range(12):
-                    g.ik_device(npose, d_in[k % sets].data_ptr(), d_out[k % sets].data_ptr()); single.append(g.last_kernel_ms)
-                s = torch.cuda.Stream(device=device)
-                g.set_stream(s.cuda_stream)
-                reps = 10 * sets
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                with torch.cuda.stream(s):
-                    for k in range(sets):
-                        g.ik_device(npose, d_in[k].data_ptr(), d_out[k].data_ptr())
-                    e0.record(s)
-                    for k in range(reps):
-                        g.ik_device(npose, d_in[k % sets].data_ptr(), d_out[k % sets].data_ptr())
-                    e1.record(s)
-                    s.synchronize()
-                steady = e0.elapsed_time(e1) / reps
-            t1 = float(np.median(single[2:]))
-            gbs = ik_bytes_per_pose(nc) * npose / (steady * 1e-3) / 1e9
-            out[f"ik_sweep_nc{nc}_{npose}"] = {"poses_per_s": npose / (steady * 1e-3), "kernel_us_steady": steady * 1e3, "kernel_us_single_shot": t1 * 1e3,
-                                               "GBps": gbs, "hbm_frac": gbs / hbm_peak,
-                                               "note": f"steady = {reps} back-to-back launches over {sets} rotating buffer sets (> L2 in total); single shot = one launch between two events (includes launch latency)"}
-    return out
+            r = ik_c2_measurement(cb, wl, torch, device, hbm_peak, nc, npose)
+            if nc == 8 and npose == 65536:
+                ik_c2 = r                                  # BASELINE.json configs[1] at its stated size
+            out[f"ik_sweep_nc{nc}_{npose}"] = r
+    return out, ik_c2
+
+
+def plugin_update_rate(g, axes, reps):
+    """One fused update per physics step (command in, step, joint + platform state out in ONE call, CUDA graph inside)."""
+    for kk in range(50):
+        g.update(axes if kk % 10 == 0 else None)
+    t0 = time.perf_counter()
+    for kk in range(reps):
+        g.update(axes if kk % 10 == 0 else None)
+    dt = (time.perf_counter() - t0) / reps
+    return {"updates_per_s_fused_call": 1.0 / dt,
+            "fused_call": "cdpr_update: command scatter + k=1 step + joint states + platform state + D2H as one CUDA graph replay per call"}
 
 
 def batch_state_gb(batch) -> float:
-    import ctypes
     return batch._L.cdpr_state_bytes(batch._h) / 1e9
 
 
@@ -475,10 +713,12 @@ def main():
     ap.add_argument("--sim-steps", type=int, default=1000, help="physics steps per pass (one kernel launch)")
     ap.add_argument("--snapshot-every", type=int, default=100)
     ap.add_argument("--gather", default="fused", choices=["fused", "nccl"], help="multi-GPU trajectory gather implementation")
+    ap.add_argument("--rollout-robots", type=int, default=64, help="robots per GPU of the config-5 rollout batch (x 4096 sequences x 256 steps)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--ref-seconds", type=float, default=6.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-rollouts", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "own":
         args.warmup = 3

@@ -18,6 +18,7 @@ from . import build as _build
 
 MAX_CABLES = 8
 MODE_FORCE, MODE_POSITION, MODE_VELOCITY = 0, 1, 2
+OPT_DTERM_FIR, OPT_KERNEL_TIMING = 1, 2
 
 OK = 0
 ERR_BAD_ARG, ERR_BAD_CABLE_COUNT, ERR_BAD_LENGTH, ERR_NO_DEVICE, ERR_CUDA, ERR_UNSUPPORTED, ERR_NOMEM = -1, -2, -3, -4, -5, -6, -7
@@ -25,9 +26,9 @@ ERR_BAD_ARG, ERR_BAD_CABLE_COUNT, ERR_BAD_LENGTH, ERR_NO_DEVICE, ERR_CUDA, ERR_U
 # every symbol include/cdpr_b200.h declares (checked by tests/test_abi.py)
 EXPORTS = [
     "cdpr_config_default", "cdpr_create", "cdpr_destroy", "cdpr_reset", "cdpr_last_error", "cdpr_set_stream", "cdpr_synchronize", "cdpr_set_async",
-    "cdpr_set_velocity_cmd", "cdpr_set_position_cmd", "cdpr_set_effort_cmd", "cdpr_set_sine_cmd",
+    "cdpr_set_option", "cdpr_set_velocity_cmd", "cdpr_set_position_cmd", "cdpr_set_effort_cmd", "cdpr_set_sine_cmd",
     "cdpr_step", "cdpr_step_count", "cdpr_sim_time",
-    "cdpr_get_joint_states", "cdpr_get_platform_state", "cdpr_set_platform_state", "cdpr_get_pid_state",
+    "cdpr_get_joint_states", "cdpr_get_platform_state", "cdpr_set_platform_state", "cdpr_get_pid_state", "cdpr_get_pid_terms",
     "cdpr_state_bytes", "cdpr_get_state", "cdpr_set_state",
     "cdpr_set_snapshots", "cdpr_set_snapshot_peers", "cdpr_set_snapshot_multicast", "cdpr_snapshot_count",
     "cdpr_ik", "cdpr_ik_device", "cdpr_rollout",
@@ -97,6 +98,7 @@ def load():
     L.cdpr_set_stream.argtypes = [vp, vp]
     L.cdpr_synchronize.argtypes = [vp]
     L.cdpr_set_async.argtypes = [vp, C.c_int]
+    L.cdpr_set_option.argtypes = [vp, C.c_int, i64]
     for f in (L.cdpr_set_velocity_cmd, L.cdpr_set_position_cmd, L.cdpr_set_effort_cmd):
         f.argtypes = [vp, vp, i64, C.c_int]
     L.cdpr_set_sine_cmd.argtypes = [vp, vp, vp, vp, i64]
@@ -107,6 +109,7 @@ def load():
     L.cdpr_get_platform_state.argtypes = [vp, vp, vp]
     L.cdpr_set_platform_state.argtypes = [vp, vp, vp]
     L.cdpr_get_pid_state.argtypes = [vp, vp]
+    L.cdpr_get_pid_terms.argtypes = [vp, vp]
     L.cdpr_state_bytes.argtypes = [vp]; L.cdpr_state_bytes.restype = C.c_size_t
     L.cdpr_get_state.argtypes = [vp, vp, C.c_size_t]
     L.cdpr_set_state.argtypes = [vp, vp, C.c_size_t]
@@ -193,6 +196,9 @@ class CdprBatch:
         """Host-buffer calls only enqueue; keep the (pinned) buffers alive until synchronize()."""
         self._ck(self._L.cdpr_set_async(self._h, 1 if on else 0))
 
+    def set_option(self, option: int, value: int):
+        self._ck(self._L.cdpr_set_option(self._h, int(option), int(value)))
+
     def synchronize(self):
         self._ck(self._L.cdpr_synchronize(self._h))
 
@@ -259,6 +265,12 @@ class CdprBatch:
     def pid_state(self):
         out = np.empty((self.n, self.nc, 6))
         self._ck(self._L.cdpr_get_pid_state(self._h, _ptr(out)))
+        return out
+
+    def pid_terms(self):
+        """Topic `pid` for every cable: [n][nc][5] = pTerm, pre-clamp iTerm, dTerm, desired, applied force (last step)."""
+        out = np.empty((self.n, self.nc, 5))
+        self._ck(self._L.cdpr_get_pid_terms(self._h, _ptr(out)))
         return out
 
     # -- checkpoint --------------------------------------------------------------------------

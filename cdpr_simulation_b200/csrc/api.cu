@@ -28,6 +28,7 @@ struct cdpr_batch {
   double fir[2][kMaxDbuf]{};
   double dmom[2][3]{};
   bool dmom_ok[2]{};
+  bool force_fir = false;  // CDPR_OPT_DTERM_FIR
   int mode = MODE_POSITION;
   bool vel_pending = false, pos_pending = false;
   int sec = 0, nsec = 0, dt_ns = 0;
@@ -49,6 +50,7 @@ struct cdpr_batch {
   cudaEvent_t io_done = nullptr, main_done = nullptr;
   bool io_pending = false, main_pending = false;
   bool timed = false;
+  bool timing = true;  // CDPR_OPT_KERNEL_TIMING: event records around the launches
   bool async_copies = false;  // host-buffer calls only enqueue; the caller synchronises (pinned buffers)
   bool targets_uniform = false;  // all cables of an instance hold the same velocity target (zeros after Load, or written by the sine publisher)
   long long launches = 0;
@@ -347,6 +349,9 @@ extern "C" int cdpr_create(const cdpr_config *cfg, int64_t n_instances, int devi
   fir_weights(cfg->pos_pid.d_degree, cfg->pos_pid.d_buffer_length, cfg->dt, h->fir[PID_POS]);
   h->dmom_ok[PID_VEL] = fir_as_quadratic(h->fir[PID_VEL], cfg->vel_pid.d_buffer_length, h->dmom[PID_VEL]);
   h->dmom_ok[PID_POS] = fir_as_quadratic(h->fir[PID_POS], cfg->pos_pid.d_buffer_length, h->dmom[PID_POS]);
+  if (!(cfg->sine_publish_hz > 0.0) || !std::isfinite(cfg->sine_publish_hz)) {
+    g_create_error = "sine_publish_hz must be positive and finite"; delete h; return CDPR_ERR_BAD_ARG;
+  }
   h->dt_ns = (int)std::llround(ns);
   h->sine_pub_dt = 1.0 / cfg->sine_publish_hz;  // sinevelocitytest.cpp:48
   h->sine_period = (int)std::llround(h->sine_pub_dt / cfg->dt);
@@ -462,6 +467,22 @@ extern "C" int cdpr_synchronize(cdpr_handle h) {
   CK(h, cudaStreamSynchronize(h->stream));
   CK(h, cudaStreamSynchronize(h->io_stream));
   return CDPR_OK;
+}
+
+extern "C" int cdpr_set_option(cdpr_handle h, int option, int64_t value) {
+  if (!h) return CDPR_ERR_BAD_ARG;
+  switch (option) {
+    case CDPR_OPT_KERNEL_TIMING:
+      h->timing = value != 0;
+      if (!h->timing) h->timed = false;
+      return CDPR_OK;
+    case CDPR_OPT_DTERM_FIR:
+      if (h->step_count != 0) return fail(h, CDPR_ERR_BAD_ARG, "the D-term form can only change before the first step");
+      h->force_fir = value != 0;
+      return CDPR_OK;
+    default:
+      return fail(h, CDPR_ERR_BAD_ARG, "unknown option");
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -581,7 +602,7 @@ static int launch_step(cdpr_handle h, const StepArgs &A) {
   if (h->general) {
     general_launch(std::max(h->pc[PID_VEL].degree, h->pc[PID_POS].degree), (unsigned)(h->np / kTpb), A, h->stream);
   } else {
-    const bool dm = h->dmom_ok[A.live_idx] && A.mode != MODE_FORCE;
+    const bool dm = h->dmom_ok[A.live_idx] && !h->force_fir && A.mode != MODE_FORCE;
     // the velocity and position modes with the moment D-term are specialised on the robot constants; every
     // other combination runs the diagonal-inertia or fully general instance
     const int spec_full = h->rc.spec, spec_base = h->rc.spec & SPEC_DIAG;
@@ -601,9 +622,11 @@ static int launch_step(cdpr_handle h, const StepArgs &A) {
 }
 
 static void advance_host_clock(cdpr_handle h, long long k, bool sine) {
-  if (sine) {  // one publish at every step n with (n - 1) % period == 0
-    for (long long n = h->step_count + 1; n <= h->step_count + k; ++n)
-      if ((n - 1) % h->sine_period == 0) h->sine_time = h->sine_time + h->sine_pub_dt;
+  if (sine) {  // one publish before every step whose 0-based index m is a multiple of the period, m in [step_count, step_count + k)
+    const long long p = h->sine_period, lo = h->step_count, hi = h->step_count + k;
+    const long long publishes = (hi + p - 1) / p - (lo + p - 1) / p;
+    // repeated addition, like the device (and the driver's `time += 1.0 / 100.0`, sinevelocitytest.cpp:48): bitwise the same
+    for (long long e = 0; e < publishes; ++e) h->sine_time = h->sine_time + h->sine_pub_dt;
   }
   if (h->n_snap_peers > 0 && h->snap_every > 0) h->snap_written += (h->step_count + k) / h->snap_every - h->step_count / h->snap_every;
   long long ns = (long long)h->nsec + (long long)h->dt_ns * k;
@@ -617,12 +640,16 @@ extern "C" int cdpr_step(cdpr_handle h, int64_t k_steps) {
   if (k_steps == 0) return CDPR_OK;
   cudaSetDevice(h->device);
   main_begin(h);
-  CK(h, cudaEventRecord(h->ev0, h->stream));
+  if (h->timing) CK(h, cudaEventRecord(h->ev0, h->stream));
   long long remaining = k_steps;
   while (remaining > 0) {
-    // CdprGazeboPlugin::update, .cpp:206-221: a pending velocity command is fanned out first, then a
-    // pending position command; each setter resets its Pid when the mode changes (JointForceCalculator.cpp:99-119)
-    if (h->vel_pending) {
+    // CdprGazeboPlugin::update, .cpp:206-221: a pending velocity command is fanned out first, then a pending
+    // position command; each setter resets its Pid when the mode changes (JointForceCalculator.cpp:99-119).
+    // A publish of the in-kernel sine generator IS a velocity command arriving with this step, so it takes part in
+    // the velocity fan-out -- a position command pending at a publish step is applied after it and wins until the
+    // next publish.
+    const bool publish_now = h->sine_on && (h->step_count % h->sine_period == 0);
+    if (h->vel_pending || publish_now) {
       if (h->mode != MODE_VELOCITY) { int rc = reset_pid(h, PID_VEL); if (rc) return rc; }
       h->mode = MODE_VELOCITY; h->vel_pending = false;
     }
@@ -631,15 +658,13 @@ extern "C" int cdpr_step(cdpr_handle h, int64_t k_steps) {
       h->mode = MODE_POSITION; h->pos_pending = false;
     }
     long long seg = std::min<long long>(remaining, 1 << 30);
-    bool sine = false;
+    bool sine = false, silent_publish = false;
     if (h->sine_on) {
       if (h->mode == MODE_VELOCITY) sine = true;
-      else {
+      else {  // Force / Position mode runs until the next publish switches back to Velocity
         const long long r = h->step_count % h->sine_period;
-        if (r == 0) {  // the next step publishes: setVelocityTarget switches the mode and resets the Pid
-          int rc = reset_pid(h, PID_VEL); if (rc) return rc;
-          h->mode = MODE_VELOCITY; sine = true;
-        } else seg = std::min<long long>(seg, h->sine_period - r);
+        seg = std::min<long long>(seg, h->sine_period - r);
+        silent_publish = (r == 0);  // the publisher ticked, but its target was overridden in the same update
       }
     }
     StepArgs A;
@@ -651,10 +676,10 @@ extern "C" int cdpr_step(cdpr_handle h, int64_t k_steps) {
       if (first < h->step_count + seg) h->targets_uniform = true;
     }
     advance_host_clock(h, seg, sine);
+    if (silent_publish) h->sine_time = h->sine_time + h->sine_pub_dt;
     remaining -= seg;
   }
-  CK(h, cudaEventRecord(h->ev1, h->stream));
-  h->timed = true;
+  if (h->timing) { CK(h, cudaEventRecord(h->ev1, h->stream)); h->timed = true; }
   main_end(h);
   return CDPR_OK;
 }
@@ -732,6 +757,21 @@ extern "C" int cdpr_get_pid_state(cdpr_handle h, double *out) {
   return CDPR_OK;
 }
 
+extern "C" int cdpr_get_pid_terms(cdpr_handle h, double *out) {
+  if (!h || !out) return CDPR_ERR_BAD_ARG;
+  cudaSetDevice(h->device);
+  const size_t nb = sizeof(double) * (size_t)h->n * h->L.nc * 5;
+  int rc = ensure_stage(h, nb);
+  if (rc) return rc;
+  cudaStream_t st = io_begin(h);
+  k_pid_terms<<<grid_for(h->n, 256), 256, 0, st>>>(h->L, (double *)h->stage);
+  CK(h, cudaGetLastError());
+  CK(h, cudaMemcpyAsync(out, h->stage, nb, cudaMemcpyDeviceToHost, st));
+  io_end(h);
+  CK(h, sync_unless_async(h));
+  return CDPR_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // checkpoint / resume: header + the raw device arrays in the order of common.cuh
 // ---------------------------------------------------------------------------------------------
@@ -741,8 +781,15 @@ struct BlobHeader {
   int32_t nc, len, casc, general, mode, vel_pending, pos_pending, sec, nsec, sine_on;
   int64_t step_count;
   double sine_time;
-  uint8_t pad[160];
+  uint64_t cfg_hash;  // FNV-1a of the cdpr_config the blob was taken under (gains and dt shape the window state)
+  uint8_t pad[152];
 };
+static uint64_t config_hash(const cdpr_config &c) {
+  uint64_t hsh = 1469598103934665603ULL;
+  const unsigned char *p = (const unsigned char *)&c;
+  for (size_t i = 0; i < sizeof(c); ++i) { hsh ^= p[i]; hsh *= 1099511628211ULL; }
+  return hsh;
+}
 static const uint64_t kMagic = 0x3030324252504443ULL;  // "CDPRB200"
 
 struct Section { void *ptr; size_t bytes; };
@@ -773,7 +820,7 @@ extern "C" int cdpr_get_state(cdpr_handle h, void *blob, size_t bytes) {
   std::memset(&hd, 0, sizeof(hd));
   hd.magic = kMagic; hd.n = h->n; hd.np = h->np; hd.nc = h->L.nc; hd.len = h->L.len; hd.casc = h->L.casc; hd.general = h->general;
   hd.mode = h->mode; hd.vel_pending = h->vel_pending; hd.pos_pending = h->pos_pending; hd.sec = h->sec; hd.nsec = h->nsec;
-  hd.sine_on = h->sine_on; hd.step_count = h->step_count; hd.sine_time = h->sine_time;
+  hd.sine_on = h->sine_on; hd.step_count = h->step_count; hd.sine_time = h->sine_time; hd.cfg_hash = config_hash(h->cfg);
   std::memcpy(blob, &hd, sizeof(hd));
   uint8_t *o = (uint8_t *)blob + sizeof(hd);
   for (auto &s : sections(h)) {
@@ -791,6 +838,8 @@ extern "C" int cdpr_set_state(cdpr_handle h, const void *blob, size_t bytes) {
   if (hd.magic != kMagic || hd.n != h->n || hd.np != h->np || hd.nc != h->L.nc || hd.len != h->L.len || hd.casc != h->L.casc ||
       hd.general != (int)h->general)
     return fail(h, CDPR_ERR_BAD_ARG, "checkpoint does not match this handle's shape");
+  if (hd.cfg_hash != config_hash(h->cfg)) return fail(h, CDPR_ERR_BAD_ARG, "checkpoint was taken under a different cdpr_config");
+  if (hd.mode < MODE_FORCE || hd.mode > MODE_VELOCITY || hd.step_count < 0) return fail(h, CDPR_ERR_BAD_ARG, "corrupt checkpoint header");
   cudaSetDevice(h->device);
   main_begin(h);
   const uint8_t *o = (const uint8_t *)blob + sizeof(hd);
@@ -845,6 +894,13 @@ extern "C" int64_t cdpr_snapshot_count(cdpr_handle h) { return h ? std::min(h->s
 // ---------------------------------------------------------------------------------------------
 static int launch_ik(cdpr_handle h, const IkArgs &A, bool aos) {
   const unsigned grid = grid_for(A.n, 256);
+  // device path, even pose count and 16-byte aligned buffers: one thread per (cable, pose pair), double2 accesses
+  if (!aos && (A.n % 2) == 0 && ((uintptr_t)A.state13 % 16) == 0 && ((uintptr_t)A.out % 16) == 0 && (h->L.nc == 4 || h->L.nc == 8)) {
+    k_ik_pair<<<dim3(grid_for(A.n / 2, 256), (unsigned)h->L.nc), 256, 0, h->stream>>>(A);
+    CK(h, cudaGetLastError());
+    ++h->launches;
+    return CDPR_OK;
+  }
   if (h->L.nc == 4) { if (aos) k_ik<4, true><<<grid, 256, 0, h->stream>>>(A); else k_ik<4, false><<<grid, 256, 0, h->stream>>>(A); }
   else if (h->L.nc == 8) { if (aos) k_ik<8, true><<<grid, 256, 0, h->stream>>>(A); else k_ik<8, false><<<grid, 256, 0, h->stream>>>(A); }
   else return fail(h, CDPR_ERR_UNSUPPORTED, "cdpr_ik supports 4 or 8 cables");
@@ -860,11 +916,10 @@ extern "C" int cdpr_ik_device(cdpr_handle h, int64_t n, const void *dev_state13,
   IkArgs A;
   std::memset(&A, 0, sizeof(A));
   A.rc = h->rc; A.nc = h->L.nc; A.n = n; A.state13 = (const double *)dev_state13; A.out = (double *)dev_out;
-  CK(h, cudaEventRecord(h->ev0, h->stream));
+  if (h->timing) CK(h, cudaEventRecord(h->ev0, h->stream));
   int rc = launch_ik(h, A, false);
   if (rc) return rc;
-  CK(h, cudaEventRecord(h->ev1, h->stream));
-  h->timed = true;
+  if (h->timing) { CK(h, cudaEventRecord(h->ev1, h->stream)); h->timed = true; }
   return CDPR_OK;
 }
 
@@ -882,11 +937,10 @@ extern "C" int cdpr_ik(cdpr_handle h, int64_t n, const double *pose7, const doub
   IkArgs A;
   std::memset(&A, 0, sizeof(A));
   A.rc = h->rc; A.nc = nc; A.n = n; A.pose7 = dp; A.twist6 = dt; A.length = dl; A.length_rate = dr; A.wmat = dw;
-  CK(h, cudaEventRecord(h->ev0, h->stream));
+  if (h->timing) CK(h, cudaEventRecord(h->ev0, h->stream));
   rc = launch_ik(h, A, true);
   if (rc) return rc;
-  CK(h, cudaEventRecord(h->ev1, h->stream));
-  h->timed = true;
+  if (h->timing) { CK(h, cudaEventRecord(h->ev1, h->stream)); h->timed = true; }
   CK(h, cudaMemcpyAsync(length, dl, sizeof(double) * n * nc, cudaMemcpyDeviceToHost, h->stream));
   CK(h, cudaMemcpyAsync(length_rate, dr, sizeof(double) * n * nc, cudaMemcpyDeviceToHost, h->stream));
   CK(h, cudaMemcpyAsync(wmat, dw, sizeof(double) * n * nc * 6, cudaMemcpyDeviceToHost, h->stream));
@@ -934,15 +988,14 @@ extern "C" int cdpr_rollout(cdpr_handle h, int64_t n_robots, int64_t n_seq, cons
   A.n_snap_peers = 0; A.snap_every = 0;
   A.cmd_table = h->cmd_dev; A.n_seq = (int)n_seq; A.n_cmd = (int)n_cmd; A.steps_per_cmd = (int)steps_per_cmd;
   A.cost = h->cost_dev; A.target[0] = target_pos[0]; A.target[1] = target_pos[1]; A.target[2] = target_pos[2]; A.lambda = lambda;
-  CK(h, cudaEventRecord(h->ev0, h->stream));
+  if (h->timing) CK(h, cudaEventRecord(h->ev0, h->stream));
   if ((rc = launch_step(h, A))) return rc;
   if (dev_cost_seq) {
     k_reduce_cost_seq<<<grid_for(n_seq, 128), 128, 0, h->stream>>>(h->cost_dev, n_robots, n_seq, (double *)dev_cost_seq);
     CK(h, cudaGetLastError());
     ++h->launches;
   }
-  CK(h, cudaEventRecord(h->ev1, h->stream));
-  h->timed = true;
+  if (h->timing) { CK(h, cudaEventRecord(h->ev1, h->stream)); h->timed = true; }
   h->targets_uniform = false;
   const int peers_saved = h->n_snap_peers;
   h->n_snap_peers = 0;  // rollouts write no snapshots

@@ -3,7 +3,7 @@
 // HBM layout (struct-of-arrays; instance index i is the fastest-varying one; Np = N padded to a
 // multiple of 128 so every column starts 1 KB aligned):
 //   plat  [13][Np]                px py pz | qw qx qy qz | vx vy vz | wx wy wz
-//   cab   [NC][CAB_F][Np]         last_pos, force_cmd, pos_target, vel_target, effort, pid_force
+//   cab   [NC][CAB_F][Np]         last_pos, force_cmd, pos_target, vel_target, effort, pid_force, pid terms P I D, desired
 //   pid   [NC][2][PID_F][Np]      last_time, p_err, i_err, d_err, cmd      (pid 0 = velocity, 1 = position)
 //   win_y [NC][2][LEN][Np]        D-term error window, logical order (oldest first) = Pid::mDbufferY
 //   mom   [NC][2][3][Np]          window state S0, S1, Kd*D of the fast variant's D-term (see step_fast.cuh)
@@ -24,7 +24,10 @@ constexpr int kMaxDegree = 4;
 constexpr int kMaxCascade = 4;
 constexpr int kTpb = 128;  // threads per block of the step kernels = instances per block
 
-enum CabField { CAB_LAST_POS = 0, CAB_FORCE_CMD, CAB_POS_TARGET, CAB_VEL_TARGET, CAB_EFFORT, CAB_PID_FORCE, CAB_F };
+// CAB_TERM_P .. CAB_DESIRED: what the reference publishes on topic "pid" from inside Pid::update (pTerm, pre-clamp iTerm,
+// dTerm, desired; Pid.cpp:140-141,159,167) -- written by the last step of a launch, untouched by a priming update
+enum CabField { CAB_LAST_POS = 0, CAB_FORCE_CMD, CAB_POS_TARGET, CAB_VEL_TARGET, CAB_EFFORT, CAB_PID_FORCE,
+                CAB_TERM_P, CAB_TERM_I, CAB_TERM_D, CAB_DESIRED, CAB_F };
 enum PidField { PID_LAST_TIME = 0, PID_P_ERR, PID_I_ERR, PID_D_ERR, PID_CMD, PID_F };
 enum { PID_VEL = 0, PID_POS = 1 };
 enum { MODE_FORCE = 0, MODE_POSITION = 1, MODE_VELOCITY = 2 };

@@ -66,6 +66,54 @@ __global__ void __launch_bounds__(256) k_ik(const __grid_constant__ IkArgs A) {
   }
 }
 
+// K1, device (SoA) path for even n: one thread = (cable c = blockIdx.y, poses 2j and 2j+1).  Compared with one thread
+// per pose this puts NC times as many warps in flight (65,536 poses: 110 warps per SM instead of 14 -- the sweep is a
+// 6 us kernel, so memory-level parallelism is what it lives on), every access is a 16-byte double2, and a warp's store
+// covers 512 contiguous bytes of one output column.  The 13 state columns are re-read by the NC cable blocks of a pose
+// range; they stay in L2 (6.8 MB at 65,536 poses), so DRAM still sees them once.  Same arithmetic as k_ik.
+struct IkOne { double len, rate, ux, uy, uz, cx, cy, cz; };
+__device__ __forceinline__ IkOne ik_one(const RobotConsts &rc, int c, const FastState &S) {
+  const Rot R = make_rot(S);
+  const double bx = rc.b[c][0], by = rc.b[c][1], bz = rc.b[c][2];
+  const double rx = fma(R.r00, bx, fma(R.r01, by, R.r02 * bz));
+  const double ry = fma(R.r10, bx, fma(R.r11, by, R.r12 * bz));
+  const double rz = fma(R.r20, bx, fma(R.r21, by, R.r22 * bz));
+  const double dx = (rc.a[c][0] - S.px) - rx, dy = (rc.a[c][1] - S.py) - ry, dz = (rc.a[c][2] - S.pz) - rz;
+  const double l2 = fma(dx, dx, fma(dy, dy, dz * dz));
+  IkOne o;
+  o.len = sqrt(l2);
+  const double il = 1.0 / o.len;
+  o.ux = dx * il; o.uy = dy * il; o.uz = dz * il;
+  o.cx = fma(ry, o.uz, -(rz * o.uy)); o.cy = fma(rz, o.ux, -(rx * o.uz)); o.cz = fma(rx, o.uy, -(ry * o.ux));
+  o.rate = -fma(o.ux, S.vx, fma(o.uy, S.vy, fma(o.uz, S.vz, fma(o.cx, S.wx, fma(o.cy, S.wy, o.cz * S.wz)))));
+  return o;
+}
+__global__ void __launch_bounds__(256) k_ik_pair(const __grid_constant__ IkArgs A) {
+  const int c = blockIdx.y;
+  const long long i = 2 * ((long long)blockIdx.x * blockDim.x + threadIdx.x);
+  if (i >= A.n) return;
+  const long long n = A.n;
+  const double *p = A.state13 + i;
+  double2 v[13];
+#pragma unroll
+  for (int k = 0; k < 13; ++k) v[k] = __ldg(reinterpret_cast<const double2 *>(p + k * n));
+  FastState S0, S1;
+  S0.px = v[0].x; S0.py = v[1].x; S0.pz = v[2].x; S0.qw = v[3].x; S0.qx = v[4].x; S0.qy = v[5].x; S0.qz = v[6].x;
+  S0.vx = v[7].x; S0.vy = v[8].x; S0.vz = v[9].x; S0.wx = v[10].x; S0.wy = v[11].x; S0.wz = v[12].x;
+  S1.px = v[0].y; S1.py = v[1].y; S1.pz = v[2].y; S1.qw = v[3].y; S1.qx = v[4].y; S1.qy = v[5].y; S1.qz = v[6].y;
+  S1.vx = v[7].y; S1.vy = v[8].y; S1.vz = v[9].y; S1.wx = v[10].y; S1.wy = v[11].y; S1.wz = v[12].y;
+  const IkOne a = ik_one(A.rc, c, S0), b = ik_one(A.rc, c, S1);
+  double *o = A.out + (long long)c * 8 * n + i;
+  __stcs(reinterpret_cast<double2 *>(o), make_double2(a.len, b.len));
+  __stcs(reinterpret_cast<double2 *>(o + n), make_double2(a.rate, b.rate));
+  __stcs(reinterpret_cast<double2 *>(o + 2 * n), make_double2(a.ux, b.ux));
+  __stcs(reinterpret_cast<double2 *>(o + 3 * n), make_double2(a.uy, b.uy));
+  __stcs(reinterpret_cast<double2 *>(o + 4 * n), make_double2(a.uz, b.uz));
+  __stcs(reinterpret_cast<double2 *>(o + 5 * n), make_double2(a.cx, b.cx));
+  __stcs(reinterpret_cast<double2 *>(o + 6 * n), make_double2(a.cy, b.cy));
+  __stcs(reinterpret_cast<double2 *>(o + 7 * n), make_double2(a.cz, b.cz));
+}
+
 // state after CdprGazeboPlugin::Load: platform at home and at rest; every cable in Position mode,
 // target 0, both Pids reset (wasLast = false, missing = bufferLength); everything else is memset 0.
 __global__ void k_init_state(DevLayout L, RobotConsts rc, double hx, double hy, double hz, double qw, double qx, double qy, double qz,
@@ -189,6 +237,21 @@ __global__ void k_pid_state(DevLayout L, int mode, double *out) {
     o[3] = L.pid[pid_off(L, c, k, PID_D_ERR) + i];
     o[4] = L.pid[pid_off(L, c, k, PID_CMD) + i];
     o[5] = (double)mode;
+  }
+}
+
+// topic "pid" for every cable (the reference publishes cable 0 only, CdprGazeboPlugin.cpp:223-235):
+// [n][nc][5] = pTerm, iTerm before its clamp, dTerm, desired (Pid.cpp:140-141,159,167), applied force = Joint::GetForce
+__global__ void k_pid_terms(DevLayout L, double *out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= L.n) return;
+  for (int c = 0; c < L.nc; ++c) {
+    double *o = out + (i * L.nc + c) * 5;
+    o[0] = L.cab[cab_off(L, c, CAB_TERM_P) + i];
+    o[1] = L.cab[cab_off(L, c, CAB_TERM_I) + i];
+    o[2] = L.cab[cab_off(L, c, CAB_TERM_D) + i];
+    o[3] = L.cab[cab_off(L, c, CAB_DESIRED) + i];
+    o[4] = L.cab[cab_off(L, c, CAB_EFFORT) + i];
   }
 }
 

@@ -248,6 +248,11 @@ __device__ __forceinline__ bool fast_step(const StepArgs &A, FastState &S, doubl
             }
           }
           A.L.pid[pid_off(A.L, c, A.live_idx, PID_D_ERR) + i] = derr_out;
+          // topic "pid": pTerm, iTerm before its clamp, dTerm, desired (Pid.cpp:140-141,159,167)
+          A.L.cab[cab_off(A.L, c, CAB_TERM_P) + i] = pc.kp * e;
+          A.L.cab[cab_off(A.L, c, CAB_TERM_I) + i] = pc.ki * ie1;
+          A.L.cab[cab_off(A.L, c, CAB_TERM_D) + i] = pc.kd * derr_out;
+          A.L.cab[cab_off(A.L, c, CAB_DESIRED) + i] = tg;
         }
       } else {  // first update after a reset: Pid.cpp:123-126
         primed |= 1u << c;
@@ -427,7 +432,6 @@ __global__ void __launch_bounds__(FastCfg<NC, SPEC>::tpb, FastCfg<NC, SPEC>::blo
       const double amp = mysine[0], freq = mysine[kTpbL], phase = mysine[2 * kTpbL];
       const double arg = __dadd_rn(__dmul_rn(__dmul_rn(__dmul_rn(sine_time, freq), 2.0), 3.14159265358979323846), phase);
       const double vel = (double)(float)__dmul_rn(amp, sin(arg));
-#pragma unroll
       if (!kLean) {
 #pragma unroll
         for (int c = 0; c < NC; ++c) { mytgt[c * kTpbL] = vel; mytgt[(NC + c) * kTpbL] = A.live.kf * vel; }

@@ -185,6 +185,11 @@ __device__ __forceinline__ double pid_update_general(const StepArgs &A, const De
     }
     *i_err = ie;
     cmd_out = cmd;
+    // topic "pid": pTerm, iTerm before its clamp, dTerm, desired (Pid.cpp:140-141,159,167)
+    L.cab[cab_off(L, c, CAB_TERM_P) + i] = p_term;
+    L.cab[cab_off(L, c, CAB_TERM_I) + i] = pc.ki * (prev_ierr + dt * error);
+    L.cab[cab_off(L, c, CAB_TERM_D) + i] = d_term;
+    if (dt > 0.0) L.cab[cab_off(L, c, CAB_DESIRED) + i] = desired;
   }
   *cmdp = cmd_out;
   *last_time = now;

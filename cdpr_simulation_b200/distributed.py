@@ -134,15 +134,26 @@ class FusedTrajectoryGather:
 
 
 def make_trajectory_gather(batch, every, steps_per_pass, stream, prefer_fused: bool = True):
-    """Fused peer-memory gather when symmetric memory is available on this box, else NCCL all-gather on a side stream."""
+    """Fused peer-memory gather when symmetric memory is available on EVERY rank, else NCCL all-gather on a side stream.
+    The rendezvous is collective, so the ranks agree on the path (MIN over a success flag) before any of them returns:
+    a rank that failed locally must not wait in all_gather while the others wait in the fused barrier."""
     if prefer_fused:
+        g, reason = None, ""
         try:
             g = FusedTrajectoryGather(batch, every, steps_per_pass, stream)
-            how = "one NVLS multimem.st per value" if g.multicast else "one NVLink peer store per rank and value"
-            return g, f"fused: step kernel stores snapshots into every rank's symmetric-memory buffer ({how})"
         except Exception as e:  # no symmetric memory / no P2P on this box
             reason = f"{type(e).__name__}: {e}"
-            return TrajectoryGather(batch, every, steps_per_pass, stream), f"NCCL all-gather on a side stream (fused path unavailable: {reason[:120]})"
+        ok = torch.tensor([1 if g is not None else 0], dtype=torch.int32, device=torch.device("cuda", batch.device))
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 1:
+            how = "one NVLS multimem.st per value" if g.multicast else "one NVLink peer store per rank and value"
+            return g, f"fused: step kernel stores snapshots into every rank's symmetric-memory buffer ({how})"
+        if g is not None:  # some other rank failed: drop this rank's symmetric buffers and fall back with everybody
+            g.bufs.clear(); g.hdls.clear()
+            del g
+            reason = "fused path unavailable on another rank"
+        return TrajectoryGather(batch, every, steps_per_pass, stream), f"NCCL all-gather on a side stream (fused path unavailable: {reason[:120]})"
     return TrajectoryGather(batch, every, steps_per_pass, stream), "NCCL all-gather on a side stream"
 
 

@@ -107,6 +107,17 @@ int cdpr_synchronize(cdpr_handle h);
  * Default off (every call completes on the handle's stream). */
 int cdpr_set_async(cdpr_handle h, int on);
 
+/* ---- options --------------------------------------------------------------------------------------- */
+enum {
+  /* value != 0: the step kernel evaluates the D-term as the plain FIR over the window instead of the sliding-moment
+   * recursion (same law, different rounding: used to separate recursion drift from the dynamics' own error growth) */
+  CDPR_OPT_DTERM_FIR = 1,
+  /* value == 0: no CUDA event records around the launches (cdpr_last_kernel_ms then returns -1); needed when the calls
+   * are captured into a CUDA graph, and saves two driver calls per cdpr_step in plugin-style stepping. Default 1. */
+  CDPR_OPT_KERNEL_TIMING = 2
+};
+int cdpr_set_option(cdpr_handle h, int option, int64_t value);
+
 /* ---- commands (topics jointVelocities / jointPositions, CdprGazeboPlugin.cpp:67-83,206-219;
  *      JointForceCalculator::setForce, JointForceCalculator.h:92-95) ------------------------
  * n_axes != NC  =>  CDPR_ERR_BAD_LENGTH and nothing changes (the plugin drops the message).
@@ -132,6 +143,11 @@ int cdpr_get_platform_state(cdpr_handle h, double *pose7, double *twist6);
 int cdpr_set_platform_state(cdpr_handle h, const double *pose7, const double *twist6);
 /* telemetry of topic "pid" (Pid.cpp:140-167), all cables: [N][NC][6] = pid_force, p_err, i_err, d_err, cmd, mode */
 int cdpr_get_pid_state(cdpr_handle h, double *out);
+/* topic "pid" as the plugin publishes it every update (CdprGazeboPlugin.cpp:226,233-235), for EVERY cable (the reference
+ * publishes cable 0): [N][NC][5] = pTerm, iTerm BEFORE its clamp, dTerm, desired (Pid.cpp:140-141,159,167), applied force
+ * (Joint::GetForce after truncation) of the last step. A priming update (first after a Pid reset) leaves the first
+ * four untouched, like the reference's message buffer. Step with k = 1 for the per-step stream. */
+int cdpr_get_pid_terms(cdpr_handle h, double *out);
 
 /* ---- checkpoint / resume ---------------------------------------------------------------- */
 size_t cdpr_state_bytes(cdpr_handle h);

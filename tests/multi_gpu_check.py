@@ -1,6 +1,7 @@
 #!/usr/bin/env python
-"""Multi-GPU correctness check, run under torchrun on a real multi-GPU box:
-   torchrun --nproc-per-node G tools/multi_gpu_check.py
+"""Multi-GPU correctness check, run under torchrun on a real multi-GPU box (tests/test_multi_gpu.py spawns it when at
+least two GPUs are visible):
+   python -m torch.distributed.run --nproc-per-node G --master-addr 127.0.0.1 tests/multi_gpu_check.py
 1. config 4: instances sharded by contiguous range over G ranks, snapshots all-gathered over NCCL ->
    rank 0 compares the gathered trajectory bitwise with a single-GPU run over all instances.
 2. config 5: rollout cost vector, robots sharded over ranks, all-reduced -> compared with a single-GPU run."""
@@ -15,7 +16,7 @@ from cdpr_simulation_b200 import workloads as wl, distributed as D
 rank, local, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-nc, n_total, k, every = 8, 4096 * world, 300, 100
+nc, n_total, k, every = 8, 4096 * world + 3 * world, 300, 100   # not a multiple of the block size
 cfg = cb.default_config(nc)
 amp, freq, phase, pose7, twist6 = wl.c3_instances(n_total, seed=9)
 lo, hi = D.shard_range(n_total, rank, world)

@@ -13,7 +13,7 @@ from helpers import to_oracle_config, state_rel_err
 pytestmark = pytest.mark.gpu
 
 PER_STEP_TOL = 1e-9
-DIVERGENCE_TOL_1000 = 1e-7
+DIVERGENCE_TOL_1000 = 1e-9   # measured 6e-12 (NC=4), 2e-11 (NC=8)
 
 
 def make_pair(nc, n, seed=1, cfg_edit=None, sine=True):
