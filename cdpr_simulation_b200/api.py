@@ -18,7 +18,7 @@ from . import build as _build
 
 MAX_CABLES = 8
 MODE_FORCE, MODE_POSITION, MODE_VELOCITY = 0, 1, 2
-OPT_DTERM_FIR, OPT_KERNEL_TIMING = 1, 2
+OPT_DTERM_FIR, OPT_KERNEL_TIMING, OPT_INDEPENDENT = 1, 2, 3
 
 OK = 0
 ERR_BAD_ARG, ERR_BAD_CABLE_COUNT, ERR_BAD_LENGTH, ERR_NO_DEVICE, ERR_CUDA, ERR_UNSUPPORTED, ERR_NOMEM = -1, -2, -3, -4, -5, -6, -7
@@ -27,6 +27,7 @@ ERR_BAD_ARG, ERR_BAD_CABLE_COUNT, ERR_BAD_LENGTH, ERR_NO_DEVICE, ERR_CUDA, ERR_U
 EXPORTS = [
     "cdpr_config_default", "cdpr_create", "cdpr_destroy", "cdpr_reset", "cdpr_last_error", "cdpr_set_stream", "cdpr_synchronize", "cdpr_set_async",
     "cdpr_set_option", "cdpr_set_velocity_cmd", "cdpr_set_position_cmd", "cdpr_set_effort_cmd", "cdpr_set_sine_cmd",
+    "cdpr_set_velocity_cmd_masked", "cdpr_set_position_cmd_masked", "cdpr_set_effort_cmd_masked", "cdpr_get_modes",
     "cdpr_step", "cdpr_step_count", "cdpr_sim_time",
     "cdpr_get_joint_states", "cdpr_get_platform_state", "cdpr_set_platform_state", "cdpr_get_pid_state", "cdpr_get_pid_terms",
     "cdpr_state_bytes", "cdpr_get_state", "cdpr_set_state",
@@ -101,6 +102,9 @@ def load():
     L.cdpr_set_option.argtypes = [vp, C.c_int, i64]
     for f in (L.cdpr_set_velocity_cmd, L.cdpr_set_position_cmd, L.cdpr_set_effort_cmd):
         f.argtypes = [vp, vp, i64, C.c_int]
+    for f in (L.cdpr_set_velocity_cmd_masked, L.cdpr_set_position_cmd_masked, L.cdpr_set_effort_cmd_masked):
+        f.argtypes = [vp, vp, vp, i64, C.c_int]
+    L.cdpr_get_modes.argtypes = [vp, vp]
     L.cdpr_set_sine_cmd.argtypes = [vp, vp, vp, vp, i64]
     L.cdpr_step.argtypes = [vp, i64]
     L.cdpr_step_count.argtypes = [vp]; L.cdpr_step_count.restype = i64
@@ -203,20 +207,33 @@ class CdprBatch:
         self._ck(self._L.cdpr_synchronize(self._h))
 
     # -- commands: topics jointVelocities / jointPositions, JointForceCalculator::setForce -----
-    def set_velocity_cmd(self, axes):
-        axes = np.ascontiguousarray(axes, dtype=np.float32)
+    def _cmd(self, fn, axes, mask, dtype):
+        axes = np.ascontiguousarray(axes, dtype=dtype)
         n_axes = axes.shape[-1] if axes.ndim > 1 else axes.size // max(self.n, 1)
-        self._ck(self._L.cdpr_set_velocity_cmd(self._h, _ptr(axes), axes.size // max(n_axes, 1), n_axes))
+        if mask is not None:
+            mask = np.ascontiguousarray(np.asarray(mask) != 0, dtype=np.uint8)
+            if mask.shape != (self.n,):
+                raise ValueError("mask must have one entry per instance")
+        self._ck(fn(self._h, _ptr(axes), _ptr(mask), axes.size // max(n_axes, 1), n_axes))
 
-    def set_position_cmd(self, axes):
-        axes = np.ascontiguousarray(axes, dtype=np.float32)
-        n_axes = axes.shape[-1] if axes.ndim > 1 else axes.size // max(self.n, 1)
-        self._ck(self._L.cdpr_set_position_cmd(self._h, _ptr(axes), axes.size // max(n_axes, 1), n_axes))
+    def set_velocity_cmd(self, axes, mask=None):
+        """Topic jointVelocities; mask (one flag per robot) addresses a subset (independent robots only)."""
+        self._cmd(self._L.cdpr_set_velocity_cmd_masked, axes, mask, np.float32)
 
-    def set_effort_cmd(self, force):
-        force = _f64(force)
-        n_axes = force.shape[-1] if force.ndim > 1 else force.size // max(self.n, 1)
-        self._ck(self._L.cdpr_set_effort_cmd(self._h, _ptr(force), force.size // max(n_axes, 1), n_axes))
+    def set_position_cmd(self, axes, mask=None):
+        self._cmd(self._L.cdpr_set_position_cmd_masked, axes, mask, np.float32)
+
+    def set_effort_cmd(self, force, mask=None):
+        self._cmd(self._L.cdpr_set_effort_cmd_masked, force, mask, np.float64)
+
+    def set_independent(self, on: bool = True):
+        """Every robot gets its own mode and command latch (CDPR_OPT_INDEPENDENT); before the first step."""
+        self.set_option(OPT_INDEPENDENT, 1 if on else 0)
+
+    def modes(self) -> np.ndarray:
+        out = np.empty(self.n, dtype=np.int32)
+        self._ck(self._L.cdpr_get_modes(self._h, _ptr(out)))
+        return out
 
     def set_sine_cmd(self, amp, freq=None, phase=None):
         """sinevelocitytest.cpp run inside the kernel; per-instance amp / freq / phase."""

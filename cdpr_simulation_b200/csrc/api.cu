@@ -21,7 +21,11 @@ struct cdpr_batch {
   cdpr_config cfg;
   int device = 0;
   long long n = 0, np = 0;
-  bool general = false;
+  bool general = false;  // controller state in the general layout (time-stamp rings, biquad state): flex and HBM variants
+  bool flex = false;     // the on-chip full-semantics kernel (step_flex.cuh): per-instance modes and commands
+  bool flex_capable = false;
+  int flex_tpb = 0, flex_ps = 0, flex_ds = 0;
+  size_t flex_smem = 0;
   DevLayout L{};
   RobotConsts rc{};
   PidConsts pc[2]{};
@@ -362,6 +366,23 @@ extern "C" int cdpr_create(const cdpr_config *cfg, int64_t n_instances, int devi
                        cfg->pos_pid.cmd_limit != 0.0 && cfg->vel_pid.i_gain >= 0.0 && cfg->pos_pid.i_gain >= 0.0 && cfg->vel_pid.d_buffer_length == 11 && cfg->pos_pid.d_buffer_length == 11 &&
                        (cfg->n_cables == 4 || cfg->n_cables == 8);
   h->general = !fast_ok;
+  // The on-chip full-semantics variant (step_flex.cuh): windows of 11 fitted with one degree, cmdLimit != 0, 4 or 8
+  // cables, and a block shape whose controller state fits in shared memory.
+  h->flex_ps = std::max(cfg->vel_pid.p_cascade, cfg->pos_pid.p_cascade);
+  h->flex_ds = std::max(cfg->vel_pid.d_cascade, cfg->pos_pid.d_cascade);
+  {
+    const bool shape_ok = (cfg->n_cables == 4 || cfg->n_cables == 8) && cfg->vel_pid.d_buffer_length == 11 && cfg->pos_pid.d_buffer_length == 11 &&
+                          cfg->vel_pid.d_degree == cfg->pos_pid.d_degree && cfg->vel_pid.cmd_limit != 0.0 && cfg->pos_pid.cmd_limit != 0.0;
+    int best_threads = 0;
+    for (int tpb : {128, 96, 64, 32}) {  // most resident instances per SM (227 KB shared memory, 1 KB reserved per block)
+      const size_t smem = flex_smem_bytes(cfg->n_cables, h->flex_ps, h->flex_ds, tpb);
+      if (smem > 227u * 1024u) continue;
+      const int blocks = std::min<int>(256 / tpb, (int)((228u * 1024u) / (smem + 1024u)));
+      if (blocks * tpb > best_threads) { best_threads = blocks * tpb; h->flex_tpb = tpb; h->flex_smem = smem; }
+    }
+    h->flex_capable = shape_ok && best_threads >= 32;
+  }
+  h->flex = h->general && h->flex_capable;
 
   auto bail = [&](int code) { g_create_error = h->err; cdpr_destroy(h); return code; };
   if (cudaSetDevice(device) != cudaSuccess) { h->err = "cudaSetDevice failed"; return bail(CDPR_ERR_CUDA); }
@@ -393,6 +414,7 @@ extern "C" int cdpr_create(const cdpr_config *cfg, int64_t n_instances, int devi
     if (L.casc > 0 && (rc = dev_alloc(h, (void **)&L.filt, col * L.nc * 2 * 2 * L.casc * 4))) return bail(rc);
   }
   if ((rc = dev_alloc(h, (void **)&L.ctl, sizeof(uint32_t) * (size_t)L.np * L.nc))) return bail(rc);
+  if ((rc = dev_alloc(h, (void **)&L.ictl, sizeof(uint32_t) * (size_t)L.np))) return bail(rc);
   if ((rc = dev_alloc(h, (void **)&L.sine, col * 3))) return bail(rc);
   if (cudaMemsetAsync(L.sine, 0, col * 3, h->stream) != cudaSuccess) { h->err = "memset failed"; return bail(CDPR_ERR_CUDA); }
   if ((rc = reset_to_load_state(h, h->stream))) return bail(rc);
@@ -403,6 +425,7 @@ extern "C" int cdpr_create(const cdpr_config *cfg, int64_t n_instances, int devi
       cudaFuncSetAttribute(e.func, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     }
   }
+  if (h->flex) flex_prepare(cfg->n_cables, h->flex_smem);
   if (cudaStreamSynchronize(h->stream) != cudaSuccess) { h->err = "initialisation kernels failed"; return bail(CDPR_ERR_CUDA); }
   *out = h;
   return CDPR_OK;
@@ -476,6 +499,26 @@ extern "C" int cdpr_set_option(cdpr_handle h, int option, int64_t value) {
       h->timing = value != 0;
       if (!h->timing) h->timed = false;
       return CDPR_OK;
+    case CDPR_OPT_INDEPENDENT: {
+      if (h->flex) return CDPR_OK;  // the flex variant is always per-instance
+      if (value == 0) return CDPR_OK;
+      if (!h->flex_capable) return fail(h, CDPR_ERR_UNSUPPORTED, "this configuration has no on-chip full-semantics kernel (needs 4 or 8 cables, windows of 11, cmdLimit != 0)");
+      if (h->step_count != 0) return fail(h, CDPR_ERR_BAD_ARG, "switch to independent robots before the first step (or right after cdpr_reset)");
+      cudaSetDevice(h->device);
+      DevLayout &L = h->L;
+      const size_t col = sizeof(double) * (size_t)L.np;
+      int rc;
+      if (!L.win_x && (rc = dev_alloc(h, (void **)&L.win_x, col * L.nc * 2 * L.len))) return rc;
+      if (!L.filt && L.casc > 0 && (rc = dev_alloc(h, (void **)&L.filt, col * L.nc * 2 * 2 * L.casc * 4))) return rc;
+      h->general = true; h->flex = true;
+      flex_prepare(L.nc, h->flex_smem);
+      cudaStream_t st = io_begin(h);
+      rc = reset_to_load_state(h, st);
+      io_end(h);
+      if (rc) return rc;
+      CK(h, sync_unless_async(h));
+      return CDPR_OK;
+    }
     case CDPR_OPT_DTERM_FIR:
       if (h->step_count != 0) return fail(h, CDPR_ERR_BAD_ARG, "the D-term form can only change before the first step");
       h->force_fir = value != 0;
@@ -489,38 +532,80 @@ extern "C" int cdpr_set_option(cdpr_handle h, int option, int64_t value) {
 // commands
 // ---------------------------------------------------------------------------------------------
 template <typename T>
-static int scatter_cmd(cdpr_handle h, const T *host, int64_t n_instances, int n_axes, int field) {
+static int scatter_cmd(cdpr_handle h, const T *host, const unsigned char *mask, int64_t n_instances, int n_axes, int field) {
   if (!h || !host) return CDPR_ERR_BAD_ARG;
   // the plugin drops a Joy message whose axes.size() != cWireCount (CdprGazeboPlugin.cpp:68,77)
   if (n_axes != h->L.nc) return fail(h, CDPR_ERR_BAD_LENGTH, "command length != cable count: dropped");
   if (n_instances != h->n) return fail(h, CDPR_ERR_BAD_ARG, "n_instances does not match the handle");
+  if (mask && !h->flex)
+    return fail(h, CDPR_ERR_UNSUPPORTED, "per-instance commands need the flex variant: cdpr_set_option(h, CDPR_OPT_INDEPENDENT, 1) before the first step");
   cudaSetDevice(h->device);
   const size_t bytes = sizeof(T) * (size_t)h->n * h->L.nc;
-  int rc = ensure_stage(h, bytes);
+  const size_t mask_off = (bytes + 255) / 256 * 256;
+  int rc = ensure_stage(h, mask_off + (mask ? (size_t)h->n : 0));
   if (rc) return rc;
   cudaStream_t st = io_begin(h);
   CK(h, cudaMemcpyAsync(h->stage, host, bytes, cudaMemcpyHostToDevice, st));
-  k_scatter_cab<T><<<grid_for(h->n, 256), 256, 0, st>>>(h->L, field, (const T *)h->stage);
+  const unsigned char *dmask = nullptr;
+  if (mask) {
+    CK(h, cudaMemcpyAsync((char *)h->stage + mask_off, mask, (size_t)h->n, cudaMemcpyHostToDevice, st));
+    dmask = (const unsigned char *)h->stage + mask_off;
+  }
+  if (h->flex) {
+    const unsigned bit = (field == CAB_VEL_TARGET) ? 4u : (field == CAB_POS_TARGET) ? 8u : 0u;
+    k_scatter_cab_masked<T><<<grid_for(h->n, 256), 256, 0, st>>>(h->L, field, (const T *)h->stage, dmask, bit, field == CAB_FORCE_CMD ? 1 : 0);
+  } else {
+    k_scatter_cab<T><<<grid_for(h->n, 256), 256, 0, st>>>(h->L, field, (const T *)h->stage);
+  }
   CK(h, cudaGetLastError());
+  ++h->launches;
   io_end(h);
-  CK(h, sync_unless_async(h));  // the caller may reuse its buffer
+  CK(h, sync_unless_async(h));  // the caller may reuse its buffers
   return CDPR_OK;
 }
 
-extern "C" int cdpr_set_velocity_cmd(cdpr_handle h, const float *axes, int64_t n_instances, int n_axes) {
-  int rc = scatter_cmd<float>(h, axes, n_instances, n_axes, CAB_VEL_TARGET);
+extern "C" int cdpr_set_velocity_cmd_masked(cdpr_handle h, const float *axes, const unsigned char *mask, int64_t n_instances, int n_axes) {
+  int rc = scatter_cmd<float>(h, axes, mask, n_instances, n_axes, CAB_VEL_TARGET);
   if (rc == CDPR_OK) { h->vel_pending = true; h->targets_uniform = false; }
   return rc;
 }
-extern "C" int cdpr_set_position_cmd(cdpr_handle h, const float *axes, int64_t n_instances, int n_axes) {
-  int rc = scatter_cmd<float>(h, axes, n_instances, n_axes, CAB_POS_TARGET);
+extern "C" int cdpr_set_position_cmd_masked(cdpr_handle h, const float *axes, const unsigned char *mask, int64_t n_instances, int n_axes) {
+  int rc = scatter_cmd<float>(h, axes, mask, n_instances, n_axes, CAB_POS_TARGET);
   if (rc == CDPR_OK) h->pos_pending = true;
   return rc;
 }
-extern "C" int cdpr_set_effort_cmd(cdpr_handle h, const double *force, int64_t n_instances, int n_axes) {
-  int rc = scatter_cmd<double>(h, force, n_instances, n_axes, CAB_FORCE_CMD);
+extern "C" int cdpr_set_effort_cmd_masked(cdpr_handle h, const double *force, const unsigned char *mask, int64_t n_instances, int n_axes) {
+  int rc = scatter_cmd<double>(h, force, mask, n_instances, n_axes, CAB_FORCE_CMD);
   if (rc == CDPR_OK) h->mode = MODE_FORCE;  // JointForceCalculator.h:92-95: immediate
   return rc;
+}
+extern "C" int cdpr_set_velocity_cmd(cdpr_handle h, const float *axes, int64_t n_instances, int n_axes) {
+  return cdpr_set_velocity_cmd_masked(h, axes, nullptr, n_instances, n_axes);
+}
+extern "C" int cdpr_set_position_cmd(cdpr_handle h, const float *axes, int64_t n_instances, int n_axes) {
+  return cdpr_set_position_cmd_masked(h, axes, nullptr, n_instances, n_axes);
+}
+extern "C" int cdpr_set_effort_cmd(cdpr_handle h, const double *force, int64_t n_instances, int n_axes) {
+  return cdpr_set_effort_cmd_masked(h, force, nullptr, n_instances, n_axes);
+}
+
+extern "C" int cdpr_get_modes(cdpr_handle h, int32_t *modes) {
+  if (!h || !modes) return CDPR_ERR_BAD_ARG;
+  cudaSetDevice(h->device);
+  if (!h->flex) {  // batch-uniform mode; commands still pending are applied by the next step, like in the plugin
+    cudaStreamSynchronize(h->stream);
+    for (long long i = 0; i < h->n; ++i) modes[i] = h->mode;
+    return CDPR_OK;
+  }
+  int rc = ensure_stage(h, sizeof(int) * (size_t)h->n);
+  if (rc) return rc;
+  cudaStream_t st = io_begin(h);
+  k_modes<<<grid_for(h->n, 256), 256, 0, st>>>(h->L, (int *)h->stage);
+  CK(h, cudaGetLastError());
+  CK(h, cudaMemcpyAsync(modes, h->stage, sizeof(int) * (size_t)h->n, cudaMemcpyDeviceToHost, st));
+  io_end(h);
+  CK(h, sync_unless_async(h));
+  return CDPR_OK;
 }
 
 extern "C" int cdpr_set_sine_cmd(cdpr_handle h, const double *amp, const double *freq, const double *phase, int64_t n_instances) {
@@ -571,13 +656,14 @@ static void fill_args(cdpr_handle h, StepArgs &A, int k_steps, bool sine) {
     A.dk[2] = -2.0 * kd * c;
     A.dk[3] = -kd * a;
   }
+  A.flex_ps = h->flex_ps; A.flex_ds = h->flex_ds;
   A.effort_ge_cmd = h->rc.effort_limit_abs >= A.live.cmd_max ? 1 : 0;
   A.sat_thr = fmin(A.live.cmd_max, h->rc.effort_limit_abs);
   A.mode = h->mode; A.k_steps = k_steps; A.n0 = h->step_count;
   A.sec0 = h->sec; A.nsec0 = h->nsec; A.dt_ns = h->dt_ns; A.t0 = time_double(h->sec, h->nsec);
   A.sine_on = sine ? 1 : 0; A.sine_period = h->sine_period; A.sine_time0 = h->sine_time; A.sine_pub_dt = h->sine_pub_dt;
   for (int p = 0; p < 8; ++p) A.snap_peers[p] = h->snap_peers[p];
-  A.snap_multimem = (h->snap_multimem && !h->general) ? 1 : 0;
+  A.snap_multimem = (h->snap_multimem && (!h->general || h->flex)) ? 1 : 0;
   A.n_snap_peers = h->n_snap_peers; A.snap_stride = h->snap_stride; A.snap_offset = h->snap_offset;
   A.snap_every = h->n_snap_peers > 0 ? h->snap_every : 0; A.snap_written0 = h->snap_written; A.snap_capacity = h->snap_capacity;
 }
@@ -599,7 +685,9 @@ static const FastEntry *fast_find(int nc, int mode, bool dmom, int spec) {
 }
 
 static int launch_step(cdpr_handle h, const StepArgs &A) {
-  if (h->general) {
+  if (h->flex) {
+    flex_launch(h->L.nc, grid_for(h->n, h->flex_tpb), h->flex_tpb, h->flex_smem, A, h->stream);
+  } else if (h->general) {
     general_launch(std::max(h->pc[PID_VEL].degree, h->pc[PID_POS].degree), (unsigned)(h->np / kTpb), A, h->stream);
   } else {
     const bool dm = h->dmom_ok[A.live_idx] && !h->force_fir && A.mode != MODE_FORCE;
@@ -642,6 +730,17 @@ extern "C" int cdpr_step(cdpr_handle h, int64_t k_steps) {
   main_begin(h);
   if (h->timing) CK(h, cudaEventRecord(h->ev0, h->stream));
   long long remaining = k_steps;
+  while (h->flex && remaining > 0) {
+    // every instance latches its own commands and switches its own mode inside the kernel (step_flex.cuh): nothing to
+    // decide on the host
+    const long long seg = std::min<long long>(remaining, 1 << 30);
+    StepArgs A;
+    fill_args(h, A, (int)seg, h->sine_on);
+    int rc = launch_step(h, A);
+    if (rc) return rc;
+    advance_host_clock(h, seg, h->sine_on);
+    remaining -= seg;
+  }
   while (remaining > 0) {
     // CdprGazeboPlugin::update, .cpp:206-221: a pending velocity command is fanned out first, then a pending
     // position command; each setter resets its Pid when the mode changes (JointForceCalculator.cpp:99-119).
@@ -749,7 +848,7 @@ extern "C" int cdpr_get_pid_state(cdpr_handle h, double *out) {
   int rc = ensure_stage(h, nb);
   if (rc) return rc;
   cudaStream_t st = io_begin(h);
-  k_pid_state<<<grid_for(h->n, 256), 256, 0, st>>>(h->L, h->mode, (double *)h->stage);
+  k_pid_state<<<grid_for(h->n, 256), 256, 0, st>>>(h->L, h->mode, h->flex ? 1 : 0, (double *)h->stage);
   CK(h, cudaGetLastError());
   CK(h, cudaMemcpyAsync(out, h->stage, nb, cudaMemcpyDeviceToHost, st));
   io_end(h);
@@ -801,6 +900,7 @@ static std::vector<Section> sections(cdpr_handle h) {
   if (L.win_x) s.push_back({L.win_x, col * L.nc * 2 * L.len});
   if (L.filt) s.push_back({L.filt, col * L.nc * 2 * 2 * L.casc * 4});
   s.push_back({L.ctl, sizeof(uint32_t) * (size_t)L.np * L.nc});
+  s.push_back({L.ictl, sizeof(uint32_t) * (size_t)L.np});
   s.push_back({L.sine, col * 3});
   return s;
 }
@@ -818,7 +918,7 @@ extern "C" int cdpr_get_state(cdpr_handle h, void *blob, size_t bytes) {
   main_begin(h);
   BlobHeader hd;
   std::memset(&hd, 0, sizeof(hd));
-  hd.magic = kMagic; hd.n = h->n; hd.np = h->np; hd.nc = h->L.nc; hd.len = h->L.len; hd.casc = h->L.casc; hd.general = h->general;
+  hd.magic = kMagic; hd.n = h->n; hd.np = h->np; hd.nc = h->L.nc; hd.len = h->L.len; hd.casc = h->L.casc; hd.general = (int)h->general + (int)h->flex;
   hd.mode = h->mode; hd.vel_pending = h->vel_pending; hd.pos_pending = h->pos_pending; hd.sec = h->sec; hd.nsec = h->nsec;
   hd.sine_on = h->sine_on; hd.step_count = h->step_count; hd.sine_time = h->sine_time; hd.cfg_hash = config_hash(h->cfg);
   std::memcpy(blob, &hd, sizeof(hd));
@@ -836,7 +936,7 @@ extern "C" int cdpr_set_state(cdpr_handle h, const void *blob, size_t bytes) {
   BlobHeader hd;
   std::memcpy(&hd, blob, sizeof(hd));
   if (hd.magic != kMagic || hd.n != h->n || hd.np != h->np || hd.nc != h->L.nc || hd.len != h->L.len || hd.casc != h->L.casc ||
-      hd.general != (int)h->general)
+      hd.general != (int)h->general + (int)h->flex)
     return fail(h, CDPR_ERR_BAD_ARG, "checkpoint does not match this handle's shape");
   if (hd.cfg_hash != config_hash(h->cfg)) return fail(h, CDPR_ERR_BAD_ARG, "checkpoint was taken under a different cdpr_config");
   if (hd.mode < MODE_FORCE || hd.mode > MODE_VELOCITY || hd.step_count < 0) return fail(h, CDPR_ERR_BAD_ARG, "corrupt checkpoint header");
@@ -875,7 +975,7 @@ extern "C" int cdpr_set_snapshot_peers(cdpr_handle h, int64_t every, void *const
 extern "C" int cdpr_set_snapshot_multicast(cdpr_handle h, int64_t every, void *multicast_buf, int64_t instance_offset,
                                            int64_t total_instances, int64_t capacity) {
   if (!h) return CDPR_ERR_BAD_ARG;
-  if (h->general) return fail(h, CDPR_ERR_UNSUPPORTED, "multicast snapshots need the fast kernel variant");
+  if (h->general && !h->flex) return fail(h, CDPR_ERR_UNSUPPORTED, "multicast snapshots need the fast or flex kernel variant");
   void *one[1] = {multicast_buf};
   int rc = cdpr_set_snapshot_peers(h, multicast_buf ? every : 0, one, multicast_buf ? 1 : 0, instance_offset, total_instances, capacity);
   if (rc == CDPR_OK && multicast_buf && every > 0) h->snap_multimem = true;
@@ -896,7 +996,7 @@ static int launch_ik(cdpr_handle h, const IkArgs &A, bool aos) {
   const unsigned grid = grid_for(A.n, 256);
   // device path, even pose count and 16-byte aligned buffers: one thread per (cable, pose pair), double2 accesses
   if (!aos && (A.n % 2) == 0 && ((uintptr_t)A.state13 % 16) == 0 && ((uintptr_t)A.out % 16) == 0 && (h->L.nc == 4 || h->L.nc == 8)) {
-    k_ik_pair<<<dim3(grid_for(A.n / 2, 256), (unsigned)h->L.nc), 256, 0, h->stream>>>(A);
+    k_ik_pair<<<grid_for(A.n / 2, 256) * (unsigned)h->L.nc, 256, 0, h->stream>>>(A);
     CK(h, cudaGetLastError());
     ++h->launches;
     return CDPR_OK;
@@ -1029,7 +1129,7 @@ extern "C" int cdpr_dterm_weights(const cdpr_pid_params *pid, double dt, double 
 extern "C" int64_t cdpr_padded_instances(cdpr_handle h) { return h ? h->np : -1; }
 extern "C" void *cdpr_device_platform_state(cdpr_handle h) { return h ? h->L.plat : nullptr; }
 extern "C" int64_t cdpr_launch_count(cdpr_handle h) { return h ? h->launches : -1; }
-extern "C" const char *cdpr_kernel_variant(cdpr_handle h) { return !h ? "" : (h->general ? "general" : "fast"); }
+extern "C" const char *cdpr_kernel_variant(cdpr_handle h) { return !h ? "" : (h->flex ? "flex" : h->general ? "general" : "fast"); }
 
 extern "C" float cdpr_last_kernel_ms(cdpr_handle h) {
   if (!h || !h->timed) return -1.0f;

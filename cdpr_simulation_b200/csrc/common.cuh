@@ -11,6 +11,7 @@
 //                                 rings whose head lives in ctl, see step_general.cuh)
 //   filt  [NC][2][2][CASC][4][Np] biquad x1 x2 y1 y2 (P filter, D filter)  (general variant only)
 //   ctl   [NC][Np] uint32         bit0 vel.wasLast, bit1 pos.wasLast, bits8-15 vel.missing, 16-23 pos.missing
+//   ictl  [Np] uint32             flex variant: bits 0-1 UpdateMode of the instance, bit 2 / 3 velocity / position command pending
 //   sine  [3][Np]                 amp, freq, phase of the in-kernel sinevelocitytest generator
 #pragma once
 #include <cstdint>
@@ -35,6 +36,7 @@ enum { MODE_FORCE = 0, MODE_POSITION = 1, MODE_VELOCITY = 2 };
 struct DevLayout {
   double *plat, *cab, *pid, *win_y, *win_x, *filt, *sine, *mom;
   uint32_t *ctl;
+  uint32_t *ictl;  // [Np] per-instance word of the flex variant: UpdateMode + pending-command bits (step_flex.cuh)
   long long np;  // padded instance count (column stride)
   int n;         // live instances
   int nc, len, casc;
@@ -83,6 +85,7 @@ struct StepArgs {
   double fir2[2][kMaxDbuf];  // FIR weights of BOTH pids (general variant: used whenever a window's time stamps are uniform)
   double dmom[3];        // the same weights as a quadratic in the centred sample position: w_j = dmom[0] + dmom[1] k + dmom[2] k^2
   double dk[4];          // Kd * D recursion of the fast variant (step_fast.cuh): coefficients of y_new, S0, S1, y_old
+  int flex_ps, flex_ds;  // flex variant: biquad stages held on chip for the P input / D output (max over the two Pids)
   int effort_ge_cmd;     // effort limit >= cmdMax of the live pid: truncation can only bite on a saturated command
   double sat_thr;        // min(cmdMax, effort limit): an unclamped command within it passes every clamp unchanged
   int mode;            // batch-uniform JointForceCalculator::UpdateMode

@@ -29,4 +29,9 @@ void fast_entries_nc8_spec(std::vector<FastEntry> &out);
 // k_step_general<DMAX> (step_general.cuh), DMAX in {2, 4}
 void general_launch(int dmax, unsigned grid, const StepArgs &A, cudaStream_t st);
 
+// k_step_flex<NC> (step_flex.cuh), NC in {4, 8}; tpb threads per block, smem bytes of dynamic shared memory
+void flex_launch(int nc, unsigned grid, int tpb, size_t smem, const StepArgs &A, cudaStream_t st);
+void flex_prepare(int nc, size_t smem);
+size_t flex_smem_bytes(int nc, int ps, int ds, int tpb);
+
 }  // namespace cdpr

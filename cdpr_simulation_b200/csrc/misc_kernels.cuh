@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(256) k_ik(const __grid_constant__ IkArgs A) {
   }
 }
 
-// K1, device (SoA) path for even n: one thread = (cable c = blockIdx.y, poses 2j and 2j+1).  Compared with one thread
+// K1, device (SoA) path for even n: one thread = (cable c, poses 2j and 2j+1).  Compared with one thread
 // per pose this puts NC times as many warps in flight (65,536 poses: 110 warps per SM instead of 14 -- the sweep is a
 // 6 us kernel, so memory-level parallelism is what it lives on), every access is a 16-byte double2, and a warp's store
 // covers 512 contiguous bytes of one output column.  The 13 state columns are re-read by the NC cable blocks of a pose
@@ -89,8 +89,10 @@ __device__ __forceinline__ IkOne ik_one(const RobotConsts &rc, int c, const Fast
   return o;
 }
 __global__ void __launch_bounds__(256) k_ik_pair(const __grid_constant__ IkArgs A) {
-  const int c = blockIdx.y;
-  const long long i = 2 * ((long long)blockIdx.x * blockDim.x + threadIdx.x);
+  // cable index fastest across the grid: the NC blocks that share a pose range are scheduled together, so the range's
+  // state columns are fetched from DRAM once and served to the other cables from L2 whatever the sweep size
+  const int c = (int)(blockIdx.x % (unsigned)A.nc);
+  const long long i = 2 * ((long long)(blockIdx.x / (unsigned)A.nc) * blockDim.x + threadIdx.x);
   if (i >= A.n) return;
   const long long n = A.n;
   const double *p = A.state13 + i;
@@ -127,6 +129,7 @@ __global__ void k_init_state(DevLayout L, RobotConsts rc, double hx, double hy, 
   // control word: fast variant = wasLast bits 0-1, missing counters in bytes 1-2; general variant: see step_general.cuh
   const unsigned ctl0 = general ? ((vel_len << 2) | (pos_len << 8)) : ((vel_len << 8) | (pos_len << 16));
   for (int c = 0; c < L.nc; ++c) L.ctl[(long long)c * L.np + i] = ctl0;
+  L.ictl[i] = (unsigned)MODE_POSITION;  // CdprGazeboPlugin.cpp:154, no command pending
 }
 
 // Pid::reset (Pid.cpp:100-115) for pid k of every cable of every instance; mLastTime is kept.
@@ -166,6 +169,27 @@ __global__ void k_scatter_cab(DevLayout L, int field, const T *aos) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= L.n) return;
   for (int c = 0; c < L.nc; ++c) L.cab[cab_off(L, c, field) + i] = (double)aos[i * L.nc + c];
+}
+
+// The same for the flex variant, where every instance latches its own commands: only instances with mask[i] != 0 (all
+// when mask is null) receive the message; `pending_bit` marks it for the instance's next update (bit 2 velocity, bit 3
+// position, CdprGazeboPlugin.cpp:67-83); force_mode: JointForceCalculator::setForce switches the mode at once (.h:92-95)
+template <typename T>
+__global__ void k_scatter_cab_masked(DevLayout L, int field, const T *aos, const unsigned char *mask, unsigned pending_bit, int force_mode) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= L.n) return;
+  if (mask && !mask[i]) return;
+  for (int c = 0; c < L.nc; ++c) L.cab[cab_off(L, c, field) + i] = (double)aos[i * L.nc + c];
+  unsigned w = L.ictl[i] | pending_bit;
+  if (force_mode) w = (w & ~3u) | (unsigned)MODE_FORCE;
+  L.ictl[i] = w;
+}
+
+// UpdateMode of every instance (flex variant)
+__global__ void k_modes(DevLayout L, int *out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= L.n) return;
+  out[i] = (int)(L.ictl[i] & 3u);
 }
 
 __global__ void k_pack_platform(DevLayout L, double *pose7, double *twist6) {
@@ -225,11 +249,16 @@ __global__ void k_joint_states(DevLayout L, RobotConsts rc, double *pos, double 
 }
 
 // [n][nc][6] = pid_force, p_err, i_err, d_err, cmd (of the Pid the mode runs), mode
-__global__ void k_pid_state(DevLayout L, int mode, double *out) {
+__global__ void k_pid_state(DevLayout L, int mode, int flex, double *out) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= L.n) return;
-  const int k = (mode == MODE_POSITION) ? PID_POS : PID_VEL;
+  if (flex) mode = (int)(L.ictl[i] & 3u);
+  int k = (mode == MODE_POSITION) ? PID_POS : PID_VEL;
   for (int c = 0; c < L.nc; ++c) {
+    if (flex) {  // the Pid that ran last on this cable (bits 28-29 of the control word, step_flex.cuh)
+      const unsigned live = (L.ctl[(long long)c * L.np + i] >> 28) & 3u;
+      if (live) k = (int)live - 1;
+    }
     double *o = out + (i * L.nc + c) * 6;
     o[0] = L.cab[cab_off(L, c, CAB_PID_FORCE) + i];
     o[1] = L.pid[pid_off(L, c, k, PID_P_ERR) + i];

@@ -63,27 +63,6 @@ template <int NC, int SPEC = 0> struct FastCfg {
   static constexpr int blocks = (NC <= 4) ? CDPR_NC4_BLOCKS : (lean ? CDPR_NC8_LEAN_BLOCKS : CDPR_NC8_BLOCKS);
 };
 
-// ---- inverse kinematics of one cable (a7).  With g = a - p (anchor seen from the platform origin): d = g - R b = L u,
-// and r x u = (g - d) x u = g x u because d is parallel to u -- so neither r nor u is formed:
-//   m = g x d = L (r x u),  joint rate = (d.v + m.w) / L,  and the wrench scales d and m by tension / L.
-struct CableKin { double dx, dy, dz, cx, cy, cz, il, qd, qp; };
-template <int SPEC, bool WANT_QP>
-__device__ __forceinline__ CableKin cable_kin(const RobotConsts &rc, const FastState &S, const Rot &R, int c) {
-  CableKin k;
-  const double bx = rc.b[c][0], by = rc.b[c][1], bz = rc.b[c][2];
-  const double gx = rc.a[c][0] - S.px, gy = rc.a[c][1] - S.py, gz = rc.a[c][2] - S.pz;
-  k.dx = fma(-R.r00, bx, fma(-R.r01, by, (SPEC & SPEC_BZ0) ? gx : fma(-R.r02, bz, gx)));
-  k.dy = fma(-R.r10, bx, fma(-R.r11, by, (SPEC & SPEC_BZ0) ? gy : fma(-R.r12, bz, gy)));
-  k.dz = fma(-R.r20, bx, fma(-R.r21, by, (SPEC & SPEC_BZ0) ? gz : fma(-R.r22, bz, gz)));
-  const double l2 = fma(k.dx, k.dx, fma(k.dy, k.dy, k.dz * k.dz));
-  k.il = rsqrt_nr(l2);
-  k.cx = fma(gy, k.dz, -(gz * k.dy)); k.cy = fma(gz, k.dx, -(gx * k.dz)); k.cz = fma(gx, k.dy, -(gy * k.dx));
-  k.qd = (fma(k.dx, S.vx, fma(k.dy, S.vy, k.dz * S.vz)) + fma(k.cx, S.wx, fma(k.cy, S.wy, k.cz * S.wz))) * k.il;
-  k.qp = 0.0;
-  if (WANT_QP) k.qp = rc.home_len[c] - l2 * k.il;
-  return k;
-}
-
 // P + I + D (+ feed-forward `ff`) before any clamp (Pid.cpp:140-172).  DMOM: `d` is Kd * dErr already.
 template <int SPEC, bool DMOM>
 __device__ __forceinline__ double pid_command(const PidConsts &pc, double e, double ie, double d, double ff) {
@@ -326,16 +305,6 @@ __device__ __forceinline__ void resync_moments(const StepArgs &A, double (&mom)[
   }
 #pragma unroll
   for (int c = 0; c < NC; ++c) mom[c][2] = A.live.kd * fma(A.dmom[0], mom[c][0], fma(A.dmom[1], mom[c][1], A.dmom[2] * s2[c]));
-}
-
-// rare path (every snap_every steps), kept out of line so the hot loop's register allocation does not see it
-static __device__ __noinline__ void write_snapshot(const StepArgs &A, FastState S, long long o) {
-  if (A.snap_multimem) {
-    store_plat_multicast(A.snap_peers[0] + o, A.snap_stride, S);
-  } else {
-    for (int p = 0; p < A.n_snap_peers; ++p)  // plain stores; peer buffers are NVLink-mapped device memory
-      store_plat(A.snap_peers[p] + o, A.snap_stride, S);
-  }
 }
 
 // shared memory per block (doubles): ring [LEN][NC][tpb], targets [NC][tpb], feed-forward terms Kf*target [NC][tpb],

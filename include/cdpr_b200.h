@@ -114,7 +114,13 @@ enum {
   CDPR_OPT_DTERM_FIR = 1,
   /* value == 0: no CUDA event records around the launches (cdpr_last_kernel_ms then returns -1); needed when the calls
    * are captured into a CUDA graph, and saves two driver calls per cdpr_step in plugin-style stepping. Default 1. */
-  CDPR_OPT_KERNEL_TIMING = 2
+  CDPR_OPT_KERNEL_TIMING = 2,
+  /* value != 0: INDEPENDENT ROBOTS. Every instance gets its own UpdateMode and its own command latch, like N separate
+   * plugin instances (CdprGazeboPlugin.cpp:67-83,206-219): the *_masked commands address subsets, robots may sit in
+   * different modes and receive commands at different steps. Runs the on-chip full-semantics kernel ("flex"); allowed
+   * before the first step or right after cdpr_reset (the state is re-initialised to the post-Load state). Handles whose
+   * configuration needs hold / biquad stages are independent from the start. */
+  CDPR_OPT_INDEPENDENT = 3
 };
 int cdpr_set_option(cdpr_handle h, int option, int64_t value);
 
@@ -125,6 +131,15 @@ int cdpr_set_option(cdpr_handle h, int option, int64_t value);
 int cdpr_set_velocity_cmd(cdpr_handle h, const float *axes, int64_t n_instances, int n_axes);
 int cdpr_set_position_cmd(cdpr_handle h, const float *axes, int64_t n_instances, int n_axes);
 int cdpr_set_effort_cmd(cdpr_handle h, const double *force, int64_t n_instances, int n_axes);
+/* The same messages addressed to a SUBSET of the robots: mask[N] (uint8), instance i receives its row of axes iff
+ * mask[i] != 0; the others keep their targets, modes and pending commands. mask == NULL addresses all. Needs independent
+ * robots (CDPR_OPT_INDEPENDENT), else CDPR_ERR_UNSUPPORTED and nothing changes. */
+int cdpr_set_velocity_cmd_masked(cdpr_handle h, const float *axes, const unsigned char *mask, int64_t n_instances, int n_axes);
+int cdpr_set_position_cmd_masked(cdpr_handle h, const float *axes, const unsigned char *mask, int64_t n_instances, int n_axes);
+int cdpr_set_effort_cmd_masked(cdpr_handle h, const double *force, const unsigned char *mask, int64_t n_instances, int n_axes);
+/* JointForceCalculator::mUpdateMode of every instance after the last step (commands still pending are not applied yet):
+ * modes[N], CDPR_MODE_* */
+int cdpr_get_modes(cdpr_handle h, int32_t *modes);
 /* sinevelocitytest.cpp:33-49 run inside the step kernel, per instance: every
  * (1/sine_publish_hz)/dt steps a new command (float)(amp*sin(time*freq*2*M_PI + phase)) goes to
  * all cables; `time` accumulates in double from 0. amp == NULL disables the generator. */
@@ -205,7 +220,7 @@ double cdpr_measure_fp64_tflops(int device, int iters);
  * from CUDA events recorded on the handle's stream around the launch */
 float cdpr_last_kernel_ms(cdpr_handle h);
 int64_t cdpr_launch_count(cdpr_handle h);
-const char *cdpr_kernel_variant(cdpr_handle h); /* "fast" or "general" */
+const char *cdpr_kernel_variant(cdpr_handle h); /* "fast", "flex" (full semantics, on chip) or "general" (catch-all, state in HBM) */
 
 #ifdef __cplusplus
 }

@@ -79,6 +79,8 @@ def lib():
         L.orc_batch_velocity_cmd.argtypes = [C.c_void_p, C.c_int64, _fp]
         L.orc_batch_position_cmd.argtypes = [C.c_void_p, C.c_int64, _fp]
         L.orc_batch_effort_cmd.argtypes = [C.c_void_p, C.c_int64, _dp]
+        for f in (L.orc_robot_velocity_cmd, L.orc_robot_position_cmd, L.orc_robot_effort_cmd):
+            f.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.orc_batch_platform_state.argtypes = [C.c_void_p, C.c_int64, _dp, _dp]
         L.orc_batch_joint_states.argtypes = [C.c_void_p, C.c_int64, _dp, _dp, _dp]
         L.orc_batch_ik.argtypes = [C.POINTER(Config), C.c_int64, _dp, _dp, _dp, _dp, _dp, C.c_int]
@@ -180,6 +182,25 @@ class Batch:
 
     def effort_cmd(self, force):
         lib().orc_batch_effort_cmd(self.ptr, self.n, np.ascontiguousarray(force, dtype=np.float64).reshape(self.n, self.nc))
+
+    def _robot_ptr(self, i: int):
+        return C.c_void_p(self._buf.ctypes.data + i * lib().orc_sizeof_robot())
+
+    def velocity_cmd_masked(self, axes, mask):
+        """The message reaches only robots with mask[i] set (each plugin instance latches its own, CdprGazeboPlugin.cpp:67-74)."""
+        axes = np.ascontiguousarray(axes, dtype=np.float32).reshape(self.n, self.nc)
+        for i in np.flatnonzero(np.asarray(mask)):
+            lib().orc_robot_velocity_cmd(self._robot_ptr(int(i)), axes[i].ctypes.data_as(C.c_void_p), self.nc)
+
+    def position_cmd_masked(self, axes, mask):
+        axes = np.ascontiguousarray(axes, dtype=np.float32).reshape(self.n, self.nc)
+        for i in np.flatnonzero(np.asarray(mask)):
+            lib().orc_robot_position_cmd(self._robot_ptr(int(i)), axes[i].ctypes.data_as(C.c_void_p), self.nc)
+
+    def effort_cmd_masked(self, force, mask):
+        force = np.ascontiguousarray(force, dtype=np.float64).reshape(self.n, self.nc)
+        for i in np.flatnonzero(np.asarray(mask)):
+            lib().orc_robot_effort_cmd(self._robot_ptr(int(i)), force[i].ctypes.data_as(C.c_void_p), self.nc)
 
     def platform_state(self):
         pose = np.empty((self.n, 7)); twist = np.empty((self.n, 6))

@@ -1,0 +1,160 @@
+"""GPU parity of the on-chip full-semantics kernel ("flex", step_flex.cuh): independent robots (per-instance modes and
+command latches, CdprGazeboPlugin.cpp:67-83,206-219), hold and biquad cascades, launch-split and checkpoint invariance."""
+import numpy as np
+import pytest
+
+import cdpr_simulation_b200 as cb
+from cdpr_simulation_b200 import workloads as wl
+from oracle import binding as ob
+from helpers import to_oracle_config, state_rel_err
+from test_gpu_parity import make_pair, general_cfg
+
+pytestmark = pytest.mark.gpu
+
+
+def _pair_independent(nc, n, seed, cfg_edit=None, sine=False):
+    cfg = cb.default_config(nc)
+    if cfg_edit:
+        cfg_edit(cfg)
+    amp, freq, phase, pose7, twist6 = wl.c3_instances(n, seed)
+    gpu = cb.CdprBatch(cfg, n)
+    gpu.set_independent(True)
+    assert gpu.kernel_variant == "flex"
+    gpu.set_platform_state(pose7, twist6)
+    if sine:
+        gpu.set_sine_cmd(amp, freq, phase)
+        orc = ob.Batch(to_oracle_config(cfg), n, pose7, twist6, amp, freq, phase)
+    else:
+        orc = ob.Batch(to_oracle_config(cfg), n, pose7, twist6)
+    return cfg, gpu, orc
+
+
+def _check(gpu, orc, tol, tag):
+    pg, tg = gpu.platform_state(); po, to = orc.platform_state()
+    e = state_rel_err(pg, tg, po, to)
+    assert e < tol, (tag, e)
+    for a, b in zip(gpu.joint_states(), orc.joint_states()):
+        assert np.max(np.abs(a - b)) < tol * max(1.0, np.max(np.abs(b))), tag
+
+
+@pytest.mark.parametrize("nc", [4, 8])
+def test_flex_on_the_launch_configuration_matches_the_oracle_per_step(built_lib, nc):
+    """The reference's launch values (no hold, no filters) through the flex kernel: every one of the first 40 steps at 1e-9,
+    then 1000 more."""
+    cfg, gpu, orc = _pair_independent(nc, 200, seed=81, sine=True)
+    for step in range(1, 41):
+        gpu.step(1); orc.step(1)
+        _check(gpu, orc, 1e-9, f"step {step}")
+    gpu.step(1000); orc.step(1000)
+    _check(gpu, orc, 1e-9, "after 1040")
+    gpu.close()
+
+
+@pytest.mark.parametrize("nc", [4, 8])
+def test_independent_robots_modes_and_commands(built_lib, nc):
+    """Robots of one batch in different modes, commanded at different steps: thirds of the batch get velocity, position and
+    effort commands; later a subset is re-commanded while the rest keeps running."""
+    n = 150
+    cfg, gpu, orc = _pair_independent(nc, n, seed=82)
+    rng = np.random.default_rng(4)
+    third = np.arange(n) % 3
+    v = rng.uniform(-0.05, 0.05, (n, nc)).astype(np.float32)
+    p = rng.uniform(-0.02, 0.02, (n, nc)).astype(np.float32)
+    f = rng.uniform(2.0, 6.0, (n, nc))
+    gpu.step(12); orc.step(12); _check(gpu, orc, 1e-9, "position hold after Load")
+    gpu.set_velocity_cmd(v, mask=third == 0); orc.velocity_cmd_masked(v, third == 0)
+    gpu.step(7); orc.step(7); _check(gpu, orc, 1e-9, "first third in velocity")
+    gpu.set_position_cmd(p, mask=third == 1); orc.position_cmd_masked(p, third == 1)
+    gpu.set_effort_cmd(f, mask=third == 2); orc.effort_cmd_masked(f, third == 2)
+    gpu.step(30); orc.step(30); _check(gpu, orc, 1e-9, "three modes side by side")
+    assert np.array_equal(gpu.modes(), orc.targets()[2][:, 0].astype(np.int32))
+    assert set(np.unique(gpu.modes())) == {0, 1, 2}
+    # both messages pending for some robots in the same update: velocity first, position wins (.cpp:206-219)
+    both = (np.arange(n) % 5) == 0
+    gpu.set_velocity_cmd(v[::-1].copy(), mask=both); gpu.set_position_cmd(p[::-1].copy(), mask=both)
+    orc.velocity_cmd_masked(v[::-1].copy(), both); orc.position_cmd_masked(p[::-1].copy(), both)
+    gpu.step(25); orc.step(25); _check(gpu, orc, 1e-9, "velocity + position pending")
+    # effort robots back to velocity: the velocity Pid is reset on the mode change
+    gpu.set_velocity_cmd(v, mask=third == 2); orc.velocity_cmd_masked(v, third == 2)
+    for k in (1, 1, 11, 200):
+        gpu.step(k); orc.step(k)
+    _check(gpu, orc, 1e-8, "force -> velocity")
+    assert np.array_equal(gpu.modes(), orc.targets()[2][:, 0].astype(np.int32))
+    gpu.close()
+
+
+def test_masked_commands_need_independent_robots(built_lib):
+    cfg, gpu, _ = make_pair(4, 40, sine=False)
+    assert gpu.kernel_variant == "fast"
+    before = gpu.get_state()
+    with pytest.raises(cb.CdprError) as e:
+        gpu.set_velocity_cmd(np.zeros((40, 4), dtype=np.float32), mask=np.ones(40))
+    assert e.value.code == cb.api.ERR_UNSUPPORTED
+    assert np.array_equal(before, gpu.get_state())
+    gpu.step(3)
+    with pytest.raises(cb.CdprError):
+        gpu.set_independent(True)          # only before the first step
+    gpu.close()
+
+
+@pytest.mark.parametrize("nc", [4, 8])
+def test_flex_launch_split_and_checkpoint_bitwise(built_lib, nc):
+    """Hold / release cycles with filters: K steps in one launch == the same steps in uneven launches == a run resumed from a
+    checkpoint taken in the middle of a hold transition, bit for bit."""
+    _, a, _ = make_pair(nc, 180, seed=83, cfg_edit=general_cfg)
+    _, b, _ = make_pair(nc, 180, seed=83, cfg_edit=general_cfg)
+    _, c, _ = make_pair(nc, 180, seed=83, cfg_edit=general_cfg)
+    assert a.kernel_variant == "flex"
+    a.step(1237)
+    for k in (1, 2, 10, 11, 13, 100, 500, 600):
+        b.step(k)
+    c.step(333)
+    blob = c.get_state()
+    c.step(50)
+    c.set_state(blob)
+    assert c.step_count == 333
+    c.step(1237 - 333)
+    pa, ta = a.platform_state()
+    for other in (b, c):
+        po, to = other.platform_state()
+        assert np.array_equal(pa, po) and np.array_equal(ta, to)
+        for x, y in zip(a.joint_states(), other.joint_states()):
+            assert np.array_equal(x, y)
+        assert np.array_equal(a.pid_terms(), other.pid_terms())
+    a.close(); b.close(); c.close()
+
+
+def test_flex_snapshots_and_rollouts(built_lib):
+    """The flex kernel behind the other entry points: decimated snapshots equal stepwise states; rollout costs match the oracle."""
+    import torch
+    n, every, k = 100, 20, 120
+    _, a, _ = make_pair(4, n, seed=84, cfg_edit=general_cfg)
+    _, b, _ = make_pair(4, n, seed=84, cfg_edit=general_cfg)
+    buf = torch.zeros((k // every, 13, n), dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    a.set_snapshots(every, buf.data_ptr(), buf.shape[0])
+    a.step(k); a.synchronize()
+    snaps = buf.cpu().numpy()
+    for s in range(k // every):
+        b.step(every)
+        pose, twist = b.platform_state()
+        assert np.array_equal(snaps[s, 0:3].T, pose[:, 0:3]) and np.array_equal(snaps[s, 7:13].T, twist)
+    a.close(); b.close()
+    nc, n_robots, n_seq, n_cmd, spc = 4, 2, 16, 5, 10
+    cfg = cb.default_config(nc)
+    general_cfg(cfg)
+    cmds = wl.c5_rollouts(n_seq, n_cmd, nc)
+    _, _, _, pose7, twist6 = wl.c3_instances(n_robots, 11)
+    target, lam = np.array([0.0, 0.0, 0.31]), 0.1
+    with cb.CdprBatch(cfg, n_robots * n_seq) as g:
+        assert g.kernel_variant == "flex"
+        cost = g.rollout(n_robots, n_seq, cmds, spc, target, lam, pose7, twist6)
+    ocost = np.zeros(n_robots * n_seq)
+    o = ob.Batch(to_oracle_config(cfg), n_robots * n_seq, np.repeat(pose7, n_seq, axis=0), np.repeat(twist6, n_seq, axis=0))
+    for cc in range(n_cmd):
+        o.velocity_cmd(np.tile(cmds[:, cc, :], (n_robots, 1)))
+        for _ in range(spc):
+            o.step(1)
+            pose, twist = o.platform_state()
+            ocost += np.sum((pose[:, :3] - target) ** 2, axis=1) + lam * np.sum(twist[:, 3:] ** 2, axis=1)
+    assert np.max(np.abs(cost - ocost) / ocost) < 1e-9

@@ -171,7 +171,7 @@ def general_cfg(cfg):
 @pytest.mark.parametrize("nc", [4, 8])
 def test_general_variant_hold_and_filters(built_lib, nc):
     cfg, gpu, orc = make_pair(nc, 150, cfg_edit=general_cfg)
-    assert gpu.kernel_variant == "general"
+    assert gpu.kernel_variant == "flex"
     worst = 0.0
     for k in (1, 1, 1, 7, 20, 70, 400, 1500):   # sine commands cross the epsilon band several times
         gpu.step(k); orc.step(k)
@@ -364,7 +364,7 @@ class _OracleTarget:
     def step(self, k): self.b.step(k)
 
 
-@pytest.mark.parametrize("driver_name,eps,variant", [("SquareVelocity", -0.001, "fast"), ("SquareVelocity", 0.001, "general"),
+@pytest.mark.parametrize("driver_name,eps,variant", [("SquareVelocity", -0.001, "fast"), ("SquareVelocity", 0.001, "flex"),
                                                      ("SquarePosition", -0.001, "fast"), ("SineVelocity", -0.001, "fast")])
 def test_reference_drivers_against_oracle(built_lib, driver_name, eps, variant):
     """The reference's three manual test drivers (square velocity with dead band -> hold when eps > 0, square position,
