@@ -17,8 +17,14 @@ ap.add_argument("--cmd-limit", type=float, default=None, help="shrink the comman
 ap.add_argument("--i-limit", type=float, default=None)
 ap.add_argument("--sine-hz", type=float, default=None, help="publisher rate of the in-kernel sine generator")
 ap.add_argument("--mode", default="sine", choices=["sine", "position", "velocity"], help="sine publisher | per-cable position targets | per-cable velocity targets")
+ap.add_argument("--eps", type=float, default=None, help="velocityEpsilon (>= 0 enables hold: the flex kernel)")
+ap.add_argument("--p-cascade", type=int, default=0)
+ap.add_argument("--d-cascade", type=int, default=0)
+ap.add_argument("--independent", action="store_true", help="per-instance modes: the flex kernel on the launch configuration")
 a = ap.parse_args()
 cfg = cb.default_config(a.nc)
+if a.eps is not None: cfg.velocity_epsilon = a.eps
+cfg.vel_pid.p_cascade, cfg.vel_pid.d_cascade = a.p_cascade, a.d_cascade
 if a.sine_hz: cfg.sine_publish_hz = a.sine_hz
 for pid in (cfg.vel_pid, cfg.pos_pid):
     if a.cmd_limit is not None: pid.cmd_limit = a.cmd_limit
@@ -35,6 +41,8 @@ if a.ik:
 else:
     amp, freq, phase, pose7, twist6 = wl.c3_instances(a.instances, 1)
     with cb.CdprBatch(cfg, a.instances) as g:
+        if a.independent: g.set_independent(True)
+        print("variant", g.kernel_variant)
         g.set_platform_state(pose7, twist6)
         rng = np.random.default_rng(3)
         if a.mode == "sine": g.set_sine_cmd(amp, freq, phase)
