@@ -28,7 +28,7 @@ EXPORTS = [
     "cdpr_config_default", "cdpr_create", "cdpr_destroy", "cdpr_reset", "cdpr_last_error", "cdpr_set_stream", "cdpr_synchronize", "cdpr_set_async",
     "cdpr_set_option", "cdpr_set_velocity_cmd", "cdpr_set_position_cmd", "cdpr_set_effort_cmd", "cdpr_set_sine_cmd",
     "cdpr_set_velocity_cmd_masked", "cdpr_set_position_cmd_masked", "cdpr_set_effort_cmd_masked", "cdpr_get_modes",
-    "cdpr_step", "cdpr_step_count", "cdpr_sim_time",
+    "cdpr_step", "cdpr_update", "cdpr_step_count", "cdpr_sim_time",
     "cdpr_get_joint_states", "cdpr_get_platform_state", "cdpr_set_platform_state", "cdpr_get_pid_state", "cdpr_get_pid_terms",
     "cdpr_state_bytes", "cdpr_get_state", "cdpr_set_state",
     "cdpr_set_snapshots", "cdpr_set_snapshot_peers", "cdpr_set_snapshot_multicast", "cdpr_snapshot_count",
@@ -107,6 +107,7 @@ def load():
     L.cdpr_get_modes.argtypes = [vp, vp]
     L.cdpr_set_sine_cmd.argtypes = [vp, vp, vp, vp, i64]
     L.cdpr_step.argtypes = [vp, i64]
+    L.cdpr_update.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
     L.cdpr_step_count.argtypes = [vp]; L.cdpr_step_count.restype = i64
     L.cdpr_sim_time.argtypes = [vp]; L.cdpr_sim_time.restype = dbl
     L.cdpr_get_joint_states.argtypes = [vp, vp, vp, vp]
@@ -254,6 +255,20 @@ class CdprBatch:
     # -- stepping ----------------------------------------------------------------------------
     def step(self, k_steps: int = 1):
         self._ck(self._L.cdpr_step(self._h, int(k_steps)))
+
+    def update(self, vel_axes=None, pos_axes=None):
+        """One plugin update (CdprGazeboPlugin::update): latch the messages given, one physics step, and the plugin's own
+        publish: (position, velocity, effort, pose7, twist6) with position / velocity / pose / twist as read at this update
+        (before the step integrates) and the effort applied in it.  Returns views of buffers reused by the next call."""
+        if not hasattr(self, "_upd"):
+            self._upd = (np.empty((self.n, self.nc)), np.empty((self.n, self.nc)), np.empty((self.n, self.nc)), np.empty((self.n, 7)), np.empty((self.n, 6)))
+            self._upd_ptr = [_ptr(a) for a in self._upd]
+        v = None if vel_axes is None else np.ascontiguousarray(vel_axes, dtype=np.float32)
+        p = None if pos_axes is None else np.ascontiguousarray(pos_axes, dtype=np.float32)
+        if (v is not None and v.size != self.n * self.nc) or (p is not None and p.size != self.n * self.nc):
+            raise CdprError(ERR_BAD_LENGTH, "command length != instances x cable count: dropped")
+        self._ck(self._L.cdpr_update(self._h, _ptr(v), _ptr(p), *self._upd_ptr))
+        return self._upd
 
     @property
     def step_count(self) -> int:

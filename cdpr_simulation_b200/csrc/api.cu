@@ -59,6 +59,10 @@ struct cdpr_batch {
   bool targets_uniform = false;  // all cables of an instance hold the same velocity target (zeros after Load, or written by the sine publisher)
   long long launches = 0;
   void *stage = nullptr;
+  // cdpr_update: pinned, device-mapped host memory the step kernel publishes into and the command scatter reads from
+  double *pub_host = nullptr;
+  float *cmd_host[2] = {nullptr, nullptr};
+  double *pub_ptr[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // set for the duration of one cdpr_update
   size_t stage_bytes = 0;
   double *cost_dev = nullptr;
   float *cmd_dev = nullptr;
@@ -433,6 +437,8 @@ extern "C" int cdpr_destroy(cdpr_handle h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (void *p : h->allocs) cudaFree(p);
   if (h->stage) cudaFree(h->stage);
+  if (h->pub_host) cudaFreeHost(h->pub_host);
+  if (h->cmd_host[0]) cudaFreeHost(h->cmd_host[0]);
   if (h->cost_dev) cudaFree(h->cost_dev);
   if (h->cmd_dev) cudaFree(h->cmd_dev);
   if (h->ev0) cudaEventDestroy(h->ev0);
@@ -653,6 +659,7 @@ static void fill_args(cdpr_handle h, StepArgs &A, int k_steps, bool sine) {
     A.dk[3] = -kd * a;
   }
   A.flex_ps = h->flex_ps; A.flex_ds = h->flex_ds;
+  A.pub_pos = h->pub_ptr[0]; A.pub_vel = h->pub_ptr[1]; A.pub_eff = h->pub_ptr[2]; A.pub_pose = h->pub_ptr[3]; A.pub_twist = h->pub_ptr[4];
   A.effort_ge_cmd = h->rc.effort_limit_abs >= A.live.cmd_max ? 1 : 0;
   A.sat_thr = fmin(A.live.cmd_max, h->rc.effort_limit_abs);
   A.mode = h->mode; A.k_steps = k_steps; A.n0 = h->step_count;
@@ -776,6 +783,50 @@ extern "C" int cdpr_step(cdpr_handle h, int64_t k_steps) {
   }
   if (h->timing) { CK(h, cudaEventRecord(h->ev1, h->stream)); h->timed = true; }
   main_end(h);
+  return CDPR_OK;
+}
+
+// One plugin update in one call: see include/cdpr_b200.h.  The step kernel itself publishes (last-step body) into pinned host
+// memory mapped into the device, so an update is [command scatter, only when a message arrived] + ONE kernel + one
+// stream synchronisation -- no pack kernels, no memcpy calls, no event records.
+extern "C" int cdpr_update(cdpr_handle h, const float *vel_axes, const float *pos_axes, double *position, double *velocity, double *effort,
+                           double *pose7, double *twist6) {
+  if (!h) return CDPR_ERR_BAD_ARG;
+  if (h->async_copies) return fail(h, CDPR_ERR_UNSUPPORTED, "cdpr_update is synchronous: leave async mode first");
+  cudaSetDevice(h->device);
+  const size_t nj = (size_t)h->n * h->L.nc, per = 3 * nj + 13 * (size_t)h->n;
+  if (!h->pub_host) {
+    if (cudaHostAlloc((void **)&h->pub_host, sizeof(double) * per, cudaHostAllocMapped) != cudaSuccess) return fail(h, CDPR_ERR_NOMEM, "cudaHostAlloc(publish buffer) failed");
+    if (cudaHostAlloc((void **)&h->cmd_host[0], sizeof(float) * 2 * nj, cudaHostAllocMapped) != cudaSuccess) return fail(h, CDPR_ERR_NOMEM, "cudaHostAlloc(command buffer) failed");
+    h->cmd_host[1] = h->cmd_host[0] + nj;
+  }
+  // subscriber callbacks: latch the messages (CdprGazeboPlugin.cpp:67-83); the scatter kernel reads the mapped buffer
+  for (int which = 0; which < 2; ++which) {
+    const float *axes = which == 0 ? vel_axes : pos_axes;
+    if (!axes) continue;
+    std::memcpy(h->cmd_host[which], axes, sizeof(float) * nj);
+    const int field = which == 0 ? CAB_VEL_TARGET : CAB_POS_TARGET;
+    if (h->flex) k_scatter_cab_masked<float><<<grid_for(h->n, 256), 256, 0, h->stream>>>(h->L, field, h->cmd_host[which], nullptr, which == 0 ? 4u : 8u, 0);
+    else k_scatter_cab<float><<<grid_for(h->n, 256), 256, 0, h->stream>>>(h->L, field, h->cmd_host[which]);
+    CK(h, cudaGetLastError());
+    ++h->launches;
+    if (which == 0) { h->vel_pending = true; h->targets_uniform = false; } else h->pos_pending = true;
+  }
+  double *o = h->pub_host;
+  h->pub_ptr[0] = position ? o : nullptr; h->pub_ptr[1] = velocity ? o + nj : nullptr; h->pub_ptr[2] = effort ? o + 2 * nj : nullptr;
+  h->pub_ptr[3] = pose7 ? o + 3 * nj : nullptr; h->pub_ptr[4] = twist6 ? o + 3 * nj + 7 * (size_t)h->n : nullptr;
+  const bool timing = h->timing;
+  h->timing = false;
+  int rc = cdpr_step(h, 1);
+  h->timing = timing;
+  for (double *&p : h->pub_ptr) p = nullptr;
+  if (rc) return rc;
+  CK(h, cudaStreamSynchronize(h->stream));
+  if (position) std::memcpy(position, o, sizeof(double) * nj);
+  if (velocity) std::memcpy(velocity, o + nj, sizeof(double) * nj);
+  if (effort) std::memcpy(effort, o + 2 * nj, sizeof(double) * nj);
+  if (pose7) std::memcpy(pose7, o + 3 * nj, sizeof(double) * 7 * (size_t)h->n);
+  if (twist6) std::memcpy(twist6, o + 3 * nj + 7 * (size_t)h->n, sizeof(double) * 6 * (size_t)h->n);
   return CDPR_OK;
 }
 

@@ -104,6 +104,10 @@ struct StepArgs {
   int snap_multimem;  // snap_peers[0] is an NVLS multicast address: one multimem.st reaches every rank's buffer
   long long snap_stride, snap_offset;
   long long snap_every, snap_written0, snap_capacity;
+  // cdpr_update: what the plugin publishes from inside update() (CdprGazeboPlugin.cpp:248-280), written by the LAST step of the
+  // launch: joint position / velocity and platform pose / twist as read at that update (before the body integrates), and the
+  // effort applied in it. [N][NC] x 3, [N][7] (x y z qx qy qz qw), [N][6]; null = not wanted. May be mapped host memory.
+  double *pub_pos, *pub_vel, *pub_eff, *pub_pose, *pub_twist;
   // rollout mode (cdpr_rollout)
   const float *cmd_table;  // [n_seq][n_cmd][NC]
   int n_seq, n_cmd, steps_per_cmd;

@@ -153,4 +153,22 @@ static __device__ __noinline__ void write_snapshot(const StepArgs &A, FastState 
   }
 }
 
+// publishPlatformState (CdprGazeboPlugin.cpp:258-280) of the state the update sees: position, orientation x y z w, twist
+__device__ __forceinline__ void publish_platform(const StepArgs &A, const FastState &S, long long i) {
+  if (A.pub_pose) {
+    double *o = A.pub_pose + 7 * i;
+    o[0] = S.px; o[1] = S.py; o[2] = S.pz; o[3] = S.qx; o[4] = S.qy; o[5] = S.qz; o[6] = S.qw;
+  }
+  if (A.pub_twist) {
+    double *o = A.pub_twist + 6 * i;
+    o[0] = S.vx; o[1] = S.vy; o[2] = S.vz; o[3] = S.wx; o[4] = S.wy; o[5] = S.wz;
+  }
+}
+// publishJointStates (CdprGazeboPlugin.cpp:248-256): Position(), GetVelocity(0) at this update, GetForce(0) of this step
+__device__ __forceinline__ void publish_joint(const StepArgs &A, int nc, int c, double qp, double qd, double eff, long long i) {
+  if (A.pub_pos) A.pub_pos[i * nc + c] = qp;
+  if (A.pub_vel) A.pub_vel[i * nc + c] = qd;
+  if (A.pub_eff) A.pub_eff[i * nc + c] = eff;
+}
+
 }  // namespace cdpr

@@ -241,6 +241,7 @@ __device__ __forceinline__ bool fast_step(const StepArgs &A, FastState &S, doubl
       if (LAST) A.L.pid[pid_off(A.L, c, A.live_idx, PID_CMD) + i] = force;
     }
     if (LAST) {
+      publish_joint(A, NC, c, k.qp, k.qd, eff, i);
       A.L.cab[cab_off(A.L, c, CAB_LAST_POS) + i] = k.qp;
       A.L.cab[cab_off(A.L, c, CAB_EFFORT) + i] = eff;
       A.L.cab[cab_off(A.L, c, CAB_PID_FORCE) + i] = force;
@@ -276,6 +277,7 @@ __device__ __forceinline__ bool fast_step(const StepArgs &A, FastState &S, doubl
     }
   }
 
+  if (LAST) publish_platform(A, S, i);
   rigid_body_step<SPEC>(rc, S, R, fx, fy, fz, mx, my, mz);
   return fired;
 }

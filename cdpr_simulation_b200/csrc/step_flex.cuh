@@ -389,6 +389,7 @@ static __device__ __noinline__ FastState flex_general_step(const StepArgs &A, Fa
     sw[c * TPB] = w;
     const double eff = (rc.effort_limit >= 0.0) ? clampd(force, -rc.effort_limit, rc.effort_limit) : force;
     if (last) {
+      publish_joint(A, NC, c, kin.qp, kin.qd, eff, i);
       L.cab[cab_off(L, c, CAB_EFFORT) + i] = eff;
       L.cab[cab_off(L, c, CAB_PID_FORCE) + i] = force;
     }
@@ -396,6 +397,7 @@ static __device__ __noinline__ FastState flex_general_step(const StepArgs &A, Fa
     fx = fma(tl, kin.dx, fx); fy = fma(tl, kin.dy, fy); fz = fma(tl, kin.dz, fz);
     mx = fma(tl, kin.cx, mx); my = fma(tl, kin.cy, my); mz = fma(tl, kin.cz, mz);
   }
+  if (last) publish_platform(A, S, i);
   if (rc.diag_inertia) rigid_body_step<SPEC_DIAG>(rc, S, R, fx, fy, fz, mx, my, mz);
   else rigid_body_step<0>(rc, S, R, fx, fy, fz, mx, my, mz);
   return S;

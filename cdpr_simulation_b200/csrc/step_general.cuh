@@ -278,10 +278,12 @@ __global__ void __launch_bounds__(kTpb, CDPR_GEN_BLOCKS) k_step_general(const __
       const double eff = (rc.effort_limit >= 0.0) ? clampd(force, -rc.effort_limit, rc.effort_limit) : force;
       L.cab[cab_off(L, c, CAB_EFFORT) + i] = eff;
       L.cab[cab_off(L, c, CAB_PID_FORCE) + i] = force;
+      if (s == A.k_steps - 1) publish_joint(A, nc, c, qp, qd, eff, i);
       const double tl = fma(-rc.cdamp, qd, eff) * il;  // tension / L
       fx = fma(tl, dx, fx); fy = fma(tl, dy, fy); fz = fma(tl, dz, fz);
       mx = fma(tl, cx, mx); my = fma(tl, cy, my); mz = fma(tl, cz, mz);
     }
+    if (s == A.k_steps - 1) publish_platform(A, S, i);
     if (rc.diag_inertia) rigid_body_step<SPEC_DIAG>(rc, S, R, fx, fy, fz, mx, my, mz);
     else rigid_body_step<0>(rc, S, R, fx, fy, fz, mx, my, mz);
     if (A.cost) {

@@ -44,37 +44,19 @@ void CdprBatchPlugin::cablePositionCommandCallback(const Joy &msg) {
 }
 
 void CdprBatchPlugin::update() {
-  // fan-out order of CdprGazeboPlugin.cpp:206-219: velocity, then position (the library applies them in that order
-  // at the next step; the mode switch and Pid reset of the setters happen there)
-  if (mVelocityCommandReceived) {
-    check(cdpr_set_velocity_cmd(mHandle, mVelocityCommand.axes.data(), mInstances, mWireCount), "cdpr_set_velocity_cmd");
-    mVelocityCommandReceived = false;
-  }
-  if (mPositionCommandReceived) {
-    check(cdpr_set_position_cmd(mHandle, mPositionCommand.axes.data(), mInstances, mWireCount), "cdpr_set_position_cmd");
-    mPositionCommandReceived = false;
-  }
-  // the plugin publishes from inside update(): the state BEFORE this step together with the force set in this step.
-  // Position/velocity are read first, the step runs, then the effort of this step is read.
+  // One call does what CdprGazeboPlugin::update does (.cpp:202-246): the latched messages are fanned out velocity first,
+  // then position (.cpp:206-219; the mode switch and Pid reset of the setters happen inside), every cable's force is set,
+  // the step runs, and the publish pairs the state READ AT THIS UPDATE with the force of this step (.cpp:248-280).
   const double now = simTime() + mStep;  // World::Step advances sim time before the callback
   const bool publish = (now - mPreviousProcessingTime) > mPublishPeriod;  // CdprGazeboPlugin.cpp:237
-  if (publish) {
-    check(cdpr_get_joint_states(mHandle, mJointStates.position.data(), mJointStates.velocity.data(), nullptr), "cdpr_get_joint_states");
-    publishPlatformState();
-  }
-  check(cdpr_step(mHandle, 1), "cdpr_step");
-  if (publish) {
-    mPreviousProcessingTime = now;
-    publishJointStates();
-  }
-}
-
-void CdprBatchPlugin::publishJointStates() {  // effort = Joint::GetForce(0) of the step just taken (.cpp:253)
-  check(cdpr_get_joint_states(mHandle, nullptr, nullptr, mJointStates.effort.data()), "cdpr_get_joint_states");
-}
-
-void CdprBatchPlugin::publishPlatformState() {  // .cpp:258-280
-  check(cdpr_get_platform_state(mHandle, mPlatformState.pose.data(), mPlatformState.twist.data()), "cdpr_get_platform_state");
+  check(cdpr_update(mHandle, mVelocityCommandReceived ? mVelocityCommand.axes.data() : nullptr,
+                    mPositionCommandReceived ? mPositionCommand.axes.data() : nullptr,
+                    publish ? mJointStates.position.data() : nullptr, publish ? mJointStates.velocity.data() : nullptr,
+                    publish ? mJointStates.effort.data() : nullptr, publish ? mPlatformState.pose.data() : nullptr,
+                    publish ? mPlatformState.twist.data() : nullptr),
+        "cdpr_update");
+  mVelocityCommandReceived = mPositionCommandReceived = false;
+  if (publish) mPreviousProcessingTime = now;
 }
 
 double CdprBatchPlugin::simTime() const { return cdpr_sim_time(mHandle); }

@@ -58,8 +58,6 @@ public:
   cdpr_handle handle() const { return mHandle; }
 
 private:
-  void publishJointStates();
-  void publishPlatformState();
   void check(int rc, const char *what) const;
 
   cdpr_handle mHandle = nullptr;

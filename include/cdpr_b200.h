@@ -147,6 +147,14 @@ int cdpr_set_sine_cmd(cdpr_handle h, const double *amp, const double *freq, cons
 
 /* ---- stepping (CdprGazeboPlugin::update .cpp:202-246 followed by the physics step) ------- */
 int cdpr_step(cdpr_handle h, int64_t k_steps);
+/* ONE plugin update per call -- the literal drop-in for CdprGazeboPlugin::update (.cpp:202-246) at the plugin's own
+ * operating point (one call per physics step): latch the messages given (vel_axes / pos_axes float32 [N][NC], NULL = no
+ * message this step; velocity is fanned out before position), run one physics step, and publish like the plugin does from
+ * inside update(): joint position / velocity [N][NC] and platform pose7 / twist6 as READ AT THIS UPDATE (before the body
+ * integrates), effort [N][NC] = the force applied in this step (.cpp:248-280). Any output may be NULL. Synchronous. The
+ * step kernel publishes straight into pinned host memory: one kernel launch and one synchronisation per update. */
+int cdpr_update(cdpr_handle h, const float *vel_axes, const float *pos_axes, double *position, double *velocity, double *effort,
+                double *pose7, double *twist6);
 int64_t cdpr_step_count(cdpr_handle h);
 double cdpr_sim_time(cdpr_handle h);
 

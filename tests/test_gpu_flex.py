@@ -158,3 +158,41 @@ def test_flex_snapshots_and_rollouts(built_lib):
             pose, twist = o.platform_state()
             ocost += np.sum((pose[:, :3] - target) ** 2, axis=1) + lam * np.sum(twist[:, 3:] ** 2, axis=1)
     assert np.max(np.abs(cost - ocost) / ocost) < 1e-9
+
+
+def _short_window(cfg):
+    cfg.vel_pid.d_buffer_length = 5
+    cfg.vel_pid.d_degree = 1
+
+
+@pytest.mark.parametrize("variant,edit", [("fast", None), ("flex", general_cfg), ("general", _short_window)])
+def test_update_publishes_like_the_plugin(built_lib, variant, edit):
+    """cdpr_update = CdprGazeboPlugin::update in one call: messages in, one step, and the plugin's own pairing out -- joint
+    position / velocity and platform pose / twist as read at the update (before the step integrates) with the effort applied
+    in it (CdprGazeboPlugin.cpp:248-280) -- for all three kernel variants, against the oracle's record of the last update."""
+    n, nc = 37, 4
+    cfg, gpu, orc = make_pair(nc, n, seed=91, cfg_edit=edit, sine=False)
+    assert gpu.kernel_variant == variant
+    rng = np.random.default_rng(6)
+    for step in range(1, 61):
+        v = p = None
+        if step % 10 == 1:
+            v = rng.uniform(-0.05, 0.05, (n, nc)).astype(np.float32)
+            orc.velocity_cmd(v)
+        if step == 35:
+            p = rng.uniform(-0.02, 0.02, (n, nc)).astype(np.float32)
+            orc.position_cmd(p)
+        pose_pre, twist_pre = orc.platform_state()
+        orc.step(1)
+        jpos, jvel, _, eff = orc.last_outputs()
+        gpos, gvel, geff, gpose, gtwist = gpu.update(v, p)
+        tol = 1e-9
+        assert state_rel_err(gpose, gtwist, pose_pre, twist_pre) < tol, step
+        for a, b in ((gpos, jpos), (gvel, jvel), (geff, eff)):
+            assert np.max(np.abs(a - b)) < tol * max(1.0, np.max(np.abs(b))), step
+    # and the state after 60 updates is what 60 plain steps give
+    _check(gpu, orc, 1e-9, "after 60 updates")
+    with pytest.raises(cb.CdprError) as e:
+        gpu.update(np.zeros((n, nc + 1), dtype=np.float32))
+    assert e.value.code == cb.api.ERR_BAD_LENGTH
+    gpu.close()
