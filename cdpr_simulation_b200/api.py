@@ -65,6 +65,12 @@ class Config(C.Structure):
         ("dt", C.c_double),
         ("vel_pid", PidParams), ("pos_pid", PidParams),
         ("velocity_epsilon", C.c_double),
+        ("leg_model", C.c_int32),
+        ("leg_link_mass", C.c_double), ("leg_link_inertia", C.c_double), ("leg_cable_com", C.c_double), ("passive_damping", C.c_double),
+        ("leg_axis_frame", (C.c_double * 3) * MAX_CABLES),
+        ("leg_axis_cable", (C.c_double * 3) * MAX_CABLES),
+        ("leg_axis_platform", (C.c_double * 3) * MAX_CABLES),
+        ("slider_lower", C.c_double), ("slider_upper", C.c_double), ("slider_velocity_limit", C.c_double),
         ("sine_publish_hz", C.c_double),
     ]
 

@@ -121,6 +121,28 @@ extern "C" int cdpr_config_default(cdpr_config *cfg, int n_cables) {
   p.p_cascade = p.d_cascade = 0;
   cfg->velocity_epsilon = -0.001;
   cfg->sine_publish_hz = 100.0;
+  // leg links and passive joints (cube.sdf:344-518); off by default = the reduced model
+  cfg->leg_model = 0;
+  cfg->leg_link_mass = 0.001; cfg->leg_link_inertia = 0.001;
+  cfg->leg_cable_com = 0.51961524;  // l/2, l = |(0.6, 0.6, 0.6)| (gen_cdpr.py:104,124-125)
+  cfg->passive_damping = 0.01;
+  cfg->slider_lower = -0.51961524; cfg->slider_upper = 0.51961524; cfg->slider_velocity_limit = 10.0;
+  for (int c = 0; c < n_cables; ++c) {
+    // gen_cdpr.py:113-125,152: the leg frame is the rotation about z x u_fp that takes z onto the frame -> platform
+    // direction u_fp; rev_X turns about its first column (cube.sdf:390)
+    double ufp[3], n = 0.0;
+    for (int k = 0; k < 3; ++k) { ufp[k] = cfg->home_pos[k] + cfg->platform_anchor[c][k] - cfg->frame_anchor[c][k]; n += ufp[k] * ufp[k]; }
+    n = std::sqrt(n);
+    for (int k = 0; k < 3; ++k) ufp[k] /= n;
+    double ax[3] = {-ufp[1], ufp[0], 0.0};
+    const double sn = std::sqrt(ax[0] * ax[0] + ax[1] * ax[1]), cs = ufp[2];
+    if (sn > 0.0) { ax[0] /= sn; ax[1] /= sn; }
+    cfg->leg_axis_frame[c][0] = cs + ax[0] * ax[0] * (1.0 - cs);
+    cfg->leg_axis_frame[c][1] = ax[2] * sn + ax[1] * ax[0] * (1.0 - cs);
+    cfg->leg_axis_frame[c][2] = -ax[1] * sn + ax[2] * ax[0] * (1.0 - cs);
+    cfg->leg_axis_cable[c][2] = 1.0;     // "0 0 1", model frame (SDF 1.4)
+    cfg->leg_axis_platform[c][0] = 1.0;  // "1 0 0"
+  }
   return CDPR_OK;
 }
 
@@ -256,6 +278,36 @@ static int make_robot_consts(const cdpr_config &c, RobotConsts &o, std::string &
   if (bz0) o.spec |= SPEC_BZ0;
   o.cdamp = c.cable_damping; o.effort_limit = c.effort_limit; o.vel_eps = c.velocity_epsilon;
   o.effort_limit_abs = c.effort_limit >= 0.0 ? c.effort_limit : INFINITY;
+  o.mass = c.mass;
+  for (int k = 0; k < 3; ++k) o.grav[k] = c.gravity[k];
+  o.leg_model = c.leg_model;
+  if (c.leg_model) {
+    if (!(c.leg_link_mass >= 0.0) || !(c.leg_link_inertia >= 0.0) || !(c.passive_damping >= 0.0)) { err = "leg constants must be non-negative"; return CDPR_ERR_BAD_ARG; }
+    o.leg_sI = std::sqrt(c.leg_link_inertia); o.leg_s2I = std::sqrt(2.0 * c.leg_link_inertia);
+    o.leg_sm = std::sqrt(c.leg_link_mass); o.leg_s2m = std::sqrt(2.0 * c.leg_link_mass);
+    o.leg_sc = std::sqrt(c.passive_damping); o.leg_lc = c.leg_cable_com;
+    for (int i = 0; i < c.n_cables; ++i) {
+      // body triad of the leg at the home pose: e2 = (u x x0)/c, e1 = e2 x u, u; the rev_Zpf axis keeps these components
+      double d[3], u[3], x0[3], e1[3], e2[3], nx = 0.0;
+      for (int k = 0; k < 3; ++k) { x0[k] = c.leg_axis_frame[i][k]; nx += x0[k] * x0[k]; }
+      if (!(nx > 0.0)) { err = "leg_axis_frame must be non-zero"; return CDPR_ERR_BAD_ARG; }
+      for (int k = 0; k < 3; ++k) {
+        const double r = R[k][0] * o.b[i][0] + R[k][1] * o.b[i][1] + R[k][2] * o.b[i][2];
+        d[k] = o.a[i][k] - c.home_pos[k] - r;
+      }
+      const double L = std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+      for (int k = 0; k < 3; ++k) u[k] = d[k] / L;
+      const double s = u[0] * x0[0] + u[1] * x0[1] + u[2] * x0[2], cc = std::sqrt(1.0 - s * s);
+      if (!(cc > 1e-6)) { err = "leg_axis_frame must not be parallel to the leg"; return CDPR_ERR_BAD_ARG; }
+      for (int k = 0; k < 3; ++k) e1[k] = (x0[k] - s * u[k]) / cc;
+      e2[0] = u[1] * e1[2] - u[2] * e1[1]; e2[1] = u[2] * e1[0] - u[0] * e1[2]; e2[2] = u[0] * e1[1] - u[1] * e1[0];
+      const double *a3 = c.leg_axis_cable[i];
+      o.leg_alpha[i][0] = e1[0] * a3[0] + e1[1] * a3[1] + e1[2] * a3[2];
+      o.leg_alpha[i][1] = e2[0] * a3[0] + e2[1] * a3[1] + e2[2] * a3[2];
+      o.leg_alpha[i][2] = u[0] * a3[0] + u[1] * a3[1] + u[2] * a3[2];
+      for (int k = 0; k < 3; ++k) { o.leg_x0[i][k] = x0[k]; o.leg_a1[i][k] = c.leg_axis_platform[i][k]; }
+    }
+  }
   return CDPR_OK;
 }
 
@@ -368,7 +420,7 @@ extern "C" int cdpr_create(const cdpr_config *cfg, int64_t n_instances, int devi
   const bool fast_ok = cfg->velocity_epsilon < 0.0 && cfg->vel_pid.p_cascade == 0 && cfg->vel_pid.d_cascade == 0 &&
                        cfg->pos_pid.p_cascade == 0 && cfg->pos_pid.d_cascade == 0 && cfg->vel_pid.cmd_limit != 0.0 &&
                        cfg->pos_pid.cmd_limit != 0.0 && cfg->vel_pid.i_gain >= 0.0 && cfg->pos_pid.i_gain >= 0.0 && cfg->vel_pid.d_buffer_length == 11 && cfg->pos_pid.d_buffer_length == 11 &&
-                       (cfg->n_cables == 4 || cfg->n_cables == 8);
+                       (cfg->n_cables == 4 || cfg->n_cables == 8) && cfg->leg_model == 0;
   h->general = !fast_ok;
   // The on-chip full-semantics variant (step_flex.cuh): windows of 11 fitted with one degree, cmdLimit != 0, 4 or 8
   // cables, and a block shape whose controller state fits in shared memory.
@@ -383,6 +435,11 @@ extern "C" int cdpr_create(const cdpr_config *cfg, int64_t n_instances, int devi
     h->flex_capable = shape_ok && h->flex_smem <= 227u * 1024u;
   }
   h->flex = h->general && h->flex_capable;
+  if (cfg->leg_model && !h->flex) {
+    g_create_error = "leg_model = 1 runs in the flex kernel only (4 or 8 cables, windows of 11 with one degree, cmdLimit != 0)";
+    delete h;
+    return CDPR_ERR_UNSUPPORTED;
+  }
 
   auto bail = [&](int code) { g_create_error = h->err; cdpr_destroy(h); return code; };
   if (cudaSetDevice(device) != cudaSuccess) { h->err = "cudaSetDevice failed"; return bail(CDPR_ERR_CUDA); }

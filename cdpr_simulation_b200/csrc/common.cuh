@@ -73,6 +73,12 @@ struct RobotConsts {
   double cdamp, effort_limit;  // effort_limit < 0: no truncation
   double effort_limit_abs;     // effort_limit, or +inf when truncation is off
   double vel_eps;
+  // leg fidelity (legs.cuh): 0 = massless legs; square roots of link inertia / mass / passive damping (and of twice them), COM
+  // offset of the cable link, rev_X axis (frame), rev_Zpf axis in the leg triad, rev_Xpf axis (platform body)
+  int leg_model;
+  double mass, grav[3];
+  double leg_sI, leg_s2I, leg_sm, leg_s2m, leg_sc, leg_lc;
+  double leg_x0[kMaxCables][3], leg_alpha[kMaxCables][3], leg_a1[kMaxCables][3];
 };
 
 struct StepArgs {

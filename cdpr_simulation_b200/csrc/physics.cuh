@@ -69,6 +69,18 @@ __device__ __forceinline__ void store_plat_multicast(double *p, long long stride
   mc_store(p + 10 * stride, S.wx); mc_store(p + 11 * stride, S.wy); mc_store(p + 12 * stride, S.wz);
 }
 
+// pose update with the NEW velocities (App. C.6): p += h v, q += h 1/2 (0, w) (x) q, renormalise
+__device__ __forceinline__ void integrate_pose(const RobotConsts &rc, FastState &S) {
+  S.px = fma(rc.h, S.vx, S.px); S.py = fma(rc.h, S.vy, S.py); S.pz = fma(rc.h, S.vz, S.pz);
+  const double hx = rc.half_h * S.wx, hy = rc.half_h * S.wy, hz = rc.half_h * S.wz;
+  const double nw = fma(-hx, S.qx, fma(-hy, S.qy, fma(-hz, S.qz, S.qw)));
+  const double nx = fma(hx, S.qw, fma(hy, S.qz, fma(-hz, S.qy, S.qx)));
+  const double ny = fma(-hx, S.qz, fma(hy, S.qw, fma(hz, S.qx, S.qy)));
+  const double nz = fma(hx, S.qy, fma(-hy, S.qx, fma(hz, S.qw, S.qz)));
+  const double inv = rsqrt_nr(fma(nw, nw, fma(nx, nx, fma(ny, ny, nz * nz))));
+  S.qw = nw * inv; S.qx = nx * inv; S.qy = ny * inv; S.qz = nz * inv;
+}
+
 // (fx..fz, mx..mz) = net force / torque about the COM in frame axes, gravity included
 template <int SPEC>
 __device__ __forceinline__ void rigid_body_step(const RobotConsts &rc, FastState &S, const Rot &R, double fx, double fy, double fz,
@@ -111,15 +123,7 @@ __device__ __forceinline__ void rigid_body_step(const RobotConsts &rc, FastState
   }
   S.vx = fma(rc.h_over_m, fx, S.vx); S.vy = fma(rc.h_over_m, fy, S.vy); S.vz = fma(rc.h_over_m, fz, S.vz);
   S.wx = fma(rc.h, alx, S.wx); S.wy = fma(rc.h, aly, S.wy); S.wz = fma(rc.h, alz, S.wz);
-  S.px = fma(rc.h, S.vx, S.px); S.py = fma(rc.h, S.vy, S.py); S.pz = fma(rc.h, S.vz, S.pz);
-  // q += h * 1/2 (0, w) (x) q, then renormalise
-  const double hx = rc.half_h * S.wx, hy = rc.half_h * S.wy, hz = rc.half_h * S.wz;
-  const double nw = fma(-hx, S.qx, fma(-hy, S.qy, fma(-hz, S.qz, S.qw)));
-  const double nx = fma(hx, S.qw, fma(hy, S.qz, fma(-hz, S.qy, S.qx)));
-  const double ny = fma(-hx, S.qz, fma(hy, S.qw, fma(hz, S.qx, S.qy)));
-  const double nz = fma(hx, S.qy, fma(-hy, S.qx, fma(hz, S.qw, S.qz)));
-  const double inv = rsqrt_nr(fma(nw, nw, fma(nx, nx, fma(ny, ny, nz * nz))));
-  S.qw = nw * inv; S.qx = nx * inv; S.qy = ny * inv; S.qz = nz * inv;
+  integrate_pose(rc, S);
 }
 
 // ---- inverse kinematics of one cable (a7).  With g = a - p (anchor seen from the platform origin): d = g - R b = L u,

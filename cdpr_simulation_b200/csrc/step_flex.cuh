@@ -41,6 +41,7 @@
 #include "common.cuh"
 #include "physics.cuh"
 #include "step_general.cuh"
+#include "legs.cuh"
 
 namespace cdpr {
 
@@ -398,6 +399,7 @@ static __device__ __noinline__ FastState flex_general_step(const StepArgs &A, Fa
     mx = fma(tl, kin.cx, mx); my = fma(tl, kin.cy, my); mz = fma(tl, kin.cz, mz);
   }
   if (last) publish_platform(A, S, i);
+  if (rc.leg_model) return legs_step(A, S, fx, fy, fz, mx, my, mz);
   if (rc.diag_inertia) rigid_body_step<SPEC_DIAG>(rc, S, R, fx, fy, fz, mx, my, mz);
   else rigid_body_step<0>(rc, S, R, fx, fy, fz, mx, my, mz);
   return S;
@@ -546,7 +548,8 @@ __global__ void __launch_bounds__(TPB) k_step_flex(const __grid_constant__ StepA
         fx = fma(tl, kin.dx, fx); fy = fma(tl, kin.dy, fy); fz = fma(tl, kin.dz, fz);
         mx = fma(tl, kin.cx, mx); my = fma(tl, kin.cy, my); mz = fma(tl, kin.cz, mz);
       }
-      if (rc.diag_inertia) rigid_body_step<SPEC_DIAG>(rc, S, R, fx, fy, fz, mx, my, mz);
+      if (rc.leg_model) S = legs_step(A, S, fx, fy, fz, mx, my, mz);
+      else if (rc.diag_inertia) rigid_body_step<SPEC_DIAG>(rc, S, R, fx, fy, fz, mx, my, mz);
       else rigid_body_step<0>(rc, S, R, fx, fy, fz, mx, my, mz);
     } else {
       if (hot) {

@@ -42,6 +42,36 @@ def config_from_description(desc: dict, home_xyz=None) -> Config:
     act = desc.get("joints", {}).get("actuated", {})
     cfg.cable_damping = float(act.get("damping", cfg.cable_damping))
     cfg.effort_limit = float(act.get("effort", cfg.effort_limit))
+    cfg.slider_velocity_limit = float(act.get("velocity", cfg.slider_velocity_limit))
+    cfg.passive_damping = float(desc.get("joints", {}).get("passive", {}).get("damping", cfg.passive_damping))
+    set_leg_axes(cfg)
+    return cfg
+
+
+def set_leg_axes(cfg: Config) -> Config:
+    """Leg joint axes of the generator (sdf/gen_cdpr.py:113-125,152,171,209,225,237): the leg frame is the rotation about
+    z x u_fp that takes z onto the frame -> platform direction u_fp; rev_X turns about its first column; the platform-side
+    gimbal axes are written as plain "0 0 1" / "1 0 0" (model frame in SDF 1.4).  Same arithmetic, in the same order, as
+    cdpr_config_default."""
+    for c in range(MAX_CABLES):
+        for k in range(3):
+            cfg.leg_axis_frame[c][k] = cfg.leg_axis_cable[c][k] = cfg.leg_axis_platform[c][k] = 0.0
+    for c in range(cfg.n_cables):
+        ufp = [cfg.home_pos[k] + cfg.platform_anchor[c][k] - cfg.frame_anchor[c][k] for k in range(3)]
+        n = 0.0
+        for k in range(3):
+            n += ufp[k] * ufp[k]
+        n = math.sqrt(n)
+        ufp = [x / n for x in ufp]
+        ax = [-ufp[1], ufp[0], 0.0]
+        sn, cs = math.sqrt(ax[0] * ax[0] + ax[1] * ax[1]), ufp[2]
+        if sn > 0.0:
+            ax[0] /= sn; ax[1] /= sn
+        cfg.leg_axis_frame[c][0] = cs + ax[0] * ax[0] * (1.0 - cs)
+        cfg.leg_axis_frame[c][1] = ax[2] * sn + ax[1] * ax[0] * (1.0 - cs)
+        cfg.leg_axis_frame[c][2] = -ax[1] * sn + ax[2] * ax[0] * (1.0 - cs)
+        cfg.leg_axis_cable[c][2] = 1.0
+        cfg.leg_axis_platform[c][0] = 1.0
     return cfg
 
 

@@ -80,6 +80,19 @@ typedef struct cdpr_config {
   double dt;                                   /* physics step, s; must be a whole number of ns */
   cdpr_pid_params vel_pid, pos_pid;            /* launch/cdpr_gazebo.launch:19-39 */
   double velocity_epsilon;                     /* launch/cdpr_gazebo.launch:18 */
+  /* ---- leg fidelity (the five links of every UPS leg and their passive joints, cube.sdf:344-518). leg_model = 0 (default)
+   * keeps the legs massless: the reduced model. leg_model = 1 adds the configuration-dependent mass matrix of the leg links,
+   * gravity on them and the viscous damping of the five passive revolute joints of each leg (csrc/legs.cuh); it runs in the
+   * flex kernel. Integration semantics are parity-unpinned like the rest of the rigid-body model (no Gazebo/ODE to compare). */
+  int32_t leg_model;
+  double leg_link_mass, leg_link_inertia;      /* 1e-3 kg, 1e-3 kg m^2 isotropic, each link (cube.sdf:359-369,372-382,401-411,447-457,476-486) */
+  double leg_cable_com;                        /* platform anchor -> COM of the cable link along the leg, l/2 = 0.51961524 (cube.sdf:344) */
+  double passive_damping;                      /* 0.01 (cube.sdf:396,425,471,500,515) */
+  double leg_axis_frame[CDPR_MAX_CABLES][3];   /* rev_X axis, fixed in the frame (cube.sdf:390) */
+  double leg_axis_cable[CDPR_MAX_CABLES][3];   /* rev_Zpf axis at the home pose, fixed in the cable link (cube.sdf:506-512) */
+  double leg_axis_platform[CDPR_MAX_CABLES][3];/* rev_Xpf axis, platform body frame (cube.sdf:462-468) */
+  double slider_lower, slider_upper;           /* cube.sdf:436-437: +-0.51961524 m, unreachable with the platform inside the frame; constants only */
+  double slider_velocity_limit;                /* cube.sdf:439: 10 m/s; ODE does not enforce joint velocity limits; constant only */
   double sine_publish_hz;                      /* sinevelocitytest.cpp:7 (100 Hz) */
 } cdpr_config;
 

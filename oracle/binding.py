@@ -40,6 +40,12 @@ class Config(C.Structure):
         ("dt", C.c_double),
         ("vel_pid", PidParams), ("pos_pid", PidParams),
         ("velocity_epsilon", C.c_double),
+        ("leg_model", C.c_int32),
+        ("leg_link_mass", C.c_double), ("leg_link_inertia", C.c_double), ("leg_cable_com", C.c_double), ("passive_damping", C.c_double),
+        ("leg_axis_frame", (C.c_double * 3) * MAX_CABLES),
+        ("leg_axis_cable", (C.c_double * 3) * MAX_CABLES),
+        ("leg_axis_platform", (C.c_double * 3) * MAX_CABLES),
+        ("slider_lower", C.c_double), ("slider_upper", C.c_double), ("slider_velocity_limit", C.c_double),
         ("derive_absolute_time", C.c_int32),
     ]
 
@@ -89,6 +95,10 @@ def lib():
         L.orc_time_double.restype = C.c_double
         L.orc_batch_last_outputs.argtypes = [C.c_void_p, C.c_int64, _dp, _dp, _dp, _dp]
         L.orc_batch_pid_terms.argtypes = [C.c_void_p, C.c_int64, _dp]
+        L.orc_legs_mass_matrix.argtypes = [C.c_void_p, _dp]
+        L.orc_legs_kinetic_energy.argtypes = [C.c_void_p]; L.orc_legs_kinetic_energy.restype = C.c_double
+        L.orc_legs_potential_energy.argtypes = [C.c_void_p]; L.orc_legs_potential_energy.restype = C.c_double
+        L.orc_legs_joint_rates.argtypes = [C.c_void_p, C.c_int, _dp]
         L.orc_batch_targets.argtypes = [C.c_void_p, C.c_int64, _dp, _dp, _dp]
         L.orc_pid_new.argtypes = [C.POINTER(PidParams), C.c_int]; L.orc_pid_new.restype = C.c_void_p
         L.orc_pid_free.argtypes = [C.c_void_p]
@@ -201,6 +211,16 @@ class Batch:
         force = np.ascontiguousarray(force, dtype=np.float64).reshape(self.n, self.nc)
         for i in np.flatnonzero(np.asarray(mask)):
             lib().orc_robot_effort_cmd(self._robot_ptr(int(i)), force[i].ctypes.data_as(C.c_void_p), self.nc)
+
+    def legs_mass_matrix(self, i: int = 0):
+        M = np.empty((6, 6)); lib().orc_legs_mass_matrix(self._robot_ptr(i), M); return M
+
+    def legs_energy(self, i: int = 0):
+        """(kinetic, potential) energy of platform + leg links of robot i (leg model)."""
+        return lib().orc_legs_kinetic_energy(self._robot_ptr(i)), lib().orc_legs_potential_energy(self._robot_ptr(i))
+
+    def legs_joint_rates(self, leg: int, i: int = 0):
+        out = np.empty(5); lib().orc_legs_joint_rates(self._robot_ptr(i), leg, out); return out
 
     def platform_state(self):
         pose = np.empty((self.n, 7)); twist = np.empty((self.n, 6))

@@ -54,6 +54,29 @@ void orc_config_default(orc_config *cfg, int n_cables) {
   p->p_gain = 200.0; p->i_gain = 70.0; p->d_gain = 80.0;
   p->p_cascade = p->d_cascade = 0;                   /* CdprGazeboPlugin.cpp:133 */
   cfg->velocity_epsilon = -0.001;
+  /* leg links and passive joints: P/sdf/cube.sdf:359-518; off by default (reduced model) */
+  cfg->leg_model = 0;
+  cfg->leg_link_mass = 0.001; cfg->leg_link_inertia = 0.001;
+  cfg->leg_cable_com = 0.51961524;   /* l/2, l = |(0.6, 0.6, 0.6)| (gen_cdpr.py:104,124-125; cube.sdf:344) */
+  cfg->passive_damping = 0.01;
+  cfg->slider_lower = -0.51961524; cfg->slider_upper = 0.51961524; cfg->slider_velocity_limit = 10.0;
+  for (int i = 0; i < n_cables && i < ORC_MAX_CABLES; ++i) {
+    /* gen_cdpr.py:113-125,152: the leg frame is the rotation that takes z onto the frame->platform direction about
+     * z x u_fp; rev_X turns about its first column (cube.sdf:390). */
+    double ufp[3], n = 0.0;
+    for (int k = 0; k < 3; ++k) { ufp[k] = cfg->home_pos[k] + cfg->platform_anchor[i][k] - cfg->frame_anchor[i][k]; n += ufp[k] * ufp[k]; }
+    n = sqrt(n);
+    for (int k = 0; k < 3; ++k) ufp[k] /= n;
+    double ax[3] = {-ufp[1], ufp[0], 0.0}; /* z x u_fp */
+    double sn = sqrt(ax[0] * ax[0] + ax[1] * ax[1]), cs = ufp[2];
+    if (sn > 0.0) { ax[0] /= sn; ax[1] /= sn; }
+    /* Rodrigues, first column: e_x cos + (ax x e_x) sin + ax (ax . e_x)(1 - cos) */
+    cfg->leg_axis_frame[i][0] = cs + ax[0] * ax[0] * (1.0 - cs);
+    cfg->leg_axis_frame[i][1] = ax[2] * sn + ax[1] * ax[0] * (1.0 - cs);
+    cfg->leg_axis_frame[i][2] = -ax[1] * sn + ax[2] * ax[0] * (1.0 - cs);
+    cfg->leg_axis_cable[i][2] = 1.0;    /* "0 0 1" in the model frame (SDF 1.4) */
+    cfg->leg_axis_platform[i][0] = 1.0; /* "1 0 0" */
+  }
 }
 
 /* gazebo::common::Time::Double(): sec + nsec * 1e-9 */
@@ -389,6 +412,218 @@ void orc_kinematics_eval(const orc_config *cfg, const double *home_len, const do
   }
 }
 
+/* ------------------------------------------------------------------------- */
+/* Leg fidelity -- PARITY UNPINNED (no Gazebo/ODE here).   */
+/* ------------------------------------------------------------------------- */
+/*
+ * Every UPS leg of P/sdf/cube.sdf:344-518 is a chain  frame -rev_X- virt_X -rev_Y- virt_Y -cable(prismatic)- cable
+ * -rev_Zpf- virt_Ypf -rev_Ypf- virt_Xpf -rev_Xpf- platform  with five links of mass m_l and isotropic inertia I_l.  Its six
+ * joint coordinates are functions of the platform pose, so the robot keeps 6 degrees of freedom; the legs add a
+ * configuration-dependent term to the generalised mass matrix, gravity on the moving leg links and viscous torques on
+ * the five passive revolute joints.
+ *
+ * Geometry (frame coordinates): A frame anchor, B = p + R b platform anchor, u = (A - B)/L.  virt_X and virt_Y have their
+ * centre of mass at A (at rest), virt_Xpf and virt_Ypf at B, the cable link at B + l_c u (cube.sdf:344: a rod centred l/2 from
+ * the platform anchor).  Body triad of the leg (fixed in virt_Y / cable): e2 = rev_Y axis = (u x x0)/c, e1 = e2 x u, u, with x0 the
+ * frame-fixed rev_X axis, s = u.x0, c = sqrt(1 - s^2).  With v_B = v + w x r the anchor velocity:
+ *     rev_Y rate  thy = -(e1 . v_B)/L,   rev_X rate  thx = (e2 . v_B)/(L c),   w_leg = thx x0 + thy e2,
+ *     cable COM velocity  v_c = v_B - (l_c/L)(v_B - u (u . v_B)).
+ * Gimbal at B: a3 = rev_Zpf axis (fixed in the cable link: constant components in the leg triad), a1 = R a1_body the rev_Xpf
+ * axis (fixed in the platform), a2 = (a3 x a1)/|a3 x a1| the rev_Ypf axis.  Closing the loop, w_leg + phi a3 = w + psx a1 + psy a2:
+ *     psy = D . a2,  psx = (D . a1 - t D . a3)/(1 - t^2),  phi = psx t - D . a3,   D = w_leg - w,  t = a3 . a1,
+ *     w(virt_Ypf) = w_leg + phi a3,   w(virt_Xpf) = w + psx a1.
+ * All of these are linear in the platform twist xi = (v, w).  Kinetic energy of the leg = 1/2 |y|^2 with
+ *     y = [ sqrt(I_l) thx | sqrt(2 I_l) w_leg | sqrt(I_l) w(virt_Ypf) | sqrt(I_l) w(virt_Xpf) | sqrt(m_l) v_c | sqrt(2 m_l) v_B ]  (16 rows)
+ * so M(x) = diag(m, m, m, R I_b R^T) + sum_legs Jy^T Jy.  Passive damping: Rayleigh function 1/2 c_p |z|^2, z = the five joint
+ * rates, generalised force -Jz^T z (explicit, like the actuated joint's damping).  Gravity: m_l g . (v_c + 2 v_B) per leg.
+ * Step (same semi-implicit order as App. C.6):  M(x_n) (xi+ - xi)/h = Q_cables + Q_gravity + Q_passive - gyro(platform).
+ * NEGLECTED, stated: the legs' own velocity-product (Coriolis/centrifugal) terms, O(m_l |xi|^2) ~ 1e-6 N at the speeds of
+ * the reference's drivers; ODE's constraint softness; the slider's position stops (|q| <= 0.5196 m cannot be reached with
+ * the platform inside the 0.6 m frame) and velocity limit (ODE does not enforce joint velocity limits).
+ */
+typedef struct {
+  double r[3], u[3], e1[3], e2[3], a1[3], a2[3], a3[3];
+  double L, c, t;
+  const double *x0;
+} leg_geom;
+
+static void leg_triad(const double x0[3], const double u[3], double e1[3], double e2[3], double *c_out) {
+  double s = dot3(u, x0), c = sqrt(1.0 - s * s);
+  for (int k = 0; k < 3; ++k) e1[k] = (x0[k] - s * u[k]) / c;
+  cross(u, e1, e2);
+  *c_out = c;
+}
+
+static void leg_geometry(const orc_config *cfg, const double alpha[3], int i, const double p[3], const double R[3][3], leg_geom *g) {
+  double d[3];
+  mat_vec(R, cfg->platform_anchor[i], g->r);
+  for (int k = 0; k < 3; ++k) d[k] = cfg->frame_anchor[i][k] - p[k] - g->r[k];
+  g->L = sqrt(dot3(d, d));
+  for (int k = 0; k < 3; ++k) g->u[k] = d[k] / g->L;
+  g->x0 = cfg->leg_axis_frame[i];
+  leg_triad(g->x0, g->u, g->e1, g->e2, &g->c);
+  for (int k = 0; k < 3; ++k) g->a3[k] = alpha[0] * g->e1[k] + alpha[1] * g->e2[k] + alpha[2] * g->u[k];
+  mat_vec(R, cfg->leg_axis_platform[i], g->a1);
+  g->t = dot3(g->a3, g->a1);
+  double n[3];
+  cross(g->a3, g->a1, n);
+  double nn = sqrt(1.0 - g->t * g->t);
+  for (int k = 0; k < 3; ++k) g->a2[k] = n[k] / nn;
+}
+
+/* y[16], z[5] (see above) for platform twist (v, w) */
+static void leg_rates(const orc_config *cfg, const leg_geom *g, const double v[3], const double w[3], double y[16], double z[5]) {
+  double wr[3], vB[3];
+  cross(w, g->r, wr);
+  for (int k = 0; k < 3; ++k) vB[k] = v[k] + wr[k];
+  double thy = -dot3(g->e1, vB) / g->L;
+  double thx = dot3(g->e2, vB) / (g->L * g->c);
+  double wleg[3], D[3];
+  for (int k = 0; k < 3; ++k) { wleg[k] = thx * g->x0[k] + thy * g->e2[k]; D[k] = wleg[k] - w[k]; }
+  double psy = dot3(D, g->a2);
+  double Da3 = dot3(D, g->a3);
+  double psx = (dot3(D, g->a1) - g->t * Da3) / (1.0 - g->t * g->t);
+  double phi = psx * g->t - Da3;
+  double uv = dot3(g->u, vB), lam = cfg->leg_cable_com / g->L;
+  double sI = sqrt(cfg->leg_link_inertia), s2I = sqrt(2.0 * cfg->leg_link_inertia);
+  double sm = sqrt(cfg->leg_link_mass), s2m = sqrt(2.0 * cfg->leg_link_mass), sc = sqrt(cfg->passive_damping);
+  y[0] = sI * thx;
+  for (int k = 0; k < 3; ++k) {
+    y[1 + k] = s2I * wleg[k];
+    y[4 + k] = sI * (wleg[k] + phi * g->a3[k]);
+    y[7 + k] = sI * (w[k] + psx * g->a1[k]);
+    y[10 + k] = sm * (vB[k] - lam * (vB[k] - g->u[k] * uv));
+    y[13 + k] = s2m * vB[k];
+  }
+  z[0] = sc * thx; z[1] = sc * thy; z[2] = sc * phi; z[3] = sc * psy; z[4] = sc * psx;
+}
+
+static void legs_home_alpha(const orc_config *cfg, double alpha[ORC_MAX_CABLES][3]) {
+  double R[3][3];
+  quat_to_rot(cfg->home_quat, R);
+  for (int i = 0; i < cfg->n_cables; ++i) {
+    double r[3], d[3], u[3], e1[3], e2[3], c;
+    mat_vec(R, cfg->platform_anchor[i], r);
+    for (int k = 0; k < 3; ++k) d[k] = cfg->frame_anchor[i][k] - cfg->home_pos[k] - r[k];
+    double L = sqrt(dot3(d, d));
+    for (int k = 0; k < 3; ++k) u[k] = d[k] / L;
+    leg_triad(cfg->leg_axis_frame[i], u, e1, e2, &c);
+    alpha[i][0] = dot3(e1, cfg->leg_axis_cable[i]);
+    alpha[i][1] = dot3(e2, cfg->leg_axis_cable[i]);
+    alpha[i][2] = dot3(u, cfg->leg_axis_cable[i]);
+  }
+}
+
+/* M (6x6, symmetric, row-major) of platform + legs, and the extra generalised forces of the legs (gravity on the links,
+ * passive joint damping) added to Q[6] */
+static void legs_assemble(const orc_robot *r, const double R[3][3], double M[6][6], double Q[6]) {
+  const orc_config *cfg = &r->cfg;
+  const double *I = cfg->inertia;
+  double Ib[3][3] = {{I[0], I[3], I[4]}, {I[3], I[1], I[5]}, {I[4], I[5], I[2]}};
+  memset(M, 0, sizeof(double) * 36);
+  for (int k = 0; k < 3; ++k) M[k][k] = cfg->mass;
+  for (int a = 0; a < 3; ++a)
+    for (int b = 0; b < 3; ++b) {
+      double s = 0.0;
+      for (int j = 0; j < 3; ++j)
+        for (int l = 0; l < 3; ++l) s += R[a][j] * Ib[j][l] * R[b][l];
+      M[3 + a][3 + b] = s;
+    }
+  double sm = sqrt(cfg->leg_link_mass), s2m = sqrt(2.0 * cfg->leg_link_mass);
+  for (int i = 0; i < cfg->n_cables; ++i) {
+    leg_geom g;
+    leg_geometry(cfg, r->leg_alpha[i], i, r->p, R, &g);
+    double Jy[16][6], Jz[5][6];
+    for (int k = 0; k < 6; ++k) {
+      double ev[3] = {0, 0, 0}, ew[3] = {0, 0, 0}, y[16], z[5];
+      if (k < 3) ev[k] = 1.0; else ew[k - 3] = 1.0;
+      leg_rates(cfg, &g, ev, ew, y, z);
+      for (int j = 0; j < 16; ++j) Jy[j][k] = y[j];
+      for (int j = 0; j < 5; ++j) Jz[j][k] = z[j];
+    }
+    for (int a = 0; a < 6; ++a)
+      for (int b = 0; b < 6; ++b) {
+        double s = 0.0;
+        for (int j = 0; j < 16; ++j) s += Jy[j][a] * Jy[j][b];
+        M[a][b] += s;
+      }
+    if (Q) {
+      double y[16], z[5];
+      leg_rates(cfg, &g, r->v, r->w, y, z);
+      for (int k = 0; k < 6; ++k) {
+        double damp = 0.0;
+        for (int j = 0; j < 5; ++j) damp += Jz[j][k] * z[j];
+        double grav = 0.0;
+        for (int j = 0; j < 3; ++j) grav += cfg->gravity[j] * (sm * Jy[10 + j][k] + s2m * Jy[13 + j][k]);
+        Q[k] += grav - damp;
+      }
+    }
+  }
+}
+
+/* Cholesky solve of the 6x6 SPD system M x = b */
+static void chol6_solve(double M[6][6], const double b[6], double x[6]) {
+  double Lc[6][6];
+  memset(Lc, 0, sizeof(Lc));
+  for (int j = 0; j < 6; ++j) {
+    double s = M[j][j];
+    for (int k = 0; k < j; ++k) s -= Lc[j][k] * Lc[j][k];
+    Lc[j][j] = sqrt(s);
+    for (int i = j + 1; i < 6; ++i) {
+      double t = M[i][j];
+      for (int k = 0; k < j; ++k) t -= Lc[i][k] * Lc[j][k];
+      Lc[i][j] = t / Lc[j][j];
+    }
+  }
+  double yv[6];
+  for (int i = 0; i < 6; ++i) {
+    double s = b[i];
+    for (int k = 0; k < i; ++k) s -= Lc[i][k] * yv[k];
+    yv[i] = s / Lc[i][i];
+  }
+  for (int i = 5; i >= 0; --i) {
+    double s = yv[i];
+    for (int k = i + 1; k < 6; ++k) s -= Lc[k][i] * x[k];
+    x[i] = s / Lc[i][i];
+  }
+}
+
+void orc_legs_mass_matrix(const orc_robot *r, double Mout[36]) {
+  double R[3][3], M[6][6];
+  quat_to_rot(r->q, R);
+  legs_assemble(r, R, M, NULL);
+  memcpy(Mout, M, sizeof(M));
+}
+double orc_legs_kinetic_energy(const orc_robot *r) {
+  double M[36], xi[6] = {r->v[0], r->v[1], r->v[2], r->w[0], r->w[1], r->w[2]}, e = 0.0;
+  orc_legs_mass_matrix(r, M);
+  for (int a = 0; a < 6; ++a)
+    for (int b = 0; b < 6; ++b) e += 0.5 * xi[a] * M[6 * a + b] * xi[b];
+  return e;
+}
+double orc_legs_potential_energy(const orc_robot *r) {
+  const orc_config *cfg = &r->cfg;
+  double R[3][3], e = -cfg->mass * dot3(cfg->gravity, r->p);
+  quat_to_rot(r->q, R);
+  for (int i = 0; i < cfg->n_cables; ++i) {
+    leg_geom g;
+    leg_geometry(cfg, r->leg_alpha[i], i, r->p, R, &g);
+    double B[3], C[3];
+    for (int k = 0; k < 3; ++k) { B[k] = r->p[k] + g.r[k]; C[k] = B[k] + cfg->leg_cable_com * g.u[k]; }
+    e -= cfg->leg_link_mass * (dot3(cfg->gravity, C) + 2.0 * dot3(cfg->gravity, B));
+  }
+  return e;
+}
+void orc_legs_joint_rates(const orc_robot *r, int leg, double rates[5]) {
+  double R[3][3], y[16], z[5];
+  leg_geom g;
+  quat_to_rot(r->q, R);
+  leg_geometry(&r->cfg, r->leg_alpha[leg], leg, r->p, R, &g);
+  leg_rates(&r->cfg, &g, r->v, r->w, y, z);
+  double sc = sqrt(r->cfg.passive_damping);
+  for (int k = 0; k < 5; ++k) rates[k] = sc > 0.0 ? z[k] / sc : 0.0;
+}
+
 void orc_home_lengths(const orc_config *cfg, double *len) {
   orc_kinematics k;
   double zero[3] = {0, 0, 0};
@@ -400,6 +635,7 @@ void orc_robot_init(orc_robot *r, const orc_config *cfg) {
   memset(r, 0, sizeof(*r));
   r->cfg = *cfg;
   orc_home_lengths(cfg, r->home_len);
+  legs_home_alpha(cfg, r->leg_alpha);
   for (int k = 0; k < 3; ++k) r->p[k] = cfg->home_pos[k];
   for (int k = 0; k < 4; ++k) r->q[k] = cfg->home_quat[k];
   for (int i = 0; i < cfg->n_cables; ++i) orc_cable_init(&r->cable[i], cfg, 0, 0);
@@ -509,6 +745,15 @@ static void robot_step_impl(orc_robot *r, orc_force_fn fn, void *ctx) {
   mat_vec(R, ab, alpha);
 
   const double h = cfg->dt;
+  if (cfg->leg_model) { /* N2: platform + legs, M(x) (xi+ - xi)/h = Q */
+    double Mm[6][6], Q[6] = {F[0], F[1], F[2], M[0], M[1], M[2]}, acc[6]; /* M[] already carries -gyro */
+    legs_assemble(r, R, Mm, Q);
+    chol6_solve(Mm, Q, acc);
+    for (int k = 0; k < 3; ++k) {
+      r->v[k] += h * acc[k];
+      r->w[k] += h * acc[3 + k];
+    }
+  } else
   for (int k = 0; k < 3; ++k) {
     r->v[k] += h * (F[k] / cfg->mass);
     r->w[k] += h * alpha[k];

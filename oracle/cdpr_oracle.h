@@ -65,6 +65,17 @@ typedef struct {
   double dt;                                 /* physics step, s (integer ns) */
   orc_pid_params vel_pid, pos_pid;
   double velocity_epsilon;
+  /* ---- leg fidelity: the five links of every UPS leg and their passive joints, P/sdf/cube.sdf:359-518.
+   * PARITY UNPINNED like the rest of the rigid-body model (no Gazebo/ODE here); see orc_legs_* in cdpr_oracle.c. */
+  int32_t leg_model;                       /* 0: massless legs (reduced model); 1: leg links + passive damping */
+  double leg_link_mass, leg_link_inertia;  /* 1e-3 kg, 1e-3 kg m^2 isotropic, each link (cube.sdf:359-369,372-382,401-411,447-457,476-486) */
+  double leg_cable_com;                    /* platform anchor -> COM of the cable link, along the leg: l/2 = 0.51961524 (cube.sdf:344) */
+  double passive_damping;                  /* 0.01 N m s on the five revolute joints (cube.sdf:396,425,471,500,515) */
+  double leg_axis_frame[ORC_MAX_CABLES][3];    /* rev_X axis, fixed in the frame (cube.sdf:390) */
+  double leg_axis_cable[ORC_MAX_CABLES][3];    /* rev_Zpf axis at home, fixed in the cable link (cube.sdf:506-512: "0 0 1", model frame) */
+  double leg_axis_platform[ORC_MAX_CABLES][3]; /* rev_Xpf axis, platform body frame (cube.sdf:462-468: "1 0 0") */
+  double slider_lower, slider_upper;       /* cube.sdf:436-437 (unreachable inside the frame; carried as constants) */
+  double slider_velocity_limit;            /* cube.sdf:439 (ODE does not enforce joint velocity limits; carried as a constant) */
   int32_t derive_absolute_time; /* 0: window-relative fit (default); 1: reference-style absolute time */
 } orc_config;
 
@@ -103,6 +114,7 @@ typedef struct {
 typedef struct {
   orc_config cfg;
   double home_len[ORC_MAX_CABLES]; /* L0_i */
+  double leg_alpha[ORC_MAX_CABLES][3]; /* rev_Zpf axis in the leg's body triad (e1, e2, u), fixed at the home pose */
   /* platform state in frame coordinates */
   double p[3], q[4] /* w x y z */, v[3], w[3];
   orc_cable cable[ORC_MAX_CABLES];
@@ -162,6 +174,12 @@ void orc_robot_sine(orc_robot *r, double amp, double freq, double phase);
 void orc_robot_step(orc_robot *r);
 void orc_robot_step_ext(orc_robot *r, orc_force_fn fn, void *ctx);
 void orc_robot_platform_state(const orc_robot *r, double pose7[7], double twist6[6]);
+/* leg model diagnostics (tests): 6x6 generalised mass matrix of platform + legs at the robot's pose, row-major; kinetic energy
+ * 1/2 xi^T M xi; potential energy of platform + leg links; the five passive joint rates of leg i for the current twist */
+void orc_legs_mass_matrix(const orc_robot *r, double M[36]);
+double orc_legs_kinetic_energy(const orc_robot *r);
+double orc_legs_potential_energy(const orc_robot *r);
+void orc_legs_joint_rates(const orc_robot *r, int leg, double rates[5]);
 
 /* batched helpers used by the tests and the CPU baseline (OpenMP over robots) */
 void orc_batch_step(orc_robot *robots, int64_t n, int64_t k_steps, int n_threads);

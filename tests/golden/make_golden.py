@@ -46,11 +46,20 @@ def main():
             "parent": j.find("parent").text, "child": j.find("child").text,
             "passive_damping": float(joints[f"rev_X{i}"].find("axis/dynamics/damping").text),
             "leg_link_mass": float(links[f"virt_X{i}"].find("inertial/mass").text),
+            # the five links of the leg and its five passive revolute joints
+            "leg_links": {nm: {"mass": float(links[f"{nm}{i}"].find("inertial/mass").text),
+                               "inertia": [float(links[f"{nm}{i}"].find("inertial/inertia/" + k).text) for k in ("ixx", "iyy", "izz", "ixy", "ixz", "iyz")],
+                               "pose": floats(links[f"{nm}{i}"].find("pose").text)}
+                          for nm in ("cable", "virt_X", "virt_Y", "virt_Xpf", "virt_Ypf")},
+            "leg_joints": {nm: {"axis": floats(joints[f"{nm}{i}"].find("axis/xyz").text), "parent": joints[f"{nm}{i}"].find("parent").text,
+                                "child": joints[f"{nm}{i}"].find("child").text, "damping": float(joints[f"{nm}{i}"].find("axis/dynamics/damping").text)}
+                           for nm in ("rev_X", "rev_Y", "rev_Xpf", "rev_Ypf", "rev_Zpf")},
         })
         i += 1
     g["cables"] = cables
     g["n_links"] = len(links)
     g["n_joints"] = len(joints)
+    g["sdf_version"] = sdf.get("version")
     launch = ET.parse(os.path.join(REF, "launch/cdpr_gazebo.launch")).getroot()
     g["launch_params"] = {p.get("name"): float(p.get("value")) for p in launch.iter("param")}
     hdr = open(os.path.join(REF, "include/cdpr_gazebo/CdprGazeboPlugin.h")).read()

@@ -28,6 +28,13 @@ def to_oracle_config(cfg: cb.Config) -> ob.Config:
         for f in PID_FIELDS:
             setattr(getattr(o, name), f, getattr(getattr(cfg, name), f))
     o.velocity_epsilon = cfg.velocity_epsilon
+    for f in ("leg_model", "leg_link_mass", "leg_link_inertia", "leg_cable_com", "passive_damping", "slider_lower", "slider_upper", "slider_velocity_limit"):
+        setattr(o, f, getattr(cfg, f))
+    for c in range(cb.api.MAX_CABLES):
+        for k in range(3):
+            o.leg_axis_frame[c][k] = cfg.leg_axis_frame[c][k]
+            o.leg_axis_cable[c][k] = cfg.leg_axis_cable[c][k]
+            o.leg_axis_platform[c][k] = cfg.leg_axis_platform[c][k]
     o.derive_absolute_time = 0
     return o
 

@@ -121,7 +121,7 @@ def test_library_exports_every_declared_symbol(built_lib):
     lib = C.CDLL(built_lib)
     for name in declared:
         assert hasattr(lib, name), name
-    assert C.sizeof(cb.Config) == 8 + 8 * (24 + 24 + 3 + 4 + 1 + 6 + 3 + 3) + 2 * C.sizeof(cb.PidParams) + 16
+    assert C.sizeof(cb.Config) == 8 + 8 * (24 + 24 + 3 + 4 + 1 + 6 + 3 + 3) + 2 * C.sizeof(cb.PidParams) + 8 + 8 + 8 * (4 + 72 + 3) + 8
 
 
 def test_create_fails_loudly_without_a_gpu(built_lib):
