@@ -33,6 +33,8 @@ EXPORTS = [
     "cdpr_state_bytes", "cdpr_get_state", "cdpr_set_state",
     "cdpr_set_snapshots", "cdpr_set_snapshot_peers", "cdpr_set_snapshot_multicast", "cdpr_snapshot_count",
     "cdpr_ik", "cdpr_ik_device", "cdpr_rollout",
+    "cdpr_comm_create", "cdpr_comm_destroy", "cdpr_comm_size", "cdpr_comm_last_error", "cdpr_comm_attach_gather", "cdpr_comm_gather_buffer",
+    "cdpr_comm_step", "cdpr_comm_allreduce",
     "cdpr_dterm_weights", "cdpr_padded_instances", "cdpr_device_platform_state",
     "cdpr_measure_fp64_tflops", "cdpr_last_kernel_ms", "cdpr_launch_count", "cdpr_kernel_variant",
 ]
@@ -131,6 +133,14 @@ def load():
     L.cdpr_ik.argtypes = [vp, i64, vp, vp, vp, vp, vp]
     L.cdpr_ik_device.argtypes = [vp, i64, vp, vp]
     L.cdpr_rollout.argtypes = [vp, i64, i64, vp, vp, vp, i64, i64, C.POINTER(dbl * 3), dbl, vp, vp]
+    L.cdpr_comm_create.argtypes = [C.c_int, vp, C.POINTER(vp)]
+    L.cdpr_comm_destroy.argtypes = [vp]
+    L.cdpr_comm_size.argtypes = [vp]
+    L.cdpr_comm_last_error.argtypes = [vp]; L.cdpr_comm_last_error.restype = C.c_char_p
+    L.cdpr_comm_attach_gather.argtypes = [vp, C.POINTER(vp), C.POINTER(i64), i64, i64]
+    L.cdpr_comm_gather_buffer.argtypes = [vp, C.c_int]; L.cdpr_comm_gather_buffer.restype = vp
+    L.cdpr_comm_step.argtypes = [vp, C.POINTER(vp), i64]
+    L.cdpr_comm_allreduce.argtypes = [vp, C.POINTER(vp), i64]
     L.cdpr_dterm_weights.argtypes = [C.POINTER(PidParams), dbl, vp, vp, C.POINTER(C.c_int)]
     L.cdpr_padded_instances.argtypes = [vp]; L.cdpr_padded_instances.restype = i64
     L.cdpr_device_platform_state.argtypes = [vp]; L.cdpr_device_platform_state.restype = vp

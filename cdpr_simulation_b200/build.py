@@ -9,7 +9,7 @@ CSRC = os.path.join(HERE, "csrc")
 # CDPR_B200_LIB selects another build of the same library (kernel tuning experiments only)
 LIB = os.environ.get("CDPR_B200_LIB") or os.path.join(HERE, "libcdpr_b200.so")
 # one translation unit per group of kernel instances: they compile in parallel, then link into the one .so
-SOURCES = ["api.cu", "general.cu", "flex.cu", "fast_nc4_base.cu", "fast_nc4_diag.cu", "fast_nc4_spec.cu", "fast_nc8_base.cu", "fast_nc8_diag.cu",
+SOURCES = ["api.cu", "comm.cu", "general.cu", "flex.cu", "fast_nc4_base.cu", "fast_nc4_diag.cu", "fast_nc4_spec.cu", "fast_nc8_base.cu", "fast_nc8_diag.cu",
            "fast_nc8_spec.cu"]
 HEADERS = ["common.cuh", "physics.cuh", "step_fast.cuh", "step_general.cuh", "step_flex.cuh", "legs.cuh", "misc_kernels.cuh", "launch.h", "fast_inst.cuh",
            "../../include/cdpr_b200.h"]
@@ -60,6 +60,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 HOST_DIR = os.path.join(HERE, "host")
 HOST_BIN = os.path.join(HOST_DIR, "cdpr_sinevelocitytest")
+HOST_MULTI_BIN = os.path.join(HOST_DIR, "cdpr_multigpu_check")   # configs 4 and 5 from a C++ host, one process, G devices
 
 
 def build_host(force: bool = False) -> str:
@@ -71,6 +72,14 @@ def build_host(force: bool = False) -> str:
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("host shim build failed:\n" + r.stdout + r.stderr)
+    multi = os.path.join(HOST_DIR, "multi_gpu_main.cpp")
+    if force or not os.path.exists(HOST_MULTI_BIN) or any(os.path.getmtime(d) > os.path.getmtime(HOST_MULTI_BIN) for d in (multi, build())):
+        cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+        cmd = ["g++", "-O2", "-std=c++17", "-o", HOST_MULTI_BIN, multi, "-I" + os.path.join(cuda, "include"), "-L" + HERE, "-lcdpr_b200",
+               "-L" + os.path.join(cuda, "lib64"), "-lcudart", "-Wl,-rpath,$ORIGIN/..", "-Wl,-rpath," + os.path.join(cuda, "lib64")]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("multi-GPU host driver build failed:\n" + r.stdout + r.stderr)
     return HOST_BIN
 
 

@@ -224,6 +224,28 @@ int cdpr_rollout(cdpr_handle h, int64_t n_robots, int64_t n_seq, const double *p
                  const float *cmds, int64_t n_cmd, int64_t steps_per_cmd, const double target_pos[3], double lambda,
                  void *dev_cost_seq, double *host_cost /* [N] or NULL */);
 
+/* ---- multi-GPU for a C++ host: ONE process, G devices of one box ------------------------- */
+/* Instances shard by contiguous range, one handle per device (created by the caller with cdpr_create(..., device_r, ...)),
+ * no exchange inside a step. The two exchanges of the path run over NVLink peer memory, written by this library's kernels;
+ * no NCCL, no torch. (The one-rank-per-GPU form with NVLS multicast is cdpr_simulation_b200/distributed.py.) */
+typedef struct cdpr_comm *cdpr_comm_t;
+/* enables peer access between all pairs of `devices` (NULL = 0 .. n_devices-1); CDPR_ERR_UNSUPPORTED without P2P */
+int cdpr_comm_create(int n_devices, const int *devices, cdpr_comm_t *out);
+int cdpr_comm_destroy(cdpr_comm_t c);
+int cdpr_comm_size(cdpr_comm_t c);
+const char *cdpr_comm_last_error(cdpr_comm_t c);
+/* Config 4, fused trajectory gather: allocates on every device the FULL buffer [capacity][13][sum instances] and points
+ * handle r (instances[r] robots, on device r of the comm) at all of them: its step kernel stores every snapshot of its
+ * shard into its column range of EVERY device's buffer (cdpr_set_snapshot_peers). */
+int cdpr_comm_attach_gather(cdpr_comm_t c, cdpr_handle *handles, const int64_t *instances, int64_t every, int64_t capacity);
+void *cdpr_comm_gather_buffer(cdpr_comm_t c, int rank); /* device pointer on device `rank` */
+/* one pass of k steps on every device (launches enqueued back to back, then all devices synchronised: after it every
+ * gather buffer holds the snapshots of ALL shards in global instance order) */
+int cdpr_comm_step(cdpr_comm_t c, cdpr_handle *handles, int64_t k_steps);
+/* Config 5, cost all-reduce: dev_vectors[r] = float64 [n_elements] on device r (e.g. the dev_cost_seq of cdpr_rollout);
+ * afterwards every vector holds the sum over the ranks in ascending rank order -- the same bits on every device. */
+int cdpr_comm_allreduce(cdpr_comm_t c, void *const *dev_vectors, int64_t n_elements);
+
 /* ---- D-term constants (host only, no device needed) ---------------------------------------- */
 /* With uniform time stamps Pid::derive (Pid.cpp:193-247) is a fixed FIR: derivative = sum_j fir[j] * y[j], j = 0
  * oldest. fir: [d_buffer_length]. quadratic[3] (may be NULL): fir[j] = q0 + q1 p + q2 p^2 with p = j + 1, valid when

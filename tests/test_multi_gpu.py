@@ -39,3 +39,17 @@ def test_sharded_gather_and_cost_allreduce_equal_single_gpu(built_lib, multicast
     assert "[config 4]" in r.stdout and "bitwise equal to 1-GPU run: True" in r.stdout
     assert "[config 5]" in r.stdout
     assert r.stdout.count("== NCCL all-gather result: True") == world or "symmetric memory unavailable" in r.stdout
+
+
+def test_cpp_host_drives_configs_4_and_5_without_python(built_lib):
+    """The same two exchanges from a C++ host through the C ABI alone (cdpr_comm_*: one process, peer memory over NVLink, the
+    library's own kernels): gathered trajectory bitwise equal to the 1-GPU run on every device, rank-ordered cost all-reduce
+    identical on every device."""
+    g = _gpu_count()
+    if g < 2:
+        pytest.skip(f"needs >= 2 GPUs, {g} visible")
+    from cdpr_simulation_b200 import build as b
+    b.build_host()
+    r = subprocess.run([b.HOST_MULTI_BIN, str(8 if g >= 8 else (4 if g >= 4 else 2))], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    sys.stdout.write(r.stdout[-3000:])
+    assert r.returncode == 0 and "MULTI-GPU C++ HOST CHECK PASSED" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
