@@ -31,6 +31,7 @@ for pid in (cfg.vel_pid, cfg.pos_pid):
     if a.i_limit is not None: pid.i_limit = a.i_limit
 if a.ik:
     import torch
+    if a.instances == 1 << 20: a.instances = 65536       # config 2 at its stated size unless asked otherwise
     pose7, twist6 = wl.c2_poses(a.instances, 0)
     st = np.concatenate([pose7[:, :3], pose7[:, 6:7], pose7[:, 3:6], twist6], axis=1).T.copy()
     d_in = torch.from_numpy(st).cuda(); d_out = torch.empty((a.nc, 8, a.instances), dtype=torch.float64, device="cuda")
