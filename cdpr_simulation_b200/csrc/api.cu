@@ -1099,8 +1099,8 @@ extern "C" int64_t cdpr_snapshot_count(cdpr_handle h) { return h ? std::min(h->s
 static int launch_ik(cdpr_handle h, const IkArgs &A, bool aos) {
   const unsigned grid = grid_for(A.n, 256);
   // device path, even pose count and 16-byte aligned buffers: one thread per (cable, pose pair), double2 accesses
-  if (!aos && (A.n % 2) == 0 && ((uintptr_t)A.state13 % 16) == 0 && ((uintptr_t)A.out % 16) == 0 && (h->L.nc == 4 || h->L.nc == 8)) {
-    k_ik_pair<<<grid_for(A.n / 2, 256) * (unsigned)h->L.nc, 256, 0, h->stream>>>(A);
+  if (!aos && A.n <= (1 << 19) && (A.n % 2) == 0 && ((uintptr_t)A.state13 % 16) == 0 && ((uintptr_t)A.out % 16) == 0 && (h->L.nc == 4 || h->L.nc == 8)) {
+    k_ik_pair<<<dim3(grid_for(A.n / 2, 256), (unsigned)h->L.nc), 256, 0, h->stream>>>(A);
     CK(h, cudaGetLastError());
     ++h->launches;
     return CDPR_OK;

@@ -70,7 +70,10 @@ __global__ void __launch_bounds__(256) k_ik(const __grid_constant__ IkArgs A) {
 // per pose this puts NC times as many warps in flight (65,536 poses: 110 warps per SM instead of 14 -- the sweep is a
 // 6 us kernel, so memory-level parallelism is what it lives on), every access is a 16-byte double2, and a warp's store
 // covers 512 contiguous bytes of one output column.  The 13 state columns are re-read by the NC cable blocks of a pose
-// range; they stay in L2 (6.8 MB at 65,536 poses), so DRAM still sees them once.  Same arithmetic as k_ik.
+// range; they stay in L2 (6.8 MB at 65,536 poses), so DRAM still sees them once -- which is why the host picks this kernel
+// only while the state fits comfortably in L2 (<= 2^19 poses; measured: 10.1 us against 15.5 us for one thread per pose at
+// 65,536 poses, NC = 8) and the one-thread-per-pose k_ik beyond (96 % of the copy bandwidth at 4.2 M poses, where this
+// one drops to 71 % because the re-reads reach DRAM).  Same arithmetic as k_ik.
 struct IkOne { double len, rate, ux, uy, uz, cx, cy, cz; };
 __device__ __forceinline__ IkOne ik_one(const RobotConsts &rc, int c, const FastState &S) {
   const Rot R = make_rot(S);
@@ -89,10 +92,8 @@ __device__ __forceinline__ IkOne ik_one(const RobotConsts &rc, int c, const Fast
   return o;
 }
 __global__ void __launch_bounds__(256) k_ik_pair(const __grid_constant__ IkArgs A) {
-  // cable index fastest across the grid: the NC blocks that share a pose range are scheduled together, so the range's
-  // state columns are fetched from DRAM once and served to the other cables from L2 whatever the sweep size
-  const int c = (int)(blockIdx.x % (unsigned)A.nc);
-  const long long i = 2 * ((long long)(blockIdx.x / (unsigned)A.nc) * blockDim.x + threadIdx.x);
+  const int c = blockIdx.y;
+  const long long i = 2 * ((long long)blockIdx.x * blockDim.x + threadIdx.x);
   if (i >= A.n) return;
   const long long n = A.n;
   const double *p = A.state13 + i;
