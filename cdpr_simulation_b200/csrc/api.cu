@@ -24,7 +24,7 @@ struct cdpr_batch {
   bool general = false;  // controller state in the general layout (time-stamp rings, biquad state): flex and HBM variants
   bool flex = false;     // the on-chip full-semantics kernel (step_flex.cuh): per-instance modes and commands
   bool flex_capable = false;
-  int flex_tpb = 0, flex_ps = 0, flex_ds = 0, flex_nf = 0;
+  int flex_tpb = 0, flex_ps = 0, flex_ds = 0, flex_nf = 0, flex_unroll = 2;
   size_t flex_smem = 0;
   DevLayout L{};
   RobotConsts rc{};
@@ -430,6 +430,7 @@ extern "C" int cdpr_create(const cdpr_config *cfg, int64_t n_instances, int devi
     const bool shape_ok = (cfg->n_cables == 4 || cfg->n_cables == 8) && cfg->vel_pid.d_buffer_length == 11 && cfg->pos_pid.d_buffer_length == 11 &&
                           cfg->vel_pid.d_degree == cfg->pos_pid.d_degree && cfg->vel_pid.cmd_limit != 0.0 && cfg->pos_pid.cmd_limit != 0.0;
     h->flex_nf = flex_stage_slots(h->flex_ps, h->flex_ds);
+    h->flex_unroll = cfg->velocity_epsilon < 0.0 ? 4 : 2;
     h->flex_tpb = flex_tpb();
     h->flex_smem = shape_ok ? flex_smem_bytes(cfg->n_cables, h->flex_nf) : 0;
     h->flex_capable = shape_ok && h->flex_smem <= 227u * 1024u;
@@ -482,7 +483,7 @@ extern "C" int cdpr_create(const cdpr_config *cfg, int64_t n_instances, int devi
       cudaFuncSetAttribute(e.func, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     }
   }
-  if (h->flex) flex_prepare(cfg->n_cables, h->flex_nf);
+  if (h->flex) flex_prepare(cfg->n_cables, h->flex_nf, h->flex_unroll);
   if (cudaStreamSynchronize(h->stream) != cudaSuccess) { h->err = "initialisation kernels failed"; return bail(CDPR_ERR_CUDA); }
   *out = h;
   return CDPR_OK;
@@ -570,7 +571,7 @@ extern "C" int cdpr_set_option(cdpr_handle h, int option, int64_t value) {
       if (!L.win_x && (rc = dev_alloc(h, (void **)&L.win_x, col * L.nc * 2 * L.len))) return rc;
       if (!L.filt && L.casc > 0 && (rc = dev_alloc(h, (void **)&L.filt, col * L.nc * 2 * 2 * L.casc * 4))) return rc;
       h->general = true; h->flex = true;
-      flex_prepare(L.nc, h->flex_nf);
+      flex_prepare(L.nc, h->flex_nf, h->flex_unroll);
       cudaStream_t st = io_begin(h);
       rc = reset_to_load_state(h, st);
       io_end(h);
@@ -746,7 +747,7 @@ static const FastEntry *fast_find(int nc, int mode, bool dmom, int spec) {
 
 static int launch_step(cdpr_handle h, const StepArgs &A) {
   if (h->flex) {
-    flex_launch(h->L.nc, h->flex_nf, grid_for(h->n, h->flex_tpb), A, h->stream);
+    flex_launch(h->L.nc, h->flex_nf, h->flex_unroll, grid_for(h->n, h->flex_tpb), A, h->stream);
   } else if (h->general) {
     general_launch(std::max(h->pc[PID_VEL].degree, h->pc[PID_POS].degree), (unsigned)(h->np / kTpb), A, h->stream);
   } else {

@@ -11,7 +11,7 @@
 //   * the exact clamp chain of Pid::update, statement by statement (no algebraic rewrite; any sign of iGain).
 //
 // On-chip residency per instance:
-//   registers       platform state (13); inside runs of steady steps also the integral errors
+//   registers       platform state (13)
 //   shared memory   per cable: the LIVE Pid's D-term window (ring of 11, slot = step index mod 11 as in the fast kernel),
 //                   its biquad state, integral error and last update time; the latched hold position; the target of the
 //                   instance's mode; the control words
@@ -46,6 +46,11 @@
 namespace cdpr {
 
 constexpr int kFlexLen = 11;
+// UNR = unroll factor of the hot body's cable loop (template parameter of the kernel).  The flex kernel is bound by latency
+// and instruction fetch, not by FP64 issue (1-1.5 warps per scheduler; fully unrolled, 21 % of the stall samples were
+// instruction-cache misses), so a SMALLER body is faster: measured at NC=8 (2^20 x 1000): steady 7.4e9 / 9.5e9 / 8.6e9 / 7.2e9
+// instance-steps/s for UNR = 8 / 4 / 2 / 1, with hold transitions 2.7e9 / 3.4e9 / 4.1e9 / 4.1e9.  The host picks 4 when hold is
+// impossible (velocityEpsilon < 0) and 2 otherwise.  The integrals live in shared memory (rolled loops need runtime indices).
 
 // control word, per (instance, cable): the general variant's layout (step_general.cuh) plus
 //   bits 24-27  fresh: consecutive samples since the live Pid woke up, saturating at 11
@@ -300,10 +305,10 @@ static __device__ __noinline__ int flex_apply_pending(const StepArgs &A, double 
 // least-squares derivative over the HBM ring of a window that spans a gap (degree from the Pid's parameters)
 static __device__ __noinline__ double flex_gap_fit(const StepArgs &A, int c, int k, unsigned oldest, double now, long long i) {
   const int deg = A.pc[k].degree;
-  if (deg == 1) return ls_derivative<1>(A.L, c, k, kFlexLen, oldest, now, i);
-  if (deg == 2) return ls_derivative<2>(A.L, c, k, kFlexLen, oldest, now, i);
-  if (deg == 3) return ls_derivative<3>(A.L, c, k, kFlexLen, oldest, now, i);
-  if (deg == 4) return ls_derivative<4>(A.L, c, k, kFlexLen, oldest, now, i);
+  if (deg == 1) return ls_derivative<1, kFlexLen>(A.L, c, k, kFlexLen, oldest, now, i);
+  if (deg == 2) return ls_derivative<2, kFlexLen>(A.L, c, k, kFlexLen, oldest, now, i);
+  if (deg == 3) return ls_derivative<3, kFlexLen>(A.L, c, k, kFlexLen, oldest, now, i);
+  if (deg == 4) return ls_derivative<4, kFlexLen>(A.L, c, k, kFlexLen, oldest, now, i);
   return 0.0;
 }
 
@@ -405,7 +410,7 @@ static __device__ __noinline__ FastState flex_general_step(const StepArgs &A, Fa
   return S;
 }
 
-template <int NC, int TPB, int NF>
+template <int NC, int TPB, int NF, int UNR>
 __global__ void __launch_bounds__(TPB) k_step_flex(const __grid_constant__ StepArgs A) {
   using M = FlexSmem<NC, TPB, NF>;
   extern __shared__ double smem[];
@@ -467,10 +472,7 @@ __global__ void __launch_bounds__(TPB) k_step_flex(const __grid_constant__ StepA
     return ok;
   };
   bool steady = false, recheck = true;
-  bool hot = false;  // the previous step ran the hot body: integrals live in registers, mLastTime == tprev implicitly
-  double ierr[NC];
-#pragma unroll
-  for (int c = 0; c < NC; ++c) ierr[c] = 0.0;
+  bool hot = false;  // the previous step ran the hot body: mLastTime == tprev implicitly (written back when the run ends)
 
   for (int s = 0; s < A.k_steps; ++s) {
     const bool last = (s == A.k_steps - 1);
@@ -506,7 +508,7 @@ __global__ void __launch_bounds__(TPB) k_step_flex(const __grid_constant__ StepA
     if (pending || (vel_event && mode != MODE_VELOCITY)) {  // rare: a mode may change
       if (hot) {
 #pragma unroll
-        for (int c = 0; c < NC; ++c) { sm[(M::kIerr + c) * TPB] = ierr[c]; sm[(M::kLtime + c) * TPB] = tprev; }
+        for (int c = 0; c < NC; ++c) sm[(M::kLtime + c) * TPB] = tprev;
         hot = false;
       }
       mode = pending ? flex_apply_pending<NC, TPB, NF>(A, sm, sw, mode, vel_pending0, pos_pending0, vel_event, i)
@@ -519,14 +521,12 @@ __global__ void __launch_bounds__(TPB) k_step_flex(const __grid_constant__ StepA
     if (steady && !last) {
       // ================= hot body: straight-line, every cable on its live Pid =================
       if (!hot) {
-#pragma unroll
-        for (int c = 0; c < NC; ++c) ierr[c] = sm[(M::kIerr + c) * TPB];
         hot = true;
       }
       const double dt = __dsub_rn(now, tprev);  // == now - mLastTime of every live Pid
       const Rot R = make_rot(S);
       double fx = rc.mg[0], fy = rc.mg[1], fz = rc.mg[2], mx = 0.0, my = 0.0, mz = 0.0;
-#pragma unroll
+#pragma unroll UNR
       for (int c = 0; c < NC; ++c) {
         const CableKin kin = cable_kin<0, true>(rc, S, R, c);
         double lp = sm[(M::kLastp + c) * TPB], desired, actual;
@@ -541,8 +541,8 @@ __global__ void __launch_bounds__(TPB) k_step_flex(const __grid_constant__ StepA
         if (A.pc[0].degree >= 1) derived = flex_fir<NC * TPB>(A, sm + (M::kRing + c) * TPB, head, e);
         double de = derived;
         if (NF > 0) de = flex_cascade<TPB, NF>(sm + (M::kFilt + c * M::FS + 4 * NF) * TPB, pos ? A.pc[1].d_casc : A.pc[0].d_casc, A.pc[0].df, A.pc[1].df, pos, derived);
-        const FlexPidOut o = flex_pid(g, desired, e, dt, pe, de, ierr[c]);
-        ierr[c] = o.ierr;
+        const FlexPidOut o = flex_pid(g, desired, e, dt, pe, de, sm[(M::kIerr + c) * TPB]);
+        sm[(M::kIerr + c) * TPB] = o.ierr;
         const double eff = (rc.effort_limit >= 0.0) ? clampd(o.cmd, -rc.effort_limit, rc.effort_limit) : o.cmd;
         const double tl = __dmul_rn(fma(-rc.cdamp, kin.qd, eff), kin.il);  // tension / L
         fx = fma(tl, kin.dx, fx); fy = fma(tl, kin.dy, fy); fz = fma(tl, kin.dz, fz);
@@ -554,7 +554,7 @@ __global__ void __launch_bounds__(TPB) k_step_flex(const __grid_constant__ StepA
     } else {
       if (hot) {
 #pragma unroll
-        for (int c = 0; c < NC; ++c) { sm[(M::kIerr + c) * TPB] = ierr[c]; sm[(M::kLtime + c) * TPB] = tprev; }
+        for (int c = 0; c < NC; ++c) sm[(M::kLtime + c) * TPB] = tprev;
         hot = false;
       }
       S = flex_general_step<NC, TPB, NF>(A, S, sm, sw, mode, now, head, sec, nsec, last, i);

@@ -40,31 +40,10 @@ __device__ __forceinline__ unsigned gctl_set(unsigned ctl, int k, unsigned missi
   return ctl | (missing << (2 + 6 * k)) | (head << (14 + 5 * k));
 }
 
-// Derivative at `now` of the degree-D least-squares polynomial through the window (Pid.cpp:203-212 + 219-247), fitted
-// in window-relative, span-scaled time (same polynomial as the reference's absolute-time fit, but well conditioned):
-// one pass over the ring accumulates the normal equations, Gaussian elimination with partial pivoting solves them.
+// normal equations -> derivative coefficient: Gaussian elimination with partial pivoting by compare-and-swap (every index static)
 template <int D>
-__device__ __forceinline__ double ls_derivative(const DevLayout &L, int c, int k, int len, unsigned oldest, double now, long long i) {
+__device__ __forceinline__ double ls_solve(const double (&sx)[2 * D + 1], const double (&sy)[D + 1], double inv_span) {
   constexpr int M = D + 1;
-  const double span = now - L.win_x[win_off(L, c, k, (int)oldest) + i];
-  const double inv_span = 1.0 / span;
-  double sx[2 * D + 1], sy[M];
-#pragma unroll
-  for (int p = 0; p <= 2 * D; ++p) sx[p] = 0.0;
-#pragma unroll
-  for (int p = 0; p < M; ++p) sy[p] = 0.0;
-#pragma unroll 4
-  for (int j = 0; j < len; ++j) {
-    const double x = (L.win_x[win_off(L, c, k, j) + i] - now) * inv_span;
-    const double y = L.win_y[win_off(L, c, k, j) + i];
-    double pw = 1.0;
-#pragma unroll
-    for (int p = 0; p <= 2 * D; ++p) {
-      sx[p] += pw;
-      if (p < M) sy[p] = fma(pw, y, sy[p]);
-      pw *= x;
-    }
-  }
   double A[M][M + 1];
 #pragma unroll
   for (int r = 0; r < M; ++r) {
@@ -102,6 +81,62 @@ __device__ __forceinline__ double ls_derivative(const DevLayout &L, int c, int k
     coef[r] = s / A[r][r];
   }
   return coef[1] * inv_span;
+}
+
+// Derivative at `now` of the degree-D least-squares polynomial through the window (Pid.cpp:203-212 + 219-247), fitted
+// in window-relative, span-scaled time (same polynomial as the reference's absolute-time fit, but well conditioned):
+// one pass over the ring accumulates the normal equations, Gaussian elimination with partial pivoting solves them.
+// LEN > 0: window length known at compile time -- the sample loop is fully unrolled, so all 2 LEN loads are in flight at once
+// (the flex kernel's gap fit is bound by exactly that latency)
+template <int D, int LEN = 0>
+__device__ __forceinline__ double ls_derivative(const DevLayout &L, int c, int k, int len, unsigned oldest, double now, long long i) {
+  constexpr int M = D + 1;
+  if (LEN > 0) {
+    double xs[LEN > 0 ? LEN : 1], ys[LEN > 0 ? LEN : 1];
+#pragma unroll
+    for (int j = 0; j < LEN; ++j) { xs[j] = L.win_x[win_off(L, c, k, j) + i]; ys[j] = L.win_y[win_off(L, c, k, j) + i]; }
+    double oldest_x = xs[0];
+#pragma unroll
+    for (int j = 1; j < LEN; ++j) oldest_x = ((unsigned)j == oldest) ? xs[j] : oldest_x;
+    const double span = now - oldest_x, inv_span = 1.0 / span;
+    double sx[2 * D + 1], sy[M];
+#pragma unroll
+    for (int p = 0; p <= 2 * D; ++p) sx[p] = 0.0;
+#pragma unroll
+    for (int p = 0; p < M; ++p) sy[p] = 0.0;
+#pragma unroll
+    for (int j = 0; j < LEN; ++j) {
+      const double x = (xs[j] - now) * inv_span;
+      double pw = 1.0;
+#pragma unroll
+      for (int p = 0; p <= 2 * D; ++p) {
+        sx[p] += pw;
+        if (p < M) sy[p] = fma(pw, ys[j], sy[p]);
+        pw *= x;
+      }
+    }
+    return ls_solve<D>(sx, sy, inv_span);
+  }
+  const double span = now - L.win_x[win_off(L, c, k, (int)oldest) + i];
+  const double inv_span = 1.0 / span;
+  double sx[2 * D + 1], sy[M];
+#pragma unroll
+  for (int p = 0; p <= 2 * D; ++p) sx[p] = 0.0;
+#pragma unroll
+  for (int p = 0; p < M; ++p) sy[p] = 0.0;
+#pragma unroll 4
+  for (int j = 0; j < len; ++j) {
+    const double x = (L.win_x[win_off(L, c, k, j) + i] - now) * inv_span;
+    const double y = L.win_y[win_off(L, c, k, j) + i];
+    double pw = 1.0;
+#pragma unroll
+    for (int p = 0; p <= 2 * D; ++p) {
+      sx[p] += pw;
+      if (p < M) sy[p] = fma(pw, y, sy[p]);
+      pw *= x;
+    }
+  }
+  return ls_solve<D>(sx, sy, inv_span);
 }
 
 // Pid::derive (Pid.cpp:193-217): overwrite the oldest sample, then the fit once the window is full
