@@ -368,11 +368,12 @@ def own_arm(args):
         # Two handles (A/B) on two streams, each with its own pinned buffers: while pass k computes on one, the D2H of
         # pass k-1 and the H2D of pass k+1 run on the other (calls only enqueue: cdpr_set_async). Every pass still does
         # its own reset + H2D of all inputs + step + D2H of all outputs.  N > 1: every pass also runs the trajectory
-        # gather, and each rank delivers its share of the GATHERED trajectory to the host -- the whole global snapshots
-        # s with s % N == rank, read from its own copy of the gather buffer -- so the host receives the full decimated
-        # trajectory of all N x 2^20 instances once per pass, spread over the N PCIe links.
+        # gather, and each rank delivers its share of the GATHERED trajectory to the host -- all snapshots of the columns of
+        # shard (rank + 1) mod N, read from its own copy of the gather buffer -- so the host receives the full decimated
+        # trajectory of all N x 2^20 instances once per pass, spread evenly over the N PCIe links.
         n_snap = k_sim // args.snapshot_every
-        my_snaps = [s for s in range(n_snap) if s % world == rank] if world > 1 else []
+        src_shard = (rank + 1) % world          # the columns this rank delivers to the host come from its NEIGHBOUR's shard,
+        col0 = src_shard * n                    # i.e. they exist on this GPU only because the gather put them there
         lanes = []
         for lane in range(2):
             st = stream if lane == 0 else torch.cuda.Stream()
@@ -384,7 +385,7 @@ def own_arm(args):
             gl = None
             if world > 1:
                 gl = gather if lane == 0 else make_trajectory_gather(bt, args.snapshot_every, k_sim, st, prefer_fused=(args.gather == "fused"))[0]
-            traj_host = torch.empty((len(my_snaps), 13, world * n), dtype=torch.float64, pin_memory=True) if my_snaps else None
+            traj_host = torch.empty((n_snap, 13, n), dtype=torch.float64, pin_memory=True) if world > 1 else None
             lanes.append((bt, ins, outs, gl, st, traj_host))
         if gather: gather.finish()
 
@@ -401,12 +402,11 @@ def own_arm(args):
             if gl is not None:
                 gl.after_pass(); gl.finish()
                 src = gl.latest() if hasattr(gl, "latest") else None
-                with torch.cuda.stream(st):
-                    for j, s in enumerate(my_snaps):                        # D2H of this rank's share of the gathered trajectory
-                        if src is not None:
-                            traj_host[j].copy_(src[s], non_blocking=True)
-                        else:
-                            traj_host[j].copy_(D.global_trajectory_to_instance_major(gl.recv)[s], non_blocking=True)
+                with torch.cuda.stream(st):                                 # D2H of this rank's share of the gathered trajectory
+                    if src is not None:
+                        traj_host.copy_(src[:, :, col0:col0 + n], non_blocking=True)
+                    else:
+                        traj_host.copy_(gl.recv[src_shard], non_blocking=True)
             bt.platform_state((outs[0].numpy(), outs[1].numpy()))            # D2H
             bt.joint_states(tuple(t.numpy() for t in outs[2:]))
 
@@ -516,7 +516,7 @@ def own_arm(args):
                     "what": "per pass and rank: reset + H2D(pose, twist, sine params) + step + D2H(platform pose/twist, joint states) through the C ABI, "
                             "pinned host buffers, two handles double-buffered so copies overlap the other handle's kernel"
                             + ("" if world == 1 else f"; plus the trajectory gather and the D2H of this rank's share of the gathered trajectory "
-                                                     f"({len(my_snaps)} of {n_snap} global snapshots x 13 x {world * n} float64)")},
+                                                     f"({n_snap} snapshots x 13 x the {n} columns of shard (rank + 1) mod {world}, read from this rank's gather buffer)")},
             "gpu_launches": int(launches),
             "roofline": roofline,
             "cpu_baseline": cpu,
@@ -661,10 +661,12 @@ def side_measurements(cb, wl, torch, device, hbm_peak, fp64_peak):
             g.step(1)
         g.synchronize()
         dt2 = (time.perf_counter() - t0) / reps
-        out["plugin_style_single_robot"] = {"updates_per_s_with_readback": 1.0 / dt1, "steps_per_s_no_readback": 1.0 / dt2,
-                                            "what": "N=1, NC=4, k=1 per call through the C ABI; with readback = set command every 10 steps + step + joint states + platform state (host buffers, synchronous)"}
-        if hasattr(g, "update"):
-            out["plugin_style_single_robot"].update(plugin_update_rate(g, axes, reps))
+        fused = plugin_update_rate(g, axes, reps)
+        out["plugin_style_single_robot"] = {"updates_per_s_with_readback": fused, "updates_per_s_separate_calls": 1.0 / dt1, "steps_per_s_no_readback": 1.0 / dt2,
+                                            "what": "N=1, NC=4, one plugin update per physics step through the C ABI, a new velocity command every 10 steps, host buffers, "
+                                                    "synchronous. with_readback = cdpr_update: command + one step + joint states + platform state in ONE call (the step "
+                                                    "kernel publishes into mapped host memory: one launch + one synchronisation); separate_calls = the round-1 path "
+                                                    "(set command + cdpr_step(1) + cdpr_get_joint_states + cdpr_get_platform_state)"}
     # the hold / filter variant (velocity hold below 2 cm/s + one biquad stage on the P input and on the D output)
     gcfg = cb.default_config(8)
     gcfg.velocity_epsilon = 0.02; gcfg.vel_pid.p_cascade = 1; gcfg.vel_pid.d_cascade = 1
@@ -693,9 +695,7 @@ def plugin_update_rate(g, axes, reps):
     t0 = time.perf_counter()
     for kk in range(reps):
         g.update(axes if kk % 10 == 0 else None)
-    dt = (time.perf_counter() - t0) / reps
-    return {"updates_per_s_fused_call": 1.0 / dt,
-            "fused_call": "cdpr_update: command scatter + k=1 step + joint states + platform state + D2H as one CUDA graph replay per call"}
+    return reps / (time.perf_counter() - t0)
 
 
 def batch_state_gb(batch) -> float:
