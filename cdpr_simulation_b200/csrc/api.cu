@@ -2,6 +2,7 @@
 // No CPU fallback anywhere: without a CUDA device every entry point fails.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -24,7 +25,7 @@ struct cdpr_batch {
   bool general = false;  // controller state in the general layout (time-stamp rings, biquad state): flex and HBM variants
   bool flex = false;     // the on-chip full-semantics kernel (step_flex.cuh): per-instance modes and commands
   bool flex_capable = false;
-  int flex_tpb = 0, flex_ps = 0, flex_ds = 0, flex_nf = 0, flex_unroll = 2;
+  int flex_tpb = 0, flex_ps = 0, flex_ds = 0, flex_nf = 0, flex_unroll = 2, flex_lanes = 1;
   size_t flex_smem = 0;
   DevLayout L{};
   RobotConsts rc{};
@@ -432,7 +433,11 @@ extern "C" int cdpr_create(const cdpr_config *cfg, int64_t n_instances, int devi
     h->flex_nf = flex_stage_slots(h->flex_ps, h->flex_ds);
     h->flex_unroll = cfg->velocity_epsilon < 0.0 ? 4 : 2;
     h->flex_tpb = flex_tpb();
-    h->flex_smem = shape_ok ? flex_smem_bytes(cfg->n_cables, h->flex_nf) : 0;
+    {  // CDPR_FLEX_LANES: tuning override of the number of lanes that share one robot (step_flex.cuh)
+      const char *env = std::getenv("CDPR_FLEX_LANES");
+      h->flex_lanes = flex_lanes_supported(cfg->n_cables, env ? std::atoi(env) : (cfg->n_cables == 8 ? 2 : 1));
+    }
+    h->flex_smem = shape_ok ? flex_smem_bytes(cfg->n_cables, h->flex_nf, h->flex_lanes) : 0;
     h->flex_capable = shape_ok && h->flex_smem <= 227u * 1024u;
   }
   h->flex = h->general && h->flex_capable;
@@ -483,7 +488,7 @@ extern "C" int cdpr_create(const cdpr_config *cfg, int64_t n_instances, int devi
       cudaFuncSetAttribute(e.func, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     }
   }
-  if (h->flex) flex_prepare(cfg->n_cables, h->flex_nf, h->flex_unroll);
+  if (h->flex) flex_prepare(cfg->n_cables, h->flex_nf, h->flex_unroll, h->flex_lanes);
   if (cudaStreamSynchronize(h->stream) != cudaSuccess) { h->err = "initialisation kernels failed"; return bail(CDPR_ERR_CUDA); }
   *out = h;
   return CDPR_OK;
@@ -571,7 +576,7 @@ extern "C" int cdpr_set_option(cdpr_handle h, int option, int64_t value) {
       if (!L.win_x && (rc = dev_alloc(h, (void **)&L.win_x, col * L.nc * 2 * L.len))) return rc;
       if (!L.filt && L.casc > 0 && (rc = dev_alloc(h, (void **)&L.filt, col * L.nc * 2 * 2 * L.casc * 4))) return rc;
       h->general = true; h->flex = true;
-      flex_prepare(L.nc, h->flex_nf, h->flex_unroll);
+      flex_prepare(L.nc, h->flex_nf, h->flex_unroll, h->flex_lanes);
       cudaStream_t st = io_begin(h);
       rc = reset_to_load_state(h, st);
       io_end(h);
@@ -747,7 +752,7 @@ static const FastEntry *fast_find(int nc, int mode, bool dmom, int spec) {
 
 static int launch_step(cdpr_handle h, const StepArgs &A) {
   if (h->flex) {
-    flex_launch(h->L.nc, h->flex_nf, h->flex_unroll, grid_for(h->n, h->flex_tpb), A, h->stream);
+    flex_launch(h->L.nc, h->flex_nf, h->flex_unroll, h->flex_lanes, grid_for(h->np * h->flex_lanes, h->flex_tpb), A, h->stream);
   } else if (h->general) {
     general_launch(std::max(h->pc[PID_VEL].degree, h->pc[PID_POS].degree), (unsigned)(h->np / kTpb), A, h->stream);
   } else {

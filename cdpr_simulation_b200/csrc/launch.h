@@ -29,12 +29,13 @@ void fast_entries_nc8_spec(std::vector<FastEntry> &out);
 // k_step_general<DMAX> (step_general.cuh), DMAX in {2, 4}
 void general_launch(int dmax, unsigned grid, const StepArgs &A, cudaStream_t st);
 
-// k_step_flex<NC, 32, NF, UNR> (step_flex.cuh), NC in {4, 8}; nf = biquad stages held on chip per filter (0, 1 or 4);
-// unroll = cable-loop unroll factor of the hot body (2 or 4)
+// k_step_flex<NC, 32, NF, UNR, LANES> (step_flex.cuh), NC in {4, 8}; nf = biquad stages held on chip per filter (0, 1 or 4);
+// unroll = cable-loop unroll factor of the hot body (2 or 4); lanes = threads that share one robot (1, 2, or 4 at 8 cables)
 int flex_tpb();
 int flex_stage_slots(int p_stages, int d_stages);
-size_t flex_smem_bytes(int nc, int nf);
-void flex_prepare(int nc, int nf, int unroll);
-void flex_launch(int nc, int nf, int unroll, unsigned grid, const StepArgs &A, cudaStream_t st);
+int flex_lanes_supported(int nc, int lanes);
+size_t flex_smem_bytes(int nc, int nf, int lanes);
+void flex_prepare(int nc, int nf, int unroll, int lanes);
+void flex_launch(int nc, int nf, int unroll, int lanes, unsigned grid, const StepArgs &A, cudaStream_t st);
 
 }  // namespace cdpr

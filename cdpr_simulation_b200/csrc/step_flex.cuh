@@ -188,116 +188,120 @@ __device__ __forceinline__ FlexPidOut flex_pid(const FlexGains &g, double desire
 // Flush the live Pid `k` of cable `c` to HBM: integral, last update time, biquad state, and -- when the window is entirely
 // fresh -- the window itself in logical order from the ring head on.  slot_now / (sec, nsec) = ring slot and time of the
 // newest sample.
-template <int NC, int TPB, int NF>
-static __device__ __noinline__ void flex_flush(const StepArgs &A, double *sm, unsigned ctl, int c, int k, int slot_now, int sec, int nsec, long long i) {
-  using M = FlexSmem<NC, TPB, NF>;
+// (c = cable index within the lane: shared-memory columns; cg = c0 + c = cable index of the robot: HBM columns)
+template <int CPL, int TPB, int NF>
+static __device__ __noinline__ void flex_flush(const StepArgs &A, double *sm, unsigned ctl, int c0, int c, int k, int slot_now, int sec, int nsec, long long i) {
+  using M = FlexSmem<CPL, TPB, NF>;
   const DevLayout &L = A.L;
-  L.pid[pid_off(L, c, k, PID_I_ERR) + i] = sm[(M::kIerr + c) * TPB];
-  L.pid[pid_off(L, c, k, PID_LAST_TIME) + i] = sm[(M::kLtime + c) * TPB];
+  const int cg = c0 + c;
+  L.pid[pid_off(L, cg, k, PID_I_ERR) + i] = sm[(M::kIerr + c) * TPB];
+  L.pid[pid_off(L, cg, k, PID_LAST_TIME) + i] = sm[(M::kLtime + c) * TPB];
   const double *filt = sm + (M::kFilt + c * M::FS) * TPB;
   for (int s = 0; s < A.flex_ps; ++s)
-    for (int f = 0; f < 4; ++f) L.filt[filt_off(L, c, k, 0, s, f) + i] = filt[(s * 4 + f) * TPB];
+    for (int f = 0; f < 4; ++f) L.filt[filt_off(L, cg, k, 0, s, f) + i] = filt[(s * 4 + f) * TPB];
   for (int s = 0; s < A.flex_ds; ++s)
-    for (int f = 0; f < 4; ++f) L.filt[filt_off(L, c, k, 1, s, f) + i] = filt[((NF + s) * 4 + f) * TPB];
+    for (int f = 0; f < 4; ++f) L.filt[filt_off(L, cg, k, 1, s, f) + i] = filt[((NF + s) * 4 + f) * TPB];
   if (fctl_fresh(ctl) >= (unsigned)kFlexLen) {
     int hd = (int)gctl_head(ctl, k);  // oldest slot of the HBM ring; unchanged by a full rewrite
     for (int j = 0; j < kFlexLen; ++j) {
       const int age = kFlexLen - 1 - j;
       int sl = slot_now - age;
       sl += (sl < 0) ? kFlexLen : 0;
-      L.win_y[win_off(L, c, k, hd) + i] = sm[(M::kRing + sl * NC + c) * TPB];
-      L.win_x[win_off(L, c, k, hd) + i] = stamp_back(sec, nsec, A.dt_ns, age);
+      L.win_y[win_off(L, cg, k, hd) + i] = sm[(M::kRing + sl * CPL + c) * TPB];
+      L.win_x[win_off(L, cg, k, hd) + i] = stamp_back(sec, nsec, A.dt_ns, age);
       hd = (hd + 1 == kFlexLen) ? 0 : hd + 1;
     }
   }
 }
 
 // Wake Pid `k` of cable `c`: biquad state, last update time and integral error into shared memory.
-template <int NC, int TPB, int NF>
-static __device__ __noinline__ void flex_wake(const StepArgs &A, double *sm, int c, int k, long long i) {
-  using M = FlexSmem<NC, TPB, NF>;
+template <int CPL, int TPB, int NF>
+static __device__ __noinline__ void flex_wake(const StepArgs &A, double *sm, int c0, int c, int k, long long i) {
+  using M = FlexSmem<CPL, TPB, NF>;
   const DevLayout &L = A.L;
+  const int cg = c0 + c;
   double *filt = sm + (M::kFilt + c * M::FS) * TPB;
   for (int s = 0; s < A.flex_ps; ++s)
-    for (int f = 0; f < 4; ++f) filt[(s * 4 + f) * TPB] = L.filt[filt_off(L, c, k, 0, s, f) + i];
+    for (int f = 0; f < 4; ++f) filt[(s * 4 + f) * TPB] = L.filt[filt_off(L, cg, k, 0, s, f) + i];
   for (int s = 0; s < A.flex_ds; ++s)
-    for (int f = 0; f < 4; ++f) filt[((NF + s) * 4 + f) * TPB] = L.filt[filt_off(L, c, k, 1, s, f) + i];
-  sm[(M::kLtime + c) * TPB] = L.pid[pid_off(L, c, k, PID_LAST_TIME) + i];
-  sm[(M::kIerr + c) * TPB] = L.pid[pid_off(L, c, k, PID_I_ERR) + i];
+    for (int f = 0; f < 4; ++f) filt[((NF + s) * 4 + f) * TPB] = L.filt[filt_off(L, cg, k, 1, s, f) + i];
+  sm[(M::kLtime + c) * TPB] = L.pid[pid_off(L, cg, k, PID_LAST_TIME) + i];
+  sm[(M::kIerr + c) * TPB] = L.pid[pid_off(L, cg, k, PID_I_ERR) + i];
 }
 
 // The window of a live Pid, HBM ring (logical order) -> shared-memory ring (step-aligned: newest sample in slot_now).
-template <int NC, int TPB, int NF>
-static __device__ __noinline__ void flex_load_window(const StepArgs &A, double *sm, unsigned ctl, int c, int k, int slot_now, long long i) {
-  using M = FlexSmem<NC, TPB, NF>;
+template <int CPL, int TPB, int NF>
+static __device__ __noinline__ void flex_load_window(const StepArgs &A, double *sm, unsigned ctl, int c0, int c, int k, int slot_now, long long i) {
+  using M = FlexSmem<CPL, TPB, NF>;
   const DevLayout &L = A.L;
   int hd = (int)gctl_head(ctl, k);
   for (int j = 0; j < kFlexLen; ++j) {
     const int age = kFlexLen - 1 - j;
     int sl = slot_now - age;
     sl += (sl < 0) ? kFlexLen : 0;
-    sm[(M::kRing + sl * NC + c) * TPB] = L.win_y[win_off(L, c, k, hd) + i];
+    sm[(M::kRing + sl * CPL + c) * TPB] = L.win_y[win_off(L, c0 + c, k, hd) + i];
     hd = (hd + 1 == kFlexLen) ? 0 : hd + 1;
   }
 }
 
 // Pid::reset (Pid.cpp:100-115) of Pid `k` on every cable of this instance (setVelocityTarget / setPositionTarget on a mode
 // change, JointForceCalculator.cpp:99-119); mLastTime is kept.
-template <int NC, int TPB, int NF>
-static __device__ __noinline__ void flex_reset_pid(const StepArgs &A, double *sm, unsigned *sw, int k, long long i) {
-  using M = FlexSmem<NC, TPB, NF>;
+template <int CPL, int TPB, int NF>
+static __device__ __noinline__ void flex_reset_pid(const StepArgs &A, double *sm, unsigned *sw, int c0, int k, long long i) {
+  using M = FlexSmem<CPL, TPB, NF>;
   const DevLayout &L = A.L;
-  for (int c = 0; c < NC; ++c) {
+  for (int c = 0; c < CPL; ++c) {
+    const int cg = c0 + c;
     unsigned ctl = sw[c * TPB];
     if (fctl_live(ctl) == (unsigned)(k + 1)) {  // the live Pid: its state is on chip
       sm[(M::kIerr + c) * TPB] = 0.0;
       for (int f = 0; f < M::FS; ++f) sm[(M::kFilt + c * M::FS + f) * TPB] = 0.0;
       ctl = fctl_set_fresh(ctl, 0u);
     }
-    L.pid[pid_off(L, c, k, PID_P_ERR) + i] = 0.0;
-    L.pid[pid_off(L, c, k, PID_I_ERR) + i] = 0.0;
-    L.pid[pid_off(L, c, k, PID_D_ERR) + i] = 0.0;
-    L.pid[pid_off(L, c, k, PID_CMD) + i] = 0.0;
+    L.pid[pid_off(L, cg, k, PID_P_ERR) + i] = 0.0;
+    L.pid[pid_off(L, cg, k, PID_I_ERR) + i] = 0.0;
+    L.pid[pid_off(L, cg, k, PID_D_ERR) + i] = 0.0;
+    L.pid[pid_off(L, cg, k, PID_CMD) + i] = 0.0;
     if (L.filt)
       for (int pd = 0; pd < 2; ++pd)
         for (int s = 0; s < L.casc; ++s)
-          for (int f = 0; f < 4; ++f) L.filt[filt_off(L, c, k, pd, s, f) + i] = 0.0;
+          for (int f = 0; f < 4; ++f) L.filt[filt_off(L, cg, k, pd, s, f) + i] = 0.0;
     ctl &= ~(1u << k);
     sw[c * TPB] = gctl_set(ctl, k, (unsigned)kFlexLen, 0u);  // wasLast cleared, missing = 11, ring head 0
   }
 }
 
-template <int NC, int TPB, int NF>
-static __device__ __noinline__ void flex_load_targets(const StepArgs &A, double *sm, int mode, long long i) {
-  using M = FlexSmem<NC, TPB, NF>;
+template <int CPL, int TPB, int NF>
+static __device__ __noinline__ void flex_load_targets(const StepArgs &A, double *sm, int c0, int mode, long long i) {
+  using M = FlexSmem<CPL, TPB, NF>;
   const int field = (mode == MODE_FORCE) ? CAB_FORCE_CMD : (mode == MODE_POSITION) ? CAB_POS_TARGET : CAB_VEL_TARGET;
-  for (int c = 0; c < NC; ++c) sm[(M::kTgt + c) * TPB] = A.L.cab[cab_off(A.L, c, field) + i];
+  for (int c = 0; c < CPL; ++c) sm[(M::kTgt + c) * TPB] = A.L.cab[cab_off(A.L, c0 + c, field) + i];
 }
 
 // A velocity command reached this instance while it was not in Velocity mode: reset the velocity Pid, switch
-template <int NC, int TPB, int NF>
-static __device__ __noinline__ int flex_enter_velocity(const StepArgs &A, double *sm, unsigned *sw, long long i) {
-  flex_reset_pid<NC, TPB, NF>(A, sm, sw, PID_VEL, i);
+template <int CPL, int TPB, int NF>
+static __device__ __noinline__ int flex_enter_velocity(const StepArgs &A, double *sm, unsigned *sw, int c0, long long i) {
+  flex_reset_pid<CPL, TPB, NF>(A, sm, sw, c0, PID_VEL, i);
   return MODE_VELOCITY;
 }
 
 // The commands latched before this launch, applied in the first step (CdprGazeboPlugin.cpp:206-219): velocity fan-out, then
 // position fan-out.  `vel_event`: a velocity command of THIS step (sine publisher / command table) already wrote the targets.
-template <int NC, int TPB, int NF>
-static __device__ __noinline__ int flex_apply_pending(const StepArgs &A, double *sm, unsigned *sw, int mode, bool vel_pending, bool pos_pending, bool vel_event, long long i) {
-  using M = FlexSmem<NC, TPB, NF>;
+template <int CPL, int TPB, int NF>
+static __device__ __noinline__ int flex_apply_pending(const StepArgs &A, double *sm, unsigned *sw, int c0, int mode, bool vel_pending, bool pos_pending, bool vel_event, long long i) {
+  using M = FlexSmem<CPL, TPB, NF>;
   const DevLayout &L = A.L;
-  if (vel_pending && !vel_event && mode != MODE_VELOCITY) flex_load_targets<NC, TPB, NF>(A, sm, MODE_VELOCITY, i);
+  if (vel_pending && !vel_event && mode != MODE_VELOCITY) flex_load_targets<CPL, TPB, NF>(A, sm, c0, MODE_VELOCITY, i);
   if (vel_pending || vel_event) {
-    if (mode != MODE_VELOCITY) flex_reset_pid<NC, TPB, NF>(A, sm, sw, PID_VEL, i);
+    if (mode != MODE_VELOCITY) flex_reset_pid<CPL, TPB, NF>(A, sm, sw, c0, PID_VEL, i);
     mode = MODE_VELOCITY;
   }
   if (pos_pending) {
     if (vel_event)  // the velocity targets just latched must survive in HBM before the position targets replace them on chip
-      for (int c = 0; c < NC; ++c) L.cab[cab_off(L, c, CAB_VEL_TARGET) + i] = sm[(M::kTgt + c) * TPB];
-    if (mode != MODE_POSITION) flex_reset_pid<NC, TPB, NF>(A, sm, sw, PID_POS, i);
+      for (int c = 0; c < CPL; ++c) L.cab[cab_off(L, c0 + c, CAB_VEL_TARGET) + i] = sm[(M::kTgt + c) * TPB];
+    if (mode != MODE_POSITION) flex_reset_pid<CPL, TPB, NF>(A, sm, sw, c0, PID_POS, i);
     mode = MODE_POSITION;
-    flex_load_targets<NC, TPB, NF>(A, sm, MODE_POSITION, i);
+    flex_load_targets<CPL, TPB, NF>(A, sm, c0, MODE_POSITION, i);
   }
   return mode;
 }
@@ -312,18 +316,31 @@ static __device__ __noinline__ double flex_gap_fit(const StepArgs &A, int c, int
   return 0.0;
 }
 
-// One physics step with every flag honoured: a rolled loop over the cables, state in the thread's shared-memory columns.
-template <int NC, int TPB, int NF>
-static __device__ __noinline__ FastState flex_general_step(const StepArgs &A, FastState S, double *sm, unsigned *sw, int mode, double now, int head, int sec,
-                                                           int nsec, bool last, long long i) {
-  using M = FlexSmem<NC, TPB, NF>;
+// Sum of one value over the LANES lanes of an instance (adjacent threads).  Pairwise, so every lane ends with the same bits.
+template <int LANES>
+__device__ __forceinline__ double lane_sum(double v) {
+  if (LANES >= 2) v += __shfl_xor_sync(0xffffffffu, v, 1);
+  if (LANES >= 4) v += __shfl_xor_sync(0xffffffffu, v, 2);
+  return v;
+}
+struct Wrench6 { double fx, fy, fz, mx, my, mz; };
+
+// One physics step of THIS LANE's cables with every flag honoured: a rolled loop over the cables, state in the thread's
+// shared-memory columns.  Returns the lane's share of the wrench (the lead lane's includes gravity).
+template <int CPL, int TPB, int NF>
+static __device__ __noinline__ Wrench6 flex_general_step(const StepArgs &A, FastState S, double *sm, unsigned *sw, int c0, bool lead, bool valid, int mode,
+                                                         double now, int head, int sec, int nsec, bool last, long long i) {
+  using M = FlexSmem<CPL, TPB, NF>;
   const DevLayout &L = A.L;
   const RobotConsts &rc = A.rc;
   const Rot R = make_rot(S);
-  double fx = rc.mg[0], fy = rc.mg[1], fz = rc.mg[2], mx = 0.0, my = 0.0, mz = 0.0;
+  Wrench6 W;
+  W.fx = lead ? rc.mg[0] : 0.0; W.fy = lead ? rc.mg[1] : 0.0; W.fz = lead ? rc.mg[2] : 0.0;
+  W.mx = 0.0; W.my = 0.0; W.mz = 0.0;
 #pragma unroll 1
-  for (int c = 0; c < NC; ++c) {
-    const CableKin kin = cable_kin<0, true>(rc, S, R, c);
+  for (int c = 0; c < CPL; ++c) {
+    const int cg = c0 + c;
+    const CableKin kin = cable_kin<0, true>(rc, S, R, cg);
     const double target = sm[(M::kTgt + c) * TPB];
     unsigned run = 0u;  // 0 none (Force mode), 1 velocity Pid, 2 position Pid
     double desired = 0.0, actual = 0.0, force = 0.0;
@@ -342,8 +359,8 @@ static __device__ __noinline__ FastState flex_general_step(const StepArgs &A, Fa
       int slot_prev = head - 1;
       slot_prev += (slot_prev < 0) ? kFlexLen : 0;
       // the ring's newest sample belongs to the PREVIOUS step (this step's has not been pushed yet)
-      if (live != 0u) flex_flush<NC, TPB, NF>(A, sm, w, c, (int)live - 1, slot_prev, sec, nsec - A.dt_ns, i);
-      if (run != 0u) flex_wake<NC, TPB, NF>(A, sm, c, (int)run - 1, i);
+      if (live != 0u) flex_flush<CPL, TPB, NF>(A, sm, w, c0, c, (int)live - 1, slot_prev, sec, nsec - A.dt_ns, i);
+      if (run != 0u) flex_wake<CPL, TPB, NF>(A, sm, c0, c, (int)run - 1, i);
       w = fctl_set_fresh(fctl_set_live(w, run), 0u);
     }
     if (run != 0u) {
@@ -352,7 +369,7 @@ static __device__ __noinline__ FastState flex_general_step(const StepArgs &A, Fa
       if (!((w >> k) & 1u)) {  // first update after a reset: Pid.cpp:123-126
         w |= 1u << k;
         force = 0.0;
-        if (last) L.pid[pid_off(L, c, k, PID_CMD) + i] = 0.0;
+        if (last) L.pid[pid_off(L, cg, k, PID_CMD) + i] = 0.0;
       } else {  // Pid.cpp:127-187
         const FlexGains g = flex_gains(A, pos);
         const double e = __dsub_rn(desired, actual);
@@ -360,20 +377,20 @@ static __device__ __noinline__ FastState flex_general_step(const StepArgs &A, Fa
         double pe = e;
         if (NF > 0) pe = flex_cascade<TPB, NF>(sm + (M::kFilt + c * M::FS) * TPB, pos ? A.pc[1].p_casc : A.pc[0].p_casc, A.pc[0].pf, A.pc[1].pf, pos, e);
         // ---- derive (Pid.cpp:193-217): dt > 0 always (sim time advances every step)
-        sm[(M::kRing + head * NC + c) * TPB] = e;
+        sm[(M::kRing + head * CPL + c) * TPB] = e;
         unsigned fresh = fctl_fresh(w), missing = gctl_missing(w, k), hd = gctl_head(w, k);
         fresh += (fresh < (unsigned)kFlexLen) ? 1u : 0u;
         missing -= (missing > 0u) ? 1u : 0u;
         if (fresh < (unsigned)kFlexLen) {  // the window still holds older samples: keep the HBM ring current
-          L.win_x[win_off(L, c, k, (int)hd) + i] = now;
-          L.win_y[win_off(L, c, k, (int)hd) + i] = e;
+          L.win_x[win_off(L, cg, k, (int)hd) + i] = now;
+          L.win_y[win_off(L, cg, k, (int)hd) + i] = e;
           hd = (hd + 1u == (unsigned)kFlexLen) ? 0u : hd + 1u;
         }
         w = fctl_set_fresh(gctl_set(w, k, missing, hd), fresh);
         double derived = 0.0;
         if (missing == 0u && A.pc[0].degree >= 1) {  // both Pids fit the same degree in this variant
-          if (fresh >= (unsigned)kFlexLen) derived = flex_fir<NC * TPB>(A, sm + (M::kRing + c) * TPB, head, e);
-          else derived = flex_gap_fit(A, c, k, hd, now, i);
+          if (fresh >= (unsigned)kFlexLen) derived = flex_fir<CPL * TPB>(A, sm + (M::kRing + c) * TPB, head, e);
+          else derived = flex_gap_fit(A, cg, k, hd, now, i);
         }
         double de = derived;
         if (NF > 0) de = flex_cascade<TPB, NF>(sm + (M::kFilt + c * M::FS + 4 * NF) * TPB, pos ? A.pc[1].d_casc : A.pc[0].d_casc, A.pc[0].df, A.pc[1].df, pos, derived);
@@ -381,13 +398,13 @@ static __device__ __noinline__ FastState flex_general_step(const StepArgs &A, Fa
         sm[(M::kIerr + c) * TPB] = o.ierr;
         force = o.cmd;
         if (last) {
-          L.pid[pid_off(L, c, k, PID_P_ERR) + i] = pe;
-          L.pid[pid_off(L, c, k, PID_D_ERR) + i] = de;
-          L.pid[pid_off(L, c, k, PID_CMD) + i] = o.cmd;
-          L.cab[cab_off(L, c, CAB_TERM_P) + i] = o.p_term;
-          L.cab[cab_off(L, c, CAB_TERM_I) + i] = o.i_term_pre;
-          L.cab[cab_off(L, c, CAB_TERM_D) + i] = o.d_term;
-          L.cab[cab_off(L, c, CAB_DESIRED) + i] = desired;
+          L.pid[pid_off(L, cg, k, PID_P_ERR) + i] = pe;
+          L.pid[pid_off(L, cg, k, PID_D_ERR) + i] = de;
+          L.pid[pid_off(L, cg, k, PID_CMD) + i] = o.cmd;
+          L.cab[cab_off(L, cg, CAB_TERM_P) + i] = o.p_term;
+          L.cab[cab_off(L, cg, CAB_TERM_I) + i] = o.i_term_pre;
+          L.cab[cab_off(L, cg, CAB_TERM_D) + i] = o.d_term;
+          L.cab[cab_off(L, cg, CAB_DESIRED) + i] = desired;
         }
       }
       sm[(M::kLtime + c) * TPB] = now;
@@ -395,31 +412,38 @@ static __device__ __noinline__ FastState flex_general_step(const StepArgs &A, Fa
     sw[c * TPB] = w;
     const double eff = (rc.effort_limit >= 0.0) ? clampd(force, -rc.effort_limit, rc.effort_limit) : force;
     if (last) {
-      publish_joint(A, NC, c, kin.qp, kin.qd, eff, i);
-      L.cab[cab_off(L, c, CAB_EFFORT) + i] = eff;
-      L.cab[cab_off(L, c, CAB_PID_FORCE) + i] = force;
+      if (valid) publish_joint(A, L.nc, cg, kin.qp, kin.qd, eff, i);
+      L.cab[cab_off(L, cg, CAB_EFFORT) + i] = eff;
+      L.cab[cab_off(L, cg, CAB_PID_FORCE) + i] = force;
     }
     const double tl = __dmul_rn(fma(-rc.cdamp, kin.qd, eff), kin.il);  // tension / L
-    fx = fma(tl, kin.dx, fx); fy = fma(tl, kin.dy, fy); fz = fma(tl, kin.dz, fz);
-    mx = fma(tl, kin.cx, mx); my = fma(tl, kin.cy, my); mz = fma(tl, kin.cz, mz);
+    W.fx = fma(tl, kin.dx, W.fx); W.fy = fma(tl, kin.dy, W.fy); W.fz = fma(tl, kin.dz, W.fz);
+    W.mx = fma(tl, kin.cx, W.mx); W.my = fma(tl, kin.cy, W.my); W.mz = fma(tl, kin.cz, W.mz);
   }
-  if (last) publish_platform(A, S, i);
-  if (rc.leg_model) return legs_step(A, S, fx, fy, fz, mx, my, mz);
-  if (rc.diag_inertia) rigid_body_step<SPEC_DIAG>(rc, S, R, fx, fy, fz, mx, my, mz);
-  else rigid_body_step<0>(rc, S, R, fx, fy, fz, mx, my, mz);
-  return S;
+  return W;
 }
 
-template <int NC, int TPB, int NF, int UNR>
+// LANES adjacent threads share one robot, CPL = NC / LANES cables each: every lane keeps a copy of the platform state, works
+// the force law of its own cables out of its own shared-memory columns, the lanes' wrench shares are summed with
+// __shfl_xor_sync and every lane integrates the same platform step (same bits).  More lanes = less shared memory and fewer
+// registers per thread = more resident warps, which is what this latency-bound kernel needs; the price is the replicated
+// platform update.  Instances beyond n (the padding of every column to a multiple of 128) run like any other and are
+// only kept from writing to the caller's buffers: the shuffles need whole warps.
+template <int NC, int TPB, int NF, int UNR, int LANES>
 __global__ void __launch_bounds__(TPB) k_step_flex(const __grid_constant__ StepArgs A) {
-  using M = FlexSmem<NC, TPB, NF>;
+  constexpr int CPL = NC / LANES;
+  static_assert(CPL * LANES == NC && (LANES == 1 || LANES == 2 || LANES == 4), "lanes must divide the cables");
+  using M = FlexSmem<CPL, TPB, NF>;
   extern __shared__ double smem[];
   const int tid = (int)threadIdx.x;
-  const long long i = (long long)blockIdx.x * TPB + tid;
-  if (i >= A.L.n) return;  // no block-level synchronisation anywhere below
+  const long long gt = (long long)blockIdx.x * TPB + tid;
+  const long long i = gt / LANES;
+  const int c0 = (int)(gt % LANES) * CPL;
+  const bool lead = (c0 == 0);
   const DevLayout &L = A.L;
   const RobotConsts &rc = A.rc;
   const long long np = L.np;
+  const bool valid = i < L.n;  // i < np always: the grid covers the padded columns
   double *sm = smem + tid;
   unsigned *sw = reinterpret_cast<unsigned *>(smem + M::kWords * TPB) + tid;
 
@@ -429,20 +453,20 @@ __global__ void __launch_bounds__(TPB) k_step_flex(const __grid_constant__ StepA
   int mode = (int)(ictl & 3u);
   const bool vel_pending0 = (ictl & ICTL_VEL_PENDING) != 0u, pos_pending0 = (ictl & ICTL_POS_PENDING) != 0u;
   const int head0 = (int)(A.n0 % kFlexLen);  // ring slot of the newest sample already in the windows
-  flex_load_targets<NC, TPB, NF>(A, sm, mode, i);
+  flex_load_targets<CPL, TPB, NF>(A, sm, c0, mode, i);
 #pragma unroll 1
-  for (int c = 0; c < NC; ++c) {
-    const unsigned w = L.ctl[(long long)c * np + i];
+  for (int c = 0; c < CPL; ++c) {
+    const unsigned w = L.ctl[(long long)(c0 + c) * np + i];
     sw[c * TPB] = w;
-    sm[(M::kLastp + c) * TPB] = L.cab[cab_off(L, c, CAB_LAST_POS) + i];
+    sm[(M::kLastp + c) * TPB] = L.cab[cab_off(L, c0 + c, CAB_LAST_POS) + i];
     sm[(M::kIerr + c) * TPB] = 0.0;
     sm[(M::kLtime + c) * TPB] = 0.0;
     const unsigned live = fctl_live(w);
     if (live != 0u) {
-      flex_wake<NC, TPB, NF>(A, sm, c, (int)live - 1, i);
+      flex_wake<CPL, TPB, NF>(A, sm, c0, c, (int)live - 1, i);
       // the HBM ring is current at a launch boundary whatever `fresh` is; its newest `fresh` samples are the consecutive
       // steps the FIR will need once 11 of them are there, the older ones land in slots that are overwritten before use
-      flex_load_window<NC, TPB, NF>(A, sm, w, c, (int)live - 1, head0, i);
+      flex_load_window<CPL, TPB, NF>(A, sm, w, c0, c, (int)live - 1, head0, i);
     }
   }
   if (A.sine_on) {
@@ -450,7 +474,7 @@ __global__ void __launch_bounds__(TPB) k_step_flex(const __grid_constant__ StepA
     for (int m = 0; m < 3; ++m) sm[(M::kSine + m) * TPB] = L.sine[m * np + i];
   }
   const float *cmd_row = nullptr;
-  if (A.cmd_table) cmd_row = A.cmd_table + (size_t)(i % A.n_seq) * A.n_cmd * NC;
+  if (A.cmd_table) cmd_row = A.cmd_table + (size_t)(i % A.n_seq) * A.n_cmd * NC + c0;
   double cost = 0.0;
   int sec = A.sec0, nsec = A.nsec0, head = head0;
   double tprev = A.t0, sine_time = A.sine_time0;
@@ -459,13 +483,13 @@ __global__ void __launch_bounds__(TPB) k_step_flex(const __grid_constant__ StepA
   long long snap_idx = A.snap_written0;
   long long snap_ctr = A.snap_every > 0 ? (A.n0 % A.snap_every) : 0;
 
-  // every cable runs its live, primed Pid on a window of the last 11 steps?  Depends on the targets and the control
-  // words only, so it is re-evaluated after a command event or a general step, not every step.
+  // every cable of this lane runs its live, primed Pid on a window of the last 11 steps?  Depends on the targets and the
+  // control words only, so it is re-evaluated after a command event or a general step, not every step.
   auto steady_now = [&]() {
     if (mode == MODE_FORCE) return false;
     bool ok = true;
 #pragma unroll
-    for (int c = 0; c < NC; ++c) {
+    for (int c = 0; c < CPL; ++c) {
       const bool pos = (mode == MODE_POSITION) || !(fabs(sm[(M::kTgt + c) * TPB]) > rc.vel_eps);
       ok = ok && fctl_steady(sw[c * TPB], pos ? PID_POS : PID_VEL);
     }
@@ -489,7 +513,7 @@ __global__ void __launch_bounds__(TPB) k_step_flex(const __grid_constant__ StepA
         const double arg = __dadd_rn(__dmul_rn(__dmul_rn(__dmul_rn(sine_time, sm[(M::kSine + 1) * TPB]), 2.0), 3.14159265358979323846), sm[(M::kSine + 2) * TPB]);
         const double vel = (double)(float)__dmul_rn(sm[M::kSine * TPB], sin(arg));
 #pragma unroll
-        for (int c = 0; c < NC; ++c) sm[(M::kTgt + c) * TPB] = vel;
+        for (int c = 0; c < CPL; ++c) sm[(M::kTgt + c) * TPB] = vel;
         sine_time = __dadd_rn(sine_time, A.sine_pub_dt);
         vel_event = true;
       }
@@ -498,37 +522,37 @@ __global__ void __launch_bounds__(TPB) k_step_flex(const __grid_constant__ StepA
     if (cmd_row) {
       if (cmd_ctr == 0 && cmd_idx < A.n_cmd) {
 #pragma unroll
-        for (int c = 0; c < NC; ++c) sm[(M::kTgt + c) * TPB] = (double)cmd_row[cmd_idx * NC + c];
+        for (int c = 0; c < CPL; ++c) sm[(M::kTgt + c) * TPB] = (double)cmd_row[cmd_idx * NC + c];
         ++cmd_idx;
         vel_event = true;
       }
       cmd_ctr = (cmd_ctr + 1 == A.steps_per_cmd) ? 0 : cmd_ctr + 1;
     }
     const bool pending = (s == 0) && (vel_pending0 || pos_pending0);
-    if (pending || (vel_event && mode != MODE_VELOCITY)) {  // rare: a mode may change
+    if (pending || (vel_event && mode != MODE_VELOCITY)) {  // rare: a mode may change (the same way in every lane of the robot)
       if (hot) {
 #pragma unroll
-        for (int c = 0; c < NC; ++c) sm[(M::kLtime + c) * TPB] = tprev;
+        for (int c = 0; c < CPL; ++c) sm[(M::kLtime + c) * TPB] = tprev;
         hot = false;
       }
-      mode = pending ? flex_apply_pending<NC, TPB, NF>(A, sm, sw, mode, vel_pending0, pos_pending0, vel_event, i)
-                     : flex_enter_velocity<NC, TPB, NF>(A, sm, sw, i);
+      mode = pending ? flex_apply_pending<CPL, TPB, NF>(A, sm, sw, c0, mode, vel_pending0, pos_pending0, vel_event, i)
+                     : flex_enter_velocity<CPL, TPB, NF>(A, sm, sw, c0, i);
       recheck = true;
     }
     if (vel_event) recheck = true;
     if (recheck) { steady = steady_now(); recheck = false; }
 
+    Wrench6 W;
     if (steady && !last) {
-      // ================= hot body: straight-line, every cable on its live Pid =================
-      if (!hot) {
-        hot = true;
-      }
+      // ================= hot body: straight-line, every cable of the lane on its live Pid =================
+      hot = true;
       const double dt = __dsub_rn(now, tprev);  // == now - mLastTime of every live Pid
       const Rot R = make_rot(S);
-      double fx = rc.mg[0], fy = rc.mg[1], fz = rc.mg[2], mx = 0.0, my = 0.0, mz = 0.0;
+      W.fx = lead ? rc.mg[0] : 0.0; W.fy = lead ? rc.mg[1] : 0.0; W.fz = lead ? rc.mg[2] : 0.0;
+      W.mx = 0.0; W.my = 0.0; W.mz = 0.0;
 #pragma unroll UNR
-      for (int c = 0; c < NC; ++c) {
-        const CableKin kin = cable_kin<0, true>(rc, S, R, c);
+      for (int c = 0; c < CPL; ++c) {
+        const CableKin kin = cable_kin<0, true>(rc, S, R, c0 + c);
         double lp = sm[(M::kLastp + c) * TPB], desired, actual;
         const bool pos = flex_select(mode, sm[(M::kTgt + c) * TPB], rc.vel_eps, kin, lp, desired, actual);
         sm[(M::kLastp + c) * TPB] = lp;
@@ -536,29 +560,37 @@ __global__ void __launch_bounds__(TPB) k_step_flex(const __grid_constant__ StepA
         const double e = __dsub_rn(desired, actual);
         double pe = e;
         if (NF > 0) pe = flex_cascade<TPB, NF>(sm + (M::kFilt + c * M::FS) * TPB, pos ? A.pc[1].p_casc : A.pc[0].p_casc, A.pc[0].pf, A.pc[1].pf, pos, e);
-        sm[(M::kRing + head * NC + c) * TPB] = e;
+        sm[(M::kRing + head * CPL + c) * TPB] = e;
         double derived = 0.0;
-        if (A.pc[0].degree >= 1) derived = flex_fir<NC * TPB>(A, sm + (M::kRing + c) * TPB, head, e);
+        if (A.pc[0].degree >= 1) derived = flex_fir<CPL * TPB>(A, sm + (M::kRing + c) * TPB, head, e);
         double de = derived;
         if (NF > 0) de = flex_cascade<TPB, NF>(sm + (M::kFilt + c * M::FS + 4 * NF) * TPB, pos ? A.pc[1].d_casc : A.pc[0].d_casc, A.pc[0].df, A.pc[1].df, pos, derived);
         const FlexPidOut o = flex_pid(g, desired, e, dt, pe, de, sm[(M::kIerr + c) * TPB]);
         sm[(M::kIerr + c) * TPB] = o.ierr;
         const double eff = (rc.effort_limit >= 0.0) ? clampd(o.cmd, -rc.effort_limit, rc.effort_limit) : o.cmd;
         const double tl = __dmul_rn(fma(-rc.cdamp, kin.qd, eff), kin.il);  // tension / L
-        fx = fma(tl, kin.dx, fx); fy = fma(tl, kin.dy, fy); fz = fma(tl, kin.dz, fz);
-        mx = fma(tl, kin.cx, mx); my = fma(tl, kin.cy, my); mz = fma(tl, kin.cz, mz);
+        W.fx = fma(tl, kin.dx, W.fx); W.fy = fma(tl, kin.dy, W.fy); W.fz = fma(tl, kin.dz, W.fz);
+        W.mx = fma(tl, kin.cx, W.mx); W.my = fma(tl, kin.cy, W.my); W.mz = fma(tl, kin.cz, W.mz);
       }
-      if (rc.leg_model) S = legs_step(A, S, fx, fy, fz, mx, my, mz);
-      else if (rc.diag_inertia) rigid_body_step<SPEC_DIAG>(rc, S, R, fx, fy, fz, mx, my, mz);
-      else rigid_body_step<0>(rc, S, R, fx, fy, fz, mx, my, mz);
     } else {
       if (hot) {
 #pragma unroll
-        for (int c = 0; c < NC; ++c) sm[(M::kLtime + c) * TPB] = tprev;
+        for (int c = 0; c < CPL; ++c) sm[(M::kLtime + c) * TPB] = tprev;
         hot = false;
       }
-      S = flex_general_step<NC, TPB, NF>(A, S, sm, sw, mode, now, head, sec, nsec, last, i);
+      W = flex_general_step<CPL, TPB, NF>(A, S, sm, sw, c0, lead, valid, mode, now, head, sec, nsec, last, i);
       recheck = true;
+    }
+    // ---- the robot's wrench = sum over its lanes; then every lane integrates the same platform step
+    W.fx = lane_sum<LANES>(W.fx); W.fy = lane_sum<LANES>(W.fy); W.fz = lane_sum<LANES>(W.fz);
+    W.mx = lane_sum<LANES>(W.mx); W.my = lane_sum<LANES>(W.my); W.mz = lane_sum<LANES>(W.mz);
+    if (last && lead && valid) publish_platform(A, S, i);
+    if (rc.leg_model) {
+      S = legs_step(A, S, W.fx, W.fy, W.fz, W.mx, W.my, W.mz);
+    } else {
+      const Rot R = make_rot(S);
+      if (rc.diag_inertia) rigid_body_step<SPEC_DIAG>(rc, S, R, W.fx, W.fy, W.fz, W.mx, W.my, W.mz);
+      else rigid_body_step<0>(rc, S, R, W.fx, W.fy, W.fz, W.mx, W.my, W.mz);
     }
     tprev = now;
     if (A.cost) {
@@ -568,26 +600,28 @@ __global__ void __launch_bounds__(TPB) k_step_flex(const __grid_constant__ StepA
     if (A.snap_every > 0) {
       if (++snap_ctr == A.snap_every) {
         snap_ctr = 0;
-        if (snap_idx < A.snap_capacity) write_snapshot(A, S, snap_idx * 13 * A.snap_stride + A.snap_offset + i);
+        if (lead && valid && snap_idx < A.snap_capacity) write_snapshot(A, S, snap_idx * 13 * A.snap_stride + A.snap_offset + i);
         ++snap_idx;
       }
     }
   }
-  // the last step always runs the general body, so the integrals and last update times are back in shared memory here
+  // the last step always runs the general body, so the last update times are back in shared memory here
 
   // ---- back to HBM
-  store_plat(L.plat + i, np, S);
-  if (A.cost) A.cost[i] = cost;
-  L.ictl[i] = (A.k_steps > 0) ? (unsigned)mode : ictl;  // pending commands are consumed by the first step
+  if (lead) {
+    store_plat(L.plat + i, np, S);
+    if (A.cost) A.cost[i] = cost;
+    L.ictl[i] = (A.k_steps > 0) ? (unsigned)mode : ictl;  // pending commands are consumed by the first step
+  }
   const int tgt_field = (mode == MODE_FORCE) ? CAB_FORCE_CMD : (mode == MODE_POSITION) ? CAB_POS_TARGET : CAB_VEL_TARGET;
 #pragma unroll 1
-  for (int c = 0; c < NC; ++c) {
+  for (int c = 0; c < CPL; ++c) {
     const unsigned w = sw[c * TPB];
     const unsigned live = fctl_live(w);
-    if (live != 0u) flex_flush<NC, TPB, NF>(A, sm, w, c, (int)live - 1, head, sec, nsec, i);
-    L.ctl[(long long)c * np + i] = w;
-    L.cab[cab_off(L, c, CAB_LAST_POS) + i] = sm[(M::kLastp + c) * TPB];
-    if (A.k_steps > 0) L.cab[cab_off(L, c, tgt_field) + i] = sm[(M::kTgt + c) * TPB];
+    if (live != 0u) flex_flush<CPL, TPB, NF>(A, sm, w, c0, c, (int)live - 1, head, sec, nsec, i);
+    L.ctl[(long long)(c0 + c) * np + i] = w;
+    L.cab[cab_off(L, c0 + c, CAB_LAST_POS) + i] = sm[(M::kLastp + c) * TPB];
+    if (A.k_steps > 0) L.cab[cab_off(L, c0 + c, tgt_field) + i] = sm[(M::kTgt + c) * TPB];
   }
 }
 
