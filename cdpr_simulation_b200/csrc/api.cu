@@ -435,7 +435,10 @@ extern "C" int cdpr_create(const cdpr_config *cfg, int64_t n_instances, int devi
     h->flex_tpb = flex_tpb();
     {  // CDPR_FLEX_LANES: tuning override of the number of lanes that share one robot (step_flex.cuh)
       const char *env = std::getenv("CDPR_FLEX_LANES");
-      h->flex_lanes = flex_lanes_supported(cfg->n_cables, env ? std::atoi(env) : (cfg->n_cables == 8 ? 2 : 1));
+      // measured (step_flex.cuh): two lanes per robot pay at 8 cables as soon as Pids can change inside a run or filters
+      // shrink residency; the steady launch configuration and the 4-cable robot are faster with one thread per robot
+      const int lanes_default = (cfg->n_cables == 8 && (cfg->velocity_epsilon >= 0.0 || h->flex_nf > 0)) ? 2 : 1;
+      h->flex_lanes = flex_lanes_supported(cfg->n_cables, env ? std::atoi(env) : lanes_default);
     }
     h->flex_smem = shape_ok ? flex_smem_bytes(cfg->n_cables, h->flex_nf, h->flex_lanes) : 0;
     h->flex_capable = shape_ok && h->flex_smem <= 227u * 1024u;

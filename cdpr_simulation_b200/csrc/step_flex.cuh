@@ -429,6 +429,9 @@ static __device__ __noinline__ Wrench6 flex_general_step(const StepArgs &A, Fast
 // registers per thread = more resident warps, which is what this latency-bound kernel needs; the price is the replicated
 // platform update.  Instances beyond n (the padding of every column to a multiple of 128) run like any other and are
 // only kept from writing to the caller's buffers: the shuffles need whole warps.
+// Measured at NC=8, 2^20 x 1000 (instance-steps/s, LANES = 1 / 2 / 4): steady launch configuration 9.3e9 / 8.0e9 / 5.3e9; hold
+// below 2 cm/s 3.8e9 / 5.2e9 / 4.0e9; hold + one P and one D biquad stage 2.2e9 / 3.8e9 / 3.3e9.  At NC=4 one lane wins
+// everywhere.  The host therefore takes 2 lanes at 8 cables when hold is possible or filters are on, else 1.
 template <int NC, int TPB, int NF, int UNR, int LANES>
 __global__ void __launch_bounds__(TPB) k_step_flex(const __grid_constant__ StepArgs A) {
   constexpr int CPL = NC / LANES;
