@@ -602,7 +602,7 @@ def ik_c2_measurement(cb, wl, torch, device, hbm_peak, nc, npose):
            "kernel_us_single_shot": float(np.median(single[2:])) * 1e3, "how": how,
            "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "traffic": None,
                         "algorithmic_bytes_per_launch": nbytes, "flops_per_pose": frozen_ik_flops_per_pose(nc),
-                        "kernel": "k_ik_pair (one thread per cable and pose pair)"},
+                        "kernel": "k_ik_pair (one thread per cable and pose pair)" if (npose <= (1 << 19) and npose % 2 == 0) else "k_ik (one thread per pose)"},
            "copy_ceiling": {"us": copy_ms * 1e3 if copy_ms else None, "GBps": copy_gbs, "bytes_read_plus_written": 2 * half,
                             "what": "cudaMemcpyAsync D2D moving the same DRAM bytes (read + write), same graph, same rotation"},
            "frac_of_copy_ceiling": (gbs / copy_gbs) if copy_gbs else None}

@@ -432,11 +432,8 @@ static __device__ __noinline__ Wrench6 flex_general_step(const StepArgs &A, Fast
 // Measured at NC=8, 2^20 x 1000 (instance-steps/s, LANES = 1 / 2 / 4): steady launch configuration 9.3e9 / 8.0e9 / 5.3e9; hold
 // below 2 cm/s 3.8e9 / 5.2e9 / 4.0e9; hold + one P and one D biquad stage 2.2e9 / 3.8e9 / 3.3e9.  At NC=4 one lane wins
 // everywhere.  The host therefore takes 2 lanes at 8 cables when hold is possible or filters are on, else 1.
-#ifndef CDPR_FLEX_MINBLOCKS
-#define CDPR_FLEX_MINBLOCKS 1
-#endif
 template <int NC, int TPB, int NF, int UNR, int LANES>
-__global__ void __launch_bounds__(TPB, CDPR_FLEX_MINBLOCKS) k_step_flex(const __grid_constant__ StepArgs A) {
+__global__ void __launch_bounds__(TPB) k_step_flex(const __grid_constant__ StepArgs A) {
   constexpr int CPL = NC / LANES;
   static_assert(CPL * LANES == NC && (LANES == 1 || LANES == 2 || LANES == 4), "lanes must divide the cables");
   using M = FlexSmem<CPL, TPB, NF>;
