@@ -386,7 +386,7 @@ def own_arm(args):
             if world > 1:
                 gl = gather if lane == 0 else make_trajectory_gather(bt, args.snapshot_every, k_sim, st, prefer_fused=(args.gather == "fused"))[0]
             traj_host = torch.empty((n_snap, 13, n), dtype=torch.float64, pin_memory=True) if world > 1 else None
-            traj_stage = torch.empty((n_snap, 13, n), dtype=torch.float64, device=f"cuda:{local_rank}") if world > 1 else None
+            traj_stage = None
             lanes.append((bt, ins, outs, gl, st, traj_host, traj_stage))
         if gather: gather.finish()
 
@@ -404,10 +404,16 @@ def own_arm(args):
                 gl.after_pass(); gl.finish()
                 src = gl.latest() if hasattr(gl, "latest") else None
                 with torch.cuda.stream(st):                                 # D2H of this rank's share of the gathered trajectory
-                    # the shard's columns are strided in the gather buffer: pack them on the device (0.3 ms), then ONE
-                    # contiguous copy to pinned memory (a strided D2H runs at half the PCIe rate)
-                    traj_stage.copy_(src[:, :, col0:col0 + n] if src is not None else gl.recv[src_shard])
-                    traj_host.copy_(traj_stage, non_blocking=True)
+                    # the shard's columns are strided in the gather buffer, but every (snapshot, field) row of them is one
+                    # contiguous 8 MB run: 130 plain D2H copies on the copy engine.  (A packing kernel, or torch's strided
+                    # copy_, needs SMs and would queue behind the OTHER lane's step kernel, which holds every SM for the
+                    # whole pass -- that serialises the two lanes.)
+                    if src is not None:
+                        for s_ in range(n_snap):
+                            for f_ in range(13):
+                                traj_host[s_, f_].copy_(src[s_, f_, col0:col0 + n], non_blocking=True)
+                    else:
+                        traj_host.copy_(gl.recv[src_shard], non_blocking=True)
             bt.platform_state((outs[0].numpy(), outs[1].numpy()))            # D2H
             bt.joint_states(tuple(t.numpy() for t in outs[2:]))
 
