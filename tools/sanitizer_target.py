@@ -43,3 +43,52 @@ for nc in (4, 8):
         g.rollout(3, 64, wl.c5_rollouts(64, 4, nc) * 10.0, 5, [0, 0, 0.3], 0.1, pose7[:3], twist6[:3])
         g.platform_state()
         print("ok saturating", nc, g.kernel_variant)
+
+# round 2: independent robots (masked commands, per-instance modes), the leg model, plugin-style updates, both kinematics
+# kernels, the flex kernel with 1 and 2 lanes per robot, the catch-all kernel
+import torch
+for nc in (4, 8):
+    n = 77                                                  # ragged: the padded instances of the last block run too
+    amp, freq, phase, pose7, twist6 = wl.c3_instances(n, 3)
+    rng = np.random.default_rng(1)
+    for legs in (0, 1):
+        cfg = cb.default_config(nc)
+        cfg.leg_model = legs
+        with cb.CdprBatch(cfg, n) as g:
+            g.set_independent(True)
+            g.set_platform_state(pose7, twist6)
+            third = np.arange(n) % 3
+            g.step(5)
+            g.set_velocity_cmd(rng.uniform(-0.05, 0.05, (n, nc)).astype(np.float32), mask=third == 0)
+            g.set_position_cmd(rng.uniform(-0.02, 0.02, (n, nc)).astype(np.float32), mask=third == 1)
+            g.set_effort_cmd(rng.uniform(2, 6, (n, nc)), mask=third == 2)
+            g.step(30); g.modes(); g.pid_terms()
+            for k in range(12):
+                g.update(rng.uniform(-0.05, 0.05, (n, nc)).astype(np.float32) if k % 5 == 0 else None)
+            blob = g.get_state(); g.set_state(blob)
+            buf = torch.zeros((3, 13, n), dtype=torch.float64, device="cuda"); torch.cuda.synchronize()
+            g.set_snapshots(10, buf.data_ptr(), 3); g.step(30); g.synchronize()
+            print("ok independent", nc, "legs", legs, g.kernel_variant)
+    for lanes in ("1", "2"):                                 # hold + filters with one and two lanes per robot
+        os.environ["CDPR_FLEX_LANES"] = lanes
+        cfg = cb.default_config(nc)
+        cfg.velocity_epsilon = 0.02; cfg.vel_pid.p_cascade = 1; cfg.vel_pid.d_cascade = 2
+        with cb.CdprBatch(cfg, n) as g:
+            g.set_platform_state(pose7, twist6); g.set_sine_cmd(amp, freq, phase)
+            g.step(1); g.step(300)
+            g.rollout(7, 11, wl.c5_rollouts(11, 4, nc), 5, [0, 0, 0.3], 0.1, pose7[:7], twist6[:7])
+            print("ok flex lanes", lanes, nc, g.kernel_variant)
+    os.environ.pop("CDPR_FLEX_LANES", None)
+    cfg = cb.default_config(nc)
+    cfg.vel_pid.cmd_limit = 0.0; cfg.vel_pid.d_buffer_length = 5; cfg.vel_pid.d_degree = 1
+    with cb.CdprBatch(cfg, n) as g:                          # catch-all kernel
+        g.set_platform_state(pose7, twist6); g.set_sine_cmd(amp, freq, phase); g.step(60)
+        g.update(None)
+        print("ok", nc, g.kernel_variant)
+    for npose in (4096, 4097):                               # pair kernel (even) and per-pose kernel (odd)
+        p7, t6 = wl.c2_poses(npose, 0)
+        st = np.ascontiguousarray(np.concatenate([p7[:, :3], p7[:, 6:7], p7[:, 3:6], t6], axis=1).T)
+        d_in = torch.from_numpy(st).cuda(); d_out = torch.empty((nc, 8, npose), dtype=torch.float64, device="cuda"); torch.cuda.synchronize()
+        with cb.CdprBatch(cb.default_config(nc), 1) as g:
+            g.ik_device(npose, d_in.data_ptr(), d_out.data_ptr()); g.synchronize()
+    print("ok ik", nc)
