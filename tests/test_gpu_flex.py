@@ -243,3 +243,76 @@ def test_leg_model_launch_split_bitwise_and_unsupported_shapes(built_lib):
     with pytest.raises(cb.CdprError) as e:
         cb.CdprBatch(cfg, 8)
     assert e.value.code == cb.api.ERR_UNSUPPORTED
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3, 4, 5])
+def test_flex_random_command_sequences_against_the_oracle(built_lib, seed):
+    """Fuzz of the rare paths: random configurations (hold band, cascades on either Pid, feed-forward, limits that bite),
+    random sequences of masked velocity / position / effort commands landing at random steps -- hold entered and left from
+    every mode, Pids reset while live or asleep, windows spanning several gaps, launches of random length -- against the
+    oracle after every segment, and bitwise against the same sequence cut into different launches."""
+    rng = np.random.default_rng(1000 + seed)
+    nc = int(rng.choice([4, 8]))
+    n = int(rng.integers(40, 90))
+
+    def edit(cfg):
+        cfg.velocity_epsilon = float(rng.choice([-0.001, 0.0, 0.01, 0.03]))
+        cfg.vel_pid.p_cascade = int(rng.integers(0, 3)); cfg.vel_pid.d_cascade = int(rng.integers(0, 3))
+        cfg.pos_pid.p_cascade = int(rng.integers(0, 2)); cfg.pos_pid.d_cascade = int(rng.integers(0, 2))
+        cfg.vel_pid.forward_gain = float(rng.choice([0.0, 1.5]))
+        if rng.random() < 0.5:
+            for pid in (cfg.vel_pid, cfg.pos_pid):
+                pid.i_limit, pid.cmd_limit = 0.5, 6.0
+            cfg.effort_limit = 5.0
+        if rng.random() < 0.3:
+            cfg.vel_pid.d_degree = cfg.pos_pid.d_degree = int(rng.choice([1, 3]))
+        cfg.leg_model = int(rng.random() < 0.25)
+
+    cfg = cb.default_config(nc)
+    edit(cfg)
+    amp, freq, phase, pose7, twist6 = wl.c3_instances(n, 200 + seed)
+    use_sine = bool(rng.random() < 0.5)
+    ops = []
+    for _ in range(14):
+        kind = rng.choice(["vel", "pos", "eff", "step", "step"])
+        mask = rng.random(n) < rng.choice([0.3, 0.7, 1.0])
+        if kind == "vel":
+            ops.append(("vel", (rng.uniform(-0.05, 0.05, (n, nc)) * (rng.random((n, nc)) < 0.8)).astype(np.float32), mask))
+        elif kind == "pos":
+            ops.append(("pos", rng.uniform(-0.02, 0.02, (n, nc)).astype(np.float32), mask))
+        elif kind == "eff":
+            ops.append(("eff", rng.uniform(2.0, 6.0, (n, nc)), mask))
+        ops.append(("step", int(rng.choice([1, 2, 9, 10, 11, 12, 13, 37, 120])), None))
+
+    def play(split):
+        g = cb.CdprBatch(cfg, n)
+        g.set_independent(True)
+        assert g.kernel_variant == "flex"
+        g.set_platform_state(pose7, twist6)
+        if use_sine:
+            g.set_sine_cmd(amp, freq, phase)
+        o = ob.Batch(to_oracle_config(cfg), n, pose7, twist6, *( (amp, freq, phase) if use_sine else ()))
+        for kind, val, mask in ops:
+            if kind == "vel":
+                g.set_velocity_cmd(val, mask=mask); o.velocity_cmd_masked(val, mask)
+            elif kind == "pos":
+                g.set_position_cmd(val, mask=mask); o.position_cmd_masked(val, mask)
+            elif kind == "eff":
+                g.set_effort_cmd(val, mask=mask); o.effort_cmd_masked(val, mask)
+            else:
+                if split and val > 3:
+                    g.step(1); g.step(val - 3); g.step(2)
+                else:
+                    g.step(val)
+                o.step(val)
+                _check(g, o, 2e-8, (seed, kind, val))
+                assert np.array_equal(g.modes(), o.targets()[2][:, 0].astype(np.int32))
+        out = (g.platform_state(), g.joint_states(), g.pid_terms(), g.get_state())
+        g.close()
+        return out
+
+    a, b = play(False), play(True)
+    assert np.array_equal(a[0][0], b[0][0]) and np.array_equal(a[0][1], b[0][1])
+    for x, y in zip(a[1], b[1]):
+        assert np.array_equal(x, y)
+    assert np.array_equal(a[2], b[2])
