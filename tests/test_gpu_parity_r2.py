@@ -234,3 +234,64 @@ def test_checkpoint_of_another_config_is_refused(built_lib):
     a.set_state(blob)
     assert a.step_count == 5
     a.close(); b.close()
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3, 4, 5, 6, 7])
+def test_fast_kernel_random_command_sequences_against_the_oracle(built_lib, seed):
+    """Fuzz of the HOST-side command logic of the batch-uniform path (cdpr_step: velocity fan-out, then position, the sine
+    publisher as a velocity command of its step, Force mode until the next publish, launches cut at publish boundaries):
+    random sequences of batch-wide commands and launches of random length, with and without the in-kernel publisher,
+    against the oracle after every launch, and bitwise against the same sequence with every launch cut in three."""
+    rng = np.random.default_rng(500 + seed)
+    nc = int(rng.choice([4, 8]))
+    n = int(rng.integers(33, 70))
+    cfg = cb.default_config(nc)
+    if rng.random() < 0.4:
+        for pid in (cfg.vel_pid, cfg.pos_pid):
+            pid.i_limit, pid.cmd_limit = 0.5, 6.0
+        cfg.effort_limit = 5.0
+    cfg.vel_pid.forward_gain = float(rng.choice([0.0, 2.0]))
+    amp, freq, phase, pose7, twist6 = wl.c3_instances(n, 300 + seed)
+    use_sine = bool(rng.random() < 0.6)
+    ops = []
+    for _ in range(16):
+        kind = rng.choice(["vel", "pos", "eff", "both", "none"])
+        if kind in ("vel", "both"):
+            ops.append(("vel", rng.uniform(-0.05, 0.05, (n, nc)).astype(np.float32)))
+        if kind in ("pos", "both"):
+            ops.append(("pos", rng.uniform(-0.02, 0.02, (n, nc)).astype(np.float32)))
+        if kind == "eff":
+            ops.append(("eff", rng.uniform(2.0, 6.0, (n, nc))))
+        ops.append(("step", int(rng.choice([1, 3, 7, 10, 10, 20, 30, 64, 101]))))
+
+    def play(split):
+        g = cb.CdprBatch(cfg, n)
+        assert g.kernel_variant == "fast"
+        g.set_platform_state(pose7, twist6)
+        if use_sine:
+            g.set_sine_cmd(amp, freq, phase)
+        o = ob.Batch(to_oracle_config(cfg), n, pose7, twist6, *((amp, freq, phase) if use_sine else ()))
+        for kind, val in ops:
+            if kind == "vel":
+                g.set_velocity_cmd(val); o.velocity_cmd(val)
+            elif kind == "pos":
+                g.set_position_cmd(val); o.position_cmd(val)
+            elif kind == "eff":
+                g.set_effort_cmd(val); o.effort_cmd(val)
+            else:
+                if split and val > 3:
+                    g.step(1); g.step(val - 3); g.step(2)
+                else:
+                    g.step(val)
+                o.step(val)
+                pg, tg = g.platform_state(); po, to = o.platform_state()
+                assert state_rel_err(pg, tg, po, to) < 2e-8, (seed, val)
+                assert np.all(g.modes() == o.targets()[2][:, 0].astype(np.int32)), (seed, val)
+        out = (g.platform_state(), g.joint_states())
+        g.close()
+        return out
+
+    a, b = play(False), play(True)
+    assert np.array_equal(a[0][0], b[0][0]) and np.array_equal(a[0][1], b[0][1])
+    for x, y in zip(a[1], b[1]):
+        assert np.array_equal(x, y)
