@@ -432,7 +432,8 @@ extern "C" int cdpr_create(const cdpr_config *cfg, int64_t n_instances, int devi
                           cfg->vel_pid.d_degree == cfg->pos_pid.d_degree && cfg->vel_pid.cmd_limit != 0.0 && cfg->pos_pid.cmd_limit != 0.0;
     h->flex_nf = flex_stage_slots(h->flex_ps, h->flex_ds);
     h->flex_unroll = cfg->velocity_epsilon < 0.0 ? 4 : 2;
-    if (const char *env = std::getenv("CDPR_FLEX_UNROLL")) h->flex_unroll = std::atoi(env) >= 4 ? 4 : 2;  // tuning override
+    // tuning override; unroll 4 is compiled without the hold test, so it is only allowed when hold is impossible
+    if (const char *env = std::getenv("CDPR_FLEX_UNROLL")) h->flex_unroll = (std::atoi(env) >= 4 && cfg->velocity_epsilon < 0.0) ? 4 : 2;
     h->flex_tpb = flex_tpb();
     {  // CDPR_FLEX_LANES: tuning override of the number of lanes that share one robot (step_flex.cuh)
       const char *env = std::getenv("CDPR_FLEX_LANES");

@@ -109,9 +109,11 @@ __device__ __forceinline__ FlexGains flex_gains(const StepArgs &A, bool pos) {
 
 // JointForceCalculator::update (.cpp:67-89) for the two Pid modes: which Pid runs (true = position Pid), its set point
 // and its measurement; `lastp` is mLastPosition (updated unless the cable holds)
+// HOLD = false: velocityEpsilon < 0, |target| > eps always holds, so the Pid follows the instance's mode alone
+template <bool HOLD>
 __device__ __forceinline__ bool flex_select(int mode, double target, double vel_eps, const CableKin &kin, double &lastp, double &desired, double &actual) {
   const bool pos_mode = (mode == MODE_POSITION);
-  const bool hold = !pos_mode && !(fabs(target) > vel_eps);
+  const bool hold = HOLD && !pos_mode && !(fabs(target) > vel_eps);
   const bool pos = pos_mode || hold;
   desired = hold ? lastp : target;
   actual = pos ? kin.qp : kin.qd;
@@ -349,7 +351,7 @@ static __device__ __noinline__ Wrench6 flex_general_step(const StepArgs &A, Fast
       force = target;
     } else {
       double lp = sm[(M::kLastp + c) * TPB];
-      const bool pos = flex_select(mode, target, rc.vel_eps, kin, lp, desired, actual);
+      const bool pos = flex_select<true>(mode, target, rc.vel_eps, kin, lp, desired, actual);
       sm[(M::kLastp + c) * TPB] = lp;
       run = pos ? 2u : 1u;
     }
@@ -435,6 +437,7 @@ static __device__ __noinline__ Wrench6 flex_general_step(const StepArgs &A, Fast
 template <int NC, int TPB, int NF, int UNR, int LANES>
 __global__ void __launch_bounds__(TPB) k_step_flex(const __grid_constant__ StepArgs A) {
   constexpr int CPL = NC / LANES;
+  constexpr bool kHold = (UNR < 4);  // the host launches UNR = 4 exactly when velocityEpsilon < 0 (api.cu): no cable can ever hold
   static_assert(CPL * LANES == NC && (LANES == 1 || LANES == 2 || LANES == 4), "lanes must divide the cables");
   using M = FlexSmem<CPL, TPB, NF>;
   extern __shared__ double smem[];
@@ -493,7 +496,7 @@ __global__ void __launch_bounds__(TPB) k_step_flex(const __grid_constant__ StepA
     bool ok = true;
 #pragma unroll
     for (int c = 0; c < CPL; ++c) {
-      const bool pos = (mode == MODE_POSITION) || !(fabs(sm[(M::kTgt + c) * TPB]) > rc.vel_eps);
+      const bool pos = (mode == MODE_POSITION) || (kHold && !(fabs(sm[(M::kTgt + c) * TPB]) > rc.vel_eps));
       ok = ok && fctl_steady(sw[c * TPB], pos ? PID_POS : PID_VEL);
     }
     return ok;
@@ -559,9 +562,9 @@ __global__ void __launch_bounds__(TPB) k_step_flex(const __grid_constant__ StepA
       for (int c = 0; c < CPL; ++c) {
         const CableKin kin = cable_kin<0, true>(rc, S, R, c0 + c);
         double lp = sm[(M::kLastp + c) * TPB], desired, actual;
-        const bool pos = flex_select(mode, sm[(M::kTgt + c) * TPB], rc.vel_eps, kin, lp, desired, actual);
+        const bool pos = flex_select<kHold>(mode, sm[(M::kTgt + c) * TPB], rc.vel_eps, kin, lp, desired, actual);
         sm[(M::kLastp + c) * TPB] = lp;
-        const FlexGains g = flex_gains(A, pos);
+        const FlexGains g = flex_gains(A, pos);  // HOLD = false: pos is the same for every cable, the selects leave the loop
         const double e = __dsub_rn(desired, actual);
         double pe = e;
         if (NF > 0) pe = flex_cascade<TPB, NF>(sm + (M::kFilt + c * M::FS) * TPB, pos ? A.pc[1].p_casc : A.pc[0].p_casc, A.pc[0].pf, A.pc[1].pf, pos, e);
