@@ -10,8 +10,11 @@
 //       psy = D.a2,  psx = (D.a1 - t D.a3)/(1 - t^2),  phi = psx t - D.a3
 //   kinetic energy of a leg = 1/2 |y|^2,  y = [sqrt(I) thx | sqrt(2I) w_leg | sqrt(I)(w_leg + phi a3) | sqrt(I)(w + psx a1) |
 //                                               sqrt(m) v_c | sqrt(2m) v_B],  v_c = v_B - (l_c/L)(v_B - u (u.v_B))
-//   M(x) = diag(m, m, m, R I_b R^T) + sum_legs Jy^T Jy;   Q += sum_legs [ m_l g.(v_c + 2 v_B) columns - Jz^T z ],  z = sqrt(c_p) * rates
-//   step:  M(x_n) (xi+ - xi)/h = Q_cables + Q_gravity + Q_passive - gyro(platform), then the pose update of App. C.6.
+//   M(x) = diag(m, m, m, R I_b R^T) + sum_legs Jy^T Jy;   Q += sum_legs [ m_l g.(v_c + 2 v_B) columns - Jz^T z - Jy^T (J'y xi) ],
+//   z = sqrt(c_p) * rates;  J'y xi = d/dt y(x(t), xi held): the links' velocity-product terms, a one-sided difference of y
+//   along the motion over kLegBiasDt (each link obeys m a = f, I alpha = tau with a = J xi' + J' xi; isotropic inertia, so
+//   the links have no gyroscopic torque of their own)
+//   step:  M(x_n) (xi+ - xi)/h = Q_cables + Q_gravity + Q_passive - Jy^T J'y xi - gyro(platform), then the pose update of App. C.6.
 // A slow path by construction (a 6x6 system per instance and step, about 3000 extra FMAs at 8 cables): out of line, rolled
 // loops, local arrays.
 #pragma once
@@ -28,6 +31,28 @@ struct LegGeom {
 __device__ __forceinline__ double dot3d(const double *a, const double *b) { return fma(a[0], b[0], fma(a[1], b[1], a[2] * b[2])); }
 __device__ __forceinline__ void cross3d(const double *a, const double *b, double *o) {
   o[0] = fma(a[1], b[2], -(a[2] * b[1])); o[1] = fma(a[2], b[0], -(a[0] * b[2])); o[2] = fma(a[0], b[1], -(a[1] * b[0]));
+}
+
+constexpr double kLegBiasDt = 1e-6;  // s: step of the one-sided difference behind the velocity-product terms
+
+// geometry of leg i for platform position p and rotation R
+__device__ inline void leg_geometry(const RobotConsts &rc, int i, const double *p, const double (*R)[3], LegGeom &g) {
+  double d[3];
+  for (int k = 0; k < 3; ++k) g.r[k] = fma(R[k][0], rc.b[i][0], fma(R[k][1], rc.b[i][1], R[k][2] * rc.b[i][2]));
+  for (int k = 0; k < 3; ++k) d[k] = rc.a[i][k] - p[k] - g.r[k];
+  g.L = sqrt(dot3d(d, d));
+  for (int k = 0; k < 3; ++k) { g.u[k] = d[k] / g.L; g.x0[k] = rc.leg_x0[i][k]; }
+  const double s = dot3d(g.u, g.x0);
+  g.c = sqrt(1.0 - s * s);
+  for (int k = 0; k < 3; ++k) g.e1[k] = (g.x0[k] - s * g.u[k]) / g.c;
+  cross3d(g.u, g.e1, g.e2);
+  for (int k = 0; k < 3; ++k) g.a3[k] = fma(rc.leg_alpha[i][0], g.e1[k], fma(rc.leg_alpha[i][1], g.e2[k], rc.leg_alpha[i][2] * g.u[k]));
+  for (int k = 0; k < 3; ++k) g.a1[k] = fma(R[k][0], rc.leg_a1[i][0], fma(R[k][1], rc.leg_a1[i][1], R[k][2] * rc.leg_a1[i][2]));
+  g.t = dot3d(g.a3, g.a1);
+  double nrm[3];
+  cross3d(g.a3, g.a1, nrm);
+  const double nn = sqrt(1.0 - g.t * g.t);
+  for (int k = 0; k < 3; ++k) g.a2[k] = nrm[k] / nn;
 }
 
 __device__ inline void leg_rates(const RobotConsts &rc, const LegGeom &g, const double *v, const double *w, double *y, double *z) {
@@ -79,25 +104,28 @@ static __device__ __noinline__ FastState legs_step(const StepArgs &A, FastState 
   cross3d(w, Lw, gy);
   double Q[6] = {fx, fy, fz, mx - gy[0], my - gy[1], mz - gy[2]};
   const double grav[3] = {rc.grav[0], rc.grav[1], rc.grav[2]};
+  // the pose a moment later at the current twist (first order, like the integrator): behind the velocity-product terms
+  double p1[3], R1[3][3];
+  {
+    FastState S1 = S;
+    const double hb = 0.5 * kLegBiasDt;
+    const double hx = hb * S.wx, hy = hb * S.wy, hz = hb * S.wz;
+    const double nw = fma(-hx, S.qx, fma(-hy, S.qy, fma(-hz, S.qz, S.qw)));
+    const double nx = fma(hx, S.qw, fma(hy, S.qz, fma(-hz, S.qy, S.qx)));
+    const double ny = fma(-hx, S.qz, fma(hy, S.qw, fma(hz, S.qx, S.qy)));
+    const double nz = fma(hx, S.qy, fma(-hy, S.qx, fma(hz, S.qw, S.qz)));
+    const double inv = 1.0 / sqrt(fma(nw, nw, fma(nx, nx, fma(ny, ny, nz * nz))));
+    S1.qw = nw * inv; S1.qx = nx * inv; S1.qy = ny * inv; S1.qz = nz * inv;
+    const Rot Q1 = make_rot(S1);
+    R1[0][0] = Q1.r00; R1[0][1] = Q1.r01; R1[0][2] = Q1.r02; R1[1][0] = Q1.r10; R1[1][1] = Q1.r11; R1[1][2] = Q1.r12;
+    R1[2][0] = Q1.r20; R1[2][1] = Q1.r21; R1[2][2] = Q1.r22;
+    for (int k = 0; k < 3; ++k) p1[k] = fma(kLegBiasDt, v[k], p[k]);
+  }
 #pragma unroll 1
   for (int i = 0; i < A.L.nc; ++i) {
-    LegGeom g;
-    double d[3];
-    for (int k = 0; k < 3; ++k) g.r[k] = fma(R[k][0], rc.b[i][0], fma(R[k][1], rc.b[i][1], R[k][2] * rc.b[i][2]));
-    for (int k = 0; k < 3; ++k) d[k] = rc.a[i][k] - p[k] - g.r[k];
-    g.L = sqrt(dot3d(d, d));
-    for (int k = 0; k < 3; ++k) { g.u[k] = d[k] / g.L; g.x0[k] = rc.leg_x0[i][k]; }
-    const double s = dot3d(g.u, g.x0);
-    g.c = sqrt(1.0 - s * s);
-    for (int k = 0; k < 3; ++k) g.e1[k] = (g.x0[k] - s * g.u[k]) / g.c;
-    cross3d(g.u, g.e1, g.e2);
-    for (int k = 0; k < 3; ++k) g.a3[k] = fma(rc.leg_alpha[i][0], g.e1[k], fma(rc.leg_alpha[i][1], g.e2[k], rc.leg_alpha[i][2] * g.u[k]));
-    for (int k = 0; k < 3; ++k) g.a1[k] = fma(R[k][0], rc.leg_a1[i][0], fma(R[k][1], rc.leg_a1[i][1], R[k][2] * rc.leg_a1[i][2]));
-    g.t = dot3d(g.a3, g.a1);
-    double nrm[3];
-    cross3d(g.a3, g.a1, nrm);
-    const double nn = sqrt(1.0 - g.t * g.t);
-    for (int k = 0; k < 3; ++k) g.a2[k] = nrm[k] / nn;
+    LegGeom g, g1;
+    leg_geometry(rc, i, p, R, g);
+    leg_geometry(rc, i, p1, R1, g1);
     double Jy[16][6], Jz[5][6];
 #pragma unroll 1
     for (int k = 0; k < 6; ++k) {
@@ -113,13 +141,16 @@ static __device__ __noinline__ FastState legs_step(const StepArgs &A, FastState 
         for (int j = 0; j < 16; ++j) acc = fma(Jy[j][a], Jy[j][b], acc);
         M[a][b] += acc;
       }
-    double y[16], z[5];
+    double y[16], z[5], y1[16], z1[5];
     leg_rates(rc, g, v, w, y, z);
+    leg_rates(rc, g1, v, w, y1, z1);
+    for (int j = 0; j < 16; ++j) y1[j] = (y1[j] - y[j]) / kLegBiasDt;  // J'y xi
     for (int k = 0; k < 6; ++k) {
-      double damp = 0.0, gr = 0.0;
+      double damp = 0.0, gr = 0.0, bias = 0.0;
       for (int j = 0; j < 5; ++j) damp = fma(Jz[j][k], z[j], damp);
       for (int j = 0; j < 3; ++j) gr = fma(grav[j], fma(rc.leg_sm, Jy[10 + j][k], rc.leg_s2m * Jy[13 + j][k]), gr);
-      Q[k] += gr - damp;
+      for (int j = 0; j < 16; ++j) bias = fma(Jy[j][k], y1[j], bias);
+      Q[k] += gr - damp - bias;
     }
   }
   // Cholesky of the upper triangle (M = U^T U), two triangular solves

@@ -436,11 +436,14 @@ void orc_kinematics_eval(const orc_config *cfg, const double *home_len, const do
  *     y = [ sqrt(I_l) thx | sqrt(2 I_l) w_leg | sqrt(I_l) w(virt_Ypf) | sqrt(I_l) w(virt_Xpf) | sqrt(m_l) v_c | sqrt(2 m_l) v_B ]  (16 rows)
  * so M(x) = diag(m, m, m, R I_b R^T) + sum_legs Jy^T Jy.  Passive damping: Rayleigh function 1/2 c_p |z|^2, z = the five joint
  * rates, generalised force -Jz^T z (explicit, like the actuated joint's damping).  Gravity: m_l g . (v_c + 2 v_B) per leg.
- * Step (same semi-implicit order as App. C.6):  M(x_n) (xi+ - xi)/h = Q_cables + Q_gravity + Q_passive - gyro(platform).
- * NEGLECTED, stated: the legs' own velocity-product (Coriolis/centrifugal) terms, O(m_l |xi|^2) ~ 1e-6 N at the speeds of
- * the reference's drivers; ODE's constraint softness; the slider's position stops (|q| <= 0.5196 m cannot be reached with
+ * Velocity-product (Coriolis / centrifugal) terms of the leg links: each link obeys m a = f, I alpha = tau (isotropic inertia: no
+ * gyroscopic torque) with a = J xi' + J' xi, so the projected equation gains -Jy^T (J'y xi); J'y xi = d/dt y(x(t), xi held) is
+ * a one-sided difference along the motion over LEG_BIAS_DT.
+ * Step (same semi-implicit order as App. C.6):  M(x_n) (xi+ - xi)/h = Q_cables + Q_gravity + Q_passive - Jy^T J'y xi - gyro(platform).
+ * NEGLECTED, stated: ODE's constraint softness; the slider's position stops (|q| <= 0.5196 m cannot be reached with
  * the platform inside the 0.6 m frame) and velocity limit (ODE does not enforce joint velocity limits).
  */
+#define LEG_BIAS_DT 1e-6 /* s: step of the one-sided difference behind the velocity-product terms */
 typedef struct {
   double r[3], u[3], e1[3], e2[3], a1[3], a2[3], a3[3];
   double L, c, t;
@@ -530,6 +533,19 @@ static void legs_assemble(const orc_robot *r, const double R[3][3], double M[6][
       M[3 + a][3 + b] = s;
     }
   double sm = sqrt(cfg->leg_link_mass), s2m = sqrt(2.0 * cfg->leg_link_mass);
+  /* pose a moment later at the current twist (for the velocity-product terms below) */
+  double p1[3], q1[4], R1[3][3];
+  {
+    const double *w = r->w, *q = r->q;
+    double dq[4] = {0.5 * (-w[0] * q[1] - w[1] * q[2] - w[2] * q[3]), 0.5 * (w[0] * q[0] + w[1] * q[3] - w[2] * q[2]),
+                    0.5 * (-w[0] * q[3] + w[1] * q[0] + w[2] * q[1]), 0.5 * (w[0] * q[2] - w[1] * q[1] + w[2] * q[0])};
+    double n2 = 0.0;
+    for (int k = 0; k < 4; ++k) { q1[k] = q[k] + LEG_BIAS_DT * dq[k]; n2 += q1[k] * q1[k]; }
+    n2 = sqrt(n2);
+    for (int k = 0; k < 4; ++k) q1[k] /= n2;
+    for (int k = 0; k < 3; ++k) p1[k] = r->p[k] + LEG_BIAS_DT * r->v[k];
+    quat_to_rot(q1, R1);
+  }
   for (int i = 0; i < cfg->n_cables; ++i) {
     leg_geom g;
     leg_geometry(cfg, r->leg_alpha[i], i, r->p, R, &g);
@@ -548,14 +564,22 @@ static void legs_assemble(const orc_robot *r, const double R[3][3], double M[6][
         M[a][b] += s;
       }
     if (Q) {
-      double y[16], z[5];
+      double y[16], z[5], y1[16], z1[5];
       leg_rates(cfg, &g, r->v, r->w, y, z);
+      /* velocity-product terms of the leg links: a_link = J xi' + J' xi, and J' xi = d/dt y(x(t), xi held) is taken as a
+       * one-sided difference along the motion: the pose advanced by LEG_BIAS_DT at the current twist (first order, like
+       * the integrator).  Isotropic link inertia => no gyroscopic torque of the links themselves. */
+      leg_geom g1;
+      leg_geometry(cfg, r->leg_alpha[i], i, p1, R1, &g1);
+      leg_rates(cfg, &g1, r->v, r->w, y1, z1);
       for (int k = 0; k < 6; ++k) {
         double damp = 0.0;
         for (int j = 0; j < 5; ++j) damp += Jz[j][k] * z[j];
         double grav = 0.0;
         for (int j = 0; j < 3; ++j) grav += cfg->gravity[j] * (sm * Jy[10 + j][k] + s2m * Jy[13 + j][k]);
-        Q[k] += grav - damp;
+        double bias = 0.0;
+        for (int j = 0; j < 16; ++j) bias += Jy[j][k] * ((y1[j] - y[j]) / LEG_BIAS_DT);
+        Q[k] += grav - damp - bias;
       }
     }
   }
