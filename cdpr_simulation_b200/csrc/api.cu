@@ -277,6 +277,17 @@ static int make_robot_consts(const cdpr_config &c, RobotConsts &o, std::string &
   bool bz0 = true;
   for (int i = 0; i < c.n_cables; ++i) bz0 = bz0 && (c.platform_anchor[i][2] == 0.0);
   if (bz0) o.spec |= SPEC_BZ0;
+  // cables c and c + NC/2 from the same platform anchor to frame anchors above each other (same x, y)?
+  if (c.n_cables >= 2 && c.n_cables % 2 == 0) {
+    const int half = c.n_cables / 2;
+    bool pair = true;
+    for (int i = 0; i < half; ++i) {
+      for (int k = 0; k < 3; ++k) pair = pair && (c.platform_anchor[i][k] == c.platform_anchor[i + half][k]);
+      pair = pair && (c.frame_anchor[i][0] == c.frame_anchor[i + half][0]) && (c.frame_anchor[i][1] == c.frame_anchor[i + half][1]);
+      o.pair_dz[i] = c.frame_anchor[i + half][2] - c.frame_anchor[i][2];
+    }
+    if (pair) o.spec |= SPEC_PAIR;
+  }
   o.cdamp = c.cable_damping; o.effort_limit = c.effort_limit; o.vel_eps = c.velocity_epsilon;
   o.effort_limit_abs = c.effort_limit >= 0.0 ? c.effort_limit : INFINITY;
   o.mass = c.mass;
@@ -744,7 +755,7 @@ static const std::vector<FastEntry> &fast_table() {
   static const std::vector<FastEntry> table = [] {
     std::vector<FastEntry> t;
     fast_entries_nc4_base(t); fast_entries_nc4_diag(t); fast_entries_nc4_spec(t);
-    fast_entries_nc8_base(t); fast_entries_nc8_diag(t); fast_entries_nc8_spec(t);
+    fast_entries_nc8_base(t); fast_entries_nc8_diag(t); fast_entries_nc8_spec(t); fast_entries_nc8_pair(t);
     return t;
   }();
   return table;
@@ -767,10 +778,13 @@ static int launch_step(cdpr_handle h, const StepArgs &A) {
     const int spec_full = h->rc.spec, spec_base = h->rc.spec & SPEC_DIAG;
     // one target for all cables (the sine publisher) and no feed-forward term: targets live in a register
     const bool uniform_noff = A.sine_on && !A.cmd_table && A.live.kf == 0.0 && h->targets_uniform;
+    // most specialised instance first: with / without the paired-anchor form, with / without the one-target layout
     const FastEntry *e = nullptr;
-    if (dm && A.mode == MODE_VELOCITY && uniform_noff && spec_full == (SPEC_DIAG | SPEC_ISO | SPEC_BZ0))
-      e = fast_find(h->L.nc, A.mode, true, spec_full | SPEC_NOFF | SPEC_UTGT);
-    if (!e && dm) e = fast_find(h->L.nc, A.mode, true, spec_full);
+    for (int spec_try : {spec_full, spec_full & ~SPEC_PAIR}) {
+      if (e || !dm) break;
+      if (A.mode == MODE_VELOCITY && uniform_noff) e = fast_find(h->L.nc, A.mode, true, spec_try | SPEC_NOFF | SPEC_UTGT);
+      if (!e) e = fast_find(h->L.nc, A.mode, true, spec_try);
+    }
     if (!e) e = fast_find(h->L.nc, A.mode, dm, spec_base);
     if (!e) return fail(h, CDPR_ERR_UNSUPPORTED, "no step kernel instance for this configuration");
     e->launch(grid_for(h->np, e->tpb), A, h->stream);

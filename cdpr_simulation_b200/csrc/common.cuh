@@ -70,6 +70,7 @@ struct RobotConsts {
   double ib[6], ib_inv[6];  // xx yy zz xy xz yz
   int diag_inertia;
   int spec;                 // SPEC_* bits (physics.cuh) that hold for this robot
+  double pair_dz[kMaxCables / 2];  // SPEC_PAIR: a[c + NC/2][2] - a[c][2]
   double cdamp, effort_limit;  // effort_limit < 0: no truncation
   double effort_limit_abs;     // effort_limit, or +inf when truncation is off
   double vel_eps;

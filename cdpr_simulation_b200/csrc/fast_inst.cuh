@@ -32,5 +32,12 @@ static void fast_entries_spec(std::vector<FastEntry> &out) {
   out.push_back(fast_entry<NC, MODE_POSITION, true, SPEC_DIAG | SPEC_ISO | SPEC_BZ0>());
   out.push_back(fast_entry<NC, MODE_VELOCITY, true, SPEC_DIAG | SPEC_ISO | SPEC_BZ0 | SPEC_NOFF | SPEC_UTGT>());
 }
+// ... and with the cables in pairs that share a platform anchor (the 8-cable cube)
+template <int NC>
+static void fast_entries_pair(std::vector<FastEntry> &out) {
+  out.push_back(fast_entry<NC, MODE_VELOCITY, true, SPEC_DIAG | SPEC_ISO | SPEC_BZ0 | SPEC_PAIR>());
+  out.push_back(fast_entry<NC, MODE_POSITION, true, SPEC_DIAG | SPEC_ISO | SPEC_BZ0 | SPEC_PAIR>());
+  out.push_back(fast_entry<NC, MODE_VELOCITY, true, SPEC_DIAG | SPEC_ISO | SPEC_BZ0 | SPEC_PAIR | SPEC_NOFF | SPEC_UTGT>());
+}
 
 }  // namespace cdpr

@@ -25,6 +25,7 @@ void fast_entries_nc4_spec(std::vector<FastEntry> &out);
 void fast_entries_nc8_base(std::vector<FastEntry> &out);
 void fast_entries_nc8_diag(std::vector<FastEntry> &out);
 void fast_entries_nc8_spec(std::vector<FastEntry> &out);
+void fast_entries_nc8_pair(std::vector<FastEntry> &out);
 
 // k_step_general<DMAX> (step_general.cuh), DMAX in {2, 4}
 void general_launch(int dmax, unsigned grid, const StepArgs &A, cudaStream_t st);

@@ -58,7 +58,10 @@ __device__ __forceinline__ void store_plat(double *p, long long stride, const Fa
 //   SPEC_BZ0   every platform anchor has b_z == 0 (anchors in the platform's xy plane, cube.yaml:21-29)
 //   SPEC_NOFF  the live Pid has no feed-forward gain (velocityControllerForward = 0, launch:19)
 //   SPEC_UTGT  every cable has the same target (the sine publisher writes one value to all axes, sinevelocitytest.cpp:36-38)
-enum { SPEC_DIAG = 1, SPEC_ISO = 2, SPEC_BZ0 = 4, SPEC_NOFF = 8, SPEC_UTGT = 16 };
+//   SPEC_PAIR  cables c and c + NC/2 leave the SAME platform anchor for frame anchors that differ in z only (an upper and a
+//              lower frame corner above each other: the 8-cable cube of SURVEY.md App. A.2): their kinematics share d_x, d_y,
+//              g_x, g_y and everything built from them (cable_kin_pair)
+enum { SPEC_DIAG = 1, SPEC_ISO = 2, SPEC_BZ0 = 4, SPEC_NOFF = 8, SPEC_UTGT = 16, SPEC_PAIR = 32 };
 
 // NVLS multicast store: one store, replicated by the NVSwitch into the mapped buffer of every rank
 __device__ __forceinline__ void mc_store(double *p, double v) { asm volatile("multimem.st.weak.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory"); }
@@ -145,6 +148,38 @@ __device__ __forceinline__ CableKin cable_kin(const RobotConsts &rc, const FastS
   k.qp = 0.0;
   if (WANT_QP) k.qp = rc.home_len[c] - l2 * k.il;
   return k;
+}
+
+// SPEC_PAIR: the two cables of a pair (c, c2 = c + NC/2) in one go.  g2 = g + (0, 0, dz0), d2 = d + (0, 0, dz0) with
+// dz0 = a2_z - a_z, so of the second cable's 31 FP64 instructions only 17 remain:
+//   d2.d2 = (dx^2 + dy^2) + dz2^2,  (g2 x d2)_z = (g x d)_z,  d2.v = (dx vx + dy vy) + dz2 vz,  (g2 x d2).w shares (g x d)_z wz.
+template <int SPEC, bool WANT_QP>
+__device__ __forceinline__ void cable_kin_pair(const RobotConsts &rc, const FastState &S, const Rot &R, int c, int c2, double dz0, CableKin &k, CableKin &k2) {
+  const double bx = rc.b[c][0], by = rc.b[c][1], bz = rc.b[c][2];
+  const double gx = rc.a[c][0] - S.px, gy = rc.a[c][1] - S.py, gz = rc.a[c][2] - S.pz;
+  k.dx = fma(-R.r00, bx, fma(-R.r01, by, (SPEC & SPEC_BZ0) ? gx : fma(-R.r02, bz, gx)));
+  k.dy = fma(-R.r10, bx, fma(-R.r11, by, (SPEC & SPEC_BZ0) ? gy : fma(-R.r12, bz, gy)));
+  k.dz = fma(-R.r20, bx, fma(-R.r21, by, (SPEC & SPEC_BZ0) ? gz : fma(-R.r22, bz, gz)));
+  const double sxy = fma(k.dx, k.dx, k.dy * k.dy);
+  const double dvxy = fma(k.dx, S.vx, k.dy * S.vy);
+  k.cz = fma(gx, k.dy, -(gy * k.dx));
+  const double czw = k.cz * S.wz;
+  // first cable
+  const double l2 = fma(k.dz, k.dz, sxy);
+  k.il = rsqrt_nr(l2);
+  k.cx = fma(gy, k.dz, -(gz * k.dy)); k.cy = fma(gz, k.dx, -(gx * k.dz));
+  k.qd = (fma(k.dz, S.vz, dvxy) + fma(k.cx, S.wx, fma(k.cy, S.wy, czw))) * k.il;
+  k.qp = 0.0;
+  if (WANT_QP) k.qp = rc.home_len[c] - l2 * k.il;
+  // second cable: same platform anchor, frame anchor dz0 higher
+  const double gz2 = gz + dz0;
+  k2.dx = k.dx; k2.dy = k.dy; k2.dz = k.dz + dz0;
+  const double l22 = fma(k2.dz, k2.dz, sxy);
+  k2.il = rsqrt_nr(l22);
+  k2.cx = fma(gy, k2.dz, -(gz2 * k.dy)); k2.cy = fma(gz2, k.dx, -(gx * k2.dz)); k2.cz = k.cz;
+  k2.qd = (fma(k2.dz, S.vz, dvxy) + fma(k2.cx, S.wx, fma(k2.cy, S.wy, czw))) * k2.il;
+  k2.qp = 0.0;
+  if (WANT_QP) k2.qp = rc.home_len[c2] - l22 * k2.il;
 }
 
 // rare path (every snap_every steps), kept out of line so the hot loop's register allocation does not see it

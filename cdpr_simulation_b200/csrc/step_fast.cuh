@@ -33,6 +33,12 @@
 
 namespace cdpr {
 
+// Order in which the cable loop visits the cables: ascending, or -- SPEC_PAIR -- pair by pair (0, NC/2, 1, NC/2 + 1, ...), so
+// the second cable of a pair follows the first while the shared kinematics are still in registers.  Every body of the
+// kernel (hot, clamping, warm-up, last, saturated pass) uses the same order, so the wrench sums are the same bits everywhere.
+template <int NC, int SPEC>
+__device__ __forceinline__ constexpr int pair_order(int it) { return (SPEC & SPEC_PAIR) ? ((it & 1) ? (it >> 1) + NC / 2 : (it >> 1)) : it; }
+
 constexpr int kResync = 64;
 constexpr int kSatHold = 32;  // clean steps before a warp that saw a clamp fire returns to the optimistic body
 #ifndef CDPR_NC4_BLOCKS
@@ -55,7 +61,7 @@ constexpr int kSatHold = 32;  // clean steps before a warp that saw a clamp fire
 #endif
 // "lean" = SPEC_UTGT | SPEC_NOFF: the one target lives in a register, so no target / feed-forward arrays in shared memory
 template <int NC, int SPEC = 0> struct FastCfg {
-  static constexpr bool lean = (SPEC & (8 | 16)) == (8 | 16);
+  static constexpr bool lean = (SPEC & (8 | 16)) == (8 | 16);  // SPEC_NOFF | SPEC_UTGT
   // optimistic saturation handling parks the pre-update integrals in [NC][tpb] doubles of scratch; the non-lean
   // 8-cable layout has no room for it and commits the integrals after the vote instead (one more LDS + DFMA per cable)
   static constexpr bool scratch = (NC <= 4) || lean;
@@ -110,9 +116,17 @@ __device__ __noinline__ SatOut<NC> saturated_pass(const StepArgs &A, SatIn<NC, F
   SatOut<NC> o;
   o.fx = rc.mg[0]; o.fy = rc.mg[1]; o.fz = rc.mg[2];
   o.mx = 0.0; o.my = 0.0; o.mz = 0.0;
+  CableKin kpair;  // SPEC_PAIR: the second cable of the pair in flight
 #pragma unroll
-  for (int c = 0; c < NC; ++c) {
-    const CableKin k = cable_kin<SPEC, MODE == MODE_POSITION>(rc, in.S, R, c);
+  for (int it = 0; it < NC; ++it) {
+    const int c = pair_order<NC, SPEC>(it);
+    CableKin k;
+    if (SPEC & SPEC_PAIR) {
+      if (!(it & 1)) cable_kin_pair<SPEC, MODE == MODE_POSITION>(rc, in.S, R, c, c + NC / 2, rc.pair_dz[c], k, kpair);
+      else k = kpair;
+    } else {
+      k = cable_kin<SPEC, MODE == MODE_POSITION>(rc, in.S, R, c);
+    }
     const double tg = (SPEC & SPEC_UTGT) ? in.tgu : tgts[c * kT];
     const double ff = (SPEC & SPEC_NOFF) ? 0.0 : tgts[(NC + c) * kT];
     const double e = tg - ((MODE == MODE_VELOCITY) ? k.qd : k.qp);
@@ -167,9 +181,17 @@ __device__ __forceinline__ bool fast_step(const StepArgs &A, FastState &S, doubl
   };
 
   bool sat = false;
+  CableKin kpair;  // SPEC_PAIR: the second cable of the pair in flight
 #pragma unroll
-  for (int c = 0; c < NC; ++c) {
-    const CableKin k = cable_kin<SPEC, MODE == MODE_POSITION || LAST>(rc, S, R, c);
+  for (int it = 0; it < NC; ++it) {
+    const int c = pair_order<NC, SPEC>(it);
+    CableKin k;
+    if (SPEC & SPEC_PAIR) {
+      if (!(it & 1)) cable_kin_pair<SPEC, MODE == MODE_POSITION || LAST>(rc, S, R, c, c + NC / 2, rc.pair_dz[c], k, kpair);
+      else k = kpair;
+    } else {
+      k = cable_kin<SPEC, MODE == MODE_POSITION || LAST>(rc, S, R, c);
+    }
 
     // ---- force law (a3, a4, a5)
     double force, eff;

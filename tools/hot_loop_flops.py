@@ -11,7 +11,11 @@ def count(lib=DEFAULT_LIB):
     txt = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
     out = {}
     for nc in (8, 4):
-        f = [x for x in re.split(r"\n\s*Function : ", txt)[1:] if f"k_step_fastILi{nc}ELi11ELi2ELb1ELi31E" in x.split("\n", 1)[0]][0]
+        # the kernel bench.py's headline runs: velocity mode, moment D-term, every robot-constant specialisation of the default
+        # robot with that many cables (SPEC 63 = ... | SPEC_PAIR for the 8-cable cube, 31 for the 4-cable reference robot)
+        funcs = re.split(r"\n\s*Function : ", txt)[1:]
+        cand = [x for spec in (63, 31) for x in funcs if f"k_step_fastILi{nc}ELi11ELi2ELb1ELi{spec}E" in x.split("\n", 1)[0]]
+        f = cand[0]
         ins = [(int(m.group(1), 16), m.group(2).strip()) for m in re.finditer(r"/\*([0-9a-f]{4,6})\*/\s+(.*?);", f)]
         loops = []
         for a, t in ins:
