@@ -146,7 +146,7 @@ __device__ __forceinline__ CableKin cable_kin(const RobotConsts &rc, const FastS
   k.cx = fma(gy, k.dz, -(gz * k.dy)); k.cy = fma(gz, k.dx, -(gx * k.dz)); k.cz = fma(gx, k.dy, -(gy * k.dx));
   k.qd = (fma(k.dx, S.vx, fma(k.dy, S.vy, k.dz * S.vz)) + fma(k.cx, S.wx, fma(k.cy, S.wy, k.cz * S.wz))) * k.il;
   k.qp = 0.0;
-  if (WANT_QP) k.qp = rc.home_len[c] - l2 * k.il;
+  if (WANT_QP) k.qp = fma(-l2, k.il, rc.home_len[c]);  // explicit: ptxas must not get to choose between mul + sub and fma per call site
   return k;
 }
 
@@ -170,7 +170,7 @@ __device__ __forceinline__ void cable_kin_pair(const RobotConsts &rc, const Fast
   k.cx = fma(gy, k.dz, -(gz * k.dy)); k.cy = fma(gz, k.dx, -(gx * k.dz));
   k.qd = (fma(k.dz, S.vz, dvxy) + fma(k.cx, S.wx, fma(k.cy, S.wy, czw))) * k.il;
   k.qp = 0.0;
-  if (WANT_QP) k.qp = rc.home_len[c] - l2 * k.il;
+  if (WANT_QP) k.qp = fma(-l2, k.il, rc.home_len[c]);  // explicit: ptxas must not get to choose between mul + sub and fma per call site
   // second cable: same platform anchor, frame anchor dz0 higher
   const double gz2 = gz + dz0;
   k2.dx = k.dx; k2.dy = k.dy; k2.dz = k.dz + dz0;
@@ -179,7 +179,7 @@ __device__ __forceinline__ void cable_kin_pair(const RobotConsts &rc, const Fast
   k2.cx = fma(gy, k2.dz, -(gz2 * k.dy)); k2.cy = fma(gz2, k.dx, -(gx * k2.dz)); k2.cz = k.cz;
   k2.qd = (fma(k2.dz, S.vz, dvxy) + fma(k2.cx, S.wx, fma(k2.cy, S.wy, czw))) * k2.il;
   k2.qp = 0.0;
-  if (WANT_QP) k2.qp = rc.home_len[c2] - l22 * k2.il;
+  if (WANT_QP) k2.qp = fma(-l22, k2.il, rc.home_len[c2]);
 }
 
 // rare path (every snap_every steps), kept out of line so the hot loop's register allocation does not see it

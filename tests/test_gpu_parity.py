@@ -399,8 +399,19 @@ def _inertia_diag_bz(cfg):
 def _iso_bz(cfg):
     cfg.platform_anchor[1][2] = 0.02
 
+def _unpaired(cfg):
+    # the 8-cable cube pairs cables c and c + 4 (same platform anchor, frame anchors above each other): break one pair, so the
+    # kernel without the paired-anchor form runs; and give the pairs different heights otherwise
+    if cfg.n_cables == 8:
+        cfg.frame_anchor[5][0] += 0.01
+        cfg.frame_anchor[6][2] = 0.05
 
-@pytest.mark.parametrize("edit", [_inertia_general, _inertia_diag, _inertia_diag_bz, _iso_bz])
+def _paired_uneven(cfg):
+    if cfg.n_cables == 8:
+        cfg.frame_anchor[6][2] = 0.05; cfg.frame_anchor[7][2] = -0.02     # still pairs, each with its own height difference
+
+
+@pytest.mark.parametrize("edit", [_inertia_general, _inertia_diag, _inertia_diag_bz, _iso_bz, _unpaired, _paired_uneven])
 @pytest.mark.parametrize("nc", [4, 8])
 def test_robot_constant_specialisations(built_lib, nc, edit):
     """Every compile-time specialisation of the step kernel (general / diagonal / isotropic inertia, anchors in or
