@@ -289,6 +289,30 @@ def rollouts_c5(cb, wl, D, torch, dist, args, rank, world, local_rank):
     return out
 
 
+def bind_to_gpu_numa_node(gpu_index: int):
+    """Pin this rank to the CPU cores next to its GPU (sysfs local_cpulist of the GPU's PCI device) BEFORE any pinned host
+    memory is allocated, so the pinned buffers land on that NUMA node: with several ranks copying gigabytes per pass the
+    host side of the D2H copies is the bound, and cross-socket traffic halves it.  Returns a description for the JSON line."""
+    try:
+        bus = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(gpu_index)],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        if not bus:
+            return "unbound (no PCI bus id)"
+        dev = "/sys/bus/pci/devices/" + bus[-12:]                      # 00000000:1b:00.0 -> 0000:1b:00.0
+        cpus = set()
+        for part in open(dev + "/local_cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if not allowed:
+            return "unbound (no local cores in this process's affinity mask)"
+        os.sched_setaffinity(0, allowed)
+        node = open(dev + "/numa_node").read().strip()
+        return f"NUMA node {node}, {len(allowed)} cores"
+    except Exception as e:
+        return f"unbound ({type(e).__name__})"
+
+
 def own_arm(args):
     import torch
     import torch.distributed as dist
@@ -303,6 +327,7 @@ def own_arm(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the product has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa_node(local_rank) if (world > 1 and not args.no_numa_bind) else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -516,7 +541,8 @@ def own_arm(args):
                                    f"NC={nc} ({'synthetic 8-cable extension' if nc == 8 else 'reference 4-cable robot'})",
                        "instances_per_gpu": n, "sim_steps_per_pass": k_sim, "n_cables": nc,
                        "l2": "resident state per GPU (%.1f GB) is larger than L2; no flush needed" % (batch_state_gb(batch)),
-                       "multi_gpu": None if world == 1 else f"C4: snapshot every {args.snapshot_every} steps gathered to every rank -- {gather_kind}"},
+                       "multi_gpu": None if world == 1 else f"C4: snapshot every {args.snapshot_every} steps gathered to every rank -- {gather_kind}",
+                       "host_binding": numa},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / args.steps,
@@ -726,6 +752,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--no-rollouts", action="store_true")
+    ap.add_argument("--no-numa-bind", action="store_true", help="N > 1: do not pin the rank to the cores next to its GPU")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "own":
         args.warmup = 3
