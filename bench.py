@@ -292,7 +292,9 @@ def rollouts_c5(cb, wl, D, torch, dist, args, rank, world, local_rank):
 def bind_to_gpu_numa_node(gpu_index: int):
     """Pin this rank to the CPU cores next to its GPU (sysfs local_cpulist of the GPU's PCI device) BEFORE any pinned host
     memory is allocated, so the pinned buffers land on that NUMA node: with several ranks copying gigabytes per pass the
-    host side of the D2H copies is the bound, and cross-socket traffic halves it.  Returns a description for the JSON line."""
+    host side of the D2H copies is the bound, and cross-socket traffic halves it.  (On the pool's B200 boxes the guest sees ONE
+    NUMA node, so this changes nothing there -- measured at 4 GPUs: 85.4 vs 86.7 ms per pass; it matters on bare metal.)
+    Returns a description for the JSON line."""
     try:
         bus = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(gpu_index)],
                              capture_output=True, text=True, timeout=20).stdout.strip().lower()
