@@ -26,6 +26,8 @@ struct cdpr_batch {
   bool flex = false;     // the on-chip full-semantics kernel (step_flex.cuh): per-instance modes and commands
   bool flex_capable = false;
   int flex_tpb = 0, flex_ps = 0, flex_ds = 0, flex_nf = 0, flex_unroll = 2, flex_lanes = 1;
+  bool flexr = false;    // ... in its register-resident form (step_flexr.cuh): at most one biquad stage per filter, no leg model
+  bool flexr_hold = false;
   size_t flex_smem = 0;
   DevLayout L{};
   RobotConsts rc{};
@@ -390,6 +392,11 @@ static int reset_to_load_state(cdpr_handle h, cudaStream_t st) {
   return CDPR_OK;
 }
 
+static void flex_prepare_any(cdpr_handle h) {
+  if (h->flexr) flexr_prepare(h->L.nc, h->flex_nf, h->flexr_hold, h->flex_lanes);
+  else flex_prepare(h->L.nc, h->flex_nf, h->flex_unroll, h->flex_lanes);
+}
+
 extern "C" int cdpr_create(const cdpr_config *cfg, int64_t n_instances, int device, cdpr_handle *out) {
   if (!cfg || !out) return fail(nullptr, CDPR_ERR_BAD_ARG, "null argument");
   *out = nullptr;
@@ -455,6 +462,16 @@ extern "C" int cdpr_create(const cdpr_config *cfg, int64_t n_instances, int devi
     }
     h->flex_smem = shape_ok ? flex_smem_bytes(cfg->n_cables, h->flex_nf, h->flex_lanes) : 0;
     h->flex_capable = shape_ok && h->flex_smem <= 227u * 1024u;
+    // The register-resident form (step_flexr.cuh) wherever it is compiled; CDPR_FLEX_CLASSIC=1 keeps k_step_flex (A/B runs).
+    const char *classic = std::getenv("CDPR_FLEX_CLASSIC");
+    const char *env_lanes = std::getenv("CDPR_FLEX_LANES");
+    const int rl = flexr_lanes(cfg->n_cables, h->flex_nf, env_lanes ? std::atoi(env_lanes) : 2);
+    if (h->flex_capable && rl > 0 && cfg->leg_model == 0 && !(classic && std::atoi(classic) != 0)) {
+      h->flexr = true;
+      h->flexr_hold = cfg->velocity_epsilon >= 0.0;
+      h->flex_lanes = rl;
+      h->flex_smem = flexr_smem_bytes(cfg->n_cables, h->flex_nf, rl);
+    }
   }
   h->flex = h->general && h->flex_capable;
   if (cfg->leg_model && !h->flex) {
@@ -504,7 +521,7 @@ extern "C" int cdpr_create(const cdpr_config *cfg, int64_t n_instances, int devi
       cudaFuncSetAttribute(e.func, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     }
   }
-  if (h->flex) flex_prepare(cfg->n_cables, h->flex_nf, h->flex_unroll, h->flex_lanes);
+  if (h->flex) flex_prepare_any(h);
   if (cudaStreamSynchronize(h->stream) != cudaSuccess) { h->err = "initialisation kernels failed"; return bail(CDPR_ERR_CUDA); }
   *out = h;
   return CDPR_OK;
@@ -592,7 +609,7 @@ extern "C" int cdpr_set_option(cdpr_handle h, int option, int64_t value) {
       if (!L.win_x && (rc = dev_alloc(h, (void **)&L.win_x, col * L.nc * 2 * L.len))) return rc;
       if (!L.filt && L.casc > 0 && (rc = dev_alloc(h, (void **)&L.filt, col * L.nc * 2 * 2 * L.casc * 4))) return rc;
       h->general = true; h->flex = true;
-      flex_prepare(L.nc, h->flex_nf, h->flex_unroll, h->flex_lanes);
+      flex_prepare_any(h);
       cudaStream_t st = io_begin(h);
       rc = reset_to_load_state(h, st);
       io_end(h);
@@ -768,7 +785,8 @@ static const FastEntry *fast_find(int nc, int mode, bool dmom, int spec) {
 
 static int launch_step(cdpr_handle h, const StepArgs &A) {
   if (h->flex) {
-    flex_launch(h->L.nc, h->flex_nf, h->flex_unroll, h->flex_lanes, grid_for(h->np * h->flex_lanes, h->flex_tpb), A, h->stream);
+    if (h->flexr) flexr_launch(h->L.nc, h->flex_nf, h->flexr_hold, h->flex_lanes, grid_for(h->np * h->flex_lanes, h->flex_tpb), A, h->stream);
+    else flex_launch(h->L.nc, h->flex_nf, h->flex_unroll, h->flex_lanes, grid_for(h->np * h->flex_lanes, h->flex_tpb), A, h->stream);
   } else if (h->general) {
     general_launch(std::max(h->pc[PID_VEL].degree, h->pc[PID_POS].degree), (unsigned)(h->np / kTpb), A, h->stream);
   } else {

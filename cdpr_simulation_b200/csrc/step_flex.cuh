@@ -87,9 +87,11 @@ struct FlexSmem {
 };
 
 // gazebo::common::Time of the step `back` steps before (sec, nsec)
+// (borrowing second by second: no 64-bit division; nsec may come in negative, as `nsec - dt_ns` of the previous step)
 __device__ __forceinline__ double stamp_back(int sec, int nsec, int dt_ns, int back) {
-  long long ns = (long long)sec * 1000000000LL + nsec - (long long)back * dt_ns;
-  return time_double((int)(ns / 1000000000LL), (int)(ns % 1000000000LL));
+  long long ns = (long long)nsec - (long long)back * dt_ns;
+  while (ns < 0) { ns += 1000000000LL; --sec; }
+  return time_double(sec, (int)ns);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -268,7 +270,7 @@ static __device__ __noinline__ void flex_reset_pid(const StepArgs &A, double *sm
       for (int pd = 0; pd < 2; ++pd)
         for (int s = 0; s < L.casc; ++s)
           for (int f = 0; f < 4; ++f) L.filt[filt_off(L, cg, k, pd, s, f) + i] = 0.0;
-    ctl &= ~(1u << k);
+    ctl &= ~((1u << k) | (1u << (30 + k)));  // wasLast; step_flexr.cuh's "slept on 11 consecutive steps" bit
     sw[c * TPB] = gctl_set(ctl, k, (unsigned)kFlexLen, 0u);  // wasLast cleared, missing = 11, ring head 0
   }
 }
