@@ -22,9 +22,10 @@
 // Bodies are chosen per thread as in step_flex.cuh; both run the same inlined arithmetic helpers with explicit roundings, so
 // which body ran never shows in the bits (GPU tests: bitwise launch-split and checkpoint invariance through hold transitions).
 //
-// Biquad slots: NF = 0 or 1 stage per filter.  A Pid without a stage where the other Pid has one runs the identity
-// biquad (a0 = 1, rest 0; exact: 1 x + 0 = x), so the cable loop has no per-Pid stage count.  More stages, or the leg
-// model: k_step_flex.
+// Biquad slots: NF = 0 or 1 stage per filter, ONE coefficient set per filter (constant-bank operands): when only one Pid has
+// the stage, the other Pid's slot still runs the arithmetic and its output is discarded by a select (pe = e, Pid.cpp:133 with an
+// empty cascade) -- the slot's state is then a don't-care that both bodies advance the same way.  Two Pids with different
+// coefficients, more stages, or the leg model: k_step_flex.
 #pragma once
 #include "step_flex.cuh"
 
@@ -40,11 +41,13 @@ struct FlexRSmem : FlexSmem<CPL, TPB, NF> {
   static constexpr int kStale = kDes + CPL;   // [CPL] time stamp of the newest STALE sample of a window that spans a gap
   static constexpr int kPerThread = kStale + CPL;
   // block-shared table behind the per-thread columns
-  static constexpr int kRow = 17;             // kf kp ki kd i_max i_max/ki c_max | P a0 a1 a2 b1 b2 | D a0 a1 a2 b1 b2
+  static constexpr int kRow = 8;              // kf kp ki kd i_max i_max/ki c_max (pad): the gains of one Pid
   static constexpr int kTabCab = 2 * kRow;    // [LANES][CPL][7]: b xyz, a xyz, home length
   static constexpr int kTabDoubles = kTabCab + LANES * CPL * 7;
   static constexpr size_t bytes = sizeof(double) * ((size_t)kPerThread * TPB + kTabDoubles);
 };
+
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // cable_kin (physics.cuh) on explicit constants: same expressions, same bits
 __device__ __forceinline__ CableKin cable_kin_v(double bx, double by, double bz, double ax, double ay, double az, double home, const FastState &S, const Rot &R) {
@@ -80,6 +83,20 @@ __device__ __forceinline__ double biquad_step_sm(const double *co, double *q, do
   return y0;
 }
 
+// The fixed FIR over the last 11 steps, summed in the order of the ring SLOTS (slot = step index mod 11) with the weights
+// rotated to match (gw = firx + 10 - head, so gw[s] is the weight of the sample in slot s; this step's sample is already in
+// slot head): every tap is a load at an immediate offset and a constant-bank weight, no index arithmetic.
+template <int STRIDE>
+__device__ __forceinline__ double flexr_fir(const double *gw, const double *ringc) {
+  double d0 = __dmul_rn(gw[0], ringc[0]), d1 = __dmul_rn(gw[1], ringc[STRIDE]);
+#pragma unroll
+  for (int s = 2; s < kFlexLen; ++s) {
+    const double y = ringc[s * STRIDE];
+    if (s & 1) d1 = fma(gw[s], y, d1); else d0 = fma(gw[s], y, d0);
+  }
+  return __dadd_rn(d0, d1);
+}
+
 __device__ __forceinline__ FlexGains flexr_gains(const double *row) {
   FlexGains g;
   g.kf = row[0]; g.kp = row[1]; g.ki = row[2]; g.kd = row[3]; g.i_max = row[4]; g.i_max_over_ki = row[5]; g.c_max = row[6];
@@ -92,36 +109,76 @@ __device__ __forceinline__ void stamp_dec(int &sec, int &nsec, int dt_ns) {
   while (nsec < 0) { nsec += 1000000000; --sec; }
 }
 
-// Derivative at `now` of the degree-D least-squares polynomial through 11 (stamp, value) pairs; xs[10] is the oldest stamp.
-// The arithmetic of ls_derivative (step_general.cuh): window-relative, span-scaled time, normal equations, elimination.
-template <int D>
-__device__ __forceinline__ double ls_fit11(const double (&xs)[kFlexLen], const double (&ys)[kFlexLen], double now) {
-  constexpr int M = D + 1;
+// Weights of the least-squares derivative: D = sum_a w[a] y[a] for samples with time stamps xs[a] (xs[10] the oldest), the
+// derivative at `now` of the degree-DEG polynomial fitted through them (Pid.cpp:203-212 + 219-247).  The normal equations
+// of ls_derivative (step_general.cuh: window-relative, span-scaled time; elimination with partial pivoting by
+// compare-and-swap) solved for the row of the pseudo-inverse that gives the linear coefficient -- it depends on the STAMPS
+// only, so the cables of a robot that woke up in the same step share one solve.
+template <int DEG>
+__device__ __forceinline__ void ls_weights11(const double (&xs)[kFlexLen], double now, double (&w)[kFlexLen]) {
+  constexpr int M = DEG + 1;
   const double span = now - xs[kFlexLen - 1], inv_span = 1.0 / span;
-  double sx[2 * D + 1], sy[M];
+  double x[kFlexLen], sx[2 * DEG + 1];
 #pragma unroll
-  for (int p = 0; p <= 2 * D; ++p) sx[p] = 0.0;
-#pragma unroll
-  for (int p = 0; p < M; ++p) sy[p] = 0.0;
+  for (int p = 0; p <= 2 * DEG; ++p) sx[p] = 0.0;
 #pragma unroll
   for (int j = 0; j < kFlexLen; ++j) {
-    const double x = (xs[j] - now) * inv_span;
+    x[j] = (xs[j] - now) * inv_span;
     double pw = 1.0;
 #pragma unroll
-    for (int p = 0; p <= 2 * D; ++p) {
-      sx[p] += pw;
-      if (p < M) sy[p] = fma(pw, ys[j], sy[p]);
-      pw *= x;
+    for (int p = 0; p <= 2 * DEG; ++p) { sx[p] += pw; pw *= x[j]; }
+  }
+  double G[M][M + 1];  // [X^T X | e_1]
+#pragma unroll
+  for (int r = 0; r < M; ++r) {
+#pragma unroll
+    for (int q = 0; q < M; ++q) G[r][q] = sx[r + q];
+    G[r][M] = (r == 1) ? 1.0 : 0.0;
+  }
+  bool singular = false;
+#pragma unroll
+  for (int col = 0; col < M; ++col) {
+#pragma unroll
+    for (int r = col + 1; r < M; ++r) {
+      const bool swp = fabs(G[r][col]) > fabs(G[col][col]);
+#pragma unroll
+      for (int q = col; q <= M; ++q) {
+        const double a = G[col][q], b = G[r][q];
+        G[col][q] = swp ? b : a;
+        G[r][q] = swp ? a : b;
+      }
+    }
+    singular = singular || (G[col][col] == 0.0);
+    const double inv = 1.0 / G[col][col];
+#pragma unroll
+    for (int r = col + 1; r < M; ++r) {
+      const double f = G[r][col] * inv;
+#pragma unroll
+      for (int q = col + 1; q <= M; ++q) G[r][q] = fma(-f, G[col][q], G[r][q]);
     }
   }
-  return ls_solve<D>(sx, sy, inv_span);
+  double z[M];
+#pragma unroll
+  for (int r = M - 1; r >= 0; --r) {
+    double t = G[r][M];
+#pragma unroll
+    for (int q = r + 1; q < M; ++q) t = fma(-G[r][q], z[q], t);
+    z[r] = t / G[r][r];
+  }
+#pragma unroll
+  for (int j = 0; j < kFlexLen; ++j) {
+    double h = z[M - 1];
+#pragma unroll
+    for (int p = M - 2; p >= 0; --p) h = fma(h, x[j], z[p]);
+    w[j] = singular ? 0.0 : h * inv_span;
+  }
 }
 
-// Gap fit on chip: ring position (head - a) holds the sample of age a; the newest `fresh` are the last steps, the others
+// Gap window on chip: ring position (head - a) holds the sample of age a; the newest `fresh` are the last steps, the others
 // the run of consecutive steps that ended at `stale` (a gazebo time stamp: sec + nsec 1e-9 with nsec < 1e9, sec < 2^16).
-template <int STRIDE>
-static __device__ __noinline__ double flexr_gap_fit(int degree, const double *ringc, int head, unsigned fresh, double stale, int sec, int nsec, int dt_ns, double now) {
-  double xs[kFlexLen], ys[kFlexLen];
+// The weights of its least-squares derivative by sample age.
+static __device__ __noinline__ void flexr_gap_weights(int degree, unsigned fresh, double stale, int sec, int nsec, int dt_ns, double now, double (&w)[kFlexLen]) {
+  double xs[kFlexLen];
   int s = sec, ns = nsec;
 #pragma unroll
   for (int a = 0; a < kFlexLen; ++a) {
@@ -131,16 +188,57 @@ static __device__ __noinline__ double flexr_gap_fit(int degree, const double *ri
       ns = (int)__double2ll_rn(__dmul_rn(__dsub_rn(stale, fl), 1e9));
     }
     xs[a] = time_double(s, ns);
-    int sl = head - a;
-    sl += (sl < 0) ? kFlexLen : 0;
-    ys[a] = ringc[sl * STRIDE];
     stamp_dec(s, ns, dt_ns);
   }
-  if (degree == 1) return ls_fit11<1>(xs, ys, now);
-  if (degree == 2) return ls_fit11<2>(xs, ys, now);
-  if (degree == 3) return ls_fit11<3>(xs, ys, now);
-  if (degree == 4) return ls_fit11<4>(xs, ys, now);
-  return 0.0;
+  if (degree == 1) ls_weights11<1>(xs, now, w);
+  else if (degree == 2) ls_weights11<2>(xs, now, w);
+  else if (degree == 3) ls_weights11<3>(xs, now, w);
+  else if (degree == 4) ls_weights11<4>(xs, now, w);
+  else {
+#pragma unroll
+    for (int a = 0; a < kFlexLen; ++a) w[a] = 0.0;
+  }
+}
+
+// flex_wake + flex_load_window of step_flex.cuh in one go, with every load issued before the first store: the state of a
+// Pid that slept is cold in HBM, and loads that wait for each other cost a microsecond apiece with one or two threads of
+// the warp active (this was most of the cost of a hold transition).  slot_now = ring slot of the window's newest sample.
+template <int CPL, int TPB, int NF>
+static __device__ __noinline__ void flexr_wake(const StepArgs &A, double *sm, unsigned ctl, int c0, int c, int k, int slot_now, long long i) {
+  using M = FlexSmem<CPL, TPB, NF>;
+  const DevLayout &L = A.L;
+  const int cg = c0 + c;
+  double wy[kFlexLen], fs[NF > 0 ? 8 * NF : 1];
+  const double lt = L.pid[pid_off(L, cg, k, PID_LAST_TIME) + i], ie = L.pid[pid_off(L, cg, k, PID_I_ERR) + i];
+#pragma unroll
+  for (int j = 0; j < kFlexLen; ++j) wy[j] = L.win_y[win_off(L, cg, k, j) + i];
+#pragma unroll
+  for (int s = 0; s < NF; ++s) {
+#pragma unroll
+    for (int f = 0; f < 4; ++f) {
+      fs[s * 4 + f] = (s < A.flex_ps) ? L.filt[filt_off(L, cg, k, 0, s, f) + i] : 0.0;
+      fs[(NF + s) * 4 + f] = (s < A.flex_ds) ? L.filt[filt_off(L, cg, k, 1, s, f) + i] : 0.0;
+    }
+  }
+  sm[(M::kLtime + c) * TPB] = lt;
+  sm[(M::kIerr + c) * TPB] = ie;
+#pragma unroll
+  for (int s = 0; s < NF; ++s) {
+#pragma unroll
+    for (int f = 0; f < 4; ++f) {
+      if (s < A.flex_ps) sm[(M::kFilt + c * M::FS + s * 4 + f) * TPB] = fs[s * 4 + f];
+      if (s < A.flex_ds) sm[(M::kFilt + c * M::FS + (NF + s) * 4 + f) * TPB] = fs[(NF + s) * 4 + f];
+    }
+  }
+  const int hd = (int)gctl_head(ctl, k);  // physical slot of the OLDEST sample
+#pragma unroll
+  for (int j = 0; j < kFlexLen; ++j) {
+    int logical = j - hd;  // 0 = oldest
+    logical += (logical < 0) ? kFlexLen : 0;
+    int sl = slot_now - (kFlexLen - 1 - logical);
+    sl += (sl < 0) ? kFlexLen : 0;
+    sm[(M::kRing + sl * CPL + c) * TPB] = wy[j];
+  }
 }
 
 // One step of THIS LANE's cables with every flag honoured (the out-of-line body): flex_general_step of step_flex.cuh with
@@ -155,6 +253,31 @@ static __device__ __noinline__ Wrench6 flexr_general_step(const StepArgs &A, Fas
   Wrench6 W;
   W.fx = lead ? rc.mg[0] : 0.0; W.fy = lead ? rc.mg[1] : 0.0; W.fz = lead ? rc.mg[2] : 0.0;
   W.mx = 0.0; W.my = 0.0; W.mz = 0.0;
+  // A Pid that wakes up in this step: its state is cold in HBM -- ask for all of it now, for every cable of the lane, so
+  // that the loads of flexr_wake find it on its way (they wait for each other cable by cable otherwise)
+#pragma unroll 1
+  for (int c = 0; c < CPL; ++c) {
+    if (mode == MODE_FORCE) break;
+    const bool pos = (mode == MODE_POSITION) || !(fabs(sm[(M::kTgt + c) * TPB]) > rc.vel_eps);
+    const int k = pos ? PID_POS : PID_VEL;
+    if (fctl_live(sw[c * TPB]) == (unsigned)(k + 1)) continue;
+    const int cg = c0 + c;
+    prefetch_l2(L.pid + pid_off(L, cg, k, PID_LAST_TIME) + i);
+    prefetch_l2(L.pid + pid_off(L, cg, k, PID_I_ERR) + i);
+    for (int j = 0; j < kFlexLen; ++j) prefetch_l2(L.win_y + win_off(L, cg, k, j) + i);
+    if (NF > 0) {
+      for (int f = 0; f < 4; ++f) {
+        if (A.flex_ps > 0) prefetch_l2(L.filt + filt_off(L, cg, k, 0, 0, f) + i);
+        if (A.flex_ds > 0) prefetch_l2(L.filt + filt_off(L, cg, k, 1, 0, f) + i);
+      }
+    }
+  }
+  // weights of the last gap fit of this step: cables whose windows have the same time stamps (they woke up together) share them
+  double gw[kFlexLen];
+  unsigned gw_fresh = 0xffffffffu;
+  double gw_stale = 0.0;
+#pragma unroll
+  for (int a = 0; a < kFlexLen; ++a) gw[a] = 0.0;
 #pragma unroll 1
   for (int c = 0; c < CPL; ++c) {
     const int cg = c0 + c;
@@ -184,9 +307,8 @@ static __device__ __noinline__ Wrench6 flexr_general_step(const StepArgs &A, Fas
         w = (fctl_fresh(w) >= (unsigned)kFlexLen) ? (w | bit) : (w & ~bit);
       }
       if (run != 0u) {
-        flex_wake<CPL, TPB, NF>(A, sm, c0, c, (int)run - 1, i);
+        flexr_wake<CPL, TPB, NF>(A, sm, w, c0, c, (int)run - 1, slot_prev, i);
         sm[(M::kStale + c) * TPB] = sm[(M::kLtime + c) * TPB];  // its newest sample was pushed at its last update
-        flex_load_window<CPL, TPB, NF>(A, sm, w, c0, c, (int)run - 1, slot_prev, i);
       }
       w = fctl_set_fresh(fctl_set_live(w, run), 0u);
     }
@@ -202,7 +324,10 @@ static __device__ __noinline__ Wrench6 flexr_general_step(const StepArgs &A, Fas
         const double e = __dsub_rn(desired, actual);
         const double dt = __dsub_rn(now, sm[(M::kLtime + c) * TPB]);
         double pe = e;
-        if (NF > 0 && A.flex_ps > 0) pe = biquad_step_sm<TPB>(row + 7, sm + (M::kFilt + c * M::FS) * TPB, e);
+        if (NF > 0 && A.flex_ps > 0) {
+          const double y0 = biquad_step_sm<TPB>(A.flex_pf, sm + (M::kFilt + c * M::FS) * TPB, e);
+          pe = ((A.flex_p_on >> k) & 1) ? y0 : e;
+        }
         // ---- derive (Pid.cpp:193-217): dt > 0 always (sim time advances every step)
         sm[(M::kRing + head * CPL + c) * TPB] = e;
         unsigned fresh = fctl_fresh(w), missing = gctl_missing(w, k), hd = gctl_head(w, k);
@@ -217,17 +342,33 @@ static __device__ __noinline__ Wrench6 flexr_general_step(const StepArgs &A, Fas
         double derived = 0.0;
         if (missing == 0u && A.pc[0].degree >= 1) {  // both Pids fit the same degree in this variant
           if (fresh >= (unsigned)kFlexLen) {
-            derived = flex_fir<CPL * TPB>(A, sm + (M::kRing + c) * TPB, head, e);
+            derived = flexr_fir<CPL * TPB>(A.firx + (kFlexLen - 1 - head), sm + (M::kRing + c) * TPB);
           } else {
             const double stale = sm[(M::kStale + c) * TPB];
-            if (((w >> (kRunBit0 + k)) & 1u) && stale >= 0.0 && stale < 65536.0)
-              derived = flexr_gap_fit<CPL * TPB>(A.pc[0].degree, sm + (M::kRing + c) * TPB, head, fresh, stale, sec, nsec, A.dt_ns, now);
-            else
+            if (((w >> (kRunBit0 + k)) & 1u) && stale >= 0.0 && stale < 65536.0) {
+              if (fresh != gw_fresh || stale != gw_stale) {
+                flexr_gap_weights(A.pc[0].degree, fresh, stale, sec, nsec, A.dt_ns, now, gw);
+                gw_fresh = fresh; gw_stale = stale;
+              }
+              const double *ringc = sm + (M::kRing + c) * TPB;
+              double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+              for (int a = 0; a < kFlexLen; ++a) {
+                int sl = head - a;
+                sl += (sl < 0) ? kFlexLen : 0;
+                const double y = ringc[sl * (CPL * TPB)];
+                if (a & 1) d1 = fma(gw[a], y, d1); else d0 = fma(gw[a], y, d0);
+              }
+              derived = __dadd_rn(d0, d1);
+            } else
               derived = flex_gap_fit(A, cg, k, hd, now, i);
           }
         }
         double de = derived;
-        if (NF > 0 && A.flex_ds > 0) de = biquad_step_sm<TPB>(row + 12, sm + (M::kFilt + c * M::FS + 4 * NF) * TPB, derived);
+        if (NF > 0 && A.flex_ds > 0) {
+          const double y0 = biquad_step_sm<TPB>(A.flex_df, sm + (M::kFilt + c * M::FS + 4 * NF) * TPB, derived);
+          de = ((A.flex_d_on >> k) & 1) ? y0 : derived;
+        }
         const FlexPidOut o = flex_pid(g, desired, e, dt, pe, de, sm[(M::kIerr + c) * TPB]);
         sm[(M::kIerr + c) * TPB] = o.ierr;
         force = o.cmd;
@@ -257,11 +398,14 @@ static __device__ __noinline__ Wrench6 flexr_general_step(const StepArgs &A, Fas
   return W;
 }
 
+#ifndef CDPR_FLEXR_MINB0
+#define CDPR_FLEXR_MINB0 1  // resident blocks asked for at two lanes without filter slots (caps the registers per thread)
+#endif
 // HOLD = false: velocityEpsilon < 0, no cable can ever hold, the Pid follows the instance's mode alone
 template <int NC, int TPB, int NF, bool HOLD, int LANES>
-__global__ void __launch_bounds__(TPB) k_step_flexr(const __grid_constant__ StepArgs A) {
+__global__ void __launch_bounds__(TPB, (LANES == 4) ? 16 : ((LANES == 2 && NF == 0) ? CDPR_FLEXR_MINB0 : 1)) k_step_flexr(const __grid_constant__ StepArgs A) {
   constexpr int CPL = NC / LANES;
-  static_assert(CPL * LANES == NC && (LANES == 1 || LANES == 2) && NF <= 1, "lanes must divide the cables; one biquad slot per filter");
+  static_assert(CPL * LANES == NC && (LANES == 1 || LANES == 2 || LANES == 4) && NF <= 1, "lanes must divide the cables; one biquad slot per filter");
   using M = FlexRSmem<CPL, TPB, NF, LANES>;
   extern __shared__ double smem[];
   const int tid = (int)threadIdx.x;
@@ -285,13 +429,7 @@ __global__ void __launch_bounds__(TPB) k_step_flexr(const __grid_constant__ Step
     for (int k = 0; k < 2; ++k) {
       const PidConsts &pc = A.pc[k];
       double *row = tabw + k * M::kRow;
-      row[0] = pc.kf; row[1] = pc.kp; row[2] = pc.ki; row[3] = pc.kd; row[4] = pc.i_max; row[5] = pc.i_max_over_ki; row[6] = pc.cmd_max;
-#pragma unroll
-      for (int q = 0; q < 5; ++q) {
-        const double ident = (q == 0) ? 1.0 : 0.0;  // a Pid without a stage runs the identity biquad in the slot
-        row[7 + q] = (pc.p_casc > 0) ? pc.pf[q] : ident;
-        row[12 + q] = (pc.d_casc > 0) ? pc.df[q] : ident;
-      }
+      row[0] = pc.kf; row[1] = pc.kp; row[2] = pc.ki; row[3] = pc.kd; row[4] = pc.i_max; row[5] = pc.i_max_over_ki; row[6] = pc.cmd_max; row[7] = 0.0;
     }
     for (int c = 0; c < NC; ++c) {
       double *q = tabw + M::kTabCab + c * 7;
@@ -322,9 +460,8 @@ __global__ void __launch_bounds__(TPB) k_step_flexr(const __grid_constant__ Step
     const unsigned live = fctl_live(w);
     if (live != 0u) {
       const int k = (int)live - 1;
-      flex_wake<CPL, TPB, NF>(A, sm, c0, c, k, i);
       // the HBM ring is current at a launch boundary whatever `fresh` is: the whole window comes on chip
-      flex_load_window<CPL, TPB, NF>(A, sm, w, c0, c, k, head0, i);
+      flexr_wake<CPL, TPB, NF>(A, sm, w, c0, c, k, head0, i);
       const unsigned fresh = fctl_fresh(w);
       if (fresh < (unsigned)kFlexLen) {  // newest stale sample = logical position 10 - fresh from the oldest slot on
         unsigned sl = gctl_head(w, k) + (unsigned)(kFlexLen - 1) - fresh;
@@ -348,16 +485,14 @@ __global__ void __launch_bounds__(TPB) k_step_flexr(const __grid_constant__ Step
   long long snap_ctr = A.snap_every > 0 ? (A.n0 % A.snap_every) : 0;
 
   // ---- what the hot body carries in registers
-  // integrals of the live Pids; their biquad state: P y1 y2, D x1 x2 y1 y2 (the P filter's x1, x2 are the last two errors,
-  // which a hot thread finds in the ring: its live Pids have pushed every one of the last 11 steps)
-  double ierr[CPL], fst[CPL][NF > 0 ? 6 : 1];
+  // Integrals of the live Pids.  (The biquad state stays in shared memory: held in registers it raised the pressure of the
+  // unrolled cable loop past 255 registers, and with the shared-memory carve-out at its maximum a spill is an L2 round
+  // trip -- measured 25 % slower than the explicit LDS / STS.  The P filter's x1, x2 are the last two errors, which a hot
+  // thread finds in the ring: its live Pids have pushed every one of the last 11 steps.)
+  double ierr[CPL];
   unsigned posmask = 0u, holdmask = 0u;  // per cable: runs the position Pid / holds (position Pid in Velocity mode)
 #pragma unroll
-  for (int c = 0; c < CPL; ++c) {
-    ierr[c] = 0.0;
-#pragma unroll
-    for (int f = 0; f < (NF > 0 ? 6 : 1); ++f) fst[c][f] = 0.0;
-  }
+  for (int c = 0; c < CPL; ++c) ierr[c] = 0.0;
   bool hot = false;  // the previous step ran the hot body: the registers above are the truth, shared memory is stale
   const bool has_p = NF > 0 && A.flex_ps > 0, has_d = NF > 0 && A.flex_ds > 0, has_fir = A.pc[0].degree >= 1;
 
@@ -369,27 +504,16 @@ __global__ void __launch_bounds__(TPB) k_step_flexr(const __grid_constant__ Step
     for (int c = 0; c < CPL; ++c) {
       sm[(M::kIerr + c) * TPB] = ierr[c];
       sm[(M::kLtime + c) * TPB] = tprev;
-      if (NF > 0) {
+      if (NF > 0) {  // the P filter's x1, x2 as the general body keeps them
         double *q = sm + (M::kFilt + c * M::FS) * TPB;
         q[0] = sm[(M::kRing + h1 * CPL + c) * TPB]; q[TPB] = sm[(M::kRing + h2 * CPL + c) * TPB];
-        q[2 * TPB] = fst[c][0]; q[3 * TPB] = fst[c][1];
-#pragma unroll
-        for (int f = 0; f < 4; ++f) q[(4 + f) * TPB] = fst[c][2 + f];
       }
     }
     hot = false;
   };
   auto fill = [&]() {
 #pragma unroll
-    for (int c = 0; c < CPL; ++c) {
-      ierr[c] = sm[(M::kIerr + c) * TPB];
-      if (NF > 0) {
-        const double *q = sm + (M::kFilt + c * M::FS) * TPB;
-        fst[c][0] = q[2 * TPB]; fst[c][1] = q[3 * TPB];
-#pragma unroll
-        for (int f = 0; f < 4; ++f) fst[c][2 + f] = q[(4 + f) * TPB];
-      }
-    }
+    for (int c = 0; c < CPL; ++c) ierr[c] = sm[(M::kIerr + c) * TPB];
     hot = true;
   };
   // Which Pid every cable of this lane runs, on which set point, and whether all of them are live, primed and on a window
@@ -411,14 +535,43 @@ __global__ void __launch_bounds__(TPB) k_step_flexr(const __grid_constant__ Step
     return ok;
   };
   bool steady = false, recheck = true;
-
-  for (int s = 0; s < A.k_steps; ++s) {
-    const bool last = (s == A.k_steps - 1);
+  // the lanes of this robot (adjacent threads): all they exchange goes through shuffles among themselves only, because the
+  // robots of a warp are in different places of the loop below
+  const unsigned pairmask = (LANES == 1) ? (1u << (tid & 31)) : (((1u << LANES) - 1u) << ((tid & 31) & ~(LANES - 1)));
+  auto robot_sum = [&](double v) {
+    if (LANES >= 2) v += __shfl_xor_sync(pairmask, v, 1);
+    if (LANES >= 4) v += __shfl_xor_sync(pairmask, v, 2);
+    return v;
+  };
+  auto clock_tick = [&](double &now) {
     // World::Step: simTime += dt, then the plugin callback
     nsec += A.dt_ns;
     if (nsec >= 1000000000) { nsec -= 1000000000; ++sec; }
-    const double now = time_double(sec, nsec);
+    now = time_double(sec, nsec);
     head = (head + 1 == kFlexLen) ? 0 : head + 1;
+  };
+  auto platform_step = [&](const Rot &R, Wrench6 &W) {
+    // the robot's wrench = sum over its lanes; then every lane integrates the same platform step
+    W.fx = robot_sum(W.fx); W.fy = robot_sum(W.fy); W.fz = robot_sum(W.fz);
+    W.mx = robot_sum(W.mx); W.my = robot_sum(W.my); W.mz = robot_sum(W.mz);
+    if (rc.spec & SPEC_ISO) rigid_body_step<SPEC_DIAG | SPEC_ISO>(rc, S, R, W.fx, W.fy, W.fz, W.mx, W.my, W.mz);
+    else if (rc.diag_inertia) rigid_body_step<SPEC_DIAG>(rc, S, R, W.fx, W.fy, W.fz, W.mx, W.my, W.mz);
+    else rigid_body_step<0>(rc, S, R, W.fx, W.fy, W.fz, W.mx, W.my, W.mz);
+    if (A.cost) {
+      const double ex = S.px - A.target[0], ey = S.py - A.target[1], ez = S.pz - A.target[2];
+      cost += fma(ex, ex, fma(ey, ey, ez * ez)) + A.lambda * fma(S.wx, S.wx, fma(S.wy, S.wy, S.wz * S.wz));
+    }
+  };
+
+  // The K steps as in step_fast.cuh: every step whose commands, flags or bookkeeping need attention goes through the full
+  // path at the top of the loop; a robot that comes out of it steady runs the following steps up to its next event (a
+  // command of the sine publisher or the command table, a snapshot, the last step of the launch) in an inner loop that
+  // holds the hot body and nothing else -- no call, no flag -- so its registers are not shared with the rare paths.
+  int s = 0;
+  while (s < A.k_steps) {
+    const bool last = (s == A.k_steps - 1);
+    double now;
+    clock_tick(now);
 
     // ---- commands of this step (CdprGazeboPlugin::update, .cpp:206-219)
     bool vel_event = false;
@@ -450,87 +603,115 @@ __global__ void __launch_bounds__(TPB) k_step_flexr(const __grid_constant__ Step
       recheck = true;
     }
     if (vel_event) recheck = true;
-    if (recheck) { steady = evaluate(); recheck = false; }
+    if (recheck) {  // every lane of the robot gets here in the same steps (commands and general steps are the robot's)
+      bool ok = evaluate();
+      if (LANES >= 2) ok = ok && (__shfl_xor_sync(pairmask, ok ? 1 : 0, 1) != 0);
+      if (LANES >= 4) ok = ok && (__shfl_xor_sync(pairmask, ok ? 1 : 0, 2) != 0);
+      steady = ok;  // the ROBOT is steady: its lanes take the same body, so they meet at the same shuffles
+      recheck = false;
+    }
 
-    const Rot R = make_rot(S);
-    Wrench6 W;
-    if (steady && !last) {
-      // ================= hot body: straight-line, every cable of the lane on its live Pid, state in registers =================
-      if (!hot) fill();
-      const double dt = __dsub_rn(now, tprev);  // == now - mLastTime of every live Pid
-      W.fx = lead ? rc.mg[0] : 0.0; W.fy = lead ? rc.mg[1] : 0.0; W.fz = lead ? rc.mg[2] : 0.0;
-      W.mx = 0.0; W.my = 0.0; W.mz = 0.0;
-      // ring offsets by sample age, once per step for all cables (age 0 = this step's slot)
-      int ro[kFlexLen];
-#pragma unroll
-      for (int a = 0; a < kFlexLen; ++a) {
-        int sl = head - a;
-        sl += (sl < 0) ? kFlexLen : 0;
-        ro[a] = sl * (CPL * TPB);
-      }
-      double *ring = sm + M::kRing * TPB;
-#pragma unroll
-      for (int c = 0; c < CPL; ++c) {
-        CableKin kin;
-        if (LANES == 1) {
-          kin = cable_kin_v(rc.b[c][0], rc.b[c][1], rc.b[c][2], rc.a[c][0], rc.a[c][1], rc.a[c][2], rc.home_len[c], S, R);
-        } else {
-          const double *q = cabtab + c * 7;
-          kin = cable_kin_v(q[0], q[1], q[2], q[3], q[4], q[5], q[6], S, R);
-        }
-        // mLastPosition follows the joint unless the cable holds (JointForceCalculator.cpp:78,84,88)
-        if (!((holdmask >> c) & 1u)) sm[(M::kLastp + c) * TPB] = kin.qp;
-        const bool pos = ((posmask >> c) & 1u) != 0u;
-        const double *row = tab + (pos ? M::kRow : 0);
-        const double desired = sm[(M::kDes + c) * TPB];
-        const double actual = pos ? kin.qp : kin.qd;
-        const FlexGains g = flexr_gains(row);
-        const double e = __dsub_rn(desired, actual);
-        double *rc_ = ring + c * TPB;
-        double pe = e;
-        if (has_p) {
-          double x1 = rc_[ro[1]], x2 = rc_[ro[2]];
-          pe = biquad_step(row + 7, x1, x2, fst[c][0], fst[c][1], e);
-        }
-        rc_[ro[0]] = e;
-        double derived = 0.0;
-        if (has_fir) {  // flex_fir with the offsets above: same order of operations
-          double d0 = __dmul_rn(A.fir[kFlexLen - 1], e), d1 = 0.0;
-#pragma unroll
-          for (int a = 1; a < kFlexLen; ++a) {
-            const double y = rc_[ro[a]];
-            if (a & 1) d1 = fma(A.fir[kFlexLen - 1 - a], y, d1); else d0 = fma(A.fir[kFlexLen - 1 - a], y, d0);
-          }
-          derived = __dadd_rn(d0, d1);
-        }
-        double de = derived;
-        if (has_d) de = biquad_step(row + 12, fst[c][2], fst[c][3], fst[c][4], fst[c][5], derived);
-        const FlexPidOut o = flex_pid(g, desired, e, dt, pe, de, ierr[c]);
-        ierr[c] = o.ierr;
-        const double eff = (rc.effort_limit >= 0.0) ? clampd(o.cmd, -rc.effort_limit, rc.effort_limit) : o.cmd;
-        const double tl = __dmul_rn(fma(-rc.cdamp, kin.qd, eff), kin.il);  // tension / L
-        W.fx = fma(tl, kin.dx, W.fx); W.fy = fma(tl, kin.dy, W.fy); W.fz = fma(tl, kin.dz, W.fz);
-        W.mx = fma(tl, kin.cx, W.mx); W.my = fma(tl, kin.cy, W.my); W.mz = fma(tl, kin.cz, W.mz);
-      }
-    } else {
+    // The threads of a warp stay in step: as long as one of them needs the full path, the others advance one step at a time
+    // too (a robot left behind in its own loop would run the rest of the launch with a warp of its own).
+    const bool full = !(steady && !last);
+    const bool any_full = __any_sync(0xffffffffu, full);
+    if (full) {
+      // ================= full path: one step with every flag honoured =================
       if (hot) spill();
-      W = flexr_general_step<CPL, TPB, NF, LANES>(A, S, sm, sw, tab, c0, lead, valid, mode, now, head, sec, nsec, last, i);
+      const Rot R = make_rot(S);
+      Wrench6 W = flexr_general_step<CPL, TPB, NF, LANES>(A, S, sm, sw, tab, c0, lead, valid, mode, now, head, sec, nsec, last, i);
       recheck = true;
+      if (last && lead && valid) publish_platform(A, S, i);
+      platform_step(R, W);
+      tprev = now;
+      ++s;
+      if (A.snap_every > 0 && ++snap_ctr == A.snap_every) {
+        snap_ctr = 0;
+        if (lead && valid && snap_idx < A.snap_capacity) write_snapshot(A, S, snap_idx * 13 * A.snap_stride + A.snap_offset + i);
+        ++snap_idx;
+      }
+      continue;
     }
-    // ---- the robot's wrench = sum over its lanes; then every lane integrates the same platform step
-    W.fx = lane_sum<LANES>(W.fx); W.fy = lane_sum<LANES>(W.fy); W.fz = lane_sum<LANES>(W.fz);
-    W.mx = lane_sum<LANES>(W.mx); W.my = lane_sum<LANES>(W.my); W.mz = lane_sum<LANES>(W.mz);
-    if (last && lead && valid) publish_platform(A, S, i);
-    if (rc.spec & SPEC_ISO) rigid_body_step<SPEC_DIAG | SPEC_ISO>(rc, S, R, W.fx, W.fy, W.fz, W.mx, W.my, W.mz);
-    else if (rc.diag_inertia) rigid_body_step<SPEC_DIAG>(rc, S, R, W.fx, W.fy, W.fz, W.mx, W.my, W.mz);
-    else rigid_body_step<0>(rc, S, R, W.fx, W.fy, W.fz, W.mx, W.my, W.mz);
-    tprev = now;
-    if (A.cost) {
-      const double ex = S.px - A.target[0], ey = S.py - A.target[1], ez = S.pz - A.target[2];
-      cost += fma(ex, ex, fma(ey, ey, ez * ez)) + A.lambda * fma(S.wx, S.wx, fma(S.wy, S.wy, S.wz * S.wz));
+
+    // ================= hot run: this step and the steps up to the next event =================
+    int run = any_full ? 1 : A.k_steps - 1 - s;  // the last step of the launch takes the full path (it publishes)
+    if (A.sine_on) run = min(run, (sine_ctr == 0) ? 1 : A.sine_period - sine_ctr + 1);
+    if (cmd_row) run = min(run, (cmd_ctr == 0) ? 1 : A.steps_per_cmd - cmd_ctr + 1);
+    if (A.snap_every > 0) run = (int)min((long long)run, A.snap_every - snap_ctr);
+    if (!hot) fill();
+    {
+      double *ring = sm + M::kRing * TPB;
+      int r = 0;
+#pragma unroll 1
+      for (;;) {
+        // ---- hot body: straight-line, every cable of the lane on its live Pid, the integrals in registers
+        const double dt = __dsub_rn(now, tprev);  // == now - mLastTime of every live Pid
+        const Rot R = make_rot(S);
+        Wrench6 W;
+        W.fx = lead ? rc.mg[0] : 0.0; W.fy = lead ? rc.mg[1] : 0.0; W.fz = lead ? rc.mg[2] : 0.0;
+        W.mx = 0.0; W.my = 0.0; W.mz = 0.0;
+        // ring offsets of this step's slot and of the two samples before it (the P filter's x1, x2); FIR weights by slot
+        int o1 = head - 1, o2 = head - 2;
+        o1 += (o1 < 0) ? kFlexLen : 0;
+        o2 += (o2 < 0) ? kFlexLen : 0;
+        const int o0 = head * (CPL * TPB);
+        o1 *= CPL * TPB; o2 *= CPL * TPB;
+        const double *gw = A.firx + (kFlexLen - 1 - head);
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) {
+          CableKin kin;
+          if (LANES == 1) {
+            kin = cable_kin_v(rc.b[c][0], rc.b[c][1], rc.b[c][2], rc.a[c][0], rc.a[c][1], rc.a[c][2], rc.home_len[c], S, R);
+          } else {
+            const double *q = cabtab + c * 7;
+            kin = cable_kin_v(q[0], q[1], q[2], q[3], q[4], q[5], q[6], S, R);
+          }
+          // mLastPosition follows the joint unless the cable holds (JointForceCalculator.cpp:78,84,88)
+          if (!((holdmask >> c) & 1u)) sm[(M::kLastp + c) * TPB] = kin.qp;
+          const bool pos = ((posmask >> c) & 1u) != 0u;
+          const double *row = tab + (pos ? M::kRow : 0);
+          const double desired = sm[(M::kDes + c) * TPB];
+          const double actual = pos ? kin.qp : kin.qd;
+          const FlexGains g = flexr_gains(row);
+          const double e = __dsub_rn(desired, actual);
+          double *rc_ = ring + c * TPB;
+          double pe = e;
+          if (has_p) {
+            double x1 = rc_[o1], x2 = rc_[o2];
+            double *q = sm + (M::kFilt + c * M::FS) * TPB;
+            double y1 = q[2 * TPB], y2 = q[3 * TPB];
+            const double y0 = biquad_step(A.flex_pf, x1, x2, y1, y2, e);
+            q[2 * TPB] = y1; q[3 * TPB] = y2;
+            pe = ((A.flex_p_on >> (pos ? 1 : 0)) & 1) ? y0 : e;
+          }
+          rc_[o0] = e;
+          double derived = 0.0;
+          if (has_fir) derived = flexr_fir<CPL * TPB>(gw, rc_);
+          double de = derived;
+          if (has_d) {
+            const double y0 = biquad_step_sm<TPB>(A.flex_df, sm + (M::kFilt + c * M::FS + 4 * NF) * TPB, derived);
+            de = ((A.flex_d_on >> (pos ? 1 : 0)) & 1) ? y0 : derived;
+          }
+          const FlexPidOut o = flex_pid(g, desired, e, dt, pe, de, ierr[c]);
+          ierr[c] = o.ierr;
+          const double eff = (rc.effort_limit >= 0.0) ? clampd(o.cmd, -rc.effort_limit, rc.effort_limit) : o.cmd;
+          const double tl = __dmul_rn(fma(-rc.cdamp, kin.qd, eff), kin.il);  // tension / L
+          W.fx = fma(tl, kin.dx, W.fx); W.fy = fma(tl, kin.dy, W.fy); W.fz = fma(tl, kin.dz, W.fz);
+          W.mx = fma(tl, kin.cx, W.mx); W.my = fma(tl, kin.cy, W.my); W.mz = fma(tl, kin.cz, W.mz);
+        }
+        platform_step(R, W);
+        tprev = now;
+        if (++r == run) break;
+        clock_tick(now);
+      }
     }
+    // the steps of the run after the first saw no command: move the counters over them
+    if (A.sine_on) { sine_ctr += run - 1; sine_ctr -= (sine_ctr >= A.sine_period) ? A.sine_period : 0; }
+    if (cmd_row) { cmd_ctr += run - 1; cmd_ctr -= (cmd_ctr >= A.steps_per_cmd) ? A.steps_per_cmd : 0; }
+    s += run;
     if (A.snap_every > 0) {
-      if (++snap_ctr == A.snap_every) {
+      snap_ctr += run;
+      if (snap_ctr == A.snap_every) {
         snap_ctr = 0;
         if (lead && valid && snap_idx < A.snap_capacity) write_snapshot(A, S, snap_idx * 13 * A.snap_stride + A.snap_offset + i);
         ++snap_idx;
