@@ -4,13 +4,16 @@
 #include "step_flexr.cuh"
 namespace cdpr {
 constexpr int kFlexrTpb = 32;  // one warp per block, as in k_step_flex
+// the isotropic-inertia instance when the robot allows it (rc.spec, detected at cdpr_create), else the general one
 template <int NC, int NF, bool HOLD, int LANES> static void flexr_go(unsigned grid, const StepArgs &A, cudaStream_t st) {
-  k_step_flexr<NC, kFlexrTpb, NF, HOLD, LANES><<<grid, kFlexrTpb, FlexRSmem<NC / LANES, kFlexrTpb, NF, LANES>::bytes, st>>>(A);
+  if (A.rc.spec & SPEC_ISO) k_step_flexr<NC, kFlexrTpb, NF, HOLD, LANES, true><<<grid, kFlexrTpb, FlexRSmem<NC / LANES, kFlexrTpb, NF, LANES>::bytes, st>>>(A);
+  else k_step_flexr<NC, kFlexrTpb, NF, HOLD, LANES, false><<<grid, kFlexrTpb, FlexRSmem<NC / LANES, kFlexrTpb, NF, LANES>::bytes, st>>>(A);
 }
 template <int NC, int NF, bool HOLD, int LANES> static void flexr_prep() {
-  const void *f = (const void *)k_step_flexr<NC, kFlexrTpb, NF, HOLD, LANES>;
-  cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FlexRSmem<NC / LANES, kFlexrTpb, NF, LANES>::bytes);
-  cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  for (const void *f : {(const void *)k_step_flexr<NC, kFlexrTpb, NF, HOLD, LANES, true>, (const void *)k_step_flexr<NC, kFlexrTpb, NF, HOLD, LANES, false>}) {
+    cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FlexRSmem<NC / LANES, kFlexrTpb, NF, LANES>::bytes);
+    cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  }
 }
 // the four (NF, HOLD) instances of one (NC, LANES) shape
 #define CDPR_FLEXR_UNIT(NAME, NC_, L_)                                                                           \

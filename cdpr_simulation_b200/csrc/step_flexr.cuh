@@ -41,7 +41,7 @@ struct FlexRSmem : FlexSmem<CPL, TPB, NF> {
   static constexpr int kStale = kDes + CPL;   // [CPL] time stamp of the newest STALE sample of a window that spans a gap
   static constexpr int kPerThread = kStale + CPL;
   // block-shared table behind the per-thread columns
-  static constexpr int kRow = 8;              // kf kp ki kd i_max i_max/ki c_max (pad): the gains of one Pid
+  static constexpr int kRow = 8;              // kf kp ki kd i_max i_max/ki c_max min(c_max, effort limit): the gains of one Pid
   static constexpr int kTabCab = 2 * kRow;    // [LANES][CPL][7]: b xyz, a xyz, home length
   static constexpr int kTabDoubles = kTabCab + LANES * CPL * 7;
   static constexpr size_t bytes = sizeof(double) * ((size_t)kPerThread * TPB + kTabDoubles);
@@ -101,6 +101,38 @@ __device__ __forceinline__ FlexGains flexr_gains(const double *row) {
   FlexGains g;
   g.kf = row[0]; g.kp = row[1]; g.ki = row[2]; g.kd = row[3]; g.i_max = row[4]; g.i_max_over_ki = row[5]; g.c_max = row[6];
   return g;
+}
+
+// flex_pid (step_flex.cuh) without a branch: the same operations and roundings with the clamp decisions as selects (the
+// anti-windup correction is computed whether or not it is used).  A taken branch in the unrolled cable loop is an
+// instruction-fetch bubble that two warps per scheduler cannot hide (ncu: 30-60 % of the hot loop's stall samples were
+// `no_instruction`).
+__device__ __forceinline__ FlexPidOut flexr_pid(const FlexGains &g, double desired, double e, double dt, double pe, double de, double prev_ierr) {
+  FlexPidOut o;
+  const double f_term = __dmul_rn(g.kf, desired);
+  o.p_term = __dmul_rn(g.kp, pe);
+  const double ie1 = fma(dt, e, prev_ierr);
+  const double i_raw = __dmul_rn(g.ki, ie1);
+  o.i_term_pre = i_raw;
+  const bool hi = i_raw > g.i_max, lo = i_raw < -g.i_max;  // Pid.cpp:143-150 (hi wins, as the else-if does)
+  const double i_term = hi ? g.i_max : (lo ? -g.i_max : i_raw);
+  const double ie2 = hi ? g.i_max_over_ki : (lo ? -g.i_max_over_ki : ie1);
+  o.d_term = __dmul_rn(g.kd, de);
+  const double cmd_raw = __dadd_rn(__dadd_rn(__dadd_rn(f_term, o.p_term), i_term), o.d_term);
+  const double cmd_c = clampd(cmd_raw, -g.c_max, g.c_max);
+  const bool aw = (cmd_c != cmd_raw);  // Pid.cpp:181-184
+  const double cmd_aw = __dadd_rn(cmd_c, __dmul_rn(__dmul_rn(dt, e), g.ki));
+  o.cmd = aw ? cmd_aw : cmd_c;
+  o.ierr = aw ? prev_ierr : ie2;
+  return o;
+}
+
+// the exact chain of Pid::update and Joint::SetForce for a cable whose command or integral clamps (rare: out of line)
+static __device__ __noinline__ double flexr_pid_clamped(const double *row, double effort_limit, double desired, double e, double dt, double pe, double de,
+                                                        double prev_ierr, double &ierr) {
+  const FlexPidOut o = flexr_pid(flexr_gains(row), desired, e, dt, pe, de, prev_ierr);
+  ierr = o.ierr;
+  return (effort_limit >= 0.0) ? clampd(o.cmd, -effort_limit, effort_limit) : o.cmd;
 }
 
 // (sec, nsec) - back * dt_ns as a gazebo time stamp, without 64-bit divisions
@@ -369,7 +401,7 @@ static __device__ __noinline__ Wrench6 flexr_general_step(const StepArgs &A, Fas
           const double y0 = biquad_step_sm<TPB>(A.flex_df, sm + (M::kFilt + c * M::FS + 4 * NF) * TPB, derived);
           de = ((A.flex_d_on >> k) & 1) ? y0 : derived;
         }
-        const FlexPidOut o = flex_pid(g, desired, e, dt, pe, de, sm[(M::kIerr + c) * TPB]);
+        const FlexPidOut o = flexr_pid(g, desired, e, dt, pe, de, sm[(M::kIerr + c) * TPB]);
         sm[(M::kIerr + c) * TPB] = o.ierr;
         force = o.cmd;
         if (last) {
@@ -398,13 +430,25 @@ static __device__ __noinline__ Wrench6 flexr_general_step(const StepArgs &A, Fas
   return W;
 }
 
+#ifndef CDPR_FLEXR_UNR
+#define CDPR_FLEXR_UNR 0  // tuning override of the unroll factor of the hot body's cable loop (0 = the measured choice below)
+#endif
+#ifndef CDPR_FLEXR_OPTIMISTIC
+#define CDPR_FLEXR_OPTIMISTIC 0
+#endif
 #ifndef CDPR_FLEXR_MINB0
 #define CDPR_FLEXR_MINB0 1  // resident blocks asked for at two lanes without filter slots (caps the registers per thread)
 #endif
 // HOLD = false: velocityEpsilon < 0, no cable can ever hold, the Pid follows the instance's mode alone
-template <int NC, int TPB, int NF, bool HOLD, int LANES>
+template <int NC, int TPB, int NF, bool HOLD, int LANES, bool ISO>
 __global__ void __launch_bounds__(TPB, (LANES == 4) ? 16 : ((LANES == 2 && NF == 0) ? CDPR_FLEXR_MINB0 : 1)) k_step_flexr(const __grid_constant__ StepArgs A) {
   constexpr int CPL = NC / LANES;
+  // Unroll factor of the hot body's cable loop.  The kernel is bound by INSTRUCTION FETCH as soon as warps alternate between
+  // the hot loop and the full path (ncu: 30-60 % of the stall samples `no_instruction`, clustered on 128-byte line starts):
+  // the hot loop is 1237 / 759 / 487 instructions at 4 / 2 / 1 cables per iteration and the full path another ~1500.  Measured
+  // at NC=8, 2^20 x 1000 steps (ms), unroll 4 / 2 / 1: steady 82 / 88 / 92; with hold transitions 175 / 116 / 117; hold + one
+  // P and one D stage 250 / 165 / 156.  So: everything unrolled when no cable can ever hold, else 2 (1 with filter slots).
+  constexpr int kUnr = (CDPR_FLEXR_UNR > 0) ? CDPR_FLEXR_UNR : (HOLD ? (NF > 0 ? 1 : 2) : CPL);
   static_assert(CPL * LANES == NC && (LANES == 1 || LANES == 2 || LANES == 4) && NF <= 1, "lanes must divide the cables; one biquad slot per filter");
   using M = FlexRSmem<CPL, TPB, NF, LANES>;
   extern __shared__ double smem[];
@@ -429,7 +473,8 @@ __global__ void __launch_bounds__(TPB, (LANES == 4) ? 16 : ((LANES == 2 && NF ==
     for (int k = 0; k < 2; ++k) {
       const PidConsts &pc = A.pc[k];
       double *row = tabw + k * M::kRow;
-      row[0] = pc.kf; row[1] = pc.kp; row[2] = pc.ki; row[3] = pc.kd; row[4] = pc.i_max; row[5] = pc.i_max_over_ki; row[6] = pc.cmd_max; row[7] = 0.0;
+      row[0] = pc.kf; row[1] = pc.kp; row[2] = pc.ki; row[3] = pc.kd; row[4] = pc.i_max; row[5] = pc.i_max_over_ki; row[6] = pc.cmd_max;
+      row[7] = fmin(pc.cmd_max, rc.effort_limit_abs);  // a command within it passes every clamp unchanged
     }
     for (int c = 0; c < NC; ++c) {
       double *q = tabw + M::kTabCab + c * 7;
@@ -485,15 +530,13 @@ __global__ void __launch_bounds__(TPB, (LANES == 4) ? 16 : ((LANES == 2 && NF ==
   long long snap_ctr = A.snap_every > 0 ? (A.n0 % A.snap_every) : 0;
 
   // ---- what the hot body carries in registers
-  // Integrals of the live Pids.  (The biquad state stays in shared memory: held in registers it raised the pressure of the
-  // unrolled cable loop past 255 registers, and with the shared-memory carve-out at its maximum a spill is an L2 round
-  // trip -- measured 25 % slower than the explicit LDS / STS.  The P filter's x1, x2 are the last two errors, which a hot
-  // thread finds in the ring: its live Pids have pushed every one of the last 11 steps.)
-  double ierr[CPL];
+  // The controller state of the live Pids (integrals, biquad state) stays in shared memory in the hot body too.  Held in
+  // registers it raised the pressure of the unrolled cable loop past 255 registers, and with the shared-memory carve-out at
+  // its maximum a spill is an L2 round trip -- measured 25 % slower than the explicit LDS / STS.  What the hot body skips is
+  // mLastTime (the same for every live Pid: tprev) and the P filter's x1, x2 (the last two errors, which a hot thread finds
+  // in the ring: its live Pids have pushed every one of the last 11 steps); `spill` puts them back for the general body.
   unsigned posmask = 0u, holdmask = 0u;  // per cable: runs the position Pid / holds (position Pid in Velocity mode)
-#pragma unroll
-  for (int c = 0; c < CPL; ++c) ierr[c] = 0.0;
-  bool hot = false;  // the previous step ran the hot body: the registers above are the truth, shared memory is stale
+  bool hot = false;  // the previous step ran the hot body
   const bool has_p = NF > 0 && A.flex_ps > 0, has_d = NF > 0 && A.flex_ds > 0, has_fir = A.pc[0].degree >= 1;
 
   auto spill = [&]() {  // runs after the clock tick of a step: `head` is the slot this step's sample WILL take
@@ -502,19 +545,13 @@ __global__ void __launch_bounds__(TPB, (LANES == 4) ? 16 : ((LANES == 2 && NF ==
     h2 += (h2 < 0) ? kFlexLen : 0;
 #pragma unroll
     for (int c = 0; c < CPL; ++c) {
-      sm[(M::kIerr + c) * TPB] = ierr[c];
       sm[(M::kLtime + c) * TPB] = tprev;
-      if (NF > 0) {  // the P filter's x1, x2 as the general body keeps them
+      if (NF > 0) {
         double *q = sm + (M::kFilt + c * M::FS) * TPB;
         q[0] = sm[(M::kRing + h1 * CPL + c) * TPB]; q[TPB] = sm[(M::kRing + h2 * CPL + c) * TPB];
       }
     }
     hot = false;
-  };
-  auto fill = [&]() {
-#pragma unroll
-    for (int c = 0; c < CPL; ++c) ierr[c] = sm[(M::kIerr + c) * TPB];
-    hot = true;
   };
   // Which Pid every cable of this lane runs, on which set point, and whether all of them are live, primed and on a window
   // of the last 11 steps.  Depends on the targets, the latched positions and the control words only, so it is re-evaluated
@@ -535,14 +572,9 @@ __global__ void __launch_bounds__(TPB, (LANES == 4) ? 16 : ((LANES == 2 && NF ==
     return ok;
   };
   bool steady = false, recheck = true;
-  // the lanes of this robot (adjacent threads): all they exchange goes through shuffles among themselves only, because the
-  // robots of a warp are in different places of the loop below
-  const unsigned pairmask = (LANES == 1) ? (1u << (tid & 31)) : (((1u << LANES) - 1u) << ((tid & 31) & ~(LANES - 1)));
-  auto robot_sum = [&](double v) {
-    if (LANES >= 2) v += __shfl_xor_sync(pairmask, v, 1);
-    if (LANES >= 4) v += __shfl_xor_sync(pairmask, v, 2);
-    return v;
-  };
+  // the lanes of a robot are adjacent threads; the whole warp is at the same place of the loop below (see `full`), so the
+  // shuffles name every lane (a computed mask costs a MATCH + WARPSYNC per shuffle)
+  auto robot_sum = [&](double v) { return lane_sum<LANES>(v); };
   auto clock_tick = [&](double &now) {
     // World::Step: simTime += dt, then the plugin callback
     nsec += A.dt_ns;
@@ -554,7 +586,8 @@ __global__ void __launch_bounds__(TPB, (LANES == 4) ? 16 : ((LANES == 2 && NF ==
     // the robot's wrench = sum over its lanes; then every lane integrates the same platform step
     W.fx = robot_sum(W.fx); W.fy = robot_sum(W.fy); W.fz = robot_sum(W.fz);
     W.mx = robot_sum(W.mx); W.my = robot_sum(W.my); W.mz = robot_sum(W.mz);
-    if (rc.spec & SPEC_ISO) rigid_body_step<SPEC_DIAG | SPEC_ISO>(rc, S, R, W.fx, W.fy, W.fz, W.mx, W.my, W.mz);
+    // ISO: isotropic body inertia (detected at cdpr_create), compiled in so the hot loop holds one rigid-body update
+    if (ISO) rigid_body_step<SPEC_DIAG | SPEC_ISO>(rc, S, R, W.fx, W.fy, W.fz, W.mx, W.my, W.mz);
     else if (rc.diag_inertia) rigid_body_step<SPEC_DIAG>(rc, S, R, W.fx, W.fy, W.fz, W.mx, W.my, W.mz);
     else rigid_body_step<0>(rc, S, R, W.fx, W.fy, W.fz, W.mx, W.my, W.mz);
     if (A.cost) {
@@ -603,18 +636,17 @@ __global__ void __launch_bounds__(TPB, (LANES == 4) ? 16 : ((LANES == 2 && NF ==
       recheck = true;
     }
     if (vel_event) recheck = true;
-    if (recheck) {  // every lane of the robot gets here in the same steps (commands and general steps are the robot's)
-      bool ok = evaluate();
-      if (LANES >= 2) ok = ok && (__shfl_xor_sync(pairmask, ok ? 1 : 0, 1) != 0);
-      if (LANES >= 4) ok = ok && (__shfl_xor_sync(pairmask, ok ? 1 : 0, 2) != 0);
-      steady = ok;  // the ROBOT is steady: its lanes take the same body, so they meet at the same shuffles
+    if (recheck) {
+      steady = evaluate();
       recheck = false;
     }
 
-    // The threads of a warp stay in step: as long as one of them needs the full path, the others advance one step at a time
-    // too (a robot left behind in its own loop would run the rest of the launch with a warp of its own).
-    const bool full = !(steady && !last);
-    const bool any_full = __any_sync(0xffffffffu, full);
+    // The threads of a warp stay in step, and they take the same body: as soon as ONE of them needs the full path in this
+    // step, all of them run it (it is the general body -- a steady robot gets the same bits out of it).  Alternating
+    // between the two bodies step by step, which is what a per-thread choice amounts to while a neighbour is in transition,
+    // misses the instruction cache on every switch (both bodies together are > 40 KB): measured 228 ms against 162 ms per
+    // 2^20 x 1000 steps with hold transitions.  A robot left to run ahead in its own loop would be worse still.
+    const bool full = __any_sync(0xffffffffu, !(steady && !last));
     if (full) {
       // ================= full path: one step with every flag honoured =================
       if (hot) spill();
@@ -634,11 +666,11 @@ __global__ void __launch_bounds__(TPB, (LANES == 4) ? 16 : ((LANES == 2 && NF ==
     }
 
     // ================= hot run: this step and the steps up to the next event =================
-    int run = any_full ? 1 : A.k_steps - 1 - s;  // the last step of the launch takes the full path (it publishes)
+    int run = A.k_steps - 1 - s;  // the last step of the launch takes the full path (it publishes)
     if (A.sine_on) run = min(run, (sine_ctr == 0) ? 1 : A.sine_period - sine_ctr + 1);
     if (cmd_row) run = min(run, (cmd_ctr == 0) ? 1 : A.steps_per_cmd - cmd_ctr + 1);
     if (A.snap_every > 0) run = (int)min((long long)run, A.snap_every - snap_ctr);
-    if (!hot) fill();
+    hot = true;
     {
       double *ring = sm + M::kRing * TPB;
       int r = 0;
@@ -657,10 +689,10 @@ __global__ void __launch_bounds__(TPB, (LANES == 4) ? 16 : ((LANES == 2 && NF ==
         const int o0 = head * (CPL * TPB);
         o1 *= CPL * TPB; o2 *= CPL * TPB;
         const double *gw = A.firx + (kFlexLen - 1 - head);
-#pragma unroll
+#pragma unroll kUnr
         for (int c = 0; c < CPL; ++c) {
           CableKin kin;
-          if (LANES == 1) {
+          if (LANES == 1 && kUnr >= CPL) {
             kin = cable_kin_v(rc.b[c][0], rc.b[c][1], rc.b[c][2], rc.a[c][0], rc.a[c][1], rc.a[c][2], rc.home_len[c], S, R);
           } else {
             const double *q = cabtab + c * 7;
@@ -692,9 +724,25 @@ __global__ void __launch_bounds__(TPB, (LANES == 4) ? 16 : ((LANES == 2 && NF ==
             const double y0 = biquad_step_sm<TPB>(A.flex_df, sm + (M::kFilt + c * M::FS + 4 * NF) * TPB, derived);
             de = ((A.flex_d_on >> (pos ? 1 : 0)) & 1) ? y0 : derived;
           }
-          const FlexPidOut o = flex_pid(g, desired, e, dt, pe, de, ierr[c]);
-          ierr[c] = o.ierr;
+#if CDPR_FLEXR_OPTIMISTIC
+          // Pid::update from the integral on, OPTIMISTICALLY: the integral clamp, the command clamp with its anti-windup and
+          // Joint::SetForce's truncation (Pid.cpp:143-150,175-184) almost never fire on a stable loop, and as long as none does
+          // the chain returns exactly these values; two compares decide, the exact chain runs out of line for a cable that
+          // needs it.  Measured: -5 % on the launch gains, +35 % on a loop that saturates two steps out of three (the
+          // reference's filter constants with one stage switched on) -- off by default.
+          const double prev_ie = sm[(M::kIerr + c) * TPB];
+          const double ie1 = fma(dt, e, prev_ie);
+          const double i_term = __dmul_rn(g.ki, ie1);
+          const double cmd_raw = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(g.kf, desired), __dmul_rn(g.kp, pe)), i_term), __dmul_rn(g.kd, de));
+          double eff = cmd_raw, ie_new = ie1;
+          if (!(fabs(i_term) <= g.i_max) || !(fabs(cmd_raw) <= row[7]))
+            eff = flexr_pid_clamped(row, rc.effort_limit, desired, e, dt, pe, de, prev_ie, ie_new);
+          sm[(M::kIerr + c) * TPB] = ie_new;
+#else
+          const FlexPidOut o = flexr_pid(g, desired, e, dt, pe, de, sm[(M::kIerr + c) * TPB]);
+          sm[(M::kIerr + c) * TPB] = o.ierr;
           const double eff = (rc.effort_limit >= 0.0) ? clampd(o.cmd, -rc.effort_limit, rc.effort_limit) : o.cmd;
+#endif
           const double tl = __dmul_rn(fma(-rc.cdamp, kin.qd, eff), kin.il);  // tension / L
           W.fx = fma(tl, kin.dx, W.fx); W.fy = fma(tl, kin.dy, W.fy); W.fz = fma(tl, kin.dz, W.fz);
           W.mx = fma(tl, kin.cx, W.mx); W.my = fma(tl, kin.cy, W.my); W.mz = fma(tl, kin.cz, W.mz);
