@@ -107,6 +107,13 @@ __device__ __forceinline__ FlexGains flexr_gains(const double *row) {
 // anti-windup correction is computed whether or not it is used).  A taken branch in the unrolled cable loop is an
 // instruction-fetch bubble that two warps per scheduler cannot hide (ncu: 30-60 % of the hot loop's stall samples were
 // `no_instruction`).
+// v clamped to [-lim, lim], lim >= 0: one compare on |v| and the limit with v's sign (fmin / fmax cost five instructions
+// each for their NaN rules; a NaN passes through here)
+__device__ __forceinline__ double clamp_sym(double v, double lim) { return (fabs(v) > lim) ? copysign(lim, v) : v; }
+// x with its sign flipped when s is negative (x may have either sign)
+__device__ __forceinline__ double flip_sign_by(double x, double s) {
+  return __hiloint2double(__double2hiint(x) ^ (__double2hiint(s) & (int)0x80000000), __double2loint(x));
+}
 __device__ __forceinline__ FlexPidOut flexr_pid(const FlexGains &g, double desired, double e, double dt, double pe, double de, double prev_ierr) {
   FlexPidOut o;
   const double f_term = __dmul_rn(g.kf, desired);
@@ -114,12 +121,13 @@ __device__ __forceinline__ FlexPidOut flexr_pid(const FlexGains &g, double desir
   const double ie1 = fma(dt, e, prev_ierr);
   const double i_raw = __dmul_rn(g.ki, ie1);
   o.i_term_pre = i_raw;
-  const bool hi = i_raw > g.i_max, lo = i_raw < -g.i_max;  // Pid.cpp:143-150 (hi wins, as the else-if does)
-  const double i_term = hi ? g.i_max : (lo ? -g.i_max : i_raw);
-  const double ie2 = hi ? g.i_max_over_ki : (lo ? -g.i_max_over_ki : ie1);
+  // Pid.cpp:143-150: iTerm > iMax -> iMax, mIerr = iMax / Ki; iTerm < iMin = -iMax -> -iMax, mIerr = -(iMax / Ki)
+  const bool isat = fabs(i_raw) > g.i_max;
+  const double i_term = isat ? copysign(g.i_max, i_raw) : i_raw;
+  const double ie2 = isat ? flip_sign_by(g.i_max_over_ki, i_raw) : ie1;
   o.d_term = __dmul_rn(g.kd, de);
   const double cmd_raw = __dadd_rn(__dadd_rn(__dadd_rn(f_term, o.p_term), i_term), o.d_term);
-  const double cmd_c = clampd(cmd_raw, -g.c_max, g.c_max);
+  const double cmd_c = clamp_sym(cmd_raw, g.c_max);
   const bool aw = (cmd_c != cmd_raw);  // Pid.cpp:181-184
   const double cmd_aw = __dadd_rn(cmd_c, __dmul_rn(__dmul_rn(dt, e), g.ki));
   o.cmd = aw ? cmd_aw : cmd_c;
@@ -273,10 +281,22 @@ static __device__ __noinline__ void flexr_wake(const StepArgs &A, double *sm, un
   }
 }
 
+#ifndef CDPR_FLEXR_GENERAL_INLINE
+#define CDPR_FLEXR_GENERAL_INLINE __forceinline__  // inlined at its one call site: no by-value state through the stack (-6..-9 % with transitions)
+#endif
+#ifndef CDPR_FLEXR_UNR
+#define CDPR_FLEXR_UNR 0  // tuning override of the unroll factor of the hot body's cable loop (0 = the measured choice below)
+#endif
+#ifndef CDPR_FLEXR_OPTIMISTIC
+#define CDPR_FLEXR_OPTIMISTIC 0
+#endif
+#ifndef CDPR_FLEXR_MINB0
+#define CDPR_FLEXR_MINB0 1  // resident blocks asked for at two lanes without filter slots (caps the registers per thread)
+#endif
 // One step of THIS LANE's cables with every flag honoured (the out-of-line body): flex_general_step of step_flex.cuh with
 // the table-driven gains, the always-present biquad slots and the on-chip window of a Pid that woke up.
 template <int CPL, int TPB, int NF, int LANES>
-static __device__ __noinline__ Wrench6 flexr_general_step(const StepArgs &A, FastState S, double *sm, unsigned *sw, const double *tab, int c0, bool lead, bool valid,
+static __device__ CDPR_FLEXR_GENERAL_INLINE Wrench6 flexr_general_step(const StepArgs &A, const FastState &S, double *sm, unsigned *sw, const double *tab, int c0, bool lead, bool valid,
                                                           int mode, double now, int head, int sec, int nsec, bool last, long long i) {
   using M = FlexRSmem<CPL, TPB, NF, LANES>;
   const DevLayout &L = A.L;
@@ -417,7 +437,7 @@ static __device__ __noinline__ Wrench6 flexr_general_step(const StepArgs &A, Fas
       sm[(M::kLtime + c) * TPB] = now;
     }
     sw[c * TPB] = w;
-    const double eff = (rc.effort_limit >= 0.0) ? clampd(force, -rc.effort_limit, rc.effort_limit) : force;
+    const double eff = clamp_sym(force, rc.effort_limit_abs);  // +inf when Joint::SetForce does not truncate
     if (last) {
       if (valid) publish_joint(A, L.nc, cg, kin.qp, kin.qd, eff, i);
       L.cab[cab_off(L, cg, CAB_EFFORT) + i] = eff;
@@ -430,15 +450,6 @@ static __device__ __noinline__ Wrench6 flexr_general_step(const StepArgs &A, Fas
   return W;
 }
 
-#ifndef CDPR_FLEXR_UNR
-#define CDPR_FLEXR_UNR 0  // tuning override of the unroll factor of the hot body's cable loop (0 = the measured choice below)
-#endif
-#ifndef CDPR_FLEXR_OPTIMISTIC
-#define CDPR_FLEXR_OPTIMISTIC 0
-#endif
-#ifndef CDPR_FLEXR_MINB0
-#define CDPR_FLEXR_MINB0 1  // resident blocks asked for at two lanes without filter slots (caps the registers per thread)
-#endif
 // HOLD = false: velocityEpsilon < 0, no cable can ever hold, the Pid follows the instance's mode alone
 template <int NC, int TPB, int NF, bool HOLD, int LANES, bool ISO>
 __global__ void __launch_bounds__(TPB, (LANES == 4) ? 16 : ((LANES == 2 && NF == 0) ? CDPR_FLEXR_MINB0 : 1)) k_step_flexr(const __grid_constant__ StepArgs A) {
@@ -741,7 +752,7 @@ __global__ void __launch_bounds__(TPB, (LANES == 4) ? 16 : ((LANES == 2 && NF ==
 #else
           const FlexPidOut o = flexr_pid(g, desired, e, dt, pe, de, sm[(M::kIerr + c) * TPB]);
           sm[(M::kIerr + c) * TPB] = o.ierr;
-          const double eff = (rc.effort_limit >= 0.0) ? clampd(o.cmd, -rc.effort_limit, rc.effort_limit) : o.cmd;
+          const double eff = clamp_sym(o.cmd, rc.effort_limit_abs);  // +inf when Joint::SetForce does not truncate
 #endif
           const double tl = __dmul_rn(fma(-rc.cdamp, kin.qd, eff), kin.il);  // tension / L
           W.fx = fma(tl, kin.dx, W.fx); W.fy = fma(tl, kin.dy, W.fy); W.fz = fma(tl, kin.dz, W.fz);
