@@ -36,7 +36,7 @@ EXPORTS = [
     "cdpr_comm_create", "cdpr_comm_destroy", "cdpr_comm_size", "cdpr_comm_last_error", "cdpr_comm_attach_gather", "cdpr_comm_gather_buffer",
     "cdpr_comm_step", "cdpr_comm_allreduce",
     "cdpr_dterm_weights", "cdpr_padded_instances", "cdpr_device_platform_state",
-    "cdpr_measure_fp64_tflops", "cdpr_last_kernel_ms", "cdpr_launch_count", "cdpr_kernel_variant",
+    "cdpr_measure_fp64_tflops", "cdpr_last_kernel_ms", "cdpr_launch_count", "cdpr_kernel_variant", "cdpr_kernel_detail",
 ]
 
 
@@ -148,6 +148,7 @@ def load():
     L.cdpr_last_kernel_ms.argtypes = [vp]; L.cdpr_last_kernel_ms.restype = C.c_float
     L.cdpr_launch_count.argtypes = [vp]; L.cdpr_launch_count.restype = i64
     L.cdpr_kernel_variant.argtypes = [vp]; L.cdpr_kernel_variant.restype = C.c_char_p
+    L.cdpr_kernel_detail.argtypes = [vp]; L.cdpr_kernel_detail.restype = C.c_char_p
     _lib = L
     return L
 
@@ -391,6 +392,11 @@ class CdprBatch:
     @property
     def kernel_variant(self) -> str:
         return self._L.cdpr_kernel_variant(self._h).decode()
+
+    @property
+    def kernel_detail(self) -> str:
+        """Which instance of the variant runs (tests, tuning logs)."""
+        return self._L.cdpr_kernel_detail(self._h).decode()
 
 
 def dterm_weights(pid: PidParams, dt: float):

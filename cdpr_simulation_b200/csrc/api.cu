@@ -26,6 +26,7 @@ struct cdpr_batch {
   bool flex = false;     // the on-chip full-semantics kernel (step_flex.cuh): per-instance modes and commands
   bool flex_capable = false;
   int flex_tpb = 0, flex_ps = 0, flex_ds = 0, flex_nf = 0, flex_unroll = 2, flex_lanes = 1;
+  std::string detail;    // cdpr_kernel_detail
   bool flexr = false;    // ... in its register-resident form (step_flexr.cuh): at most one biquad stage per filter, no leg model
   bool flexr_hold = false;
   size_t flex_smem = 0;
@@ -1284,6 +1285,15 @@ extern "C" int cdpr_dterm_weights(const cdpr_pid_params *pid, double dt, double 
 extern "C" int64_t cdpr_padded_instances(cdpr_handle h) { return h ? h->np : -1; }
 extern "C" void *cdpr_device_platform_state(cdpr_handle h) { return h ? h->L.plat : nullptr; }
 extern "C" int64_t cdpr_launch_count(cdpr_handle h) { return h ? h->launches : -1; }
+extern "C" const char *cdpr_kernel_detail(cdpr_handle h) {
+  if (!h) return "";
+  char buf[96];
+  if (h->flex && h->flexr) std::snprintf(buf, sizeof(buf), "flex:registers,lanes=%d,nf=%d,hold=%d", h->flex_lanes, h->flex_nf, h->flexr_hold ? 1 : 0);
+  else if (h->flex) std::snprintf(buf, sizeof(buf), "flex:classic,lanes=%d,nf=%d,unroll=%d", h->flex_lanes, h->flex_nf, h->flex_unroll);
+  else std::snprintf(buf, sizeof(buf), "%s", h->general ? "general" : "fast");
+  h->detail = buf;
+  return h->detail.c_str();
+}
 extern "C" const char *cdpr_kernel_variant(cdpr_handle h) { return !h ? "" : (h->flex ? "flex" : h->general ? "general" : "fast"); }
 
 extern "C" float cdpr_last_kernel_ms(cdpr_handle h) {

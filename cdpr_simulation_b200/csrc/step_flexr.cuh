@@ -457,9 +457,10 @@ __global__ void __launch_bounds__(TPB, (LANES == 4) ? 16 : ((LANES == 2 && NF ==
   // Unroll factor of the hot body's cable loop.  The kernel is bound by INSTRUCTION FETCH as soon as warps alternate between
   // the hot loop and the full path (ncu: 30-60 % of the stall samples `no_instruction`, clustered on 128-byte line starts):
   // the hot loop is 1237 / 759 / 487 instructions at 4 / 2 / 1 cables per iteration and the full path another ~1500.  Measured
-  // at NC=8, 2^20 x 1000 steps (ms), unroll 4 / 2 / 1: steady 82 / 88 / 92; with hold transitions 175 / 116 / 117; hold + one
-  // P and one D stage 250 / 165 / 156.  So: everything unrolled when no cable can ever hold, else 2 (1 with filter slots).
-  constexpr int kUnr = (CDPR_FLEXR_UNR > 0) ? CDPR_FLEXR_UNR : (HOLD ? (NF > 0 ? 1 : 2) : CPL);
+  // at NC=8, 2^20 x 1000 steps (ms), unroll 4 / 2 / 1 (first build; the final one in brackets): steady 82 / 88 / 92 [75 / 80 / -];
+  // with hold transitions 175 / 116 / 117 [129 / 99 / -]; hold + one P and one D stage 250 / 165 / 156 [195 / 134 / 140].
+  // So: everything unrolled when no cable can ever hold, else 2.
+  constexpr int kUnr = (CDPR_FLEXR_UNR > 0) ? CDPR_FLEXR_UNR : (HOLD ? 2 : CPL);
   static_assert(CPL * LANES == NC && (LANES == 1 || LANES == 2 || LANES == 4) && NF <= 1, "lanes must divide the cables; one biquad slot per filter");
   using M = FlexRSmem<CPL, TPB, NF, LANES>;
   extern __shared__ double smem[];
