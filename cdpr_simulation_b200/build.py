@@ -9,7 +9,7 @@ CSRC = os.path.join(HERE, "csrc")
 # CDPR_B200_LIB selects another build of the same library (kernel tuning experiments only)
 LIB = os.environ.get("CDPR_B200_LIB") or os.path.join(HERE, "libcdpr_b200.so")
 # one translation unit per group of kernel instances: they compile in parallel, then link into the one .so
-SOURCES = ["api.cu", "comm.cu", "general.cu", "flex.cu", "flex_u2.cu", "flex_u4.cu", "flexr.cu", "flexr_nc8l2.cu", "flexr_nc8l4.cu", "flexr_nc4l1.cu", "flexr_nc8l1.cu", "fast_nc4_base.cu", "fast_nc4_diag.cu", "fast_nc4_spec.cu", "fast_nc8_base.cu", "fast_nc8_diag.cu",
+SOURCES = ["api.cu", "comm.cu", "general.cu", "flex.cu", "flex_u2.cu", "flex_u4.cu", "flexr.cu", "flexr_nc8l2.cu", "flexr_nc4l1.cu", "flexr_nc8l1.cu", "fast_nc4_base.cu", "fast_nc4_diag.cu", "fast_nc4_spec.cu", "fast_nc8_base.cu", "fast_nc8_diag.cu",
            "fast_nc8_spec.cu", "fast_nc8_pair.cu"]
 HEADERS = ["common.cuh", "physics.cuh", "step_fast.cuh", "step_general.cuh", "step_flex.cuh", "step_flexr.cuh", "flexr_common.cuh", "legs.cuh", "misc_kernels.cuh", "launch.h", "fast_inst.cuh",
            "../../include/cdpr_b200.h"]

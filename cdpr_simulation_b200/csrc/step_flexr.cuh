@@ -291,7 +291,7 @@ static __device__ __noinline__ void flexr_wake(const StepArgs &A, double *sm, un
 #define CDPR_FLEXR_OPTIMISTIC 0
 #endif
 #ifndef CDPR_FLEXR_MINB0
-#define CDPR_FLEXR_MINB0 1  // resident blocks asked for at two lanes without filter slots (caps the registers per thread)
+#define CDPR_FLEXR_MINB0 1  // resident blocks asked for at two lanes without filter slots (caps the registers per thread); 10: +14 %
 #endif
 // One step of THIS LANE's cables with every flag honoured (the out-of-line body): flex_general_step of step_flex.cuh with
 // the table-driven gains, the always-present biquad slots and the on-chip window of a Pid that woke up.
@@ -452,7 +452,7 @@ static __device__ CDPR_FLEXR_GENERAL_INLINE Wrench6 flexr_general_step(const Ste
 
 // HOLD = false: velocityEpsilon < 0, no cable can ever hold, the Pid follows the instance's mode alone
 template <int NC, int TPB, int NF, bool HOLD, int LANES, bool ISO>
-__global__ void __launch_bounds__(TPB, (LANES == 4) ? 16 : ((LANES == 2 && NF == 0) ? CDPR_FLEXR_MINB0 : 1)) k_step_flexr(const __grid_constant__ StepArgs A) {
+__global__ void __launch_bounds__(TPB, (LANES == 2 && NF == 0) ? CDPR_FLEXR_MINB0 : 1) k_step_flexr(const __grid_constant__ StepArgs A) {
   constexpr int CPL = NC / LANES;
   // Unroll factor of the hot body's cable loop.  The kernel is bound by INSTRUCTION FETCH as soon as warps alternate between
   // the hot loop and the full path (ncu: 30-60 % of the stall samples `no_instruction`, clustered on 128-byte line starts):
