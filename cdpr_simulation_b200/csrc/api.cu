@@ -466,7 +466,8 @@ extern "C" int cdpr_create(const cdpr_config *cfg, int64_t n_instances, int devi
     // The register-resident form (step_flexr.cuh) wherever it is compiled; CDPR_FLEX_CLASSIC=1 keeps k_step_flex (A/B runs).
     const char *classic = std::getenv("CDPR_FLEX_CLASSIC");
     const char *env_lanes = std::getenv("CDPR_FLEX_LANES");
-    const int rl = flexr_lanes(cfg->n_cables, h->flex_nf, env_lanes ? std::atoi(env_lanes) : 2);
+    const int rnf = std::max(h->flex_ps, h->flex_ds);  // k_step_flexr holds exactly the stages there are (0, 1 or 2 per filter)
+    const int rl = flexr_lanes(cfg->n_cables, rnf, env_lanes ? std::atoi(env_lanes) : 2);
     // one coefficient set per filter: two Pids that both have the stage must share its coefficients (pc is filled above)
     const bool coefs_ok = (h->pc[0].p_casc == 0 || h->pc[1].p_casc == 0 || std::memcmp(h->pc[0].pf, h->pc[1].pf, sizeof(h->pc[0].pf)) == 0) &&
                           (h->pc[0].d_casc == 0 || h->pc[1].d_casc == 0 || std::memcmp(h->pc[0].df, h->pc[1].df, sizeof(h->pc[0].df)) == 0);
@@ -474,7 +475,8 @@ extern "C" int cdpr_create(const cdpr_config *cfg, int64_t n_instances, int devi
       h->flexr = true;
       h->flexr_hold = cfg->velocity_epsilon >= 0.0;
       h->flex_lanes = rl;
-      h->flex_smem = flexr_smem_bytes(cfg->n_cables, h->flex_nf, rl);
+      h->flex_nf = rnf;
+      h->flex_smem = flexr_smem_bytes(cfg->n_cables, rnf, rl);
     }
   }
   h->flex = h->general && h->flex_capable;
@@ -761,8 +763,8 @@ static void fill_args(cdpr_handle h, StepArgs &A, int k_steps, bool sine) {
   A.flex_ps = h->flex_ps; A.flex_ds = h->flex_ds;
   for (int j = 0; j < 21; ++j) A.firx[j] = A.fir[j % 11];
   for (int k = 1; k >= 0; --k) {  // the velocity Pid's coefficients when both Pids have the stage (they are equal then)
-    if (h->pc[k].p_casc > 0) { std::memcpy(A.flex_pf, h->pc[k].pf, sizeof(A.flex_pf)); A.flex_p_on |= 1 << k; }
-    if (h->pc[k].d_casc > 0) { std::memcpy(A.flex_df, h->pc[k].df, sizeof(A.flex_df)); A.flex_d_on |= 1 << k; }
+    if (h->pc[k].p_casc > 0) std::memcpy(A.flex_pf, h->pc[k].pf, sizeof(A.flex_pf));
+    if (h->pc[k].d_casc > 0) std::memcpy(A.flex_df, h->pc[k].df, sizeof(A.flex_df));
   }
   A.pub_pos = h->pub_ptr[0]; A.pub_vel = h->pub_ptr[1]; A.pub_eff = h->pub_ptr[2]; A.pub_pose = h->pub_ptr[3]; A.pub_twist = h->pub_ptr[4];
   A.effort_ge_cmd = h->rc.effort_limit_abs >= A.live.cmd_max ? 1 : 0;

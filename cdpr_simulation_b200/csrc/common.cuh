@@ -93,10 +93,8 @@ struct StepArgs {
   double dmom[3];        // the same weights as a quadratic in the centred sample position: w_j = dmom[0] + dmom[1] k + dmom[2] k^2
   double dk[4];          // Kd * D recursion of the fast variant (step_fast.cuh): coefficients of y_new, S0, S1, y_old
   int flex_ps, flex_ds;  // flex variant: biquad stages held on chip for the P input / D output (max over the two Pids)
-  // step_flexr.cuh: the ONE coefficient set of the P-input / D-output stage (the Pids that have the stage share it, api.cu
-  // checks) and which Pid has it (bit k)
+  // step_flexr.cuh: the ONE coefficient set of the P-input / D-output stages (the Pids that have stages share it, api.cu checks)
   double flex_pf[5], flex_df[5];
-  int flex_p_on, flex_d_on;
   double firx[21];       // step_flexr.cuh: fir[0..10] twice over, so that the weight of ring SLOT s at ring head h is firx[s + 10 - h]
   int effort_ge_cmd;     // effort limit >= cmdMax of the live pid: truncation can only bite on a saturated command
   double sat_thr;        // min(cmdMax, effort limit): an unclamped command within it passes every clamp unchanged

@@ -14,7 +14,7 @@ size_t flexr_smem_nc8l1();
 // runs).  Measured at NC=8, 2^20 x 1000 steps, ms for steady / hold transitions / hold + 1 P + 1 D stage: two lanes 80 / 99 / 134,
 // one lane 82 / 122 / -, four lanes of 2 cables (16 resident warps at 128 registers, platform update four times) 89 / 128 / 174.
 int flexr_lanes(int nc, int nf, int lanes_wanted) {
-  if (nf > 1 || (nc != 4 && nc != 8)) return 0;
+  if (nf > 2 || (nc != 4 && nc != 8)) return 0;
   if (nc == 4) return 1;
   return (lanes_wanted == 1 && nf == 0) ? 1 : 2;
 }

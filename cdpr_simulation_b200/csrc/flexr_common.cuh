@@ -15,15 +15,17 @@ template <int NC, int NF, bool HOLD, int LANES> static void flexr_prep() {
     cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   }
 }
-// the four (NF, HOLD) instances of one (NC, LANES) shape
+// the six (NF, HOLD) instances of one (NC, LANES) shape
+#define CDPR_FLEXR_BY_NF(WHAT, NC_, L_, ...)                                                                     \
+  do {                                                                                                           \
+    if (nf == 0) { if (hold) WHAT<NC_, 0, true, L_>(__VA_ARGS__); else WHAT<NC_, 0, false, L_>(__VA_ARGS__); }   \
+    else if (nf == 1) { if (hold) WHAT<NC_, 1, true, L_>(__VA_ARGS__); else WHAT<NC_, 1, false, L_>(__VA_ARGS__); } \
+    else { if (hold) WHAT<NC_, 2, true, L_>(__VA_ARGS__); else WHAT<NC_, 2, false, L_>(__VA_ARGS__); }           \
+  } while (0)
 #define CDPR_FLEXR_UNIT(NAME, NC_, L_)                                                                           \
-  void flexr_prepare_##NAME(int nf, bool hold) {                                                                 \
-    if (nf == 0) { if (hold) flexr_prep<NC_, 0, true, L_>(); else flexr_prep<NC_, 0, false, L_>(); }             \
-    else { if (hold) flexr_prep<NC_, 1, true, L_>(); else flexr_prep<NC_, 1, false, L_>(); }                     \
-  }                                                                                                              \
-  void flexr_launch_##NAME(int nf, bool hold, unsigned grid, const StepArgs &A, cudaStream_t st) {               \
-    if (nf == 0) { if (hold) flexr_go<NC_, 0, true, L_>(grid, A, st); else flexr_go<NC_, 0, false, L_>(grid, A, st); } \
-    else { if (hold) flexr_go<NC_, 1, true, L_>(grid, A, st); else flexr_go<NC_, 1, false, L_>(grid, A, st); }   \
-  }                                                                                                              \
-  size_t flexr_smem_##NAME(int nf) { return nf == 0 ? FlexRSmem<NC_ / L_, kFlexrTpb, 0, L_>::bytes : FlexRSmem<NC_ / L_, kFlexrTpb, 1, L_>::bytes; }
+  void flexr_prepare_##NAME(int nf, bool hold) { CDPR_FLEXR_BY_NF(flexr_prep, NC_, L_); }                        \
+  void flexr_launch_##NAME(int nf, bool hold, unsigned grid, const StepArgs &A, cudaStream_t st) { CDPR_FLEXR_BY_NF(flexr_go, NC_, L_, grid, A, st); } \
+  size_t flexr_smem_##NAME(int nf) {                                                                             \
+    return nf == 0 ? FlexRSmem<NC_ / L_, kFlexrTpb, 0, L_>::bytes : nf == 1 ? FlexRSmem<NC_ / L_, kFlexrTpb, 1, L_>::bytes : FlexRSmem<NC_ / L_, kFlexrTpb, 2, L_>::bytes; \
+  }
 }  // namespace cdpr

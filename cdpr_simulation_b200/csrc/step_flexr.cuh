@@ -22,10 +22,10 @@
 // Bodies are chosen per thread as in step_flex.cuh; both run the same inlined arithmetic helpers with explicit roundings, so
 // which body ran never shows in the bits (GPU tests: bitwise launch-split and checkpoint invariance through hold transitions).
 //
-// Biquad slots: NF = 0 or 1 stage per filter, ONE coefficient set per filter (constant-bank operands): when only one Pid has
-// the stage, the other Pid's slot still runs the arithmetic and its output is discarded by a select (pe = e, Pid.cpp:133 with an
-// empty cascade) -- the slot's state is then a don't-care that both bodies advance the same way.  Two Pids with different
-// coefficients, more stages, or the leg model: k_step_flex.
+// Biquad slots: NF = 0, 1 or 2 stages per filter, ONE coefficient set per filter (constant-bank operands): every slot up to the
+// larger stage count of the two Pids runs the arithmetic, and a select takes the output of the last stage the RUNNING Pid has
+// (pe = e with an empty cascade, Pid.cpp:133) -- a slot beyond that is a don't-care that both bodies advance the same way.  Two
+// Pids with different coefficients, more stages, or the leg model: k_step_flex.
 #pragma once
 #include "step_flex.cuh"
 
@@ -74,15 +74,6 @@ __device__ __forceinline__ double biquad_step(const double *co, double &x1, doub
   x2 = x1; x1 = x; y2 = y1; y1 = y0;
   return y0;
 }
-// the same on the shared-memory columns of one filter (x1 x2 y1 y2)
-template <int TPB>
-__device__ __forceinline__ double biquad_step_sm(const double *co, double *q, double x) {
-  double x1 = q[0], x2 = q[TPB], y1 = q[2 * TPB], y2 = q[3 * TPB];
-  const double y0 = biquad_step(co, x1, x2, y1, y2, x);
-  q[0] = x1; q[TPB] = x2; q[2 * TPB] = y1; q[3 * TPB] = y2;
-  return y0;
-}
-
 // The fixed FIR over the last 11 steps, summed in the order of the ring SLOTS (slot = step index mod 11) with the weights
 // rotated to match (gw = firx + 10 - head, so gw[s] is the weight of the sample in slot s; this step's sample is already in
 // slot head): every tap is a load at an immediate offset and a constant-bank weight, no index arithmetic.
@@ -95,6 +86,29 @@ __device__ __forceinline__ double flexr_fir(const double *gw, const double *ring
     if (s & 1) d1 = fma(gw[s], y, d1); else d0 = fma(gw[s], y, d0);
   }
   return __dadd_rn(d0, d1);
+}
+
+// Pid::CascadeFilter::update (Pid.cpp:38-44) over the NF stage slots of one filter in shared memory (x1 x2 y1 y2 per stage,
+// one coefficient set): the slots up to `slots` (the larger stage count of the two Pids) all run, the output is the one of the
+// last stage the RUNNING Pid has (`count`), the input itself if it has none (slots >= 1: the caller skips an empty filter).  RING_X: the first stage's x1, x2 are the ring's last
+// two samples (the hot body; o1 / o2 their offsets) instead of its own columns.
+template <int TPB, int NF, bool RING_X>
+__device__ __forceinline__ double flexr_cascade(const double *co, double *q, int slots, int count, double x, const double *ringc = nullptr, int o1 = 0, int o2 = 0) {
+  double out = x;
+#pragma unroll
+  for (int st = 0; st < NF; ++st) {
+    if (st == 0 || st < slots) {  // the caller checked slots >= 1
+      double *p = q + (st * 4) * TPB;
+      double x1, x2, y1 = p[2 * TPB], y2 = p[3 * TPB];
+      if (RING_X && st == 0) { x1 = ringc[o1]; x2 = ringc[o2]; } else { x1 = p[0]; x2 = p[TPB]; }
+      const double y0 = biquad_step(co, x1, x2, y1, y2, x);
+      if (!(RING_X && st == 0)) { p[0] = x1; p[TPB] = x2; }
+      p[2 * TPB] = y1; p[3 * TPB] = y2;
+      x = y0;
+      out = (count > st) ? y0 : out;
+    }
+  }
+  return out;
 }
 
 __device__ __forceinline__ FlexGains flexr_gains(const double *row) {
@@ -319,8 +333,8 @@ static __device__ CDPR_FLEXR_GENERAL_INLINE Wrench6 flexr_general_step(const Ste
     for (int j = 0; j < kFlexLen; ++j) prefetch_l2(L.win_y + win_off(L, cg, k, j) + i);
     if (NF > 0) {
       for (int f = 0; f < 4; ++f) {
-        if (A.flex_ps > 0) prefetch_l2(L.filt + filt_off(L, cg, k, 0, 0, f) + i);
-        if (A.flex_ds > 0) prefetch_l2(L.filt + filt_off(L, cg, k, 1, 0, f) + i);
+        for (int st = 0; st < A.flex_ps; ++st) prefetch_l2(L.filt + filt_off(L, cg, k, 0, st, f) + i);
+        for (int st = 0; st < A.flex_ds; ++st) prefetch_l2(L.filt + filt_off(L, cg, k, 1, st, f) + i);
       }
     }
   }
@@ -376,10 +390,7 @@ static __device__ CDPR_FLEXR_GENERAL_INLINE Wrench6 flexr_general_step(const Ste
         const double e = __dsub_rn(desired, actual);
         const double dt = __dsub_rn(now, sm[(M::kLtime + c) * TPB]);
         double pe = e;
-        if (NF > 0 && A.flex_ps > 0) {
-          const double y0 = biquad_step_sm<TPB>(A.flex_pf, sm + (M::kFilt + c * M::FS) * TPB, e);
-          pe = ((A.flex_p_on >> k) & 1) ? y0 : e;
-        }
+        if (NF > 0 && A.flex_ps > 0) pe = flexr_cascade<TPB, NF, false>(A.flex_pf, sm + (M::kFilt + c * M::FS) * TPB, A.flex_ps, A.pc[k].p_casc, e);
         // ---- derive (Pid.cpp:193-217): dt > 0 always (sim time advances every step)
         sm[(M::kRing + head * CPL + c) * TPB] = e;
         unsigned fresh = fctl_fresh(w), missing = gctl_missing(w, k), hd = gctl_head(w, k);
@@ -417,10 +428,7 @@ static __device__ CDPR_FLEXR_GENERAL_INLINE Wrench6 flexr_general_step(const Ste
           }
         }
         double de = derived;
-        if (NF > 0 && A.flex_ds > 0) {
-          const double y0 = biquad_step_sm<TPB>(A.flex_df, sm + (M::kFilt + c * M::FS + 4 * NF) * TPB, derived);
-          de = ((A.flex_d_on >> k) & 1) ? y0 : derived;
-        }
+        if (NF > 0 && A.flex_ds > 0) de = flexr_cascade<TPB, NF, false>(A.flex_df, sm + (M::kFilt + c * M::FS + 4 * NF) * TPB, A.flex_ds, A.pc[k].d_casc, derived);
         const FlexPidOut o = flexr_pid(g, desired, e, dt, pe, de, sm[(M::kIerr + c) * TPB]);
         sm[(M::kIerr + c) * TPB] = o.ierr;
         force = o.cmd;
@@ -461,7 +469,7 @@ __global__ void __launch_bounds__(TPB, (LANES == 2 && NF == 0) ? CDPR_FLEXR_MINB
   // with hold transitions 175 / 116 / 117 [129 / 99 / -]; hold + one P and one D stage 250 / 165 / 156 [195 / 134 / 140].
   // So: everything unrolled when no cable can ever hold, else 2.
   constexpr int kUnr = (CDPR_FLEXR_UNR > 0) ? CDPR_FLEXR_UNR : (HOLD ? 2 : CPL);
-  static_assert(CPL * LANES == NC && (LANES == 1 || LANES == 2 || LANES == 4) && NF <= 1, "lanes must divide the cables; one biquad slot per filter");
+  static_assert(CPL * LANES == NC && (LANES == 1 || LANES == 2 || LANES == 4) && NF <= 2, "lanes must divide the cables; at most two biquad slots per filter");
   using M = FlexRSmem<CPL, TPB, NF, LANES>;
   extern __shared__ double smem[];
   const int tid = (int)threadIdx.x;
@@ -549,7 +557,7 @@ __global__ void __launch_bounds__(TPB, (LANES == 2 && NF == 0) ? CDPR_FLEXR_MINB
   // in the ring: its live Pids have pushed every one of the last 11 steps); `spill` puts them back for the general body.
   unsigned posmask = 0u, holdmask = 0u;  // per cable: runs the position Pid / holds (position Pid in Velocity mode)
   bool hot = false;  // the previous step ran the hot body
-  const bool has_p = NF > 0 && A.flex_ps > 0, has_d = NF > 0 && A.flex_ds > 0, has_fir = A.pc[0].degree >= 1;
+  const bool has_fir = A.pc[0].degree >= 1;
 
   auto spill = [&]() {  // runs after the clock tick of a step: `head` is the slot this step's sample WILL take
     int h1 = head - 1, h2 = head - 2;
@@ -701,8 +709,12 @@ __global__ void __launch_bounds__(TPB, (LANES == 2 && NF == 0) ? CDPR_FLEXR_MINB
         const int o0 = head * (CPL * TPB);
         o1 *= CPL * TPB; o2 *= CPL * TPB;
         const double *gw = A.firx + (kFlexLen - 1 - head);
-#pragma unroll kUnr
-        for (int c = 0; c < CPL; ++c) {
+        // kUnr cables per iteration, spelled out (an unroll pragma on the cable loop lets the compiler peel or clone it)
+#pragma unroll 1
+        for (int cb = 0; cb < CPL; cb += kUnr) {
+#pragma unroll
+        for (int cu = 0; cu < kUnr; ++cu) {
+          const int c = cb + cu;
           CableKin kin;
           if (LANES == 1 && kUnr >= CPL) {
             kin = cable_kin_v(rc.b[c][0], rc.b[c][1], rc.b[c][2], rc.a[c][0], rc.a[c][1], rc.a[c][2], rc.home_len[c], S, R);
@@ -720,22 +732,14 @@ __global__ void __launch_bounds__(TPB, (LANES == 2 && NF == 0) ? CDPR_FLEXR_MINB
           const double e = __dsub_rn(desired, actual);
           double *rc_ = ring + c * TPB;
           double pe = e;
-          if (has_p) {
-            double x1 = rc_[o1], x2 = rc_[o2];
-            double *q = sm + (M::kFilt + c * M::FS) * TPB;
-            double y1 = q[2 * TPB], y2 = q[3 * TPB];
-            const double y0 = biquad_step(A.flex_pf, x1, x2, y1, y2, e);
-            q[2 * TPB] = y1; q[3 * TPB] = y2;
-            pe = ((A.flex_p_on >> (pos ? 1 : 0)) & 1) ? y0 : e;
-          }
+          // (no test for "this filter has no stage at all": a uniform branch here makes the compiler clone the whole cable loop,
+          // and the clone costs more instruction fetch than the nine operations it saves; the select inside returns the input)
+          if (NF > 0) pe = flexr_cascade<TPB, NF, true>(A.flex_pf, sm + (M::kFilt + c * M::FS) * TPB, A.flex_ps, pos ? A.pc[1].p_casc : A.pc[0].p_casc, e, rc_, o1, o2);
           rc_[o0] = e;
           double derived = 0.0;
           if (has_fir) derived = flexr_fir<CPL * TPB>(gw, rc_);
           double de = derived;
-          if (has_d) {
-            const double y0 = biquad_step_sm<TPB>(A.flex_df, sm + (M::kFilt + c * M::FS + 4 * NF) * TPB, derived);
-            de = ((A.flex_d_on >> (pos ? 1 : 0)) & 1) ? y0 : derived;
-          }
+          if (NF > 0) de = flexr_cascade<TPB, NF, false>(A.flex_df, sm + (M::kFilt + c * M::FS + 4 * NF) * TPB, A.flex_ds, pos ? A.pc[1].d_casc : A.pc[0].d_casc, derived);
 #if CDPR_FLEXR_OPTIMISTIC
           // Pid::update from the integral on, OPTIMISTICALLY: the integral clamp, the command clamp with its anti-windup and
           // Joint::SetForce's truncation (Pid.cpp:143-150,175-184) almost never fire on a stable loop, and as long as none does
@@ -758,6 +762,7 @@ __global__ void __launch_bounds__(TPB, (LANES == 2 && NF == 0) ? CDPR_FLEXR_MINB
           const double tl = __dmul_rn(fma(-rc.cdamp, kin.qd, eff), kin.il);  // tension / L
           W.fx = fma(tl, kin.dx, W.fx); W.fy = fma(tl, kin.dy, W.fy); W.fz = fma(tl, kin.dz, W.fz);
           W.mx = fma(tl, kin.cx, W.mx); W.my = fma(tl, kin.cy, W.my); W.mz = fma(tl, kin.cz, W.mz);
+        }
         }
         platform_step(R, W);
         tprev = now;
