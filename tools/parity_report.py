@@ -73,21 +73,29 @@ if ob.ref_available():
         print(f"NC={nc}, d_gain = 0: GPU vs the reference's compiled Pid.cpp/JointForceCalculator.cpp after 1500 steps: {state_rel_err(*g.platform_state(), *o.platform_state()):.2e}")
         g.close()
 
-# (c) flex kernel (hold + filters) and leg model
-for nc in (4, 8):
-    cfg = cb.default_config(nc); general_cfg(cfg)
+# (c) full-semantics kernels (hold + filters) and leg model
+def hold_1p1d(cfg):
+    cfg.velocity_epsilon = 0.02; cfg.vel_pid.p_cascade = 1; cfg.vel_pid.d_cascade = 1
+def hold_only(cfg):
+    cfg.velocity_epsilon = 0.02
+def general_cfg_classic(cfg):
+    general_cfg(cfg); os.environ["CDPR_FLEX_CLASSIC"] = "1"
+for nc, edit, what in [(nc, e, w) for nc in (4, 8) for e, w in ((hold_only, "hold 2 cm/s"), (hold_1p1d, "hold 2 cm/s, 1 P + 1 D biquad stage"),
+                                                              (general_cfg, "hold 2 cm/s, 1 P + 2 D biquad stages"), (general_cfg_classic, "hold 2 cm/s, 1 P + 2 D biquad stages"))]:
+    cfg = cb.default_config(nc); edit(cfg)
     a_, f_, p_, po_, tw_ = wl.c3_instances(256, 61)
     g = cb.CdprBatch(cfg, 256); g.set_platform_state(po_, tw_); g.set_sine_cmd(a_, f_, p_)
     o = ob.Batch(to_oracle_config(cfg), 256, po_, tw_, a_, f_, p_)
     worst = 0.0
     for s in range(40):
         g.step(1); o.step(1); worst = max(worst, state_rel_err(*g.platform_state(), *o.platform_state()))
-    line = f"NC={nc} flex (hold 2 cm/s, 1 P + 2 D biquad stages): first 40 steps {worst:.2e}"
+    os.environ.pop("CDPR_FLEX_CLASSIC", None)
+    line = f"NC={nc} flex ({what}): first 40 steps {worst:.2e}"
     done = 40
     for m in (1000, 3000):
         g.step(m - done); o.step(m - done); done = m
         line += f"; after {m}: {state_rel_err(*g.platform_state(), *o.platform_state()):.2e}"
-    print(line + f"  [{g.kernel_variant}]")
+    print(line + f"  [{g.kernel_detail}]")
     g.close()
 for nc in (4, 8):
     cfg = cb.default_config(nc); cfg.leg_model = 1
