@@ -77,8 +77,28 @@ for nc in (4, 8):
             g.set_platform_state(pose7, twist6); g.set_sine_cmd(amp, freq, phase)
             g.step(1); g.step(300)
             g.rollout(7, 11, wl.c5_rollouts(11, 4, nc), 5, [0, 0, 0.3], 0.1, pose7[:7], twist6[:7])
-            print("ok flex lanes", lanes, nc, g.kernel_variant)
+            print("ok flex lanes", lanes, nc, g.kernel_detail)
     os.environ.pop("CDPR_FLEX_LANES", None)
+    # round 3: k_step_flexr (0, 1, 2 stages; hold transitions through the on-chip and the HBM gap fit: commands that toggle the
+    # hold band faster and slower than 11 steps; independent robots) and, with CDPR_FLEX_CLASSIC, k_step_flex on the same
+    for classic in ("0", "1"):
+        os.environ["CDPR_FLEX_CLASSIC"] = classic
+        for pc, dc in ((0, 0), (1, 1), (1, 2)):
+            cfg = cb.default_config(nc)
+            cfg.velocity_epsilon = 0.02; cfg.vel_pid.p_cascade = pc; cfg.vel_pid.d_cascade = dc
+            with cb.CdprBatch(cfg, n) as g:
+                g.set_independent(True)
+                g.set_platform_state(pose7, twist6)
+                mv = rng.uniform(0.03, 0.06, (n, nc)).astype(np.float32); st = rng.uniform(-0.01, 0.01, (n, nc)).astype(np.float32)
+                st[:, 0] = mv[:, 0]
+                for period in (14, 3, 5, 2, 13, 30):
+                    for rep in range(4):
+                        g.set_velocity_cmd(mv if rep % 2 == 0 else st, mask=rng.random(n) < 0.7)
+                        g.step(period)
+                g.set_sine_cmd(amp, freq, phase); g.step(120)
+                blob = g.get_state(); g.set_state(blob); g.step(7); g.pid_terms(); g.update(None)
+                print("ok hold toggling", nc, g.kernel_detail)
+    os.environ.pop("CDPR_FLEX_CLASSIC", None)
     cfg = cb.default_config(nc)
     cfg.vel_pid.cmd_limit = 0.0; cfg.vel_pid.d_buffer_length = 5; cfg.vel_pid.d_degree = 1
     with cb.CdprBatch(cfg, n) as g:                          # catch-all kernel
