@@ -1,4 +1,4 @@
-// step_flexr.cuh -- K2''r: the full-semantics kernel of step_flex.cuh with a REGISTER-resident hot body and on-chip gap fits.
+// step_flexr.cuh -- K2''r: the full-semantics kernel of step_flex.cuh rebuilt around what ncu showed about it.
 //
 // Same semantics, same HBM state and the same rare paths (flush / wake / reset / pending commands: the helpers of
 // step_flex.cuh) as k_step_flex -- hold through the position Pid (JointForceCalculator.cpp:72-82), biquad cascades
@@ -7,19 +7,25 @@
 //
 //   * the hot body was 291 instructions per cable, 87 of them FP64: a rolled cable loop turns every robot constant, gain and
 //     filter coefficient into an indexed constant load (48 LDC per cable) and every per-Pid value into a pair of selects
-//     (30 FSEL per cable); the biquad state and the integrals went through shared memory (16 LDS/STS per cable).
-//     Here the cable loop of the hot body is fully unrolled over the CPL = 4 (or 8) cables of a lane, the integrals and
-//     the biquad state of the live Pids stay in REGISTERS while the thread is hot, the per-Pid gains / coefficients come
-//     from a two-row table in shared memory indexed by "this cable runs the position Pid" (one broadcast LDS per value),
-//     and which Pid a cable runs (hold) and its set point are worked out when a command arrives, not every step.
+//     (30 FSEL per cable).  Here the per-Pid gains and the per-lane robot constants come from a block-shared table in shared
+//     memory (broadcast LDS.128), the filter coefficients are constant-bank operands (one set per filter), which Pid a cable
+//     runs (hold) and its set point are worked out when a command arrives, not every step, the FIR runs in ring-slot order
+//     with rotated weights (no index arithmetic), and the clamp chain is branch-free.
+//   * the steps run event-driven as in step_fast.cuh: a warp whose robots are all steady runs up to its next event in an
+//     inner loop that holds the hot body and nothing else.
+//   * the kernel turned out to be bound by INSTRUCTION FETCH whenever warps alternate between the hot loop and the full path
+//     (both together exceed the instruction cache): the whole warp takes the full path in a step in which one robot needs
+//     it, the cable loop is unrolled by 2 when hold is possible, the general step is inlined at its one call site.
 //   * a Pid that woke up fitted its gap-spanning window out of HBM for 11 steps: 22 dependent-latency loads, normal equations
-//     and 4 divisions per cable and step, with 1-2 threads of the warp active -- 40 % of the whole run with hold
-//     transitions every few hundred steps.  Here the shared-memory ring always holds the live Pid's whole window (the
-//     stale samples sit in the slots the next pushes overwrite); when the stale part is a run of consecutive steps
-//     (ctl bits 30/31, set when a Pid goes to sleep on a full window of fresh samples) its time stamps follow from one
-//     value, so the fit needs no load at all.  Windows that are stale twice over keep the HBM fit of step_flex.cuh.
+//     and 4 divisions per cable and step, with 1-2 threads of the warp active.  Here the shared-memory ring always holds the
+//     live Pid's whole window (the stale samples sit in the slots the next pushes overwrite); when the stale part is a run of
+//     consecutive steps (ctl bits 30/31, set when a Pid goes to sleep on a full window of fresh samples) its time stamps
+//     follow from one value, so the fit needs no load at all, and its weights are shared by the cables that woke together.
+//     Windows that are stale twice over keep the HBM fit of step_flex.cuh.  Wake-ups issue all their loads at once.
+//   (Tried and measured slower: integrals and biquad state in registers -- the unrolled loop passes 255 registers and a spill
+//   is an L2 round trip with the shared-memory carve-out at its maximum; optimistic clamps; 1 and 4 lanes per 8-cable robot.)
 //
-// Bodies are chosen per thread as in step_flex.cuh; both run the same inlined arithmetic helpers with explicit roundings, so
+// Both bodies run the same inlined arithmetic helpers with explicit roundings, so
 // which body ran never shows in the bits (GPU tests: bitwise launch-split and checkpoint invariance through hold transitions).
 //
 // Biquad slots: NF = 0, 1 or 2 stages per filter, ONE coefficient set per filter (constant-bank operands): every slot up to the
@@ -90,14 +96,14 @@ __device__ __forceinline__ double flexr_fir(const double *gw, const double *ring
 
 // Pid::CascadeFilter::update (Pid.cpp:38-44) over the NF stage slots of one filter in shared memory (x1 x2 y1 y2 per stage,
 // one coefficient set): the slots up to `slots` (the larger stage count of the two Pids) all run, the output is the one of the
-// last stage the RUNNING Pid has (`count`), the input itself if it has none (slots >= 1: the caller skips an empty filter).  RING_X: the first stage's x1, x2 are the ring's last
+// last stage the RUNNING Pid has (`count`), the input itself if it has none.  RING_X: the first stage's x1, x2 are the ring's last
 // two samples (the hot body; o1 / o2 their offsets) instead of its own columns.
 template <int TPB, int NF, bool RING_X>
 __device__ __forceinline__ double flexr_cascade(const double *co, double *q, int slots, int count, double x, const double *ringc = nullptr, int o1 = 0, int o2 = 0) {
   double out = x;
 #pragma unroll
   for (int st = 0; st < NF; ++st) {
-    if (st == 0 || st < slots) {  // the caller checked slots >= 1
+    if (st == 0 || st < slots) {  // (the first slot also runs for a filter without stages: count = 0 discards its output)
       double *p = q + (st * 4) * TPB;
       double x1, x2, y1 = p[2 * TPB], y2 = p[3 * TPB];
       if (RING_X && st == 0) { x1 = ringc[o1]; x2 = ringc[o2]; } else { x1 = p[0]; x2 = p[TPB]; }
@@ -696,7 +702,7 @@ __global__ void __launch_bounds__(TPB, (LANES == 2 && NF == 0) ? CDPR_FLEXR_MINB
       int r = 0;
 #pragma unroll 1
       for (;;) {
-        // ---- hot body: straight-line, every cable of the lane on its live Pid, the integrals in registers
+        // ---- hot body: every cable of the lane on its live Pid, no flag
         const double dt = __dsub_rn(now, tprev);  // == now - mLastTime of every live Pid
         const Rot R = make_rot(S);
         Wrench6 W;
