@@ -307,7 +307,7 @@ def test_flex_random_command_sequences_against_the_oracle(built_lib, seed):
                 o.step(val)
                 _check(g, o, 2e-8, (seed, kind, val))
                 assert np.array_equal(g.modes(), o.targets()[2][:, 0].astype(np.int32))
-        out = (g.platform_state(), g.joint_states(), g.pid_terms(), g.get_state())
+        out = (g.platform_state(), g.joint_states(), g.pid_terms(), g.get_state(), g.modes())
         g.close()
         return out
 
@@ -315,4 +315,9 @@ def test_flex_random_command_sequences_against_the_oracle(built_lib, seed):
     assert np.array_equal(a[0][0], b[0][0]) and np.array_equal(a[0][1], b[0][1])
     for x, y in zip(a[1], b[1]):
         assert np.array_equal(x, y)
-    assert np.array_equal(a[2], b[2])
+    # topic `pid`: the applied force always; the terms wherever a Pid PUBLISHED in the final step.  A Pid publishes from its
+    # second update on (Pid.cpp:123-126), and the telemetry columns are written by the last step of a launch only, so for a cable
+    # that primes in the final step (zero force) or is in Force mode they still show an earlier launch boundary.
+    assert np.array_equal(a[2][..., 4], b[2][..., 4])
+    published = (a[2][..., 4] != 0.0) & (a[4] != 0)[:, None]
+    assert np.array_equal(a[2][published], b[2][published])
