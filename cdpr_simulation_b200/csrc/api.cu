@@ -761,7 +761,7 @@ static void fill_args(cdpr_handle h, StepArgs &A, int k_steps, bool sine) {
     A.dk[3] = -kd * a;
   }
   A.flex_ps = h->flex_ps; A.flex_ds = h->flex_ds;
-  for (int j = 0; j < 21; ++j) A.firx[j] = A.fir[j % 11];
+  for (int j = 0; j < 21; ++j) { A.firx[j] = A.fir[j % 11]; A.firx0[j] = (j % 11 == 10) ? 0.0 : A.fir[j % 11]; }
   for (int k = 1; k >= 0; --k) {  // the velocity Pid's coefficients when both Pids have the stage (they are equal then)
     if (h->pc[k].p_casc > 0) std::memcpy(A.flex_pf, h->pc[k].pf, sizeof(A.flex_pf));
     if (h->pc[k].d_casc > 0) std::memcpy(A.flex_df, h->pc[k].df, sizeof(A.flex_df));

@@ -96,6 +96,7 @@ struct StepArgs {
   // step_flexr.cuh: the ONE coefficient set of the P-input / D-output stages (the Pids that have stages share it, api.cu checks)
   double flex_pf[5], flex_df[5];
   double firx[21];       // step_flexr.cuh: fir[0..10] twice over, so that the weight of ring SLOT s at ring head h is firx[s + 10 - h]
+  double firx0[21];      // ... with the newest sample's weight (fir[10]) replaced by 0: the weights of the ten older samples
   int effort_ge_cmd;     // effort limit >= cmdMax of the live pid: truncation can only bite on a saturated command
   double sat_thr;        // min(cmdMax, effort limit): an unclamped command within it passes every clamp unchanged
   int mode;            // batch-uniform JointForceCalculator::UpdateMode

@@ -70,26 +70,31 @@ __device__ __forceinline__ CableKin cable_kin_v(double bx, double by, double bz,
   return k;
 }
 
-// BiQuad::process (Filter.h:152-165) on four values: a0 x + a1 x1 + a2 x2 - b1 y1 - b2 y2, left to right, then the shift
+// BiQuad::process (Filter.h:152-165) on four values, y0 = a0 x + a1 x1 + a2 x2 - b1 y1 - b2 y2, then the shift.  Summed as
+// (a0 x + a1 x1) + (a2 x2 - b1 y1 - b2 y2) with fused multiply-adds: the second group does not depend on the new input, so only
+// three operations sit between x and y0 (the reference's left-to-right chain of five products and four sums is nine operations
+// deep, and the two filters of a cable are in series with the D-term between them) -- 6 FP64 instructions instead of 9.  Same
+// value up to the last rounding (the CUDA path is held to 1e-9 of the oracle per step, not to its bits); both bodies use it.
 __device__ __forceinline__ double biquad_step(const double *co, double &x1, double &x2, double &y1, double &y2, double x) {
-  double y0 = __dmul_rn(co[0], x);
-  y0 = __dadd_rn(y0, __dmul_rn(co[1], x1));
-  y0 = __dadd_rn(y0, __dmul_rn(co[2], x2));
-  y0 = __dsub_rn(y0, __dmul_rn(co[3], y1));
-  y0 = __dsub_rn(y0, __dmul_rn(co[4], y2));
+  const double hist = fma(-co[4], y2, fma(-co[3], y1, __dmul_rn(co[2], x2)));
+  const double y0 = __dadd_rn(fma(co[1], x1, __dmul_rn(co[0], x)), hist);
   x2 = x1; x1 = x; y2 = y1; y1 = y0;
   return y0;
 }
+
 // The fixed FIR over the last 11 steps, summed in the order of the ring SLOTS (slot = step index mod 11) with the weights
-// rotated to match (gw = firx + 10 - head, so gw[s] is the weight of the sample in slot s; this step's sample is already in
-// slot head): every tap is a load at an immediate offset and a constant-bank weight, no index arithmetic.
+// rotated to match: every tap is a load at an immediate offset and a constant-bank weight, no index arithmetic.  Split so
+// that nothing waits for this step's sample e: the ten OLDER samples first (gw0 = firx + 10 - head is the weight of the
+// sample in slot s, and 0 for slot `head` -- whether that slot still holds the sample that leaves the window or already e,
+// it adds +0), then D = fir[10] e + that.  The loads precede the store of e, so they and their sums run under the
+// kinematics; one operation sits between e and D (the kernel is bound by dependent FP64 chains, not by their count).
 template <int STRIDE>
-__device__ __forceinline__ double flexr_fir(const double *gw, const double *ringc) {
-  double d0 = __dmul_rn(gw[0], ringc[0]), d1 = __dmul_rn(gw[1], ringc[STRIDE]);
+__device__ __forceinline__ double flexr_fir_older(const double *gw0, const double *ringc) {
+  double d0 = __dmul_rn(gw0[0], ringc[0]), d1 = __dmul_rn(gw0[1], ringc[STRIDE]);
 #pragma unroll
   for (int s = 2; s < kFlexLen; ++s) {
     const double y = ringc[s * STRIDE];
-    if (s & 1) d1 = fma(gw[s], y, d1); else d0 = fma(gw[s], y, d0);
+    if (s & 1) d1 = fma(gw0[s], y, d1); else d0 = fma(gw0[s], y, d0);
   }
   return __dadd_rn(d0, d1);
 }
@@ -112,6 +117,24 @@ __device__ __forceinline__ double flexr_cascade(const double *co, double *q, int
       p[2 * TPB] = y1; p[3 * TPB] = y2;
       x = y0;
       out = (count > st) ? y0 : out;
+    }
+  }
+  return out;
+}
+
+// the same cascade on state already in registers (st = x1 x2 y1 y2 per stage): the hot body loads every piece of state at the
+// top of a cable and stores at the bottom, so no load waits behind a store it cannot be proven independent of
+template <int NF, bool RING_X>
+__device__ __forceinline__ double flexr_cascade_regs(const double *co, double (&st)[NF > 0 ? 4 * NF : 1], int slots, int count, double x, double rx1 = 0.0, double rx2 = 0.0) {
+  double out = x;
+#pragma unroll
+  for (int s = 0; s < NF; ++s) {
+    if (s == 0 || s < slots) {
+      double x1 = (RING_X && s == 0) ? rx1 : st[4 * s], x2 = (RING_X && s == 0) ? rx2 : st[4 * s + 1];
+      const double y0 = biquad_step(co, x1, x2, st[4 * s + 2], st[4 * s + 3], x);
+      if (!(RING_X && s == 0)) { st[4 * s] = x1; st[4 * s + 1] = x2; }
+      x = y0;
+      out = (count > s) ? y0 : out;
     }
   }
   return out;
@@ -411,7 +434,7 @@ static __device__ CDPR_FLEXR_GENERAL_INLINE Wrench6 flexr_general_step(const Ste
         double derived = 0.0;
         if (missing == 0u && A.pc[0].degree >= 1) {  // both Pids fit the same degree in this variant
           if (fresh >= (unsigned)kFlexLen) {
-            derived = flexr_fir<CPL * TPB>(A.firx + (kFlexLen - 1 - head), sm + (M::kRing + c) * TPB);
+            derived = fma(A.fir[kFlexLen - 1], e, flexr_fir_older<CPL * TPB>(A.firx0 + (kFlexLen - 1 - head), sm + (M::kRing + c) * TPB));
           } else {
             const double stale = sm[(M::kStale + c) * TPB];
             if (((w >> (kRunBit0 + k)) & 1u) && stale >= 0.0 && stale < 65536.0) {
@@ -714,13 +737,25 @@ __global__ void __launch_bounds__(TPB, (LANES == 2 && NF == 0) ? CDPR_FLEXR_MINB
         o2 += (o2 < 0) ? kFlexLen : 0;
         const int o0 = head * (CPL * TPB);
         o1 *= CPL * TPB; o2 *= CPL * TPB;
-        const double *gw = A.firx + (kFlexLen - 1 - head);
+        const double *gw0 = A.firx0 + (kFlexLen - 1 - head);
         // kUnr cables per iteration, spelled out (an unroll pragma on the cable loop lets the compiler peel or clone it)
 #pragma unroll 1
         for (int cb = 0; cb < CPL; cb += kUnr) {
 #pragma unroll
         for (int cu = 0; cu < kUnr; ++cu) {
           const int c = cb + cu;
+          // ---- every load of this cable first: nothing here depends on this step's sample
+          double *rc_ = ring + c * TPB;
+          double *fq = sm + (M::kFilt + c * M::FS) * TPB;
+          const double older = has_fir ? flexr_fir_older<CPL * TPB>(gw0, rc_) : 0.0;
+          const double desired = sm[(M::kDes + c) * TPB];
+          const double prev_ie = sm[(M::kIerr + c) * TPB];
+          double rx1 = 0.0, rx2 = 0.0, fp[NF > 0 ? 4 * NF : 1], fd[NF > 0 ? 4 * NF : 1];
+          if (NF > 0) {
+            rx1 = rc_[o1]; rx2 = rc_[o2];  // the P filter's x1, x2: the last two errors
+#pragma unroll
+            for (int f = 0; f < 4 * NF; ++f) { fp[f] = (f < 2) ? 0.0 : fq[f * TPB]; fd[f] = fq[(4 * NF + f) * TPB]; }
+          }
           CableKin kin;
           if (LANES == 1 && kUnr >= CPL) {
             kin = cable_kin_v(rc.b[c][0], rc.b[c][1], rc.b[c][2], rc.a[c][0], rc.a[c][1], rc.a[c][2], rc.home_len[c], S, R);
@@ -728,43 +763,47 @@ __global__ void __launch_bounds__(TPB, (LANES == 2 && NF == 0) ? CDPR_FLEXR_MINB
             const double *q = cabtab + c * 7;
             kin = cable_kin_v(q[0], q[1], q[2], q[3], q[4], q[5], q[6], S, R);
           }
-          // mLastPosition follows the joint unless the cable holds (JointForceCalculator.cpp:78,84,88)
-          if (!((holdmask >> c) & 1u)) sm[(M::kLastp + c) * TPB] = kin.qp;
           const bool pos = ((posmask >> c) & 1u) != 0u;
           const double *row = tab + (pos ? M::kRow : 0);
-          const double desired = sm[(M::kDes + c) * TPB];
           const double actual = pos ? kin.qp : kin.qd;
           const FlexGains g = flexr_gains(row);
           const double e = __dsub_rn(desired, actual);
-          double *rc_ = ring + c * TPB;
-          double pe = e;
           // (no test for "this filter has no stage at all": a uniform branch here makes the compiler clone the whole cable loop,
-          // and the clone costs more instruction fetch than the nine operations it saves; the select inside returns the input)
-          if (NF > 0) pe = flexr_cascade<TPB, NF, true>(A.flex_pf, sm + (M::kFilt + c * M::FS) * TPB, A.flex_ps, pos ? A.pc[1].p_casc : A.pc[0].p_casc, e, rc_, o1, o2);
-          rc_[o0] = e;
+          // and the clone costs more instruction fetch than the operations it saves; the select inside returns the input)
+          double pe = e;
+          if (NF > 0) pe = flexr_cascade_regs<NF, true>(A.flex_pf, fp, A.flex_ps, pos ? A.pc[1].p_casc : A.pc[0].p_casc, e, rx1, rx2);
           double derived = 0.0;
-          if (has_fir) derived = flexr_fir<CPL * TPB>(gw, rc_);
+          if (has_fir) derived = fma(A.fir[kFlexLen - 1], e, older);
           double de = derived;
-          if (NF > 0) de = flexr_cascade<TPB, NF, false>(A.flex_df, sm + (M::kFilt + c * M::FS + 4 * NF) * TPB, A.flex_ds, pos ? A.pc[1].d_casc : A.pc[0].d_casc, derived);
+          if (NF > 0) de = flexr_cascade_regs<NF, false>(A.flex_df, fd, A.flex_ds, pos ? A.pc[1].d_casc : A.pc[0].d_casc, derived);
 #if CDPR_FLEXR_OPTIMISTIC
           // Pid::update from the integral on, OPTIMISTICALLY: the integral clamp, the command clamp with its anti-windup and
           // Joint::SetForce's truncation (Pid.cpp:143-150,175-184) almost never fire on a stable loop, and as long as none does
           // the chain returns exactly these values; two compares decide, the exact chain runs out of line for a cable that
           // needs it.  Measured: -5 % on the launch gains, +35 % on a loop that saturates two steps out of three (the
           // reference's filter constants with one stage switched on) -- off by default.
-          const double prev_ie = sm[(M::kIerr + c) * TPB];
           const double ie1 = fma(dt, e, prev_ie);
           const double i_term = __dmul_rn(g.ki, ie1);
           const double cmd_raw = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(g.kf, desired), __dmul_rn(g.kp, pe)), i_term), __dmul_rn(g.kd, de));
           double eff = cmd_raw, ie_new = ie1;
           if (!(fabs(i_term) <= g.i_max) || !(fabs(cmd_raw) <= row[7]))
             eff = flexr_pid_clamped(row, rc.effort_limit, desired, e, dt, pe, de, prev_ie, ie_new);
-          sm[(M::kIerr + c) * TPB] = ie_new;
 #else
-          const FlexPidOut o = flexr_pid(g, desired, e, dt, pe, de, sm[(M::kIerr + c) * TPB]);
-          sm[(M::kIerr + c) * TPB] = o.ierr;
+          const FlexPidOut o = flexr_pid(g, desired, e, dt, pe, de, prev_ie);
+          const double ie_new = o.ierr;
           const double eff = clamp_sym(o.cmd, rc.effort_limit_abs);  // +inf when Joint::SetForce does not truncate
 #endif
+          // ---- every store of this cable last
+          rc_[o0] = e;
+          sm[(M::kIerr + c) * TPB] = ie_new;
+          if (!((holdmask >> c) & 1u)) sm[(M::kLastp + c) * TPB] = kin.qp;  // mLastPosition follows the joint unless the cable holds (JointForceCalculator.cpp:78,84,88)
+          if (NF > 0) {
+#pragma unroll
+            for (int f = 0; f < 4 * NF; ++f) {
+              if (f >= 2) fq[f * TPB] = fp[f];   // (the P filter's first x1, x2 live in the ring)
+              fq[(4 * NF + f) * TPB] = fd[f];
+            }
+          }
           const double tl = __dmul_rn(fma(-rc.cdamp, kin.qd, eff), kin.il);  // tension / L
           W.fx = fma(tl, kin.dx, W.fx); W.fy = fma(tl, kin.dy, W.fy); W.fz = fma(tl, kin.dz, W.fz);
           W.mx = fma(tl, kin.cx, W.mx); W.my = fma(tl, kin.cy, W.my); W.mz = fma(tl, kin.cz, W.mz);
