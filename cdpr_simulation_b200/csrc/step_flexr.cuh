@@ -157,8 +157,12 @@ __device__ __forceinline__ double clamp_sym(double v, double lim) { return (fabs
 __device__ __forceinline__ double flip_sign_by(double x, double s) {
   return __hiloint2double(__double2hiint(x) ^ (__double2hiint(s) & (int)0x80000000), __double2loint(x));
 }
-__device__ __forceinline__ FlexPidOut flexr_pid(const FlexGains &g, double desired, double e, double dt, double pe, double de, double prev_ierr) {
-  FlexPidOut o;
+// (... and arranged so that little is left to do once the last input, the filtered derivative, arrives: the anti-windup
+// correction and the sum of the other three terms are ready by then, "the clamp changed the command" is the clamp's own
+// compare, and Joint::SetForce's truncation is worked out for the clamped and the unclamped command side by side.)
+struct FlexrPidOut { double cmd, eff, ierr, p_term, i_term_pre, d_term; };
+__device__ __forceinline__ FlexrPidOut flexr_pid(const FlexGains &g, double eff_lim, double desired, double e, double dt, double pe, double de, double prev_ierr) {
+  FlexrPidOut o;
   const double f_term = __dmul_rn(g.kf, desired);
   o.p_term = __dmul_rn(g.kp, pe);
   const double ie1 = fma(dt, e, prev_ierr);
@@ -168,22 +172,17 @@ __device__ __forceinline__ FlexPidOut flexr_pid(const FlexGains &g, double desir
   const bool isat = fabs(i_raw) > g.i_max;
   const double i_term = isat ? copysign(g.i_max, i_raw) : i_raw;
   const double ie2 = isat ? flip_sign_by(g.i_max_over_ki, i_raw) : ie1;
+  const double aw_corr = __dmul_rn(__dmul_rn(dt, e), g.ki);
+  const double fpi = __dadd_rn(__dadd_rn(f_term, o.p_term), i_term);
   o.d_term = __dmul_rn(g.kd, de);
-  const double cmd_raw = __dadd_rn(__dadd_rn(__dadd_rn(f_term, o.p_term), i_term), o.d_term);
-  const double cmd_c = clamp_sym(cmd_raw, g.c_max);
-  const bool aw = (cmd_c != cmd_raw);  // Pid.cpp:181-184
-  const double cmd_aw = __dadd_rn(cmd_c, __dmul_rn(__dmul_rn(dt, e), g.ki));
-  o.cmd = aw ? cmd_aw : cmd_c;
+  const double cmd_raw = __dadd_rn(fpi, o.d_term);
+  const bool aw = fabs(cmd_raw) > g.c_max;  // the clamp changes the command (Pid.cpp:175-184): frozen integral, corrected command
+  const double cmd_sat = __dadd_rn(copysign(g.c_max, cmd_raw), aw_corr);
+  const double eff_sat = clamp_sym(cmd_sat, eff_lim), eff_raw = clamp_sym(cmd_raw, eff_lim);
+  o.cmd = aw ? cmd_sat : cmd_raw;
+  o.eff = aw ? eff_sat : eff_raw;  // Joint::SetForce's truncation; eff_lim = +inf when it is off
   o.ierr = aw ? prev_ierr : ie2;
   return o;
-}
-
-// the exact chain of Pid::update and Joint::SetForce for a cable whose command or integral clamps (rare: out of line)
-static __device__ __noinline__ double flexr_pid_clamped(const double *row, double effort_limit, double desired, double e, double dt, double pe, double de,
-                                                        double prev_ierr, double &ierr) {
-  const FlexPidOut o = flexr_pid(flexr_gains(row), desired, e, dt, pe, de, prev_ierr);
-  ierr = o.ierr;
-  return (effort_limit >= 0.0) ? clampd(o.cmd, -effort_limit, effort_limit) : o.cmd;
 }
 
 // (sec, nsec) - back * dt_ns as a gazebo time stamp, without 64-bit divisions
@@ -330,9 +329,6 @@ static __device__ __noinline__ void flexr_wake(const StepArgs &A, double *sm, un
 #ifndef CDPR_FLEXR_UNR
 #define CDPR_FLEXR_UNR 0  // tuning override of the unroll factor of the hot body's cable loop (0 = the measured choice below)
 #endif
-#ifndef CDPR_FLEXR_OPTIMISTIC
-#define CDPR_FLEXR_OPTIMISTIC 0
-#endif
 #ifndef CDPR_FLEXR_MINB0
 #define CDPR_FLEXR_MINB0 1  // resident blocks asked for at two lanes without filter slots (caps the registers per thread); 10: +14 %
 #endif
@@ -458,7 +454,7 @@ static __device__ CDPR_FLEXR_GENERAL_INLINE Wrench6 flexr_general_step(const Ste
         }
         double de = derived;
         if (NF > 0 && A.flex_ds > 0) de = flexr_cascade<TPB, NF, false>(A.flex_df, sm + (M::kFilt + c * M::FS + 4 * NF) * TPB, A.flex_ds, A.pc[k].d_casc, derived);
-        const FlexPidOut o = flexr_pid(g, desired, e, dt, pe, de, sm[(M::kIerr + c) * TPB]);
+        const FlexrPidOut o = flexr_pid(g, rc.effort_limit_abs, desired, e, dt, pe, de, sm[(M::kIerr + c) * TPB]);
         sm[(M::kIerr + c) * TPB] = o.ierr;
         force = o.cmd;
         if (last) {
@@ -480,7 +476,7 @@ static __device__ CDPR_FLEXR_GENERAL_INLINE Wrench6 flexr_general_step(const Ste
       L.cab[cab_off(L, cg, CAB_EFFORT) + i] = eff;
       L.cab[cab_off(L, cg, CAB_PID_FORCE) + i] = force;
     }
-    const double tl = __dmul_rn(fma(-rc.cdamp, kin.qd, eff), kin.il);  // tension / L
+    const double tl = fma(eff, kin.il, __dmul_rn(__dmul_rn(-rc.cdamp, kin.qd), kin.il));  // tension / L, as in the hot body
     W.fx = fma(tl, kin.dx, W.fx); W.fy = fma(tl, kin.dy, W.fy); W.fz = fma(tl, kin.dz, W.fz);
     W.mx = fma(tl, kin.cx, W.mx); W.my = fma(tl, kin.cy, W.my); W.mz = fma(tl, kin.cz, W.mz);
   }
@@ -776,23 +772,8 @@ __global__ void __launch_bounds__(TPB, (LANES == 2 && NF == 0) ? CDPR_FLEXR_MINB
           if (has_fir) derived = fma(A.fir[kFlexLen - 1], e, older);
           double de = derived;
           if (NF > 0) de = flexr_cascade_regs<NF, false>(A.flex_df, fd, A.flex_ds, pos ? A.pc[1].d_casc : A.pc[0].d_casc, derived);
-#if CDPR_FLEXR_OPTIMISTIC
-          // Pid::update from the integral on, OPTIMISTICALLY: the integral clamp, the command clamp with its anti-windup and
-          // Joint::SetForce's truncation (Pid.cpp:143-150,175-184) almost never fire on a stable loop, and as long as none does
-          // the chain returns exactly these values; two compares decide, the exact chain runs out of line for a cable that
-          // needs it.  Measured: -5 % on the launch gains, +35 % on a loop that saturates two steps out of three (the
-          // reference's filter constants with one stage switched on) -- off by default.
-          const double ie1 = fma(dt, e, prev_ie);
-          const double i_term = __dmul_rn(g.ki, ie1);
-          const double cmd_raw = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(g.kf, desired), __dmul_rn(g.kp, pe)), i_term), __dmul_rn(g.kd, de));
-          double eff = cmd_raw, ie_new = ie1;
-          if (!(fabs(i_term) <= g.i_max) || !(fabs(cmd_raw) <= row[7]))
-            eff = flexr_pid_clamped(row, rc.effort_limit, desired, e, dt, pe, de, prev_ie, ie_new);
-#else
-          const FlexPidOut o = flexr_pid(g, desired, e, dt, pe, de, prev_ie);
-          const double ie_new = o.ierr;
-          const double eff = clamp_sym(o.cmd, rc.effort_limit_abs);  // +inf when Joint::SetForce does not truncate
-#endif
+          const FlexrPidOut o = flexr_pid(g, rc.effort_limit_abs, desired, e, dt, pe, de, prev_ie);
+          const double ie_new = o.ierr, eff = o.eff;
           // ---- every store of this cable last
           rc_[o0] = e;
           sm[(M::kIerr + c) * TPB] = ie_new;
@@ -804,7 +785,7 @@ __global__ void __launch_bounds__(TPB, (LANES == 2 && NF == 0) ? CDPR_FLEXR_MINB
               fq[(4 * NF + f) * TPB] = fd[f];
             }
           }
-          const double tl = __dmul_rn(fma(-rc.cdamp, kin.qd, eff), kin.il);  // tension / L
+          const double tl = fma(eff, kin.il, __dmul_rn(__dmul_rn(-rc.cdamp, kin.qd), kin.il));  // tension / L = (effort - c q') / L, the damping part ahead of the effort
           W.fx = fma(tl, kin.dx, W.fx); W.fy = fma(tl, kin.dy, W.fy); W.fz = fma(tl, kin.dz, W.fz);
           W.mx = fma(tl, kin.cx, W.mx); W.my = fma(tl, kin.cy, W.my); W.mz = fma(tl, kin.cz, W.mz);
         }
