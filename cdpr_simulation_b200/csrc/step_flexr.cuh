@@ -74,7 +74,7 @@ __device__ __forceinline__ CableKin cable_kin_v(double bx, double by, double bz,
 // (a0 x + a1 x1) + (a2 x2 - b1 y1 - b2 y2) with fused multiply-adds: the second group does not depend on the new input, so only
 // three operations sit between x and y0 (the reference's left-to-right chain of five products and four sums is nine operations
 // deep, and the two filters of a cable are in series with the D-term between them) -- 6 FP64 instructions instead of 9.  Same
-// value up to the last rounding (the CUDA path is held to 1e-9 of the oracle per step, not to its bits); both bodies use it.
+// value up to the last rounding (the CUDA path is held to 1e-9 of the CPU checker per step, not to its bits); both bodies use it.
 __device__ __forceinline__ double biquad_step(const double *co, double &x1, double &x2, double &y1, double &y2, double x) {
   const double hist = fma(-co[4], y2, fma(-co[3], y1, __dmul_rn(co[2], x2)));
   const double y0 = __dadd_rn(fma(co[1], x1, __dmul_rn(co[0], x)), hist);
