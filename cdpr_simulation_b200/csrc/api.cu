@@ -27,7 +27,7 @@ struct cdpr_batch {
   bool flex_capable = false;
   int flex_tpb = 0, flex_ps = 0, flex_ds = 0, flex_nf = 0, flex_unroll = 2, flex_lanes = 1;
   std::string detail;    // cdpr_kernel_detail
-  bool flexr = false;    // ... in its register-resident form (step_flexr.cuh): at most one biquad stage per filter, no leg model
+  bool flexr = false;    // ... in its rebuilt form (step_flexr.cuh): at most two biquad stages per filter, no leg model
   bool flexr_hold = false;
   size_t flex_smem = 0;
   DevLayout L{};
@@ -463,7 +463,7 @@ extern "C" int cdpr_create(const cdpr_config *cfg, int64_t n_instances, int devi
     }
     h->flex_smem = shape_ok ? flex_smem_bytes(cfg->n_cables, h->flex_nf, h->flex_lanes) : 0;
     h->flex_capable = shape_ok && h->flex_smem <= 227u * 1024u;
-    // The register-resident form (step_flexr.cuh) wherever it is compiled; CDPR_FLEX_CLASSIC=1 keeps k_step_flex (A/B runs).
+    // The rebuilt kernel (step_flexr.cuh) wherever it is compiled; CDPR_FLEX_CLASSIC=1 keeps k_step_flex (A/B runs).
     const char *classic = std::getenv("CDPR_FLEX_CLASSIC");
     const char *env_lanes = std::getenv("CDPR_FLEX_LANES");
     const int rnf = std::max(h->flex_ps, h->flex_ds);  // k_step_flexr holds exactly the stages there are (0, 1 or 2 per filter)
@@ -1290,8 +1290,8 @@ extern "C" int64_t cdpr_launch_count(cdpr_handle h) { return h ? h->launches : -
 extern "C" const char *cdpr_kernel_detail(cdpr_handle h) {
   if (!h) return "";
   char buf[96];
-  if (h->flex && h->flexr) std::snprintf(buf, sizeof(buf), "flex:registers,lanes=%d,nf=%d,hold=%d", h->flex_lanes, h->flex_nf, h->flexr_hold ? 1 : 0);
-  else if (h->flex) std::snprintf(buf, sizeof(buf), "flex:classic,lanes=%d,nf=%d,unroll=%d", h->flex_lanes, h->flex_nf, h->flex_unroll);
+  if (h->flex && h->flexr) std::snprintf(buf, sizeof(buf), "flexr:lanes=%d,nf=%d,hold=%d", h->flex_lanes, h->flex_nf, h->flexr_hold ? 1 : 0);
+  else if (h->flex) std::snprintf(buf, sizeof(buf), "flex:lanes=%d,nf=%d,unroll=%d", h->flex_lanes, h->flex_nf, h->flex_unroll);
   else std::snprintf(buf, sizeof(buf), "%s", h->general ? "general" : "fast");
   h->detail = buf;
   return h->detail.c_str();

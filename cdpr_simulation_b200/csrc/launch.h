@@ -39,7 +39,7 @@ size_t flex_smem_bytes(int nc, int nf, int lanes);
 void flex_prepare(int nc, int nf, int unroll, int lanes);
 void flex_launch(int nc, int nf, int unroll, int lanes, unsigned grid, const StepArgs &A, cudaStream_t st);
 
-// k_step_flexr<NC, 32, NF, HOLD, LANES> (step_flexr.cuh): the register-resident form of the flex kernel, NF <= 1.
+// k_step_flexr<NC, 32, NF, HOLD, LANES, ISO> (step_flexr.cuh): the rebuilt form of the flex kernel, NF <= 2, ISO = isotropic body inertia.
 // flexr_lanes: lanes per robot of the instance that would run (0 = shape not compiled)
 int flexr_lanes(int nc, int nf, int lanes_wanted);
 size_t flexr_smem_bytes(int nc, int nf, int lanes);

@@ -264,8 +264,8 @@ double cdpr_measure_fp64_tflops(int device, int iters);
 float cdpr_last_kernel_ms(cdpr_handle h);
 int64_t cdpr_launch_count(cdpr_handle h);
 const char *cdpr_kernel_variant(cdpr_handle h); /* "fast", "flex" (full semantics, on chip) or "general" (catch-all, state in HBM) */
-/* which instance of the variant runs, for tests and tuning logs: "fast", "general", "flex:classic,lanes=L,nf=F,unroll=U"
- * (k_step_flex) or "flex:registers,lanes=L,nf=F,hold=H" (k_step_flexr).  The string lives in the handle. */
+/* which instance of the variant runs, for tests and tuning logs: "fast", "general", "flex:lanes=L,nf=F,unroll=U"
+ * (k_step_flex) or "flexr:lanes=L,nf=F,hold=H" (k_step_flexr).  The string lives in the handle. */
 const char *cdpr_kernel_detail(cdpr_handle h);
 
 #ifdef __cplusplus

@@ -1,4 +1,4 @@
-"""GPU parity of the register-resident form of the full-semantics kernel (k_step_flexr, step_flexr.cuh): hold through the
+"""GPU parity of the rebuilt full-semantics kernel (k_step_flexr, step_flexr.cuh): hold through the
 position Pid (JointForceCalculator.cpp:72-82) with at most one biquad stage per filter (Pid.cpp:27-44), its event-driven hot
 loop, the on-chip fits of windows that span a gap (Pid.cpp:193-247) and their HBM fallback -- against the oracle per step, and
 bit for bit across launch splits and checkpoints.  test_gpu_flex.py / test_gpu_parity*.py cover k_step_flex (two or more
@@ -50,7 +50,7 @@ def test_flexr_per_step_and_long_run(built_lib, nc, edit):
     """Sine commands that cross the hold band: each of the first 60 steps at 1e-9 (joint states, platform state, the `pid`
     topic), then 2000 more."""
     cfg, gpu, orc = make_pair(nc, 200, seed=91, cfg_edit=edit)
-    assert gpu.kernel_detail.startswith("flex:registers"), gpu.kernel_detail
+    assert gpu.kernel_detail.startswith("flexr:"), gpu.kernel_detail
     held = 0
     k_prev = None
     for step in range(1, 61):
@@ -86,7 +86,7 @@ def test_flexr_launch_split_and_checkpoint_bitwise(built_lib, nc, edit):
     arbitrary places) == a run resumed from a checkpoint, bit for bit."""
     runs = [make_pair(nc, 180, seed=92, cfg_edit=edit)[1] for _ in range(3)]
     a, b, c = runs
-    assert a.kernel_detail.startswith("flex:registers")
+    assert a.kernel_detail.startswith("flexr:")
     a.step(1511)
     splits = (1, 2, 9, 10, 11, 12, 13, 1, 100, 3, 500, 7, 600, 242)
     assert sum(splits) == 1511
@@ -125,7 +125,7 @@ def test_flexr_rapid_hold_toggling_uses_both_gap_fits(built_lib, nc):
     _, _, _, pose7, twist6 = wl.c3_instances(n, 93)
     gpu = cb.CdprBatch(cfg, n)
     gpu.set_independent(True)
-    assert gpu.kernel_detail.startswith("flex:registers")
+    assert gpu.kernel_detail.startswith("flexr:")
     gpu.set_platform_state(pose7, twist6)
     orc = ob.Batch(to_oracle_config(cfg), n, pose7, twist6)
     rng = np.random.default_rng(5)
@@ -150,7 +150,7 @@ def test_flexr_different_filter_coefficients_fall_back_to_the_classic_kernel(bui
         hold_1p1d_cfg(cfg)
         cfg.pos_pid.p_cascade = 1; cfg.pos_pid.p_cutoff = 0.2
     cfg, gpu, orc = make_pair(4, 64, seed=94, cfg_edit=edit)
-    assert gpu.kernel_detail.startswith("flex:classic"), gpu.kernel_detail
+    assert gpu.kernel_detail.startswith("flex:"), gpu.kernel_detail
     for k in (1, 1, 12, 50, 300):
         gpu.step(k); orc.step(k)
         _check(gpu, orc, 1e-9 if k < 100 else 1e-7, f"after {k}")
@@ -167,7 +167,7 @@ def test_classic_flex_kernel_on_the_same_configuration(built_lib, nc):
     finally:
         del os.environ["CDPR_FLEX_CLASSIC"]
     _, regs, _ = make_pair(nc, 128, seed=95, cfg_edit=hold_1p1d_cfg)
-    assert classic.kernel_detail.startswith("flex:classic") and regs.kernel_detail.startswith("flex:registers")
+    assert classic.kernel_detail.startswith("flex:") and regs.kernel_detail.startswith("flexr:")
     for k in (1, 5, 20, 74, 400):
         classic.step(k); regs.step(k); orc.step(k)
         _check(classic, orc, 1e-8, f"classic after {k}")
@@ -199,7 +199,7 @@ def test_flexr_snapshots_rollouts_and_update(built_lib):
     _, _, _, pose7, twist6 = wl.c3_instances(n_robots, 12)
     target, lam = np.array([0.0, 0.0, 0.32]), 0.05
     with cb.CdprBatch(cfg, n_robots * n_seq) as g:
-        assert g.kernel_detail.startswith("flex:registers")
+        assert g.kernel_detail.startswith("flexr:")
         cost = g.rollout(n_robots, n_seq, cmds, spc, target, lam, pose7, twist6)
     ocost = np.zeros(n_robots * n_seq)
     o = ob.Batch(to_oracle_config(cfg), n_robots * n_seq, np.repeat(pose7, n_seq, axis=0), np.repeat(twist6, n_seq, axis=0))
