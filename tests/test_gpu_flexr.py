@@ -210,3 +210,32 @@ def test_flexr_snapshots_rollouts_and_update(built_lib):
             pose, twist = o.platform_state()
             ocost += np.sum((pose[:, :3] - target) ** 2, axis=1) + lam * np.sum(twist[:, 3:] ** 2, axis=1)
     assert np.max(np.abs(cost - ocost) / ocost) < 1e-9
+
+
+def test_flexr_full_size_properties(built_lib):
+    """2^20 eight-cable robots with hold + one stage per filter, at a size the oracle cannot follow: finite state, unit
+    quaternions, the platform inside the frame, robots that hold and robots that do not; the first 2048 instances are bit for bit
+    what a 2048-instance batch computes (no cross-talk between robots, blocks or lanes), and cutting the launch changes nothing."""
+    n, k = 1 << 20, 400
+    cfg = cb.default_config(8)
+    hold_1p1d_cfg(cfg)
+    amp, freq, phase, pose7, twist6 = wl.c3_instances(n, 1)
+    with cb.CdprBatch(cfg, n) as g:
+        assert g.kernel_detail.startswith("flexr:")
+        g.set_platform_state(pose7, twist6); g.set_sine_cmd(amp, freq, phase)
+        g.step(k)
+        pose, twist = g.platform_state()
+        terms = g.pid_terms()
+    assert np.all(np.isfinite(pose)) and np.all(np.isfinite(twist))
+    assert np.max(np.abs(np.linalg.norm(pose[:, 3:], axis=1) - 1.0)) < 1e-14
+    assert np.all(np.abs(pose[:, :2]) < 0.3) and np.all((pose[:, 2] > 0.0) & (pose[:, 2] < 0.6))
+    with cb.CdprBatch(cfg, 2048) as a, cb.CdprBatch(cfg, 2048) as b:
+        for h in (a, b):
+            h.set_platform_state(pose7[:2048], twist6[:2048]); h.set_sine_cmd(amp[:2048], freq[:2048], phase[:2048])
+        a.step(k)
+        for part in (1, 13, 200, k - 214):
+            b.step(part)
+        pa, ta = a.platform_state(); pb, tb = b.platform_state()
+        assert np.array_equal(pa, pose[:2048]) and np.array_equal(ta, twist[:2048])
+        assert np.array_equal(pa, pb) and np.array_equal(ta, tb)
+        assert np.array_equal(a.pid_terms()[..., 4], terms[:2048, :, 4])
