@@ -15,8 +15,8 @@
 //   along the motion over kLegBiasDt (each link obeys m a = f, I alpha = tau with a = J xi' + J' xi; isotropic inertia, so
 //   the links have no gyroscopic torque of their own)
 //   step:  M(x_n) (xi+ - xi)/h = Q_cables + Q_gravity + Q_passive - Jy^T J'y xi - gyro(platform), then the pose update of App. C.6.
-// A slow path by construction (a 6x6 system per instance and step, about 3000 extra FMAs at 8 cables): out of line, rolled
-// loops, local arrays.
+// A slow path by construction (a 6x6 system per instance and step, about 10,000 FP64 instructions at 8 cables): out of line, a
+// rolled loop over the legs; inside a leg everything is unrolled (the unit twists behind the Jacobian are constants then).
 #pragma once
 #include "common.cuh"
 #include "physics.cuh"
@@ -26,6 +26,7 @@ namespace cdpr {
 struct LegGeom {
   double r[3], u[3], e1[3], e2[3], a1[3], a2[3], a3[3], x0[3];
   double L, c, t;
+  double iL, iLc, i1t2;  // 1/L, 1/(L c), 1/(1 - t^2): the rates divide by them eight times per leg and step
 };
 
 __device__ __forceinline__ double dot3d(const double *a, const double *b) { return fma(a[0], b[0], fma(a[1], b[1], a[2] * b[2])); }
@@ -41,33 +42,38 @@ __device__ inline void leg_geometry(const RobotConsts &rc, int i, const double *
   for (int k = 0; k < 3; ++k) g.r[k] = fma(R[k][0], rc.b[i][0], fma(R[k][1], rc.b[i][1], R[k][2] * rc.b[i][2]));
   for (int k = 0; k < 3; ++k) d[k] = rc.a[i][k] - p[k] - g.r[k];
   g.L = sqrt(dot3d(d, d));
-  for (int k = 0; k < 3; ++k) { g.u[k] = d[k] / g.L; g.x0[k] = rc.leg_x0[i][k]; }
+  g.iL = 1.0 / g.L;
+  for (int k = 0; k < 3; ++k) { g.u[k] = d[k] * g.iL; g.x0[k] = rc.leg_x0[i][k]; }
   const double s = dot3d(g.u, g.x0);
   g.c = sqrt(1.0 - s * s);
-  for (int k = 0; k < 3; ++k) g.e1[k] = (g.x0[k] - s * g.u[k]) / g.c;
+  const double ic = 1.0 / g.c;
+  g.iLc = g.iL * ic;
+  for (int k = 0; k < 3; ++k) g.e1[k] = (g.x0[k] - s * g.u[k]) * ic;
   cross3d(g.u, g.e1, g.e2);
   for (int k = 0; k < 3; ++k) g.a3[k] = fma(rc.leg_alpha[i][0], g.e1[k], fma(rc.leg_alpha[i][1], g.e2[k], rc.leg_alpha[i][2] * g.u[k]));
   for (int k = 0; k < 3; ++k) g.a1[k] = fma(R[k][0], rc.leg_a1[i][0], fma(R[k][1], rc.leg_a1[i][1], R[k][2] * rc.leg_a1[i][2]));
   g.t = dot3d(g.a3, g.a1);
   double nrm[3];
   cross3d(g.a3, g.a1, nrm);
-  const double nn = sqrt(1.0 - g.t * g.t);
-  for (int k = 0; k < 3; ++k) g.a2[k] = nrm[k] / nn;
+  const double omt = 1.0 - g.t * g.t;
+  g.i1t2 = 1.0 / omt;
+  const double inn = rsqrt(omt);
+  for (int k = 0; k < 3; ++k) g.a2[k] = nrm[k] * inn;
 }
 
 __device__ inline void leg_rates(const RobotConsts &rc, const LegGeom &g, const double *v, const double *w, double *y, double *z) {
   double wr[3], vB[3];
   cross3d(w, g.r, wr);
   for (int k = 0; k < 3; ++k) vB[k] = v[k] + wr[k];
-  const double thy = -dot3d(g.e1, vB) / g.L;
-  const double thx = dot3d(g.e2, vB) / (g.L * g.c);
+  const double thy = -dot3d(g.e1, vB) * g.iL;
+  const double thx = dot3d(g.e2, vB) * g.iLc;
   double wleg[3], D[3];
   for (int k = 0; k < 3; ++k) { wleg[k] = fma(thx, g.x0[k], thy * g.e2[k]); D[k] = wleg[k] - w[k]; }
   const double psy = dot3d(D, g.a2);
   const double Da3 = dot3d(D, g.a3);
-  const double psx = (dot3d(D, g.a1) - g.t * Da3) / (1.0 - g.t * g.t);
+  const double psx = (dot3d(D, g.a1) - g.t * Da3) * g.i1t2;
   const double phi = psx * g.t - Da3;
-  const double uv = dot3d(g.u, vB), lam = rc.leg_lc / g.L;
+  const double uv = dot3d(g.u, vB), lam = rc.leg_lc * g.iL;
   y[0] = rc.leg_sI * thx;
   for (int k = 0; k < 3; ++k) {
     y[1 + k] = rc.leg_s2I * wleg[k];
@@ -127,28 +133,38 @@ static __device__ __noinline__ FastState legs_step(const StepArgs &A, FastState 
     leg_geometry(rc, i, p, R, g);
     leg_geometry(rc, i, p1, R1, g1);
     double Jy[16][6], Jz[5][6];
-#pragma unroll 1
-    for (int k = 0; k < 6; ++k) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {  // unrolled: the unit twists are constants, most of leg_rates folds away
       double ev[3] = {0.0, 0.0, 0.0}, ew[3] = {0.0, 0.0, 0.0}, y[16], z[5];
       if (k < 3) ev[k] = 1.0; else ew[k - 3] = 1.0;
       leg_rates(rc, g, ev, ew, y, z);
+#pragma unroll
       for (int j = 0; j < 16; ++j) Jy[j][k] = y[j];
+#pragma unroll
       for (int j = 0; j < 5; ++j) Jz[j][k] = z[j];
     }
+#pragma unroll
     for (int a = 0; a < 6; ++a)
+#pragma unroll
       for (int b = a; b < 6; ++b) {
         double acc = 0.0;
+#pragma unroll
         for (int j = 0; j < 16; ++j) acc = fma(Jy[j][a], Jy[j][b], acc);
         M[a][b] += acc;
       }
     double y[16], z[5], y1[16], z1[5];
     leg_rates(rc, g, v, w, y, z);
     leg_rates(rc, g1, v, w, y1, z1);
-    for (int j = 0; j < 16; ++j) y1[j] = (y1[j] - y[j]) / kLegBiasDt;  // J'y xi
+#pragma unroll
+    for (int j = 0; j < 16; ++j) y1[j] = (y1[j] - y[j]) * (1.0 / kLegBiasDt);  // J'y xi
+#pragma unroll
     for (int k = 0; k < 6; ++k) {
       double damp = 0.0, gr = 0.0, bias = 0.0;
+#pragma unroll
       for (int j = 0; j < 5; ++j) damp = fma(Jz[j][k], z[j], damp);
+#pragma unroll
       for (int j = 0; j < 3; ++j) gr = fma(grav[j], fma(rc.leg_sm, Jy[10 + j][k], rc.leg_s2m * Jy[13 + j][k]), gr);
+#pragma unroll
       for (int j = 0; j < 16; ++j) bias = fma(Jy[j][k], y1[j], bias);
       Q[k] += gr - damp - bias;
     }
