@@ -705,14 +705,18 @@ def side_measurements(cb, wl, torch, device, hbm_peak, fp64_peak):
     # the full-semantics kernel (step_flexr.cuh / step_flex.cuh) at the headline size: independent robots on the launch values,
     # velocity hold below 2 cm/s, and hold + one biquad stage on the P input and on the D output with the reference's filter
     # constants (launch:27-32; that loop lives on its clamps: two steps out of three saturate)
-    def flex_case(edit, independent=False):
+    def flex_case(edit, independent=False, square=False):
         cfg = cb.default_config(8)
         if edit:
             edit(cfg)
         with cb.CdprBatch(cfg, n, device=device) as g:
             if independent:
                 g.set_independent(True)
-            g.set_platform_state(pose7, twist6); g.set_sine_cmd(amp, freq, phase)
+            g.set_platform_state(pose7, twist6)
+            if square:   # the reference's squarevelocitytest constants (0.06 m/s, 0.05 Hz, 10 Hz publisher), one phase per robot
+                g.set_square_velocity_cmd(np.full(n, 0.06), np.full(n, 0.05), phase)
+            else:
+                g.set_sine_cmd(amp, freq, phase)
             ms = []
             for _ in range(3):
                 g.step(k); ms.append(g.last_kernel_ms)
@@ -720,8 +724,10 @@ def side_measurements(cb, wl, torch, device, hbm_peak, fp64_peak):
             return {"value": n * k / (t * 1e-3), "unit": UNIT, "kernel_ms": t, "variant": g.kernel_variant, "kernel": g.kernel_detail}
     def hold(cfg): cfg.velocity_epsilon = 0.02
     def hold_1p1d(cfg): cfg.velocity_epsilon = 0.02; cfg.vel_pid.p_cascade = 1; cfg.vel_pid.d_cascade = 1
+    def hold_10hz(cfg): cfg.velocity_epsilon = 0.02; cfg.sine_publish_hz = 10.0
     out["full_semantics_nc8"] = {"independent_launch_values": flex_case(None, independent=True), "hold_2cm_s": flex_case(hold),
                                  "hold_1p_1d": flex_case(hold_1p1d),
+                                 "squarevelocitytest_hold_2cm_s": flex_case(hold_10hz, square=True),
                                  "what": "2^20 instances x 1000 steps per launch, per-instance sine commands crossing the hold band (C3 inputs)"}
     out["general_variant_nc8"] = out["full_semantics_nc8"]["hold_1p_1d"]   # the name round 1 and 2 reported it under
     ik_c2 = None

@@ -18,7 +18,8 @@ from . import build as _build
 
 MAX_CABLES = 8
 MODE_FORCE, MODE_POSITION, MODE_VELOCITY = 0, 1, 2
-OPT_DTERM_FIR, OPT_KERNEL_TIMING, OPT_INDEPENDENT = 1, 2, 3
+OPT_DTERM_FIR, OPT_KERNEL_TIMING, OPT_INDEPENDENT, OPT_PUBLISHER_SHAPE = 1, 2, 3, 4
+PUBLISHER_SINE, PUBLISHER_SQUARE_VELOCITY = 0, 1
 
 OK = 0
 ERR_BAD_ARG, ERR_BAD_CABLE_COUNT, ERR_BAD_LENGTH, ERR_NO_DEVICE, ERR_CUDA, ERR_UNSUPPORTED, ERR_NOMEM = -1, -2, -3, -4, -5, -6, -7
@@ -253,8 +254,16 @@ class CdprBatch:
         self._ck(self._L.cdpr_get_modes(self._h, _ptr(out)))
         return out
 
-    def set_sine_cmd(self, amp, freq=None, phase=None):
+    def set_square_velocity_cmd(self, amp, freq=None, phase=None):
+        """squarevelocitytest.cpp run inside the kernel (+-amp outside the dead band |sin| >= sqrt(0.5), else 0; the driver
+        publishes at 10 Hz: Config.sine_publish_hz); per-instance amp / freq / phase."""
+        self.set_option(OPT_PUBLISHER_SHAPE, PUBLISHER_SQUARE_VELOCITY)
+        self.set_sine_cmd(amp, freq, phase, _keep_shape=True)
+
+    def set_sine_cmd(self, amp, freq=None, phase=None, _keep_shape=False):
         """sinevelocitytest.cpp run inside the kernel; per-instance amp / freq / phase."""
+        if not _keep_shape:
+            self.set_option(OPT_PUBLISHER_SHAPE, PUBLISHER_SINE)
         if amp is None:
             self._ck(self._L.cdpr_set_sine_cmd(self._h, None, None, None, 0))
             return

@@ -42,6 +42,7 @@ struct cdpr_batch {
   int sec = 0, nsec = 0, dt_ns = 0;
   long long step_count = 0;
   bool sine_on = false;
+  int pub_shape = 0;     // CDPR_OPT_PUBLISHER_SHAPE: wave form of the in-kernel publisher
   int sine_period = 10;
   double sine_time = 0.0, sine_pub_dt = 0.01;
   double *snap_peers[8] = {nullptr};
@@ -623,6 +624,10 @@ extern "C" int cdpr_set_option(cdpr_handle h, int option, int64_t value) {
       CK(h, sync_unless_async(h));
       return CDPR_OK;
     }
+    case CDPR_OPT_PUBLISHER_SHAPE:
+      if (value != 0 && value != 1) return fail(h, CDPR_ERR_BAD_ARG, "publisher shape: 0 (sinevelocitytest) or 1 (squarevelocitytest)");
+      h->pub_shape = (int)value;
+      return CDPR_OK;
     case CDPR_OPT_DTERM_FIR:
       if (h->step_count != 0) return fail(h, CDPR_ERR_BAD_ARG, "the D-term form can only change before the first step");
       h->force_fir = value != 0;
@@ -771,6 +776,7 @@ static void fill_args(cdpr_handle h, StepArgs &A, int k_steps, bool sine) {
   A.sat_thr = fmin(A.live.cmd_max, h->rc.effort_limit_abs);
   A.mode = h->mode; A.k_steps = k_steps; A.n0 = h->step_count;
   A.sec0 = h->sec; A.nsec0 = h->nsec; A.dt_ns = h->dt_ns; A.t0 = time_double(h->sec, h->nsec);
+  A.pub_shape = h->pub_shape;
   A.sine_on = sine ? 1 : 0; A.sine_period = h->sine_period; A.sine_time0 = h->sine_time; A.sine_pub_dt = h->sine_pub_dt;
   for (int p = 0; p < 8; ++p) A.snap_peers[p] = h->snap_peers[p];
   A.snap_multimem = (h->snap_multimem && (!h->general || h->flex)) ? 1 : 0;
@@ -1078,7 +1084,7 @@ extern "C" int cdpr_get_state(cdpr_handle h, void *blob, size_t bytes) {
   std::memset(&hd, 0, sizeof(hd));
   hd.magic = kMagic; hd.n = h->n; hd.np = h->np; hd.nc = h->L.nc; hd.len = h->L.len; hd.casc = h->L.casc; hd.general = (int)h->general + (int)h->flex;
   hd.mode = h->mode; hd.vel_pending = h->vel_pending; hd.pos_pending = h->pos_pending; hd.sec = h->sec; hd.nsec = h->nsec;
-  hd.sine_on = h->sine_on; hd.step_count = h->step_count; hd.sine_time = h->sine_time; hd.cfg_hash = config_hash(h->cfg);
+  hd.sine_on = h->sine_on ? 1 + h->pub_shape : 0; hd.step_count = h->step_count; hd.sine_time = h->sine_time; hd.cfg_hash = config_hash(h->cfg);
   std::memcpy(blob, &hd, sizeof(hd));
   uint8_t *o = (uint8_t *)blob + sizeof(hd);
   for (auto &s : sections(h)) {
@@ -1108,7 +1114,7 @@ extern "C" int cdpr_set_state(cdpr_handle h, const void *blob, size_t bytes) {
   CK(h, cudaStreamSynchronize(h->stream));
   h->targets_uniform = false;
   h->mode = hd.mode; h->vel_pending = hd.vel_pending; h->pos_pending = hd.pos_pending; h->sec = hd.sec; h->nsec = hd.nsec;
-  h->sine_on = hd.sine_on; h->step_count = hd.step_count; h->sine_time = hd.sine_time;
+  h->sine_on = hd.sine_on != 0; if (hd.sine_on) h->pub_shape = hd.sine_on - 1; h->step_count = hd.step_count; h->sine_time = hd.sine_time;
   return CDPR_OK;
 }
 

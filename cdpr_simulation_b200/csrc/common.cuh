@@ -107,6 +107,7 @@ struct StepArgs {
   // sine generator (sinevelocitytest.cpp)
   int sine_on, sine_period;
   double sine_time0, sine_pub_dt;
+  int pub_shape;       // wave form of the in-kernel publisher: 0 sinevelocitytest, 1 squarevelocitytest (dead band)
   // snapshots
   // snapshots: every peer buffer is [capacity][13][snap_stride]; this handle's instances start at column snap_offset.
   // One local buffer (stride n, offset 0), or the gather buffers of ALL ranks mapped over NVLink (fused all-gather).
@@ -125,6 +126,19 @@ struct StepArgs {
   double *cost;            // [N] or nullptr
   double target[3], lambda;
 };
+
+// The value one loop iteration of a reference command driver publishes, from sine = sin(time * freq * 2 pi [+ phase]):
+//   shape 0  sinevelocitytest.cpp:36-38    amp * sine
+//   shape 1  squarevelocitytest.cpp:21-22  +-amp outside the dead band |sine| >= sqrt(0.5), else 0
+// stored into a float32 Joy axis like the driver does.
+__device__ __forceinline__ double publisher_value(int shape, double amp, double sine) {
+#ifdef __CUDA_ARCH__
+  const double v = (shape == 1) ? ((fabs(sine) >= 0.70710678118654757) ? copysign(amp, sine) : 0.0) : __dmul_rn(amp, sine);
+#else
+  const double v = 0.0;
+#endif
+  return (double)(float)v;
+}
 
 // gazebo::common::Time::Double(): two roundings, never contracted
 __host__ __device__ inline double time_double(int sec, int nsec) {

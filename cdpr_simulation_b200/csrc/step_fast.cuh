@@ -443,7 +443,7 @@ __global__ void __launch_bounds__(FastCfg<NC, SPEC>::tpb, FastCfg<NC, SPEC>::blo
     if (sine_on && sine_ctr == 0) {  // sinevelocitytest.cpp:35-38,48: float32 axes, accumulated publisher time
       const double amp = mysine[0], freq = mysine[kTpbL], phase = mysine[2 * kTpbL];
       const double arg = __dadd_rn(__dmul_rn(__dmul_rn(__dmul_rn(sine_time, freq), 2.0), 3.14159265358979323846), phase);
-      const double vel = (double)(float)__dmul_rn(amp, sin(arg));
+      const double vel = publisher_value(A.pub_shape, amp, sin(arg));
       if (!kLean) {
 #pragma unroll
         for (int c = 0; c < NC; ++c) { mytgt[c * kTpbL] = vel; mytgt[(NC + c) * kTpbL] = A.live.kf * vel; }

@@ -656,7 +656,7 @@ __global__ void __launch_bounds__(TPB, (LANES == 2 && NF == 0) ? CDPR_FLEXR_MINB
     if (A.sine_on) {
       if (sine_ctr == 0) {  // sinevelocitytest.cpp:35-38,48: float32 axes, accumulated publisher time
         const double arg = __dadd_rn(__dmul_rn(__dmul_rn(__dmul_rn(sine_time, sm[(M::kSine + 1) * TPB]), 2.0), 3.14159265358979323846), sm[(M::kSine + 2) * TPB]);
-        const double vel = (double)(float)__dmul_rn(sm[M::kSine * TPB], sin(arg));
+        const double vel = publisher_value(A.pub_shape, sm[M::kSine * TPB], sin(arg));
 #pragma unroll
         for (int c = 0; c < CPL; ++c) sm[(M::kTgt + c) * TPB] = vel;
         sine_time = __dadd_rn(sine_time, A.sine_pub_dt);

@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(kTpb, CDPR_GEN_BLOCKS) k_step_general(const __
     if (A.sine_on) {
       if (sine_ctr == 0) {
         const double arg = __dadd_rn(__dmul_rn(__dmul_rn(__dmul_rn(sine_time, freq), 2.0), 3.14159265358979323846), phase);
-        const double vel = (double)(float)__dmul_rn(amp, sin(arg));
+        const double vel = publisher_value(A.pub_shape, amp, sin(arg));
         for (int c = 0; c < nc; ++c) L.cab[cab_off(L, c, CAB_VEL_TARGET) + i] = vel;
         sine_time = __dadd_rn(sine_time, A.sine_pub_dt);
       }

@@ -133,7 +133,13 @@ enum {
    * different modes and receive commands at different steps. Runs the on-chip full-semantics kernel ("flex"); allowed
    * before the first step or right after cdpr_reset (the state is re-initialised to the post-Load state). Handles whose
    * configuration needs hold / biquad stages are independent from the start. */
-  CDPR_OPT_INDEPENDENT = 3
+  CDPR_OPT_INDEPENDENT = 3,
+  /* wave form of the in-kernel command publisher that cdpr_set_sine_cmd switches on (per-instance amp, freq, phase; rate
+   * cdpr_config.sine_publish_hz): 0 = sinevelocitytest (P/src/sinevelocitytest.cpp:33-49, amp * sin), 1 = squarevelocitytest
+   * (P/src/squarevelocitytest.cpp:19-33: +-amp outside the dead band |sin| >= sqrt(0.5), else 0 -- with velocityEpsilon >= 0
+   * the cables HOLD in the dead band, JointForceCalculator.cpp:72-82).  Float32 axes and accumulated publisher time as in
+   * the drivers.  May change between steps; takes effect at the next publish. */
+  CDPR_OPT_PUBLISHER_SHAPE = 4
 };
 int cdpr_set_option(cdpr_handle h, int option, int64_t value);
 

@@ -51,10 +51,15 @@ class Config(C.Structure):
 
 
 def build(force: bool = False) -> None:
-    """Compile liborc.so (always possible) and _ref/libcdpr_ref.so (only where /root/reference exists)."""
-    if force or not os.path.exists(os.path.join(HERE, "liborc.so")) or (
-        os.path.isdir("/root/reference/src/cdpr_gazebo/src") and not os.path.exists(os.path.join(HERE, "_ref", "libcdpr_ref.so"))
-    ):
+    """Compile liborc.so (always possible) and _ref/libcdpr_ref.so (only where /root/reference exists); again whenever a
+    source is newer than what was built from it."""
+    def mtime(*parts):
+        f = os.path.join(HERE, *parts)
+        return os.path.getmtime(f) if os.path.exists(f) else 0.0
+    src = max(mtime("cdpr_oracle.c"), mtime("cdpr_oracle.h"))
+    have_ref_src = os.path.isdir("/root/reference/src/cdpr_gazebo/src")
+    stale = mtime("liborc.so") < src or (have_ref_src and mtime("_ref", "libcdpr_ref.so") < max(src, mtime("ref_harness.cpp")))
+    if force or stale:
         subprocess.run(["make", "-C", HERE, "all"], check=True, capture_output=True)
 
 
@@ -82,6 +87,7 @@ def lib():
         L.orc_sizeof_robot.restype = C.c_int
         L.orc_batch_init.argtypes = [C.c_void_p, C.c_int64, C.POINTER(Config)] + [C.c_void_p] * 5
         L.orc_batch_step.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int]
+        L.orc_batch_publisher.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_double]
         L.orc_batch_velocity_cmd.argtypes = [C.c_void_p, C.c_int64, _fp]
         L.orc_batch_position_cmd.argtypes = [C.c_void_p, C.c_int64, _fp]
         L.orc_batch_effort_cmd.argtypes = [C.c_void_p, C.c_int64, _dp]
@@ -183,6 +189,10 @@ class Batch:
         """Same reduced model, but the force law is the reference's own compiled code (L0).
         Only valid from the post-Load state (a fresh reference plugin is created per call)."""
         ref().ref_batch_step(self.ptr, self.n, int(k), int(threads))
+
+    def publisher(self, shape: int, publish_hz: float):
+        """Wave form (0 sinevelocitytest, 1 squarevelocitytest) and rate of the command publisher of every robot."""
+        lib().orc_batch_publisher(self.ptr, self.n, int(shape), float(publish_hz))
 
     def velocity_cmd(self, axes):
         lib().orc_batch_velocity_cmd(self.ptr, self.n, np.ascontiguousarray(axes, dtype=np.float32).reshape(self.n, self.nc))

@@ -702,7 +702,10 @@ static void robot_step_impl(orc_robot *r, orc_force_fn fn, void *ctx) {
 
   /* sinevelocitytest.cpp:33-49, headless schedule of SURVEY.md App. A.4 */
   if (r->sine_enabled && ((r->step_count - 1) % r->sine_period_steps) == 0) {
-    double velocity = r->sine_amp * sin(r->sine_time * r->sine_freq * 2 * M_PI + r->sine_phase);
+    double sine = sin(r->sine_time * r->sine_freq * 2 * M_PI + r->sine_phase);
+    double velocity = r->sine_amp * sine;
+    /* squarevelocitytest.cpp:21-22: velocity = abs(sine) >= sqrt(0.5) ? copysign(cVelocityAmplitude, sine) : 0.0 */
+    if (r->pub_shape == 1) velocity = fabs(sine) >= sqrt(0.5) ? copysign(r->sine_amp, sine) : 0.0;
     float axes[ORC_MAX_CABLES];
     for (int i = 0; i < nc; ++i) axes[i] = (float)velocity;
     orc_robot_velocity_cmd(r, axes, nc);
@@ -857,6 +860,15 @@ void orc_batch_init(orc_robot *robots, int64_t n, const orc_config *cfg, const d
       for (int k = 0; k < 3; ++k) { r->v[k] = twist6[6 * i + k]; r->w[k] = twist6[6 * i + 3 + k]; }
     }
     if (amp) orc_robot_sine(r, amp[i], freq ? freq[i] : 0.1, phase ? phase[i] : 0.0);
+  }
+}
+void orc_batch_publisher(orc_robot *robots, int64_t n, int shape, double publish_hz) {
+  for (int64_t i = 0; i < n; ++i) {
+    orc_robot *r = &robots[i];
+    r->pub_shape = shape;
+    r->sine_pub_dt = 1.0 / publish_hz;                                   /* time += 1.0 / cPublishFrequency */
+    r->sine_period_steps = (int32_t)llround(r->sine_pub_dt / r->cfg.dt); /* headless schedule, SURVEY.md App. A.4 */
+    if (r->sine_period_steps < 1) r->sine_period_steps = 1;
   }
 }
 void orc_batch_velocity_cmd(orc_robot *robots, int64_t n, const float *axes) {

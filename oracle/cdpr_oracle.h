@@ -127,11 +127,12 @@ typedef struct {
   double joint_pos[ORC_MAX_CABLES], joint_vel[ORC_MAX_CABLES];
   double pid_force[ORC_MAX_CABLES]; /* returned by JointForceCalculator::update */
   double effort[ORC_MAX_CABLES];    /* after effort truncation (Joint::GetForce) */
-  /* sine publisher (sinevelocitytest.cpp) */
+  /* command publisher (sinevelocitytest.cpp, squarevelocitytest.cpp) */
   int32_t sine_enabled;
   double sine_amp, sine_freq, sine_phase, sine_time;
   int32_t sine_period_steps; /* physics steps per published command */
   double sine_pub_dt;        /* 1/cPublishFrequency */
+  int32_t pub_shape;         /* 0: amp * sin (sinevelocitytest.cpp:36); 1: +-amp outside the dead band, else 0 (squarevelocitytest.cpp:21-22) */
 } orc_robot;
 
 typedef struct {
@@ -190,6 +191,9 @@ int orc_sizeof_robot(void);
  * pose7 = [n][7] x y z qx qy qz qw, twist6 = [n][6]; amp/freq/phase enable the sine publisher. */
 void orc_batch_init(orc_robot *robots, int64_t n, const orc_config *cfg, const double *pose7, const double *twist6,
                     const double *amp, const double *freq, const double *phase);
+/* wave form and rate of the publisher of every robot: shape as in orc_robot.pub_shape, publish_hz = cPublishFrequency of the driver
+ * (100 for sinevelocitytest.cpp:7, 10 for squarevelocitytest.cpp:6) */
+void orc_batch_publisher(orc_robot *robots, int64_t n, int shape, double publish_hz);
 void orc_batch_velocity_cmd(orc_robot *robots, int64_t n, const float *axes /* [n][nc] */);
 void orc_batch_position_cmd(orc_robot *robots, int64_t n, const float *axes);
 void orc_batch_effort_cmd(orc_robot *robots, int64_t n, const double *force);

@@ -133,3 +133,23 @@ def test_sliding_window_recursion_of_the_step_kernel(built_lib):
             s0, s1, kdd = resum(ring)
             assert abs(kdd - exact) < 1e-12
     assert worst < 2e-11, worst                  # D itself is O(0.1 .. 1) here
+
+
+def test_oracle_square_publisher_follows_the_driver_source():
+    """The checker's in-loop square publisher (what the kernels' CDPR_OPT_PUBLISHER_SHAPE = 1 is compared with) against the
+    restated squarevelocitytest loop (P/src/squarevelocitytest.cpp:19-33): same float32 value at every one of 250 publishes,
+    both plateaus and the dead band visited."""
+    from oracle import binding as ob
+    from cdpr_simulation_b200 import drivers
+    b = ob.Batch(ob.default_config(4), 1, amp=[0.06], freq=[0.05], phase=[0.0])
+    b.publisher(1, 10.0)
+    d = drivers.SquareVelocity()
+    seen = set()
+    for _ in range(250):
+        v = d.publish()
+        b.step(1)
+        vt = b.targets()[0][0, 0]
+        assert np.float32(vt) == v
+        seen.add(float(np.sign(vt)))
+        b.step(99)
+    assert seen == {-1.0, 0.0, 1.0}

@@ -239,3 +239,54 @@ def test_flexr_full_size_properties(built_lib):
         assert np.array_equal(pa, pose[:2048]) and np.array_equal(ta, twist[:2048])
         assert np.array_equal(pa, pb) and np.array_equal(ta, tb)
         assert np.array_equal(a.pid_terms()[..., 4], terms[:2048, :, 4])
+
+
+def _square_pair(nc, n, seed, eps):
+    """squarevelocitytest.cpp inside the kernel and inside the oracle: 10 Hz publisher, per-instance amplitude / frequency / phase
+    (frequencies far above the driver's 0.05 Hz so that a short run crosses the dead band many times)."""
+    cfg = cb.default_config(nc)
+    cfg.velocity_epsilon = eps
+    cfg.sine_publish_hz = 10.0            # squarevelocitytest.cpp:6
+    rng = np.random.default_rng(seed)
+    amp, freq, phase = rng.uniform(0.03, 0.06, n), rng.uniform(0.3, 1.5, n), rng.uniform(0.0, 2 * np.pi, n)
+    _, _, _, pose7, twist6 = wl.c3_instances(n, seed)
+    gpu = cb.CdprBatch(cfg, n)
+    gpu.set_platform_state(pose7, twist6)
+    gpu.set_square_velocity_cmd(amp, freq, phase)
+    orc = ob.Batch(to_oracle_config(cfg), n, pose7, twist6, amp, freq, phase)
+    orc.publisher(1, cfg.sine_publish_hz)
+    return cfg, gpu, orc
+
+
+@pytest.mark.parametrize("nc", [4, 8])
+@pytest.mark.parametrize("eps", [-0.001, 0.02])
+def test_square_velocity_publisher_in_kernel(built_lib, nc, eps):
+    """The reference's second command driver (P/src/squarevelocitytest.cpp:19-33) run by the kernels' own publisher: +-amp
+    outside the dead band, 0 inside -- where, with velocityEpsilon >= 0, the cables hold through the position Pid
+    (JointForceCalculator.cpp:72-82).  Launch values: the fast kernel; with the hold band: k_step_flexr."""
+    cfg, gpu, orc = _square_pair(nc, 160, 97, eps)
+    assert gpu.kernel_variant == ("fast" if eps < 0 else "flex")
+    seen = set()
+    for k in [1] * 5 + [95, 1, 99, 1, 1, 98, 100, 100, 300, 700]:
+        gpu.step(k); orc.step(k)
+        _check(gpu, orc, 1e-9 if gpu.step_count <= 500 else 1e-7, f"after {gpu.step_count}")
+        seen.update(np.unique(np.sign(orc.targets()[0][:, 0])).tolist())
+    assert seen == {-1.0, 0.0, 1.0}, "the run is meant to visit both plateaus and the dead band"
+    if eps >= 0:
+        k, _ = _ran_pid(orc, cfg)
+        assert np.any(k == 1) and np.any(k == 0), "some cables hold, some move"
+    gpu.close()
+
+
+@pytest.mark.parametrize("eps", [-0.001, 0.02])
+def test_square_velocity_publisher_launch_split_bitwise(built_lib, eps):
+    _, a, _ = _square_pair(8, 128, 98, eps)
+    _, b, _ = _square_pair(8, 128, 98, eps)
+    a.step(1203)
+    for k in (1, 99, 100, 3, 250, 7, 743):
+        b.step(k)
+    pa, ta = a.platform_state(); pb, tb = b.platform_state()
+    assert np.array_equal(pa, pb) and np.array_equal(ta, tb)
+    for x, y in zip(a.joint_states(), b.joint_states()):
+        assert np.array_equal(x, y)
+    a.close(); b.close()
