@@ -99,6 +99,13 @@ for nc in (4, 8):
                 blob = g.get_state(); g.set_state(blob); g.step(7); g.pid_terms(); g.update(None)
                 print("ok hold toggling", nc, g.kernel_detail)
     os.environ.pop("CDPR_FLEX_CLASSIC", None)
+    for eps in (-0.001, 0.02):                               # the square-wave publisher: fast kernel / hold in the dead band
+        cfg = cb.default_config(nc)
+        cfg.velocity_epsilon = eps; cfg.sine_publish_hz = 10.0
+        with cb.CdprBatch(cfg, n) as g:
+            g.set_platform_state(pose7, twist6); g.set_square_velocity_cmd(amp, freq * 10.0, phase)
+            g.step(1); g.step(450)
+            print("ok square publisher", nc, g.kernel_detail)
     cfg = cb.default_config(nc)
     cfg.vel_pid.cmd_limit = 0.0; cfg.vel_pid.d_buffer_length = 5; cfg.vel_pid.d_degree = 1
     with cb.CdprBatch(cfg, n) as g:                          # catch-all kernel
