@@ -79,7 +79,7 @@ for nc in (4, 8):
             g.rollout(7, 11, wl.c5_rollouts(11, 4, nc), 5, [0, 0, 0.3], 0.1, pose7[:7], twist6[:7])
             print("ok flex lanes", lanes, nc, g.kernel_detail)
     os.environ.pop("CDPR_FLEX_LANES", None)
-    # round 3: k_step_flexr (0, 1, 2 stages; hold transitions through the on-chip and the HBM gap fit: commands that toggle the
+    # k_step_flexr (0, 1, 2 stages; hold transitions through the on-chip and the HBM gap fit: commands that toggle the
     # hold band faster and slower than 11 steps; independent robots) and, with CDPR_FLEX_CLASSIC, k_step_flex on the same
     for classic in ("0", "1"):
         os.environ["CDPR_FLEX_CLASSIC"] = classic
